@@ -1,0 +1,584 @@
+// quad_device.cuh — device-side building blocks of the batched quadrotor hot path (sm_100a).
+//
+// One CUDA thread advances one environment; the 13-float state, the rotor command and all RK stage
+// vectors live in registers.  Everything is templated on the arithmetic type R (float = production
+// mode, double = parity mode) and cites the reference lines it re-implements (paths relative to the
+// reference root; scipy/ = SciPy's integrate/_ivp package the reference calls at quadrotor_env.py:483).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+namespace qs {
+
+// --------------------------------------------------------------------------------------------
+// math dispatch
+// --------------------------------------------------------------------------------------------
+template <typename R> struct M_;
+template <> struct M_<float> {
+    static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
+    static __device__ __forceinline__ float asin(float x) { return asinf(x); }
+    static __device__ __forceinline__ float pow(float x, float y) { return powf(x, y); }
+    static __device__ __forceinline__ float log(float x) { return logf(x); }
+    static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
+    static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+    static __device__ __forceinline__ void sincospi(float x, float* s, float* c) { sincospif(x, s, c); }
+    static __device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_INF_F); }
+    static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
+};
+template <> struct M_<double> {
+    static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+    static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+    static __device__ __forceinline__ double abs(double x) { return ::fabs(x); }
+    static __device__ __forceinline__ double atan2(double y, double x) { return ::atan2(y, x); }
+    static __device__ __forceinline__ double asin(double x) { return ::asin(x); }
+    static __device__ __forceinline__ double pow(double x, double y) { return ::pow(x, y); }
+    static __device__ __forceinline__ double log(double x) { return ::log(x); }
+    static __device__ __forceinline__ double fmin(double a, double b) { return ::fmin(a, b); }
+    static __device__ __forceinline__ double fmax(double a, double b) { return ::fmax(a, b); }
+    static __device__ __forceinline__ void sincos(double x, double* s, double* c) { ::sincos(x, s, c); }
+    static __device__ __forceinline__ void sincospi(double x, double* s, double* c) { ::sincospi(x, s, c); }
+    static __device__ __forceinline__ double next_up(double x) { return ::nextafter(x, CUDART_INF); }
+    static __device__ __forceinline__ double inf() { return CUDART_INF; }
+};
+
+// --------------------------------------------------------------------------------------------
+// per-handle constants, derived on the host in double from qs_params (quadrotor_env.py:30-80)
+// --------------------------------------------------------------------------------------------
+enum : uint32_t {
+    F_DIRECT = 0x01u, F_CLIPPED = 0x02u, F_TRAINING = 0x04u, F_AUTO_RESET = 0x08u,
+    F_SENSOR = 0x10u, F_AUX = 0x20u
+};
+enum : uint32_t { EF_DONE = 1u, EF_HAS_SHAPING = 2u, EF_SOLVED = 4u };
+
+template <typename R> struct DevParams {
+    // rotor map (f2F :247-272, f2w :197-245)
+    R c8;            // T2WR*M*G/8
+    R inv_kf;        // 1/K_F
+    R arm;           // D
+    R km_over_kf;    // K_M/K_F
+    R i_r;           // I_R
+    R k_f, k_m, dkf; // K_F, K_M, D*K_F
+    R mix_f, mix_m, mix_z;   // 1/(4K_F), 1/(2 D K_F), 1/(4 K_M)
+    R u_max;         // T2WR*M*G/4/K_F
+    R effort_scale;  // K_F/(T2WR*M*G/4)*2
+    // rigid body (drone_eq :274-406)
+    R inv_m, g;
+    R kd_m[3];       // 0.5*RHO*C_D*A_i / M
+    R kdm_j[3];      // beam drag-moment coefficient / J_i   (:328-334 summed in closed form)
+    R inv_j[3];
+    R cross_j[3];    // (Jz-Jy)/Jx, (Jx-Jz)/Jy, (Jy-Jx)/Jz
+    // stepping
+    R dt, h_sub;     // env step, RK4 sub-interval
+    R bb[9];         // bb_cond :139-143
+    // reward (:511-573)
+    R sh_v, sh_psi, sh_ang;          // shaping weights folded with SHAPING_WEIGHT/sum and the normalisers
+    R tr_r[3], tr_e[3], tr_p[3];     // norm(ones(4)*TR_i), norm(ones(2)*TR_i*4), TR_P
+    R p_c, target_state, solved_reward, broken_reward;
+    R zero_control[4];
+    // reset distribution (:439-445)
+    R pos_clip, vel_clip, w_clip_lo, w_clip_hi;
+    // sensor (:587-608)
+    R s_accel_std, s_accel_drift, s_gyro_std, s_gyro_drift, s_mag_std, s_mag_drift, s_gps_p, s_gps_v;
+    int32_t n_limit; // n + T  :157
+    int32_t T;
+    int32_t substeps;
+    uint32_t flags;
+};
+
+// rotor command after the action map; constant across the RK stages of one env step
+template <typename R> struct Ctrl {
+    R f_m;           // F / M
+    R tau_j[3];      // M_i / J_i
+    R gyro_j[2];     // omega_r / Jx, omega_r / Jy
+};
+
+// --------------------------------------------------------------------------------------------
+// quaternion / Euler utilities — environment/quaternion_euler_utility.py
+// --------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void quat_normalize(const R q[4], R qn[4]) {
+    R inv = M_<R>::rsqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    qn[0] = q[0] * inv; qn[1] = q[1] * inv; qn[2] = q[2] * inv; qn[3] = q[3] * inv;
+}
+
+// quat_rot_mat :71-80 (row-major r[3*i+j])
+template <typename R>
+__device__ __forceinline__ void quat_rot_mat(const R q[4], R r[9]) {
+    R a = q[0], b = q[1], c = q[2], d = q[3];
+    R aa = a * a, bb = b * b, cc = c * c, dd = d * d;
+    R bc = b * c, ad = a * d, bd = b * d, ac = a * c, cd = c * d, ab = a * b;
+    r[0] = aa + bb - cc - dd; r[1] = R(2) * (bc - ad);  r[2] = R(2) * (bd + ac);
+    r[3] = R(2) * (bc + ad);  r[4] = aa - bb + cc - dd; r[5] = R(2) * (cd - ab);
+    r[6] = R(2) * (bd - ac);  r[7] = R(2) * (cd + ab);  r[8] = aa - bb - cc + dd;
+}
+
+// deriv_quat :58-69
+template <typename R>
+__device__ __forceinline__ void deriv_quat(const R w[3], const R q[4], R dq[4]) {
+    dq[0] = R(0.5) * (-w[0] * q[1] - w[1] * q[2] - w[2] * q[3]);
+    dq[1] = R(0.5) * (w[0] * q[0] + w[2] * q[2] - w[1] * q[3]);
+    dq[2] = R(0.5) * (w[1] * q[0] - w[2] * q[1] + w[0] * q[3]);
+    dq[3] = R(0.5) * (w[2] * q[0] + w[1] * q[1] - w[0] * q[2]);
+}
+
+// quat_euler :39-48 (no asin clamp: NaN propagates like the reference)
+template <typename R>
+__device__ __forceinline__ void quat_euler(const R q[4], R ang[3]) {
+    ang[0] = M_<R>::atan2(R(2) * (q[0] * q[1] + q[2] * q[3]), R(1) - R(2) * (q[1] * q[1] + q[2] * q[2]));
+    ang[1] = M_<R>::asin(R(2) * (q[0] * q[2] - q[3] * q[1]));
+    ang[2] = M_<R>::atan2(R(2) * (q[0] * q[3] + q[1] * q[2]), R(1) - R(2) * (q[2] * q[2] + q[3] * q[3]));
+}
+
+// euler_quat :17-36
+template <typename R>
+__device__ __forceinline__ void euler_quat(const R ang[3], R q[4]) {
+    R sp, cp, st, ct, sps, cps;
+    M_<R>::sincos(ang[0] * R(0.5), &sp, &cp);
+    M_<R>::sincos(ang[1] * R(0.5), &st, &ct);
+    M_<R>::sincos(ang[2] * R(0.5), &sps, &cps);
+    R t[4];
+    t[0] = cp * ct * cps + sp * st * sps;
+    t[1] = sp * ct * cps - cp * st * sps;
+    t[2] = cp * st * cps + sp * ct * sps;
+    t[3] = cp * ct * sps - sp * st * cps;
+    quat_normalize(t, q);
+}
+
+// --------------------------------------------------------------------------------------------
+// rotor maps
+// --------------------------------------------------------------------------------------------
+// f2F :247-272 (direct mode).  a[] already clipped to [-1,1] (:470).
+template <typename R>
+__device__ __forceinline__ void rotor_direct(const DevParams<R>& p, const R a[4], R w[4], R fm[4]) {
+    R f0 = (a[0] + R(1)) * p.c8, f1 = (a[1] + R(1)) * p.c8, f2 = (a[2] + R(1)) * p.c8, f3 = (a[3] + R(1)) * p.c8;
+    w[0] = M_<R>::sqrt(f0 * p.inv_kf); w[1] = M_<R>::sqrt(f1 * p.inv_kf);
+    w[2] = M_<R>::sqrt(f2 * p.inv_kf); w[3] = M_<R>::sqrt(f3 * p.inv_kf);
+    fm[0] = f0 + f1 + f2 + f3;
+    fm[1] = (f2 - f0) * p.arm;
+    fm[2] = (f1 - f3) * p.arm;
+    fm[3] = (-f0 + f1 - f2 + f3) * p.km_over_kf;
+}
+
+// f2w :197-245 (indirect mode): closed-form inverse of the 4x4 mixer the reference solves with LU.
+template <typename R>
+__device__ __forceinline__ void rotor_indirect(const DevParams<R>& p, bool clipped, const R fm_in[4],
+                                               R effort[4], R w[4], R fm[4]) {
+    R uf = fm_in[0] * p.mix_f, ux = fm_in[1] * p.mix_m, uy = fm_in[2] * p.mix_m, uz = fm_in[3] * p.mix_z;
+    R u[4] = {uf - ux - uz, uf + uy + uz, uf + ux - uz, uf - uy + uz};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (clipped) {
+            // np.clip(u, 0, max) == minimum(maximum(u, 0), max); NaN propagates
+            R v = u[k];
+            v = (v < R(0)) ? R(0) : v;
+            v = (v > p.u_max) ? p.u_max : v;
+            u[k] = v;
+            w[k] = M_<R>::sqrt(v);
+        } else {
+            R s = (u[k] < R(0)) ? R(-1) : R(1);
+            w[k] = M_<R>::sqrt(M_<R>::abs(u[k])) * s;
+        }
+        effort[k] = u[k] * p.effort_scale - R(1);
+    }
+    fm[0] = p.k_f * (u[0] + u[1] + u[2] + u[3]);
+    fm[1] = p.dkf * (u[2] - u[0]);
+    fm[2] = p.dkf * (u[1] - u[3]);
+    fm[3] = p.k_m * (-u[0] + u[1] - u[2] + u[3]);
+}
+
+template <typename R>
+__device__ __forceinline__ Ctrl<R> make_ctrl(const DevParams<R>& p, const R fm[4], const R w[4]) {
+    Ctrl<R> c;
+    R omega_r = (-w[0] + w[1] - w[2] + w[3]) * p.i_r;          // :345
+    c.f_m = fm[0] * p.inv_m;
+    c.tau_j[0] = fm[1] * p.inv_j[0]; c.tau_j[1] = fm[2] * p.inv_j[1]; c.tau_j[2] = fm[3] * p.inv_j[2];
+    c.gyro_j[0] = omega_r * p.inv_j[0]; c.gyro_j[1] = omega_r * p.inv_j[1];
+    return c;
+}
+
+// --------------------------------------------------------------------------------------------
+// drone_eq :274-406 — RHS of the 13-state ODE.  y = [x,vx,y,vy,z,vz,q0..q3,wx,wy,wz]
+// --------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void drone_rhs(const DevParams<R>& p, const Ctrl<R>& c, const R y[13], R dy[13]) {
+    R qn[4];
+    quat_normalize(&y[6], qn);                                   // :311-312
+    R r[9];
+    quat_rot_mat(qn, r);                                         // :315
+    R vx = y[1], vy = y[3], vz = y[5];
+    R vbx = r[0] * vx + r[3] * vy + r[6] * vz;                   // :322  R^T v
+    R vby = r[1] * vx + r[4] * vy + r[7] * vz;
+    R vbz = r[2] * vx + r[5] * vy + r[8] * vz;
+    R fx = -p.kd_m[0] * (M_<R>::abs(vbx) * vbx);                 // :323 (already / M)
+    R fy = -p.kd_m[1] * (M_<R>::abs(vby) * vby);
+    R fz = c.f_m - p.kd_m[2] * (M_<R>::abs(vbz) * vbz);          // :352-353
+    dy[0] = vx; dy[2] = vy; dy[4] = vz;
+    dy[1] = r[0] * fx + r[1] * fy + r[2] * fz;                   // :357-367
+    dy[3] = r[3] * fx + r[4] * fy + r[5] * fz;
+    dy[5] = r[6] * fx + r[7] * fy + r[8] * fz - p.g;
+    R wx = y[10], wy = y[11], wz = y[12];
+    // m_in = m_action + m_gyro + m_drag - w x Jw  (:378), times J^-1 (:384-388, J diagonal)
+    dy[10] = c.tau_j[0] - c.gyro_j[0] * wx - p.kdm_j[0] * (M_<R>::abs(wx) * wx) - p.cross_j[0] * (wy * wz);
+    dy[11] = c.tau_j[1] + c.gyro_j[1] * wy - p.kdm_j[1] * (M_<R>::abs(wy) * wy) - p.cross_j[1] * (wx * wz);
+    dy[12] = c.tau_j[2] - p.kdm_j[2] * (M_<R>::abs(wz) * wz) - p.cross_j[2] * (wx * wy);
+    deriv_quat(&y[10], qn, &dy[6]);                              // :392
+}
+
+// --------------------------------------------------------------------------------------------
+// integrators
+// --------------------------------------------------------------------------------------------
+// Fixed-step classical RK4, S sub-intervals of length p.h_sub.
+template <typename R>
+__device__ __forceinline__ void integrate_rk4(const DevParams<R>& p, const Ctrl<R>& c, R y[13]) {
+    const R h = p.h_sub, hh = p.h_sub * R(0.5), h6 = p.h_sub * R(1.0 / 6.0);
+    for (int s = 0; s < p.substeps; ++s) {
+        R k[13], acc[13], yt[13];
+        drone_rhs(p, c, y, k);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { acc[j] = k[j]; yt[j] = y[j] + hh * k[j]; }
+        drone_rhs(p, c, yt, k);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { acc[j] += R(2) * k[j]; yt[j] = y[j] + hh * k[j]; }
+        drone_rhs(p, c, yt, k);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { acc[j] += R(2) * k[j]; yt[j] = y[j] + h * k[j]; }
+        drone_rhs(p, c, yt, k);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { y[j] += h6 * (acc[j] + k[j]); }
+    }
+}
+
+// Dormand–Prince 5(4) tableau — scipy/integrate/_ivp/rk.py (class RK45: A, B, E)
+#define QS_DP_A21 (1.0 / 5)
+#define QS_DP_A31 (3.0 / 40)
+#define QS_DP_A32 (9.0 / 40)
+#define QS_DP_A41 (44.0 / 45)
+#define QS_DP_A42 (-56.0 / 15)
+#define QS_DP_A43 (32.0 / 9)
+#define QS_DP_A51 (19372.0 / 6561)
+#define QS_DP_A52 (-25360.0 / 2187)
+#define QS_DP_A53 (64448.0 / 6561)
+#define QS_DP_A54 (-212.0 / 729)
+#define QS_DP_A61 (9017.0 / 3168)
+#define QS_DP_A62 (-355.0 / 33)
+#define QS_DP_A63 (46732.0 / 5247)
+#define QS_DP_A64 (49.0 / 176)
+#define QS_DP_A65 (-5103.0 / 18656)
+#define QS_DP_B1 (35.0 / 384)
+#define QS_DP_B3 (500.0 / 1113)
+#define QS_DP_B4 (125.0 / 192)
+#define QS_DP_B5 (-2187.0 / 6784)
+#define QS_DP_B6 (11.0 / 84)
+#define QS_DP_E1 (-71.0 / 57600)
+#define QS_DP_E3 (71.0 / 16695)
+#define QS_DP_E4 (-71.0 / 1920)
+#define QS_DP_E5 (17253.0 / 339200)
+#define QS_DP_E6 (-22.0 / 525)
+#define QS_DP_E7 (1.0 / 40)
+
+template <typename R>
+__device__ __forceinline__ R rms13(const R v[13]) {           // scipy/.../common.py:63-65
+    R s = R(0);
+#pragma unroll
+    for (int j = 0; j < 13; ++j) s += v[j] * v[j];
+    return M_<R>::sqrt(s) / M_<R>::sqrt(R(13));
+}
+
+// Replica of solve_ivp(drone_eq, (0, t_bound), y0) with all defaults, as the reference calls it at
+// quadrotor_env.py:483: RungeKutta.__init__ (rk.py:85-105), select_initial_step (common.py:68-134),
+// _step_impl (rk.py:111-183), rk_step (rk.py:14-70), OdeSolver.step (base.py:179-210).
+// Keeps only y(t_bound) like the caller (`self.y[:, -1]`, :485).  Returns the number of RHS calls.
+template <typename R>
+__device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>& c, R y[13]) {
+    const R rtol = R(1e-3), atol = R(1e-6);
+    const R t_bound = p.dt;
+    R t = R(0);
+    R f[13], tmp[13], scale[13];
+    drone_rhs(p, c, y, f);
+    int nfev = 1;
+    // ---- select_initial_step
+    R h_abs;
+    {
+#pragma unroll
+        for (int j = 0; j < 13; ++j) scale[j] = atol + M_<R>::abs(y[j]) * rtol;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) tmp[j] = y[j] / scale[j];
+        R d0 = rms13(tmp);
+#pragma unroll
+        for (int j = 0; j < 13; ++j) tmp[j] = f[j] / scale[j];
+        R d1 = rms13(tmp);
+        R h0 = (d0 < R(1e-5) || d1 < R(1e-5)) ? R(1e-6) : R(0.01) * d0 / d1;
+        h0 = M_<R>::fmin(h0, t_bound);
+        R y1[13], f1[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) y1[j] = y[j] + h0 * f[j];
+        drone_rhs(p, c, y1, f1);
+        ++nfev;
+#pragma unroll
+        for (int j = 0; j < 13; ++j) tmp[j] = (f1[j] - f[j]) / scale[j];
+        R d2 = rms13(tmp) / h0;
+        R h1;
+        if (d1 <= R(1e-15) && d2 <= R(1e-15)) h1 = M_<R>::fmax(R(1e-6), h0 * R(1e-3));
+        else h1 = M_<R>::pow(R(0.01) / M_<R>::fmax(d1, d2), R(1.0 / 5));
+        h_abs = M_<R>::fmin(M_<R>::fmin(R(100) * h0, h1), t_bound);
+    }
+    // ---- solver.step() until t >= t_bound
+    R K2[13], K3[13], K4[13], K5[13], K6[13], K7[13], yn[13];
+    for (int guard = 0; guard < 100000; ++guard) {
+        R min_step = R(10) * M_<R>::abs(M_<R>::next_up(t) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false, accepted = false, failed = false;
+        while (!accepted) {
+            if (h_abs < min_step) { failed = true; break; }
+            R t_new = t + h_abs;
+            if (t_new - t_bound > R(0)) t_new = t_bound;
+            R h = t_new - t;
+            h_abs = M_<R>::abs(h);
+            // rk_step: K1 = f
+#pragma unroll
+            for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A21)) * h;
+            drone_rhs(p, c, tmp, K2);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A31) + K2[j] * R(QS_DP_A32)) * h;
+            drone_rhs(p, c, tmp, K3);
+#pragma unroll
+            for (int j = 0; j < 13; ++j)
+                tmp[j] = y[j] + (f[j] * R(QS_DP_A41) + K2[j] * R(QS_DP_A42) + K3[j] * R(QS_DP_A43)) * h;
+            drone_rhs(p, c, tmp, K4);
+#pragma unroll
+            for (int j = 0; j < 13; ++j)
+                tmp[j] = y[j] + (f[j] * R(QS_DP_A51) + K2[j] * R(QS_DP_A52) + K3[j] * R(QS_DP_A53) + K4[j] * R(QS_DP_A54)) * h;
+            drone_rhs(p, c, tmp, K5);
+#pragma unroll
+            for (int j = 0; j < 13; ++j)
+                tmp[j] = y[j] + (f[j] * R(QS_DP_A61) + K2[j] * R(QS_DP_A62) + K3[j] * R(QS_DP_A63) + K4[j] * R(QS_DP_A64) +
+                                 K5[j] * R(QS_DP_A65)) * h;
+            drone_rhs(p, c, tmp, K6);
+#pragma unroll
+            for (int j = 0; j < 13; ++j)
+                yn[j] = y[j] + h * (f[j] * R(QS_DP_B1) + K3[j] * R(QS_DP_B3) + K4[j] * R(QS_DP_B4) + K5[j] * R(QS_DP_B5) +
+                                    K6[j] * R(QS_DP_B6));
+            drone_rhs(p, c, yn, K7);
+            nfev += 6;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) {
+                R sc = atol + M_<R>::fmax(M_<R>::abs(y[j]), M_<R>::abs(yn[j])) * rtol;
+                R e = (f[j] * R(QS_DP_E1) + K3[j] * R(QS_DP_E3) + K4[j] * R(QS_DP_E4) + K5[j] * R(QS_DP_E5) +
+                       K6[j] * R(QS_DP_E6) + K7[j] * R(QS_DP_E7)) * h;
+                tmp[j] = e / sc;
+            }
+            R err = rms13(tmp);
+            if (err < R(1)) {
+                R factor = (err == R(0)) ? R(10) : M_<R>::fmin(R(10), R(0.9) * M_<R>::pow(err, R(-0.2)));
+                if (rejected) factor = M_<R>::fmin(R(1), factor);
+                h_abs *= factor;
+                accepted = true;
+                t = t_new;
+            } else if (err != err) {
+                // NaN error norm: the reference would spin forever; leave the poisoned state and stop.
+                accepted = true; failed = true; t = t_bound;
+            } else {
+                h_abs *= M_<R>::fmax(R(0.2), R(0.9) * M_<R>::pow(err, R(-0.2)));
+                rejected = true;
+            }
+        }
+        if (failed && !accepted) break;          // TOO_SMALL_STEP: solve_ivp stops, last accepted y is kept
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { y[j] = yn[j]; f[j] = K7[j]; }
+        if (failed || t - t_bound >= R(0)) break;
+    }
+    return nfev;
+}
+
+// --------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11) — counter-based RNG for resets / noise / action sampling
+// --------------------------------------------------------------------------------------------
+enum : uint32_t { RNG_RESET = 0, RNG_SENSOR = 1, RNG_ACTION = 2, RNG_POLICY = 3 };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+        k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t block,
+                                              uint32_t stream) {
+    return philox4x32_10(make_uint4(env_id, episode, block, stream),
+                         make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+
+template <typename R> __device__ __forceinline__ R u32_to_unit(uint32_t u) {     // (u + 0.5) * 2^-32 in (0,1]
+    return (R(u) + R(0.5)) * R(1.0 / 4294967296.0);
+}
+
+template <typename R> __device__ __forceinline__ void box_muller(R u1, R u2, R* n0, R* n1) {
+    R r = M_<R>::sqrt(R(-2) * M_<R>::log(u1));
+    R s, c;
+    M_<R>::sincospi(R(2) * u2, &s, &c);
+    *n0 = r * c; *n1 = r * s;
+}
+
+template <typename R> __device__ __forceinline__ R clampr(R v, R lo, R hi) {
+    return M_<R>::fmin(M_<R>::fmax(v, lo), hi);
+}
+
+// Random branch of quad.reset (:439-445): ang ~ U(-.5,.5)^3, pos ~ clip(N(0,2),+-2.5),
+// vel ~ clip(N(0,2),+-5), w ~ clip(N(0,2),-15,+7.5) (asymmetric, as in the reference).
+template <typename R>
+__device__ __forceinline__ void sample_reset_state(const DevParams<R>& p, uint64_t seed, uint32_t env_id,
+                                                   uint32_t episode, R y[13], R ang[3]) {
+    uint4 b0 = philox_block(seed, env_id, episode, 0, RNG_RESET);
+    ang[0] = u32_to_unit<R>(b0.x) - R(0.5);
+    ang[1] = u32_to_unit<R>(b0.y) - R(0.5);
+    ang[2] = u32_to_unit<R>(b0.z) - R(0.5);
+    R n[12];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) {
+        uint4 u = philox_block(seed, env_id, episode, b + 1, RNG_RESET);
+        box_muller(u32_to_unit<R>(u.x), u32_to_unit<R>(u.y), &n[4 * b + 0], &n[4 * b + 1]);
+        box_muller(u32_to_unit<R>(u.z), u32_to_unit<R>(u.w), &n[4 * b + 2], &n[4 * b + 3]);
+    }
+    y[0] = clampr(n[0] * R(2), -p.pos_clip, p.pos_clip);
+    y[2] = clampr(n[1] * R(2), -p.pos_clip, p.pos_clip);
+    y[4] = clampr(n[2] * R(2), -p.pos_clip, p.pos_clip);
+    y[1] = clampr(n[3] * R(2), -p.vel_clip, p.vel_clip);
+    y[3] = clampr(n[4] * R(2), -p.vel_clip, p.vel_clip);
+    y[5] = clampr(n[5] * R(2), -p.vel_clip, p.vel_clip);
+    euler_quat(ang, &y[6]);
+    y[10] = clampr(n[6] * R(2), p.w_clip_lo, p.w_clip_hi);
+    y[11] = clampr(n[7] * R(2), p.w_clip_lo, p.w_clip_hi);
+    y[12] = clampr(n[8] * R(2), p.w_clip_lo, p.w_clip_hi);
+}
+
+// --------------------------------------------------------------------------------------------
+// one environment, in registers
+// --------------------------------------------------------------------------------------------
+template <typename R> struct Env {
+    R y[13];
+    R prev_ang[3];       // quad.prev_ang — NOT cleared by reset (reference quirk, :171-172/:492-493)
+    R prev_shaping;
+    R abs_sum;
+    R ep_return;
+    int32_t i;
+    uint32_t flags;      // EF_*
+    uint32_t episode;
+};
+
+template <typename R> struct StepOut {
+    R vq[4];             // V_q of the trailing drone_eq call (FSAL stage) :392,:486
+    R ang[3];
+    R ang_vel[3];
+    R reward;
+    R effort[4];
+    R w[4];
+    R clipped[4];        // quad.clipped_action :472,:477
+    R fm[4];             // body thrust and moments applied
+    bool done;           // value `quad.step` returns
+    bool solved;
+    bool broken, timeout;
+};
+
+// quad.step :458-498 for one env.  `a_in` = action as given by the caller.
+template <typename R, int INTEG, bool DIRECT>
+__device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o,
+                                          Ctrl<R>* ctrl_out = nullptr) {
+    e.i += 1;                                                    // :467
+    R act[4], fm[4];
+    if (DIRECT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {                            // np.clip(action,-1,1) :470
+            R v = a_in[k];
+            v = (v < R(-1)) ? R(-1) : v;
+            v = (v > R(1)) ? R(1) : v;
+            act[k] = v; o.effort[k] = v;
+        }
+        rotor_direct(p, act, o.w, fm);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) act[k] = a_in[k];            // reward uses the RAW action :476,:553
+        rotor_indirect(p, (p.flags & F_CLIPPED) != 0, a_in, o.effort, o.w, fm);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o.fm[k] = fm[k]; o.clipped[k] = DIRECT ? act[k] : fm[k]; }
+    Ctrl<R> c = make_ctrl(p, fm, o.w);
+    if (ctrl_out) *ctrl_out = c;
+    if (INTEG == 1) integrate_rk45(p, c, e.y);                   // :483
+    else integrate_rk4(p, c, e.y);
+    // observation tail: V_q = 1/2 Omega(w_new) normalize(q_new)  (:392 evaluated at the FSAL stage)
+    R qn[4];
+    quat_normalize(&e.y[6], qn);                                 // :488-489
+    deriv_quat(&e.y[10], qn, o.vq);
+    quat_euler(qn, o.ang);                                       // :491
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.ang_vel[k] = (o.ang[k] - e.prev_ang[k]) / p.dt;        // :492
+        e.prev_ang[k] = o.ang[k];                                // :493
+    }
+    // done_condition :500-509 (>=, sticky; NaN compares false)
+    bool done = (e.flags & EF_DONE) != 0;
+    {
+        const R cx[9] = {e.y[1], e.y[3], e.y[5], o.ang[0], o.ang[1], o.ang[2], e.y[10], e.y[11], e.y[12]};
+#pragma unroll
+        for (int k = 0; k < 9; ++k) done = done || (M_<R>::abs(cx[k]) >= p.bb[k]);
+    }
+    // reward_function :511-573
+    R v2 = e.y[1] * e.y[1] + e.y[3] * e.y[3] + e.y[5] * e.y[5];
+    R e2 = o.ang[0] * o.ang[0] + o.ang[1] * o.ang[1];
+    R psi = o.ang[2];
+    R nv = M_<R>::sqrt(v2), ne = M_<R>::sqrt(e2);
+    R shaping = -(p.sh_v * nv + p.sh_psi * M_<R>::abs(psi) + p.sh_ang * ne);          // :529-531
+    R nr = M_<R>::sqrt(v2 + psi * psi);
+    {
+        bool taken = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {                            // cascade :535-542
+            bool c1 = !taken && (nr < p.tr_r[k]);
+            bool c2 = c1 && (ne < p.tr_e[k]);
+            shaping += c1 ? p.tr_p[k] : R(0);
+            shaping += c2 ? p.tr_p[k] : R(0);
+            taken = taken || c1;
+        }
+    }
+    R reward = (e.flags & EF_HAS_SHAPING) ? (shaping - e.prev_shaping) : R(0);       // :545-547
+    e.prev_shaping = shaping;
+    R pen = R(0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { R d = act[k] - p.zero_control[k]; pen += d * d; }
+    reward += -pen * p.p_c;                                      // :553-554
+    R cur = v2 + (e2 + psi * psi) + (e.y[10] * e.y[10] + e.y[11] * e.y[11] + e.y[12] * e.y[12]);   // :558
+    bool solved = (e.flags & EF_SOLVED) != 0;
+    bool broken = false, timeout = false;
+    if (cur < p.target_state) {                                  // :562-566
+        reward += p.solved_reward; solved = true;
+        if (p.flags & F_TRAINING) done = true;
+    } else if (e.i >= p.n_limit) {                               // :567-570
+        solved = false; done = true; timeout = true;
+    } else if (done) {                                           // :571-573
+        reward += p.broken_reward; solved = false; broken = true;
+    }
+    e.flags = (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u);
+    e.abs_sum += M_<R>::sqrt(o.effort[0] * o.effort[0] + o.effort[1] * o.effort[1] + o.effort[2] * o.effort[2] +
+                             o.effort[3] * o.effort[3]);         // :575-577
+    o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
+}
+
+// head of quad.reset :428-438 for one env (state already chosen); the T warm-up steps follow in the caller
+template <typename R>
+__device__ __forceinline__ void reset_head(Env<R>& e) {
+    e.flags = 0u;            // solved=0, done=False, prev_shaping=None
+    e.i = 0;
+    e.abs_sum = R(0);
+    e.ep_return = R(0);
+}
+
+}  // namespace qs

@@ -1,0 +1,963 @@
+// quadsim.cu — kernels and C ABI of libquadsim.so (see include/quadsim.h).  sm_100a only, no CPU fallback.
+//
+// HBM layout (per handle, structure-of-arrays, env index fastest, row stride ld = N rounded up to 32):
+//   obs17   [17][ld]  rows 0..9 = state[0:10], rows 10..13 = V_q, rows 14..16 = body rates
+//                     -> the 14-float observation of quad.step (:486) is rows 0..13 *zero-copy*, and the
+//                        13-float state is rows 0..9 ++ 14..16, so a step never writes the same value twice.
+//   prev_ang[3][ld]   Euler angles of the last step (= quad.ang = quad.prev_ang after a step)
+//   prev_shaping, abs_sum, ep_return, reward [ld];  step_i i32[ld]; episode u32[ld]; flags/done/solved u8[ld]
+//   (+ AUX rows and sensor rows when enabled)
+// A warp reads/writes 32 consecutive envs of one row = one 128-byte line per request (FP32).
+#include "../../include/quadsim.h"
+#include "quad_device.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace qs;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+#define QS_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e_ = (call);                                                        \
+        if (e_ != cudaSuccess) return fail(QS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+extern "C" const char* qs_last_error(void) { return g_err; }
+extern "C" int qs_version(void) { return QS_VERSION; }
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+template <typename R> struct SimView {
+    int64_t N, ld;
+    R* obs17;
+    R* prev_ang;
+    R* prev_shaping;
+    R* abs_sum;
+    R* ep_return;
+    R* reward;
+    int32_t* step_i;
+    uint32_t* episode;
+    uint8_t* flags;
+    uint8_t* done;
+    uint8_t* solved;
+    R* ang_vel;       // AUX (nullable)
+    R* step_effort;
+    R* w;
+    R* accel;
+    R* acc_read;
+    R* mat_rot;
+    R* clipped_action;
+    R* fm;
+    R* sensed_obs;    // SENSOR (nullable)
+    R* sensor_state;
+    double* stats;
+    uint64_t seed;
+    uint32_t env_id_offset;
+};
+
+struct Slot { void* ptr; int32_t channels; int32_t elem; };
+
+struct qs_sim {
+    qs_config cfg;
+    int64_t N, ld;
+    int rs;                 // sizeof(real)
+    char* ws;
+    size_t ws_bytes;
+    bool owns_ws;
+    Slot slot[QS_FIELD_COUNT_];
+    void* obs17;
+    void* action_stage;     // [4][ld] staging for qs_step_host
+    double* stats;
+    DevParams<float> pf;
+    DevParams<double> pd;
+    int sm_count;
+    uint64_t seed;
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+template <typename R> static DevParams<R> make_params(const qs_config& c) {
+    const qs_params& q = c.params;
+    DevParams<R> p;
+    memset(&p, 0, sizeof(p));
+    const double tmg = q.t2wr * q.mass * q.gravity;
+    p.c8 = R(tmg / 8);
+    p.inv_kf = R(1.0 / q.k_f);
+    p.arm = R(q.arm);
+    p.km_over_kf = R(q.k_m / q.k_f);
+    p.i_r = R(q.i_r);
+    p.k_f = R(q.k_f); p.k_m = R(q.k_m); p.dkf = R(q.arm * q.k_f);
+    p.mix_f = R(1.0 / (4 * q.k_f)); p.mix_m = R(1.0 / (2 * q.arm * q.k_f)); p.mix_z = R(1.0 / (4 * q.k_m));
+    p.u_max = R(tmg / 4 / q.k_f);
+    p.effort_scale = R(q.k_f / (tmg / 4) * 2);
+    p.inv_m = R(1.0 / q.mass); p.g = R(q.gravity);
+    const double area[3] = {q.beam_thickness * 2 * q.arm, q.beam_thickness * 2 * q.arm, q.beam_thickness * 2 * q.arm * 2};
+    for (int k = 0; k < 3; ++k) p.kd_m[k] = R(0.5 * q.rho * q.c_d * area[k] / q.mass);
+    double s3 = 0;                                    // sum over np.linspace(0, D, 10) of xx^3   (:328-334)
+    for (int k = 0; k < 10; ++k) { double xx = q.arm * k / 9.0; s3 += xx * xx * xx; }
+    const double c0 = q.rho * q.c_d * q.beam_thickness * q.arm / 10;
+    p.kdm_j[0] = R(c0 * s3 / q.j[0]); p.kdm_j[1] = R(c0 * s3 / q.j[1]); p.kdm_j[2] = R(2 * c0 * s3 / q.j[2]);
+    for (int k = 0; k < 3; ++k) p.inv_j[k] = R(1.0 / q.j[k]);
+    p.cross_j[0] = R((q.j[2] - q.j[1]) / q.j[0]);
+    p.cross_j[1] = R((q.j[0] - q.j[2]) / q.j[1]);
+    p.cross_j[2] = R((q.j[1] - q.j[0]) / q.j[2]);
+    p.dt = R(c.t_step); p.h_sub = R(c.t_step / c.substeps);
+    const double bb[9] = {q.bb_vel, q.bb_vel, q.bb_vel, q.bb_ang, q.bb_ang, 3.0 / 4 * M_PI,
+                          q.bb_vel * 2, q.bb_vel * 2, q.bb_vel * 2};                       // :139-143
+    for (int k = 0; k < 9; ++k) p.bb[k] = R(bb[k]);
+    const double sw = q.shaping_weight / (q.shaping_internal_weights[0] + q.shaping_internal_weights[1] +
+                                          q.shaping_internal_weights[2]);
+    p.sh_v = R(sw * q.shaping_internal_weights[0] / q.bb_vel);
+    p.sh_psi = R(sw * q.shaping_internal_weights[1] / 4);
+    p.sh_ang = R(sw * q.shaping_internal_weights[2] / q.bb_ang);
+    for (int k = 0; k < 3; ++k) {
+        p.tr_r[k] = R(std::sqrt(4 * (q.tr[k] * q.tr[k])));                                 // norm(ones(4)*TR_i)
+        p.tr_e[k] = R(std::sqrt(2 * ((q.tr[k] * 4) * (q.tr[k] * 4))));                     // norm(ones(2)*TR_i*4)
+        p.tr_p[k] = R(q.tr_p[k]);
+    }
+    p.p_c = R(q.p_c);
+    p.target_state = R(9 * (q.tr[0] * q.tr[0]));
+    p.solved_reward = R(q.solved_reward); p.broken_reward = R(q.broken_reward);
+    if (c.flags & QS_FLAG_DIRECT_CONTROL) {
+        for (int k = 0; k < 4; ++k) p.zero_control[k] = R(2 / q.t2wr - 1);                 // :164-165
+    } else {
+        p.zero_control[0] = R(q.mass * q.gravity);                                         // :166-167
+    }
+    p.pos_clip = R(q.bb_pos / 2); p.vel_clip = R(q.bb_vel / 2);
+    p.w_clip_lo = R(-q.bb_vel * 1.5); p.w_clip_hi = R(q.bb_pos * 1.5);                     // :445 (asymmetric)
+    p.s_accel_std = R(q.accel_std); p.s_accel_drift = R(q.accel_bias_drift);
+    p.s_gyro_std = R(q.gyro_std); p.s_gyro_drift = R(q.gyro_bias_drift);
+    p.s_mag_std = R(q.magnet_std); p.s_mag_drift = R(q.magnet_bias_drift);
+    p.s_gps_p = R(q.gps_std_p); p.s_gps_v = R(q.gps_std_v);
+    p.n_limit = c.n_max + c.T;                                                             // :157
+    p.T = c.T;
+    p.substeps = c.substeps;
+    p.flags = c.flags;
+    return p;
+}
+
+extern "C" int qs_default_config(qs_config* cfg) {
+    if (!cfg) return fail(QS_EINVAL, "qs_default_config: cfg is NULL");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->n_envs = 1;
+    cfg->t_step = 0.01;
+    cfg->n_max = 1000;
+    cfg->T = 1;
+    cfg->substeps = 1;
+    cfg->precision = QS_F32;
+    cfg->integrator = QS_RK4;
+    cfg->flags = QS_FLAG_DIRECT_CONTROL | QS_FLAG_CLIPPED | QS_FLAG_TRAINING;
+    qs_params& p = cfg->params;
+    p.mass = 1.03; p.gravity = 9.82; p.rho = 1.2041; p.c_d = 1.1;
+    p.k_f = 1.435e-5; p.k_m = 2.4086e-7; p.i_r = 5e-5; p.t2wr = 2;
+    p.j[0] = 16.83e-3; p.j[1] = 16.83e-3; p.j[2] = 28.34e-3;
+    p.arm = 0.26; p.beam_thickness = 0.05;
+    p.bb_vel = 10; p.bb_ang = M_PI / 2; p.bb_pos = 5;
+    p.solved_reward = 20; p.broken_reward = -20; p.shaping_weight = 5;
+    p.shaping_internal_weights[0] = 15; p.shaping_internal_weights[1] = 4; p.shaping_internal_weights[2] = 1;
+    p.p_c = 0.003;
+    p.tr[0] = 0.005; p.tr[1] = 0.01; p.tr[2] = 0.1;
+    p.tr_p[0] = 3; p.tr_p[1] = 2; p.tr_p[2] = 1;
+    p.accel_std = 0.1; p.accel_bias_drift = 0.0005; p.gyro_std = 0.035; p.gyro_bias_drift = 0.00015;
+    p.magnet_std = 15; p.magnet_bias_drift = 0.075; p.gps_std_p = 1.71; p.gps_std_v = 0.5;
+    return QS_OK;
+}
+
+// row tables -------------------------------------------------------------------------------------
+struct RowSpec { int field; int channels; int elem; /*0 = real*/ uint32_t need_flag; };
+static const RowSpec kRows[] = {
+    {QS_FIELD_OBS, 17, 0, 0},            // obs17 (OBS = rows 0..13)
+    {QS_FIELD_ANG, 3, 0, 0},             // prev_ang
+    {QS_FIELD_PREV_SHAPING, 1, 0, 0},
+    {QS_FIELD_ABS_SUM, 1, 0, 0},
+    {QS_FIELD_EP_RETURN, 1, 0, 0},
+    {QS_FIELD_REWARD, 1, 0, 0},
+    {QS_FIELD_I, 1, 4, 0},
+    {QS_FIELD_EPISODE, 1, 4, 0},
+    {QS_FIELD_FLAGS, 1, 1, 0},
+    {QS_FIELD_DONE, 1, 1, 0},
+    {QS_FIELD_SOLVED, 1, 1, 0},
+    {QS_FIELD_ANG_VEL, 3, 0, QS_FLAG_AUX},
+    {QS_FIELD_STEP_EFFORT, 4, 0, QS_FLAG_AUX},
+    {QS_FIELD_W, 4, 0, QS_FLAG_AUX},
+    {QS_FIELD_ACCEL, 3, 0, QS_FLAG_AUX},
+    {QS_FIELD_ACC_READ, 3, 0, QS_FLAG_AUX},
+    {QS_FIELD_MAT_ROT, 9, 0, QS_FLAG_AUX},
+    {QS_FIELD_CLIPPED_ACTION, 4, 0, QS_FLAG_AUX},
+    {QS_FIELD_FM, 4, 0, QS_FLAG_AUX},
+    {QS_FIELD_SENSED_OBS, 14, 0, QS_FLAG_SENSOR_NOISE},
+    {QS_FIELD_SENSOR_STATE, QS_SENSOR_STATE_DIM, 0, QS_FLAG_SENSOR_NOISE},
+};
+static const int kNumRows = sizeof(kRows) / sizeof(kRows[0]);
+
+static int validate(const qs_config* c) {
+    if (!c) return fail(QS_EINVAL, "config is NULL");
+    if (c->n_envs < 1) return fail(QS_EINVAL, "n_envs must be >= 1");
+    if (c->n_envs + c->env_id_offset > 0xFFFFFFFFll || c->env_id_offset < 0)
+        return fail(QS_EINVAL, "global env ids must fit in 32 bits");
+    if (!(c->t_step > 0)) return fail(QS_EINVAL, "t_step must be > 0");
+    if (c->T < 1 || c->T > 64) return fail(QS_EINVAL, "T must be in [1,64]");
+    if (c->substeps < 1) return fail(QS_EINVAL, "substeps must be >= 1");
+    if (c->precision != QS_F32 && c->precision != QS_F64) return fail(QS_EINVAL, "bad precision");
+    if (c->integrator != QS_RK4 && c->integrator != QS_RK45) return fail(QS_EINVAL, "bad integrator");
+    if (c->n_max < 1) return fail(QS_EINVAL, "n_max must be >= 1");
+    return QS_OK;
+}
+
+static size_t layout(const qs_config* c, qs_sim* s /*nullable*/) {
+    const int rs = c->precision == QS_F64 ? 8 : 4;
+    const int64_t ld = (int64_t)align_up((size_t)c->n_envs, 32);
+    size_t off = 0;
+    for (int r = 0; r < kNumRows; ++r) {
+        const RowSpec& rw = kRows[r];
+        if (rw.need_flag && !(c->flags & rw.need_flag)) continue;
+        const int elem = rw.elem ? rw.elem : rs;
+        if (s) { s->slot[rw.field] = Slot{s->ws + off, rw.channels, elem}; }
+        off = align_up(off + (size_t)rw.channels * ld * elem, 256);
+    }
+    if (s) s->action_stage = s->ws + off;
+    off = align_up(off + (size_t)4 * ld * rs, 256);
+    if (s) s->stats = (double*)(s->ws + off);
+    off = align_up(off + 2 * QS_STATS_DIM * sizeof(double), 256);
+    return off;
+}
+
+extern "C" int64_t qs_workspace_bytes(const qs_config* cfg) {
+    if (validate(cfg) != QS_OK) return QS_EINVAL;
+    return (int64_t)layout(cfg, nullptr);
+}
+
+template <typename R> static SimView<R> make_view(const qs_sim* s) {
+    SimView<R> v;
+    memset(&v, 0, sizeof(v));
+    v.N = s->N; v.ld = s->ld;
+    v.obs17 = (R*)s->obs17;
+    v.prev_ang = (R*)s->slot[QS_FIELD_ANG].ptr;
+    v.prev_shaping = (R*)s->slot[QS_FIELD_PREV_SHAPING].ptr;
+    v.abs_sum = (R*)s->slot[QS_FIELD_ABS_SUM].ptr;
+    v.ep_return = (R*)s->slot[QS_FIELD_EP_RETURN].ptr;
+    v.reward = (R*)s->slot[QS_FIELD_REWARD].ptr;
+    v.step_i = (int32_t*)s->slot[QS_FIELD_I].ptr;
+    v.episode = (uint32_t*)s->slot[QS_FIELD_EPISODE].ptr;
+    v.flags = (uint8_t*)s->slot[QS_FIELD_FLAGS].ptr;
+    v.done = (uint8_t*)s->slot[QS_FIELD_DONE].ptr;
+    v.solved = (uint8_t*)s->slot[QS_FIELD_SOLVED].ptr;
+    v.ang_vel = (R*)s->slot[QS_FIELD_ANG_VEL].ptr;
+    v.step_effort = (R*)s->slot[QS_FIELD_STEP_EFFORT].ptr;
+    v.w = (R*)s->slot[QS_FIELD_W].ptr;
+    v.accel = (R*)s->slot[QS_FIELD_ACCEL].ptr;
+    v.acc_read = (R*)s->slot[QS_FIELD_ACC_READ].ptr;
+    v.mat_rot = (R*)s->slot[QS_FIELD_MAT_ROT].ptr;
+    v.clipped_action = (R*)s->slot[QS_FIELD_CLIPPED_ACTION].ptr;
+    v.fm = (R*)s->slot[QS_FIELD_FM].ptr;
+    v.sensed_obs = (R*)s->slot[QS_FIELD_SENSED_OBS].ptr;
+    v.sensor_state = (R*)s->slot[QS_FIELD_SENSOR_STATE].ptr;
+    v.stats = s->stats;
+    v.seed = s->seed;
+    v.env_id_offset = (uint32_t)s->cfg.env_id_offset;
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// kernels
+// ------------------------------------------------------------------------------------------------
+constexpr int kBlock = 256;
+
+template <typename R>
+__device__ __forceinline__ void load_env(const SimView<R>& v, int64_t n, Env<R>& e) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) e.y[k] = v.obs17[k * v.ld + n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.y[10 + k] = v.obs17[(14 + k) * v.ld + n];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) e.prev_ang[k] = v.prev_ang[k * v.ld + n];
+    e.prev_shaping = v.prev_shaping[n];
+    e.abs_sum = v.abs_sum[n];
+    e.ep_return = v.ep_return[n];
+    e.i = v.step_i[n];
+    e.flags = v.flags[n];
+    e.episode = v.episode[n];
+}
+
+template <typename R>
+__device__ __forceinline__ void store_env(const SimView<R>& v, int64_t n, const Env<R>& e, const R vq[4]) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v.obs17[k * v.ld + n] = e.y[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v.obs17[(10 + k) * v.ld + n] = vq[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v.obs17[(14 + k) * v.ld + n] = e.y[10 + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v.prev_ang[k * v.ld + n] = e.prev_ang[k];
+    v.prev_shaping[n] = e.prev_shaping;
+    v.abs_sum[n] = e.abs_sum;
+    v.ep_return[n] = e.ep_return;
+    v.step_i[n] = e.i;
+    v.flags[n] = (uint8_t)e.flags;
+    v.episode[n] = e.episode;
+}
+
+// AUX attributes the single-env compatibility class exposes (quad.ang_vel, step_effort, w, accel,
+// accelerometer_read, mat_rot); evaluated at the new state like the reference's trailing drone_eq call.
+template <typename R>
+__device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R>& e,
+                                       const StepOut<R>& o, const Ctrl<R>& c) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v.ang_vel[k * v.ld + n] = o.ang_vel[k];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v.step_effort[k * v.ld + n] = o.effort[k]; v.w[k * v.ld + n] = o.w[k];
+        v.clipped_action[k * v.ld + n] = o.clipped[k]; v.fm[k * v.ld + n] = o.fm[k];
+    }
+    R dy[13], qn[4], r[9];
+    drone_rhs(p, c, e.y, dy);
+    quat_normalize(&e.y[6], qn);
+    quat_rot_mat(qn, r);
+    R a[3] = {dy[1], dy[3], dy[5]};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v.accel[k * v.ld + n] = a[k];
+    R g[3] = {a[0], a[1], a[2] - p.g};                                   // :371  R^T (accel + [0,0,-G])
+    v.acc_read[0 * v.ld + n] = r[0] * g[0] + r[3] * g[1] + r[6] * g[2];
+    v.acc_read[1 * v.ld + n] = r[1] * g[0] + r[4] * g[1] + r[7] * g[2];
+    v.acc_read[2 * v.ld + n] = r[2] * g[0] + r[5] * g[1] + r[8] * g[2];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) v.mat_rot[k * v.ld + n] = r[k];
+}
+
+// quad.reset (:408-454) for one env held in registers: (optionally) sample the initial state with Philox,
+// clear the episode bookkeeping, then take T hover steps.  obs_hist/act_hist: [T][14][N] / [T][4][N] or NULL.
+template <typename R, int INTEG, bool DIRECT>
+__device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& v, int64_t n, Env<R>& e,
+                                       bool sample, StepOut<R>& o, R* obs_hist, R* act_hist) {
+    if (sample) {
+        R ang[3];
+        sample_reset_state(p, v.seed, v.env_id_offset + (uint32_t)n, e.episode, e.y, ang);
+    }
+    reset_head(e);
+    for (int t = 0; t < p.T; ++t) {
+        Ctrl<R> c;
+        step_core<R, INTEG, DIRECT>(p, e, p.zero_control, o, &c);
+        if (obs_hist) {
+            R* oh = obs_hist + (int64_t)t * 14 * v.N;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) oh[k * v.N + n] = e.y[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) oh[(10 + k) * v.N + n] = o.vq[k];
+        }
+        if (act_hist) {
+            R* ah = act_hist + (int64_t)t * 4 * v.N;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ah[k * v.N + n] = p.zero_control[k];
+        }
+        if ((p.flags & F_AUX) && t == p.T - 1) store_aux(p, v, n, e, o, c);
+    }
+    e.ep_return = R(0);
+}
+
+// thread-local episode statistics, reduced warp -> block -> device accumulators
+struct LocalStats {
+    float v[7];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] = 0.f;
+    }
+};
+
+__device__ __forceinline__ void flush_stats(const LocalStats& ls, bool any_local, double* stats) {
+    __shared__ float s_acc[7];
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    if (threadIdx.x < 7) s_acc[threadIdx.x] = 0.f;
+    __syncthreads();
+    const unsigned full = 0xffffffffu;
+    if (__any_sync(full, any_local)) {
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+            float x = ls.v[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(full, x, d);
+            if ((threadIdx.x & 31) == 0 && x != 0.f) atomicAdd(&s_acc[k], x);
+        }
+        if ((threadIdx.x & 31) == 0) s_any = 1;
+    }
+    __syncthreads();
+    if (s_any && threadIdx.x < 7 && s_acc[threadIdx.x] != 0.f) atomicAdd(&stats[threadIdx.x], (double)s_acc[threadIdx.x]);
+}
+
+template <typename R>
+__device__ __forceinline__ void count_episode(LocalStats& ls, const DevParams<R>& p, const Env<R>& e, const StepOut<R>& o) {
+    ls.v[0] += (float)e.ep_return;
+    ls.v[1] += (float)(e.i - p.T);
+    ls.v[2] += 1.f;
+    ls.v[3] += o.solved ? 1.f : 0.f;
+    ls.v[4] += o.broken ? 1.f : 0.f;
+    ls.v[5] += o.timeout ? 1.f : 0.f;
+    ls.v[6] += (float)e.abs_sum;
+}
+
+template <typename R> struct StepIO {
+    const R* action;     // [4][N]
+    R* obs;              // [14][N] or NULL
+    R* reward;           // [N] or NULL
+    uint8_t* done;       // [N] or NULL
+    uint8_t* solved;     // [N] or NULL
+};
+
+// quad.step for every env of the shard.  One thread per env, grid-stride.
+template <typename R, int INTEG, bool DIRECT>
+__global__ void __launch_bounds__(kBlock)
+step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
+            const __grid_constant__ StepIO<R> io) {
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
+        Env<R> e;
+        load_env(v, n, e);
+        R a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = io.action[k * v.N + n];
+        const bool was_done = (e.flags & EF_DONE) != 0;
+        StepOut<R> o;
+        Ctrl<R> c;
+        step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
+        e.ep_return += o.reward;
+        const R reward = o.reward;
+        const bool done = o.done, solved = o.solved;
+        if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+        if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
+        if ((p.flags & F_AUTO_RESET) && done) {
+            e.episode += 1;
+            reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+        }
+        store_env(v, n, e, o.vq);
+        v.reward[n] = reward;
+        v.done[n] = done;
+        v.solved[n] = solved;
+        if (io.obs) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
+        }
+        if (io.reward) io.reward[n] = reward;
+        if (io.done) io.done[n] = done;
+        if (io.solved) io.solved[n] = solved;
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N);
+}
+
+// quad.reset for the masked envs (det_state given or Philox-sampled).
+template <typename R, int INTEG, bool DIRECT>
+__global__ void __launch_bounds__(kBlock)
+reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v, const R* det_state,
+             const uint8_t* mask, R* obs_hist, R* act_hist) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
+        if (mask && !mask[n]) continue;
+        Env<R> e;
+        load_env(v, n, e);
+        if (det_state) {
+#pragma unroll
+            for (int k = 0; k < 13; ++k) e.y[k] = det_state[k * v.N + n];
+        } else {
+            e.episode += 1;
+        }
+        StepOut<R> o;
+        reset_env<R, INTEG, DIRECT>(p, v, n, e, det_state == nullptr, o, obs_hist, act_hist);
+        store_env(v, n, e, o.vq);
+        v.reward[n] = R(0);
+        v.done[n] = o.done;
+        v.solved[n] = o.solved;
+    }
+}
+
+// K fused env steps per launch: state stays in registers, only actions/outputs stream through HBM.
+template <typename R> struct RolloutIO {
+    int32_t horizon;
+    int32_t action_source;
+    const R* actions;
+    R* obs_out;
+    R* action_out;
+    R* reward_out;
+    uint8_t* done_out;
+};
+
+template <typename R, int INTEG, bool DIRECT>
+__global__ void __launch_bounds__(kBlock)
+rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
+               const __grid_constant__ RolloutIO<R> io) {
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
+        Env<R> e;
+        load_env(v, n, e);
+        StepOut<R> o;
+        R reward = R(0);
+        bool done = false, solved = false;
+        for (int t = 0; t < io.horizon; ++t) {
+            R a[4];
+            if (io.action_source == QS_ACT_PHILOX_UNIFORM) {
+                uint4 u = philox_block(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, RNG_ACTION);
+                a[0] = R(2) * u32_to_unit<R>(u.x) - R(1); a[1] = R(2) * u32_to_unit<R>(u.y) - R(1);
+                a[2] = R(2) * u32_to_unit<R>(u.z) - R(1); a[3] = R(2) * u32_to_unit<R>(u.w) - R(1);
+            } else {
+                const R* at = io.actions + (int64_t)t * 4 * v.N;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) a[k] = at[k * v.N + n];
+            }
+            const bool was_done = (e.flags & EF_DONE) != 0;
+            step_core<R, INTEG, DIRECT>(p, e, a, o, nullptr);
+            e.ep_return += o.reward;
+            reward = o.reward; done = o.done; solved = o.solved;
+            if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+            if ((p.flags & F_AUTO_RESET) && done) {
+                e.episode += 1;
+                reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+            }
+            if (io.obs_out) {
+                R* ot = io.obs_out + (int64_t)t * 14 * v.N;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) ot[k * v.N + n] = e.y[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ot[(10 + k) * v.N + n] = o.vq[k];
+            }
+            if (io.action_out) {
+                R* at = io.action_out + (int64_t)t * 4 * v.N;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) at[k * v.N + n] = a[k];
+            }
+            if (io.reward_out) io.reward_out[(int64_t)t * v.N + n] = reward;
+            if (io.done_out) io.done_out[(int64_t)t * v.N + n] = done;
+        }
+        store_env(v, n, e, o.vq);
+        v.reward[n] = reward;
+        v.done[n] = done;
+        v.solved[n] = solved;
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static int grid_for(const qs_sim* s, int64_t n) {
+    int64_t blocks = (n + kBlock - 1) / kBlock;
+    int64_t cap = (int64_t)s->sm_count * 16;          // grid-stride beyond 16 resident-CTA-equivalents per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+#define QS_DISPATCH(s, FN, ...)                                                                          \
+    do {                                                                                                 \
+        const bool direct_ = ((s)->cfg.flags & QS_FLAG_DIRECT_CONTROL) != 0;                             \
+        const bool rk45_ = (s)->cfg.integrator == QS_RK45;                                               \
+        if ((s)->cfg.precision == QS_F32) {                                                              \
+            if (rk45_) { if (direct_) FN<float, 1, true>(__VA_ARGS__); else FN<float, 1, false>(__VA_ARGS__); } \
+            else       { if (direct_) FN<float, 0, true>(__VA_ARGS__); else FN<float, 0, false>(__VA_ARGS__); } \
+        } else {                                                                                         \
+            if (rk45_) { if (direct_) FN<double, 1, true>(__VA_ARGS__); else FN<double, 1, false>(__VA_ARGS__); } \
+            else       { if (direct_) FN<double, 0, true>(__VA_ARGS__); else FN<double, 0, false>(__VA_ARGS__); } \
+        }                                                                                                \
+    } while (0)
+
+template <typename R> static const DevParams<R>& params_of(const qs_sim* s);
+template <> const DevParams<float>& params_of<float>(const qs_sim* s) { return s->pf; }
+template <> const DevParams<double>& params_of<double>(const qs_sim* s) { return s->pd; }
+
+template <typename R, int INTEG, bool DIRECT>
+static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
+                        cudaStream_t st) {
+    StepIO<R> io{(const R*)action, (R*)obs, (R*)reward, done, solved};
+    step_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+}
+
+template <typename R, int INTEG, bool DIRECT>
+static void launch_reset(qs_sim* s, const void* det, const uint8_t* mask, void* oh, void* ah, cudaStream_t st) {
+    reset_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s),
+                                                                         (const R*)det, mask, (R*)oh, (R*)ah);
+}
+
+template <typename R, int INTEG, bool DIRECT>
+static void launch_rollout(qs_sim* s, const qs_rollout_args* a, cudaStream_t st) {
+    RolloutIO<R> io{a->horizon, a->action_source, (const R*)a->actions, (R*)a->obs_out, (R*)a->action_out,
+                    (R*)a->reward_out, a->done_out};
+    rollout_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+}
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
+    if (!out) return fail(QS_EINVAL, "qs_create: out is NULL");
+    *out = nullptr;
+    int rc = validate(cfg);
+    if (rc != QS_OK) return rc;
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(QS_ECUDA, "qs_create: no CUDA device (%s); libquadsim has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(QS_EINVAL, "qs_create: bad device ordinal");
+    QS_CUDA(cudaSetDevice(cfg->device));
+    qs_sim* s = new (std::nothrow) qs_sim();
+    if (!s) return fail(QS_ENOMEM, "qs_create: host allocation failed");
+    memset(s, 0, sizeof(*s));
+    s->cfg = *cfg;
+    s->N = cfg->n_envs;
+    s->ld = (int64_t)align_up((size_t)cfg->n_envs, 32);
+    s->rs = cfg->precision == QS_F64 ? 8 : 4;
+    s->seed = cfg->seed;
+    s->ws_bytes = layout(cfg, nullptr);
+    if (cfg->workspace) {
+        s->ws = (char*)cfg->workspace; s->owns_ws = false;
+    } else {
+        void* p = nullptr;
+        if (cudaMalloc(&p, s->ws_bytes) != cudaSuccess) { delete s; return fail(QS_ENOMEM, "qs_create: cudaMalloc failed"); }
+        s->ws = (char*)p; s->owns_ws = true;
+    }
+    layout(cfg, s);
+    s->obs17 = s->slot[QS_FIELD_OBS].ptr;
+    // derived views: OBS = rows 0..13 of obs17; STATE is gathered (rows 0..9 ++ 14..16)
+    s->slot[QS_FIELD_OBS].channels = 14;
+    s->slot[QS_FIELD_STATE] = Slot{nullptr, 13, s->rs};
+    s->pf = make_params<float>(*cfg);
+    s->pd = make_params<double>(*cfg);
+    cudaDeviceProp prop;
+    cudaError_t e1 = cudaGetDeviceProperties(&prop, cfg->device);
+    s->sm_count = (e1 == cudaSuccess) ? prop.multiProcessorCount : 148;
+    cudaError_t e2 = cudaMemset(s->ws, 0, s->ws_bytes);
+    if (e2 == cudaSuccess) {
+        // quad.__init__ leaves done=True (:154): flags = EF_DONE, done out = 1, quaternion undefined until reset
+        e2 = cudaMemset(s->slot[QS_FIELD_FLAGS].ptr, EF_DONE, (size_t)s->ld);
+        if (e2 == cudaSuccess) e2 = cudaMemset(s->slot[QS_FIELD_DONE].ptr, 1, (size_t)s->ld);
+    }
+    if (e2 != cudaSuccess) {
+        if (s->owns_ws) cudaFree(s->ws);
+        delete s;
+        return fail(QS_ECUDA, "qs_create: cudaMemset: %s", cudaGetErrorString(e2));
+    }
+    *out = s;
+    return QS_OK;
+}
+
+extern "C" int qs_destroy(qs_handle h) {
+    if (!h) return QS_OK;
+    if (h->owns_ws && h->ws) cudaFree(h->ws);
+    delete h;
+    return QS_OK;
+}
+
+extern "C" int qs_seed(qs_handle h, uint64_t seed) {
+    if (!h) return fail(QS_EINVAL, "qs_seed: NULL handle");
+    h->seed = seed;
+    return QS_OK;
+}
+
+extern "C" int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_hist, void* act_hist,
+                        void* stream) {
+    if (!h) return fail(QS_EINVAL, "qs_reset: NULL handle");
+    QS_CUDA(cudaSetDevice(h->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    QS_DISPATCH(h, launch_reset, h, det_state, mask, obs_hist, act_hist, st);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+extern "C" int qs_step(qs_handle h, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
+                       void* stream) {
+    if (!h) return fail(QS_EINVAL, "qs_step: NULL handle");
+    if (!action) return fail(QS_EINVAL, "qs_step: action is NULL");
+    cudaStream_t st = (cudaStream_t)stream;
+    QS_DISPATCH(h, launch_step, h, action, obs, reward, done, solved, st);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream) {
+    if (!h || !args) return fail(QS_EINVAL, "qs_rollout: NULL argument");
+    if (args->horizon < 1) return fail(QS_EINVAL, "qs_rollout: horizon must be >= 1");
+    if (args->action_source == QS_ACT_BUFFER && !args->actions) return fail(QS_EINVAL, "qs_rollout: actions is NULL");
+    if (args->action_source != QS_ACT_BUFFER && args->action_source != QS_ACT_PHILOX_UNIFORM)
+        return fail(QS_EINVAL, "qs_rollout: bad action_source");
+    if (h->cfg.flags & QS_FLAG_AUX) return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX");
+    cudaStream_t st = (cudaStream_t)stream;
+    QS_DISPATCH(h, launch_rollout, h, args, st);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+extern "C" int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host,
+                            uint8_t* done_host, void* stream) {
+    if (!h || !action_host) return fail(QS_EINVAL, "qs_step_host: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t rs = (size_t)h->rs, N = (size_t)h->N, ld = (size_t)h->ld;
+    QS_CUDA(cudaMemcpyAsync(h->action_stage, action_host, 4 * N * rs, cudaMemcpyHostToDevice, st));
+    int rc = qs_step(h, h->action_stage, nullptr, nullptr, nullptr, nullptr, stream);
+    if (rc != QS_OK) return rc;
+    if (obs_host)
+        QS_CUDA(cudaMemcpy2DAsync(obs_host, N * rs, h->obs17, ld * rs, N * rs, 14, cudaMemcpyDeviceToHost, st));
+    if (reward_host)
+        QS_CUDA(cudaMemcpyAsync(reward_host, h->slot[QS_FIELD_REWARD].ptr, N * rs, cudaMemcpyDeviceToHost, st));
+    if (done_host)
+        QS_CUDA(cudaMemcpyAsync(done_host, h->slot[QS_FIELD_DONE].ptr, N, cudaMemcpyDeviceToHost, st));
+    QS_CUDA(cudaStreamSynchronize(st));
+    return QS_OK;
+}
+
+extern "C" int qs_field_info(qs_handle h, qs_field f, qs_field_desc* out) {
+    if (!h || !out) return fail(QS_EINVAL, "qs_field_info: NULL argument");
+    if ((int)f < 0 || f >= QS_FIELD_COUNT_) return fail(QS_EINVAL, "qs_field_info: bad field");
+    const Slot& sl = h->slot[f];
+    if (sl.channels == 0) return fail(QS_ESTATE, "qs_field_info: field not enabled for this handle");
+    out->channels = sl.channels;
+    out->elem_bytes = sl.elem;
+    out->ld = h->ld;
+    out->ptr = sl.ptr;
+    out->ws_offset = sl.ptr ? (int64_t)((char*)sl.ptr - h->ws) : -1;
+    return QS_OK;
+}
+
+static int copy_field(qs_handle h, qs_field f, void* ext, bool to_ext, cudaStream_t st) {
+    if (!h || !ext) return fail(QS_EINVAL, "qs_get/qs_set: NULL argument");
+    if ((int)f < 0 || f >= QS_FIELD_COUNT_) return fail(QS_EINVAL, "qs_get/qs_set: bad field");
+    const size_t N = (size_t)h->N, ld = (size_t)h->ld;
+    if (f == QS_FIELD_STATE) {
+        const size_t rs = (size_t)h->rs;
+        char* in0 = (char*)h->obs17;
+        char* in1 = in0 + 14 * ld * rs;
+        char* ex0 = (char*)ext;
+        char* ex1 = ex0 + 10 * N * rs;
+        if (to_ext) {
+            QS_CUDA(cudaMemcpy2DAsync(ex0, N * rs, in0, ld * rs, N * rs, 10, cudaMemcpyDeviceToDevice, st));
+            QS_CUDA(cudaMemcpy2DAsync(ex1, N * rs, in1, ld * rs, N * rs, 3, cudaMemcpyDeviceToDevice, st));
+        } else {
+            QS_CUDA(cudaMemcpy2DAsync(in0, ld * rs, ex0, N * rs, N * rs, 10, cudaMemcpyDeviceToDevice, st));
+            QS_CUDA(cudaMemcpy2DAsync(in1, ld * rs, ex1, N * rs, N * rs, 3, cudaMemcpyDeviceToDevice, st));
+        }
+        return QS_OK;
+    }
+    const Slot& sl = h->slot[f];
+    if (sl.channels == 0 || !sl.ptr) return fail(QS_ESTATE, "qs_get/qs_set: field not enabled for this handle");
+    const size_t eb = (size_t)sl.elem;
+    if (to_ext)
+        QS_CUDA(cudaMemcpy2DAsync(ext, N * eb, sl.ptr, ld * eb, N * eb, sl.channels, cudaMemcpyDeviceToDevice, st));
+    else
+        QS_CUDA(cudaMemcpy2DAsync(sl.ptr, ld * eb, ext, N * eb, N * eb, sl.channels, cudaMemcpyDeviceToDevice, st));
+    return QS_OK;
+}
+
+extern "C" int qs_get(qs_handle h, qs_field f, void* dst, void* stream) {
+    return copy_field(h, f, dst, true, (cudaStream_t)stream);
+}
+extern "C" int qs_set(qs_handle h, qs_field f, const void* src, void* stream) {
+    return copy_field(h, f, const_cast<void*>(src), false, (cudaStream_t)stream);
+}
+
+extern "C" int qs_stats_device(qs_handle h, double** dptr) {
+    if (!h || !dptr) return fail(QS_EINVAL, "qs_stats_device: NULL argument");
+    *dptr = h->stats;
+    return QS_OK;
+}
+
+extern "C" int qs_stats_read(qs_handle h, qs_stats* out_host, int reset_after, void* stream) {
+    if (!h || !out_host) return fail(QS_EINVAL, "qs_stats_read: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    QS_CUDA(cudaMemcpyAsync(out_host, h->stats, sizeof(qs_stats), cudaMemcpyDeviceToHost, st));
+    if (reset_after) QS_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(qs_stats), st));
+    QS_CUDA(cudaStreamSynchronize(st));
+    return QS_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stateless batched device functions
+// ------------------------------------------------------------------------------------------------
+template <typename R> __global__ void k_euler_quat(int64_t n, const R* ang, R* q) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R a[3] = {ang[i], ang[n + i], ang[2 * n + i]}, o[4];
+    euler_quat(a, o);
+    for (int k = 0; k < 4; ++k) q[k * n + i] = o[k];
+}
+template <typename R> __global__ void k_quat_euler(int64_t n, const R* q, R* ang) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R a[4] = {q[i], q[n + i], q[2 * n + i], q[3 * n + i]}, o[3];
+    quat_euler(a, o);
+    for (int k = 0; k < 3; ++k) ang[k * n + i] = o[k];
+}
+template <typename R> __global__ void k_deriv_quat(int64_t n, const R* w, const R* q, R* dq) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R a[4] = {q[i], q[n + i], q[2 * n + i], q[3 * n + i]}, ww[3] = {w[i], w[n + i], w[2 * n + i]}, o[4];
+    deriv_quat(ww, a, o);
+    for (int k = 0; k < 4; ++k) dq[k * n + i] = o[k];
+}
+template <typename R> __global__ void k_quat_rot_mat(int64_t n, const R* q, R* r) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R a[4] = {q[i], q[n + i], q[2 * n + i], q[3 * n + i]}, o[9];
+    quat_rot_mat(a, o);
+    for (int k = 0; k < 9; ++k) r[k * n + i] = o[k];
+}
+template <typename R>
+__global__ void k_drone_eq(const __grid_constant__ DevParams<R> p, int64_t n, int direct, const R* x, const R* action,
+                           const R* w_rotor, R* dx) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R y[13], a[4], w[4], fm[4], dy[13];
+    for (int k = 0; k < 13; ++k) y[k] = x[k * n + i];
+    for (int k = 0; k < 4; ++k) a[k] = action[k * n + i];
+    if (direct) {
+        rotor_direct(p, a, w, fm);
+    } else {
+        for (int k = 0; k < 4; ++k) { fm[k] = a[k]; w[k] = w_rotor ? w_rotor[k * n + i] : R(0); }
+    }
+    Ctrl<R> c = make_ctrl(p, fm, w);
+    drone_rhs(p, c, y, dy);
+    for (int k = 0; k < 13; ++k) dx[k * n + i] = dy[k];
+}
+template <typename R>
+__global__ void k_f2w(const __grid_constant__ DevParams<R> p, int64_t n, int clipped, const R* fm_in, R* effort, R* w,
+                      R* fm_new) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R a[4], e[4], ww[4], f[4];
+    for (int k = 0; k < 4; ++k) a[k] = fm_in[k * n + i];
+    rotor_indirect(p, clipped != 0, a, e, ww, f);
+    for (int k = 0; k < 4; ++k) { effort[k * n + i] = e[k]; w[k * n + i] = ww[k]; fm_new[k * n + i] = f[k]; }
+}
+__global__ void k_philox_raw(uint64_t seed, uint32_t env0, int64_t n, uint32_t episode, uint32_t block, uint32_t sid,
+                             uint32_t* out) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 r = philox_block(seed, env0 + (uint32_t)i, episode, block, sid);
+    out[i] = r.x; out[n + i] = r.y; out[2 * n + i] = r.z; out[3 * n + i] = r.w;
+}
+
+static int check_util(int precision, int64_t n) {
+    if (precision != QS_F32 && precision != QS_F64) return fail(QS_EINVAL, "bad precision");
+    if (n < 1) return fail(QS_EINVAL, "n must be >= 1");
+    return QS_OK;
+}
+#define QS_UTIL_GRID(n) (unsigned)(((n) + 255) / 256), 256, 0, (cudaStream_t)stream
+
+extern "C" int qs_euler_quat(int precision, int64_t n, const void* ang, void* q, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    if (precision == QS_F32) k_euler_quat<float><<<QS_UTIL_GRID(n)>>>(n, (const float*)ang, (float*)q);
+    else k_euler_quat<double><<<QS_UTIL_GRID(n)>>>(n, (const double*)ang, (double*)q);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+extern "C" int qs_quat_euler(int precision, int64_t n, const void* q, void* ang, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    if (precision == QS_F32) k_quat_euler<float><<<QS_UTIL_GRID(n)>>>(n, (const float*)q, (float*)ang);
+    else k_quat_euler<double><<<QS_UTIL_GRID(n)>>>(n, (const double*)q, (double*)ang);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+extern "C" int qs_deriv_quat(int precision, int64_t n, const void* w, const void* q, void* dq, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    if (precision == QS_F32) k_deriv_quat<float><<<QS_UTIL_GRID(n)>>>(n, (const float*)w, (const float*)q, (float*)dq);
+    else k_deriv_quat<double><<<QS_UTIL_GRID(n)>>>(n, (const double*)w, (const double*)q, (double*)dq);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+extern "C" int qs_quat_rot_mat(int precision, int64_t n, const void* q, void* R, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    if (precision == QS_F32) k_quat_rot_mat<float><<<QS_UTIL_GRID(n)>>>(n, (const float*)q, (float*)R);
+    else k_quat_rot_mat<double><<<QS_UTIL_GRID(n)>>>(n, (const double*)q, (double*)R);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+static qs_config cfg_from_params(const qs_params* p, int direct) {
+    qs_config c;
+    qs_default_config(&c);
+    if (p) c.params = *p;
+    c.flags = direct ? (c.flags | QS_FLAG_DIRECT_CONTROL) : (c.flags & ~QS_FLAG_DIRECT_CONTROL);
+    return c;
+}
+extern "C" int qs_drone_eq(int precision, const qs_params* p, int64_t n, int direct, const void* x, const void* action,
+                           const void* w_rotor, void* dx, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    qs_config c = cfg_from_params(p, direct);
+    if (precision == QS_F32)
+        k_drone_eq<float><<<QS_UTIL_GRID(n)>>>(make_params<float>(c), n, direct, (const float*)x, (const float*)action,
+                                               (const float*)w_rotor, (float*)dx);
+    else
+        k_drone_eq<double><<<QS_UTIL_GRID(n)>>>(make_params<double>(c), n, direct, (const double*)x,
+                                                (const double*)action, (const double*)w_rotor, (double*)dx);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+extern "C" int qs_f2w(int precision, const qs_params* p, int64_t n, int clipped, const void* fm, void* step_effort,
+                      void* w, void* fm_new, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    qs_config c = cfg_from_params(p, 0);
+    if (precision == QS_F32)
+        k_f2w<float><<<QS_UTIL_GRID(n)>>>(make_params<float>(c), n, clipped, (const float*)fm, (float*)step_effort,
+                                          (float*)w, (float*)fm_new);
+    else
+        k_f2w<double><<<QS_UTIL_GRID(n)>>>(make_params<double>(c), n, clipped, (const double*)fm, (double*)step_effort,
+                                           (double*)w, (double*)fm_new);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+extern "C" int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, uint32_t block,
+                             uint32_t stream_id, uint32_t* out, void* stream) {
+    if (n < 1 || !out) return fail(QS_EINVAL, "qs_philox_raw: bad argument");
+    k_philox_raw<<<QS_UTIL_GRID(n)>>>(seed, (uint32_t)env_id0, n, episode, block, stream_id, out);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+// FP32 FFMA peak probe: 8 independent dependent-chains per thread.
+__global__ void k_fp32_peak(int iters, float* sink) {
+    float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
+          a6 = a0 + 6.f, a7 = a0 + 7.f;
+    const float m = 0.999f, c = 1e-3f;
+    for (int i = 0; i < iters; i += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fmaf(a0, m, c); a1 = fmaf(a1, m, c); a2 = fmaf(a2, m, c); a3 = fmaf(a3, m, c);
+            a4 = fmaf(a4, m, c); a5 = fmaf(a5, m, c); a6 = fmaf(a6, m, c); a7 = fmaf(a7, m, c);
+        }
+    }
+    float s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 123456.789f) sink[0] = s;
+}
+extern "C" int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_out, void* stream) {
+    if (blocks < 1 || threads < 32 || iters < 8 || !ms_out) return fail(QS_EINVAL, "qs_fp32_peak_probe: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    float* sink = nullptr;
+    QS_CUDA(cudaMalloc(&sink, sizeof(float)));
+    cudaEvent_t e0, e1;
+    QS_CUDA(cudaEventCreate(&e0));
+    QS_CUDA(cudaEventCreate(&e1));
+    k_fp32_peak<<<blocks, threads, 0, st>>>(iters, sink);           // warm-up
+    QS_CUDA(cudaEventRecord(e0, st));
+    k_fp32_peak<<<blocks, threads, 0, st>>>(iters, sink);
+    QS_CUDA(cudaEventRecord(e1, st));
+    QS_CUDA(cudaEventSynchronize(e1));
+    QS_CUDA(cudaEventElapsedTime(ms_out, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}

@@ -1,0 +1,230 @@
+/*
+ * quadsim.h — C ABI of the B200-native batched quadrotor simulator (libquadsim.so).
+ *
+ * Drop-in boundary for ONE hot path of rafaelcostafrf/autonomous_quadrotor_environment:
+ * `quad.reset` / `quad.step` of environment/quadrotor_env.py (rotor map -> drone_eq -> per-step
+ * ODE integration -> quaternion/Euler conversion -> done/reward), re-designed for N independent
+ * environments advanced in lock-step, one CUDA thread per environment.
+ *
+ * The reference has no FFI of its own (its boundary is the Python class API);
+ * every entry point below names the reference interface it replaces (paths relative to the
+ * reference root).  Python/PyTorch host code binds these with ctypes.
+ *
+ * Conventions
+ *  - return 0 (QS_OK) on success, a negative QS_E* code otherwise; qs_last_error() gives the
+ *    thread-local message of the last failure.  No exceptions cross the boundary.
+ *  - every data pointer is a DEVICE pointer owned by the caller unless the name ends in `_host`;
+ *    element type is float for QS_F32 handles and double for QS_F64 handles.
+ *  - layout is structure-of-arrays with the env index fastest: a buffer documented as [C][N] holds
+ *    channel c of env n at  ptr[c*N + n].
+ *  - calls are asynchronous and ordered on the `stream` argument (a cudaStream_t passed as void*,
+ *    NULL = legacy default stream).  There is no host synchronisation inside qs_step: resets are
+ *    handled by a predicated sub-pass inside the kernel.
+ *  - a handle is not thread-safe (one host thread per handle / GPU).
+ *  - there is NO CPU fallback: every entry point that computes returns QS_ECUDA without a device.
+ */
+#ifndef QUADSIM_H
+#define QUADSIM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_VERSION 100
+
+/* error codes */
+#define QS_OK 0
+#define QS_EINVAL (-1)   /* bad argument */
+#define QS_ECUDA (-2)    /* CUDA runtime error (no device, launch failure, ...) */
+#define QS_ENOMEM (-3)   /* device allocation failed */
+#define QS_ESTATE (-4)   /* call not valid for this handle's configuration */
+
+/* precision (arithmetic AND boundary element type) */
+#define QS_F32 0
+#define QS_F64 1
+
+/* integrator */
+#define QS_RK4 0    /* fixed-step classical RK4, cfg.substeps sub-intervals (FP32 production mode)        */
+#define QS_RK45 1   /* per-thread replica of scipy.integrate.solve_ivp's default RK45 as the reference     */
+                    /* calls it at environment/quadrotor_env.py:483 (rtol 1e-3, atol 1e-6) — parity mode   */
+
+/* qs_config.flags */
+#define QS_FLAG_DIRECT_CONTROL 0x01u /* quad(direct_control=1): actions are 4 normalised rotor thrusts       */
+#define QS_FLAG_CLIPPED        0x02u /* quad(clipped=True): indirect-mode mixer clips rotor speeds^2          */
+#define QS_FLAG_TRAINING       0x04u /* quad(training=True): "solved" ends the episode                        */
+#define QS_FLAG_AUTO_RESET     0x08u /* re-sample + T warm-up steps inside the step kernel when done          */
+#define QS_FLAG_SENSOR_NOISE   0x10u /* run the `sensor` model (quadrotor_env.py:579-724) each step           */
+#define QS_FLAG_AUX            0x20u /* also store ang_vel, step_effort, w, accel, mat_rot, accelerometer_read */
+
+/* Physical / reward constants.  Defaults (qs_default_config) = environment/quadrotor_env.py:30-80. */
+typedef struct qs_params {
+    double mass, gravity;              /* M, G                        :39          */
+    double rho, c_d;                   /* RHO, C_D                    :42,45       */
+    double k_f, k_m, i_r, t2wr;        /* K_F, K_M, I_R, T2WR         :48-51       */
+    double j[3];                       /* diag(J)                     :55-57       */
+    double arm;                        /* D                           :60          */
+    double beam_thickness;             /* BEAM_THICKNESS              :63          */
+    double bb_vel, bb_ang, bb_pos;     /* BB_VEL, BB_ANG, BB_POS      :31-34       */
+    double solved_reward, broken_reward, shaping_weight;   /*         :70-72       */
+    double shaping_internal_weights[3];                    /*         :73          */
+    double p_c;                        /* P_C                         :76          */
+    double tr[3], tr_p[3];             /* TR, TR_P                    :80-81       */
+    /* sensor model defaults: sensor.__init__ :587-591 */
+    double accel_std, accel_bias_drift, gyro_std, gyro_bias_drift;
+    double magnet_std, magnet_bias_drift, gps_std_p, gps_std_v;
+} qs_params;
+
+/* Mirrors quad.__init__(t_step, n, training, euler, direct_control, T, clipped)  quadrotor_env.py:112 */
+typedef struct qs_config {
+    int64_t  n_envs;          /* environments owned by this handle (this GPU's shard)                      */
+    int64_t  env_id_offset;   /* global id of local env 0; Philox streams are keyed by GLOBAL env id        */
+    double   t_step;          /* quad(t_step)                                                               */
+    int32_t  n_max;           /* quad(n): step limit (the reference adds T internally, :157)                */
+    int32_t  T;               /* quad(T): warm-up hover steps performed by reset (:447-453)                 */
+    int32_t  substeps;        /* RK4 sub-intervals per env step (>=1); ignored by QS_RK45                   */
+    int32_t  precision;       /* QS_F32 | QS_F64                                                            */
+    int32_t  integrator;      /* QS_RK4 | QS_RK45                                                           */
+    uint32_t flags;           /* QS_FLAG_*                                                                  */
+    uint64_t seed;            /* Philox key (quad.seed, :189-193)                                           */
+    int32_t  device;          /* CUDA device ordinal                                                        */
+    int32_t  reserved;
+    void*    workspace;       /* optional caller-owned device memory (>= qs_workspace_bytes) so that the    */
+                              /* host framework's allocator owns the bytes; NULL -> cudaMalloc              */
+    qs_params params;
+} qs_config;
+
+typedef struct qs_sim* qs_handle;
+
+/* Fields addressable through qs_get / qs_set / qs_field_info.  Names follow the attributes of the
+ * reference `quad` object that callers read. */
+typedef enum qs_field {
+    QS_FIELD_OBS = 0,         /* [14][N] real  quat_state = state[0:10] ++ V_q          :486             */
+    QS_FIELD_STATE = 1,       /* [13][N] real  [x,vx,y,vy,z,vz,q0..q3,wx,wy,wz]         :399-405,:485    */
+    QS_FIELD_ANG = 2,         /* [3][N]  real  Euler angles of the normalised quaternion :488-491        */
+    QS_FIELD_ANG_VEL = 3,     /* [3][N]  real  finite-difference Euler rates (AUX)       :492             */
+    QS_FIELD_STEP_EFFORT = 4, /* [4][N]  real  (AUX)                                     :474,:476,:243  */
+    QS_FIELD_W = 5,           /* [4][N]  real  rotor speeds rad/s (AUX)                  :288,:476       */
+    QS_FIELD_REWARD = 6,      /* [N]     real  reward of the last step                   :511-573        */
+    QS_FIELD_DONE = 7,        /* [N]     u8    done returned by the last step            :498            */
+    QS_FIELD_SOLVED = 8,      /* [N]     u8    quad.solved                               :564            */
+    QS_FIELD_I = 9,           /* [N]     i32   quad.i step counter                       :467            */
+    QS_FIELD_ABS_SUM = 10,    /* [N]     real  accumulated control effort                :575-577        */
+    QS_FIELD_PREV_SHAPING = 11,/*[N]     real  reward shaping memory                     :545-547        */
+    QS_FIELD_EP_RETURN = 12,  /* [N]     real  sum of rewards since the last reset                        */
+    QS_FIELD_EPISODE = 13,    /* [N]     u32   episode counter (Philox counter word)                      */
+    QS_FIELD_FLAGS = 14,      /* [N]     u8    bit0 sticky done (:509), bit1 prev_shaping valid, bit2 solved */
+    QS_FIELD_ACCEL = 15,      /* [3][N]  real  inertial acceleration (AUX)               :368            */
+    QS_FIELD_ACC_READ = 16,   /* [3][N]  real  accelerometer_read (AUX)                  :371            */
+    QS_FIELD_MAT_ROT = 17,    /* [9][N]  real  body->inertial rotation, row-major (AUX)  :315            */
+    QS_FIELD_SENSED_OBS = 18, /* [14][N] real  sensor-based observation (SENSOR_NOISE)   visual_landing/rl_worker.py:171-174 */
+    QS_FIELD_SENSOR_STATE = 19,/*[QS_SENSOR_STATE_DIM][N] real (SENSOR_NOISE)                             */
+    QS_FIELD_CLIPPED_ACTION = 20,/*[4][N] real quad.clipped_action (AUX)                  :472,:477          */
+    QS_FIELD_FM = 21,         /* [4][N]  real  body thrust + moments applied [F,Mx,My,Mz] (AUX) :287-291        */
+    QS_FIELD_COUNT_
+} qs_field;
+
+#define QS_SENSOR_STATE_DIM 28
+
+typedef struct qs_field_desc {
+    int32_t channels;     /* C of [C][N]                                             */
+    int32_t elem_bytes;   /* 1, 4 or 8                                               */
+    int64_t ld;           /* element stride between channels inside the handle       */
+    void*   ptr;          /* handle-owned device pointer (zero-copy view), or NULL   */
+    int64_t ws_offset;    /* byte offset of ptr inside the workspace                 */
+} qs_field_desc;
+
+/* Episode statistics accumulated on the device by warp-shuffle/block reductions inside the step
+ * kernels (replaces the host-side aggregation of worker results, environment/controller/ppo.py:371-382). */
+#define QS_STATS_DIM 8
+typedef struct qs_stats {
+    double sum_return;    /* sum over finished episodes of the episode return               */
+    double sum_length;    /* sum of episode lengths (steps after the T warm-up steps)       */
+    double n_episodes;
+    double n_solved;
+    double n_broken;      /* ended by a bounding-box breach                                 */
+    double n_timeout;     /* ended by i >= n                                                */
+    double sum_effort;    /* sum of quad.abs_sum at episode end                             */
+    double n_steps;       /* env steps executed                                             */
+} qs_stats;
+
+/* Optional fused rollout (K env steps per launch, state kept in registers). */
+#define QS_ACT_BUFFER 0          /* actions read from `actions` [K][4][N]                          */
+#define QS_ACT_PHILOX_UNIFORM 1  /* a ~ U(-1,1)^4 drawn in-kernel (BASELINE.json configs[2])        */
+typedef struct qs_rollout_args {
+    int32_t horizon;             /* K                                                              */
+    int32_t action_source;       /* QS_ACT_*                                                       */
+    const void* actions;         /* [K][4][N] or NULL                                              */
+    void* obs_out;               /* [K][14][N] or NULL                                             */
+    void* action_out;            /* [K][4][N] or NULL                                              */
+    void* reward_out;            /* [K][N] or NULL                                                 */
+    uint8_t* done_out;           /* [K][N] or NULL                                                 */
+} qs_rollout_args;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+/* Fill *cfg with the reference defaults (constants quadrotor_env.py:30-80; quad() keyword defaults :112). */
+int qs_default_config(qs_config* cfg);
+/* Bytes of device memory a handle built from *cfg needs (for caller-provided workspaces). */
+int64_t qs_workspace_bytes(const qs_config* cfg);
+/* quad.__init__  quadrotor_env.py:112-187 */
+int qs_create(qs_handle* out, const qs_config* cfg);
+int qs_destroy(qs_handle h);
+/* quad.seed  :189-193 — re-keys the Philox streams */
+int qs_seed(qs_handle h, uint64_t seed);
+
+/* ---- the hot path --------------------------------------------------------------------------- */
+/* quad.reset(det_state)  :408-454.  det_state [13][N] or NULL (random branch, Philox in place of the
+ * NumPy global RNG); mask u8[N] or NULL (= all envs); obs_hist [T][14][N] / act_hist [T][4][N] or NULL. */
+int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_hist, void* act_hist, void* stream);
+/* quad.step(action)  :458-498 (+ f2F :247-272 / f2w :197-245, drone_eq :274-406, solve_ivp :483,
+ * quat_euler utility:39-48, done_condition :500-509, reward_function :511-573, control_effort :575-577).
+ * action [4][N]; obs [14][N], reward [N], done u8[N], solved u8[N] may each be NULL (the results are
+ * always available zero-copy through qs_field_info(QS_FIELD_OBS/REWARD/DONE/SOLVED)). */
+int qs_step(qs_handle h, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved, void* stream);
+/* K fused env steps (see qs_rollout_args). */
+int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream);
+/* Same contract as qs_step but with HOST buffers (pinned or pageable): H2D of the actions, the step
+ * kernel and D2H of obs/reward/done are enqueued on `stream` and the call returns after they finish. */
+int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);
+
+/* ---- state access --------------------------------------------------------------------------- */
+int qs_field_info(qs_handle h, qs_field f, qs_field_desc* out);
+int qs_get(qs_handle h, qs_field f, void* dst /* device, [C][N] contiguous */, void* stream);
+int qs_set(qs_handle h, qs_field f, const void* src /* device, [C][N] contiguous */, void* stream);
+
+/* ---- statistics ----------------------------------------------------------------------------- */
+/* Device pointer to the QS_STATS_DIM doubles (for an in-place NCCL all-reduce by the host framework). */
+int qs_stats_device(qs_handle h, double** dptr);
+/* Copy the accumulators to host (synchronises `stream`), optionally zeroing them afterwards. */
+int qs_stats_read(qs_handle h, qs_stats* out_host, int reset_after, void* stream);
+
+/* ---- stateless batched device functions (unit-testable pieces of the path) ------------------ */
+/* precision: QS_F32/QS_F64; all pointers device, SoA [C][n]. */
+int qs_euler_quat(int precision, int64_t n, const void* ang /*[3][n]*/, void* q /*[4][n]*/, void* stream);      /* utility:17-36 */
+int qs_quat_euler(int precision, int64_t n, const void* q /*[4][n]*/, void* ang /*[3][n]*/, void* stream);      /* utility:39-48 */
+int qs_deriv_quat(int precision, int64_t n, const void* w /*[3][n]*/, const void* q, void* dq, void* stream);   /* utility:58-69 */
+int qs_quat_rot_mat(int precision, int64_t n, const void* q, void* R /*[9][n] row-major*/, void* stream);       /* utility:71-80 */
+/* drone_eq :274-406.  direct!=0: action = normalised rotor thrusts (f2F); else action = [F,Mx,My,Mz] and
+ * w_rotor [4][n] are the rotor speeds f2w left in self.w. */
+int qs_drone_eq(int precision, const qs_params* p, int64_t n, int direct, const void* x /*[13][n]*/,
+                const void* action /*[4][n]*/, const void* w_rotor /*[4][n] or NULL*/, void* dx /*[13][n]*/, void* stream);
+/* f2w :197-245 -> step_effort [4][n], w [4][n], FM_new [4][n] */
+int qs_f2w(int precision, const qs_params* p, int64_t n, int clipped, const void* fm /*[4][n]*/,
+           void* step_effort, void* w, void* fm_new, void* stream);
+/* Philox4x32-10 raw blocks: out[4][n] u32 for counter (env_id0+i, episode, block, stream_id). */
+int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, uint32_t block, uint32_t stream_id,
+                  uint32_t* out /*[4][n]*/, void* stream);
+
+/* ---- misc ----------------------------------------------------------------------------------- */
+const char* qs_last_error(void);
+int qs_version(void);
+/* peak-FP32 micro-benchmark (dependent FFMA chains); returns elapsed ms for `iters` FFMA per thread
+ * over blocks*threads threads via *ms_out, so that bench.py can state the FP32 roof it compares with. */
+int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QUADSIM_H */

@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE — generate tests/golden/*.npz by running the UNMODIFIED reference in the build
+container (it cannot travel to the GPU box).  Re-run with:  python oracle/gen_golden.py
+
+Fixtures (all float64 unless noted):
+  utility_vectors.npz   euler_quat / quat_euler / deriv_quat / quat_rot_mat on random inputs
+  drone_eq_vectors.npz  quad.drone_eq in direct and indirect mode (+ quad.f2w clipped / unclipped)
+  step_direct.npz       32 envs x 120 steps of quad.step, direct control, random actions, T=1, training
+  step_indirect.npz     16 envs x 80 steps, indirect control ([F,M] actions), clipped mixer, T=5
+  step_eval.npz         8 envs x 200 steps, training=False + small actions (solved does not end the episode)
+  lqr_log.npz           slice of the reference's SHIPPED log classical_controller_results/lqr_log_same_start.npy
+                        (written by the author's 2021 run) + the LQR gains of lqr_quad.py:25-111 + initial states
+  pid_log.npz           same for pid_log_same_start.npy (first episodes)
+  actor_128.npz         float32 weights of solved/nn_old_solved_128_32000_*.pth (actor only) and a reference
+                        closed-loop episode driven by it (ppo_quad_eval.py protocol)
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_import  # noqa: E402
+from oracle import quad_oracle as qo  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+REF = ref_import.REFERENCE_ROOT
+
+
+def quiet_quad(ref, *a, **k):
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        return ref.quad(*a, **k)
+
+
+def gen_utility(ref_u, rng):
+    n = 128
+    ang = rng.uniform(-np.pi, np.pi, (n, 3)) * np.array([1, 0.49, 1])
+    q = rng.normal(0, 1, (n, 4))
+    qn = q / np.linalg.norm(q, axis=1, keepdims=True)
+    w = rng.normal(0, 3, (n, 3))
+    out = dict(ang=ang, q=q, qn=qn, w=w)
+    out["euler_quat"] = np.array([ref_u.euler_quat(a).flatten() for a in ang])
+    out["quat_euler"] = np.array([ref_u.quat_euler(x.reshape(4, 1)) for x in qn])
+    out["deriv_quat"] = np.array([ref_u.deriv_quat(ww, x.reshape(4, 1)) for ww, x in zip(w, qn)])
+    out["quat_rot_mat"] = np.array([ref_u.quat_rot_mat(x) for x in qn])
+    np.savez_compressed(os.path.join(OUT, "utility_vectors.npz"), **out)
+
+
+def gen_drone_eq(ref, rng):
+    n = 256
+    x = rng.normal(0, 2, (n, 13))
+    x[:, 6:10] = rng.normal(0, 1, (n, 4))          # un-normalised on purpose (drone_eq normalises on read)
+    x[:, 10:13] = rng.normal(0, 4, (n, 3))
+    a = rng.uniform(-1, 1, (n, 4))
+    env = quiet_quad(ref, 0.01, 1000, training=True, direct_control=1, T=1)
+    dx_direct = np.array([env.drone_eq(0, xi, ai) for xi, ai in zip(x, a)])
+    envi = quiet_quad(ref, 0.01, 1000, training=True, direct_control=0, T=1, clipped=True)
+    fm = np.stack([rng.uniform(0, 25, n), rng.normal(0, 0.4, n), rng.normal(0, 0.4, n), rng.normal(0, 0.05, n)], axis=1)
+    eff_c, w_c, fmn_c, dx_ind = [], [], [], []
+    for xi, f in zip(x, fm):
+        se, w, F_new, M_new = envi.f2w(f[0], f[1:4].reshape(3, 1))
+        envi.w = w
+        u = np.append([F_new], M_new)
+        eff_c.append(se); w_c.append(w.flatten()); fmn_c.append(u)
+        dx_ind.append(envi.drone_eq(0, xi, u))
+    envu = quiet_quad(ref, 0.01, 1000, training=True, direct_control=0, T=1, clipped=False)
+    eff_u, w_u, fmn_u = [], [], []
+    for f in fm:
+        se, w, F_new, M_new = envu.f2w(f[0], f[1:4].reshape(3, 1))
+        eff_u.append(se); w_u.append(w.flatten()); fmn_u.append(np.append([F_new], M_new))
+    np.savez_compressed(os.path.join(OUT, "drone_eq_vectors.npz"), x=x, a=a, dx_direct=dx_direct, fm=fm,
+                        effort_clipped=np.array(eff_c), w_clipped=np.array(w_c), fm_new_clipped=np.array(fmn_c),
+                        dx_indirect=np.array(dx_ind), effort_unclipped=np.array(eff_u), w_unclipped=np.array(w_u),
+                        fm_new_unclipped=np.array(fmn_u))
+
+
+def run_reference_batch(ref, n_env, steps, init_states, actions, **kw):
+    """Drive n_env reference quads with given (steps,n_env,4) actions; returns dict of per-step records."""
+    import scipy.integrate as integ
+    envs = [quiet_quad(ref, 0.01, kw.pop("n", 1000) if False else kw.get("n", 1000),
+                       training=kw.get("training", True), direct_control=kw.get("direct_control", 1),
+                       T=kw.get("T", 1), clipped=kw.get("clipped", True)) for _ in range(n_env)]
+    T = kw.get("T", 1)
+    rec = dict(obs=np.zeros((steps, n_env, 14)), reward=np.zeros((steps, n_env)), done=np.zeros((steps, n_env), bool),
+               state=np.zeros((steps, n_env, 13)), ang=np.zeros((steps, n_env, 3)), ang_vel=np.zeros((steps, n_env, 3)),
+               solved=np.zeros((steps, n_env), np.int64), step_effort=np.zeros((steps, n_env, 4)),
+               w=np.zeros((steps, n_env, 4)), accel=np.zeros((steps, n_env, 3)), abs_sum=np.zeros((steps, n_env)),
+               nfev=np.zeros((steps, n_env), np.int64), clipped_action=np.zeros((steps, n_env, 4)),
+               acc_read=np.zeros((steps, n_env, 3)), mat_rot=np.zeros((steps, n_env, 3, 3)))
+    reset_obs = np.zeros((T, n_env, 14))
+    reset_state = np.zeros((n_env, 13))
+    orig = integ.solve_ivp
+    last = {}
+
+    def spy(*a, **k):
+        r = orig(*a, **k)
+        last["nfev"] = r.nfev
+        return r
+
+    ref.integrate.solve_ivp = spy
+    try:
+        for j, e in enumerate(envs):
+            s, _ = e.reset(init_states[j].copy())
+            reset_obs[:, j] = s
+            reset_state[j] = e.state
+        for t in range(steps):
+            for j, e in enumerate(envs):
+                o, r, d = e.step(actions[t, j])
+                rec["obs"][t, j] = o[0]; rec["reward"][t, j] = r; rec["done"][t, j] = d
+                rec["state"][t, j] = e.state; rec["ang"][t, j] = e.ang; rec["ang_vel"][t, j] = e.ang_vel
+                rec["solved"][t, j] = e.solved; rec["step_effort"][t, j] = e.step_effort
+                rec["w"][t, j] = e.w.flatten(); rec["accel"][t, j] = e.accel.flatten()
+                rec["abs_sum"][t, j] = e.abs_sum; rec["nfev"][t, j] = last["nfev"]
+                rec["clipped_action"][t, j] = e.clipped_action
+                rec["acc_read"][t, j] = np.asarray(e.accelerometer_read).flatten()
+                rec["mat_rot"][t, j] = e.mat_rot
+    finally:
+        ref.integrate.solve_ivp = orig
+    rec["reset_obs"] = reset_obs
+    rec["reset_state"] = reset_state
+    return rec
+
+
+def gen_steps(ref, rng):
+    # direct control, random actions (episodes end by bounding box within ~40-90 steps; stepping continues, done sticky)
+    n_env, steps = 32, 120
+    init, _ = qo.sample_reset_state(2024, np.arange(n_env), 0)
+    actions = rng.uniform(-1.2, 1.2, (steps, n_env, 4))            # some outside [-1,1] to exercise the clip
+    rec = run_reference_batch(ref, n_env, steps, init, actions, n=100, training=True, direct_control=1, T=1)
+    np.savez_compressed(os.path.join(OUT, "step_direct.npz"), init=init, actions=actions, n=100, T=1, **rec)
+
+    n_env, steps = 16, 80
+    init, _ = qo.sample_reset_state(2025, np.arange(n_env), 0)
+    actions = np.stack([rng.uniform(5, 16, (steps, n_env)), rng.normal(0, 0.25, (steps, n_env)),
+                        rng.normal(0, 0.25, (steps, n_env)), rng.normal(0, 0.04, (steps, n_env))], axis=2)
+    rec = run_reference_batch(ref, n_env, steps, init, actions, n=1000, training=True, direct_control=0, T=5, clipped=True)
+    np.savez_compressed(os.path.join(OUT, "step_indirect.npz"), init=init, actions=actions, n=1000, T=5, **rec)
+
+    n_env, steps = 8, 200
+    init = np.zeros((n_env, 13)); init[:, 6] = 1.0
+    init[:, 1:6:2] = rng.normal(0, 0.02, (n_env, 3))
+    init[:, 10:13] = rng.normal(0, 0.02, (n_env, 3))
+    init[0, 1:6:2] = 0; init[0, 10:13] = 0                         # env 0 starts exactly solved
+    actions = rng.uniform(-0.01, 0.01, (steps, n_env, 4))
+    rec = run_reference_batch(ref, n_env, steps, init, actions, n=150, training=False, direct_control=1, T=1)
+    np.savez_compressed(os.path.join(OUT, "step_eval.npz"), init=init, actions=actions, n=150, T=1, **rec)
+
+
+def lqr_gains(clipped=True):
+    """Gains exactly as lqr_quad.py:25-111 computes them (clipped branch)."""
+    from scipy.linalg import solve_continuous_are as solve_lqr
+    I_xx, I_yy, I_zz, M = 16.83e-3, 16.83e-3, 28.34e-3, 1.03
+    Q_att = np.array([[5, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0], [0, 0, 5, 0, 0, 0], [0, 0, 0, 1, 0, 0],
+                      [0, 0, 0, 0, 0.05, 0], [0, 0, 0, 0, 0, 0.01]]) * 50
+    R_att = np.diag(np.ones(4)) * 40
+    Q_t = np.array([[1e-08, 0, 0, 0, 0, 0], [0, 1, 0, 0, 0, 0], [0, 0, 1e-08, 0, 0, 0], [0, 0, 0, 1, 0, 0],
+                    [0, 0, 0, 0, 1e-08, 0], [0, 0, 0, 0, 0, 0.8]]) * 10
+    R_t = np.diag(np.ones(3)) * 10
+    A_att = np.array([[0, 1, 0, 0, 0, 0], [0, 0, 0, 0, 0, 0], [0, 0, 0, 1, 0, 0], [0, 0, 0, 0, 0, 0],
+                      [0, 0, 0, 0, 0, 1], [0, 0, 0, 0, 0, 0]])
+    B_att = np.array([[0, 0, 0, 0], [0, 1 / I_xx, 0, 0], [0, 0, 0, 0], [0, 0, 1 / I_yy, 0], [0, 0, 0, 0],
+                      [0, 0, 0, 1 / I_zz]])
+    K_att = -np.dot(np.linalg.inv(R_att), np.dot(B_att.T, solve_lqr(A_att, B_att, Q_att, R_att)))
+    A_t = A_att
+    B_t = np.array([[0, 0, 0], [1, 0, 0], [0, 0, 0], [0, 1, 0], [0, 0, 0], [0, 0, 1]]) / M
+    K_t = -np.dot(np.linalg.inv(R_t), np.dot(B_t.T, solve_lqr(A_t, B_t, Q_t, R_t)))
+    return K_t, K_att
+
+
+def gen_logs(ref):
+    res = os.path.join(REF, "environment", "controller", "classical_controller_results")
+    lqr = np.load(os.path.join(res, "lqr_log_same_start.npy"))
+    pid = np.load(os.path.join(res, "pid_log_same_start.npy"))
+    K_t, K_att = lqr_gains()
+    # initial states of the 20 episodes for seed 1 (robust RNG draws post-date the logs: suppressed)
+    np.random.seed(1)
+    inits = []
+    u = ref_import.load_reference_utility()
+    for _ in range(20):
+        ang = np.random.rand(3) - 0.5
+        s = np.zeros(13)
+        Q_in = u.euler_quat(ang)
+        s[0:5:2] = np.clip((np.random.normal([0, 0, 0], 2)), -2.5, 2.5)
+        s[1:6:2] = np.clip((np.random.normal([0, 0, 0], 2)), -5, 5)
+        s[6:10] = Q_in.T
+        s[10:13] = np.clip((np.random.normal([0, 0, 0], 2)), -15, 7.5)
+        inits.append(s)
+    np.savez_compressed(os.path.join(OUT, "lqr_log.npz"), log=lqr[:6], K_t=K_t, K_att=K_att, inits=np.array(inits),
+                        source="environment/controller/classical_controller_results/lqr_log_same_start.npy[:6]")
+    np.savez_compressed(os.path.join(OUT, "pid_log.npz"), log=pid[:4], inits=np.array(inits),
+                        source="environment/controller/classical_controller_results/pid_log_same_start.npy[:4]")
+
+
+def gen_actor(ref):
+    import glob
+    import torch
+    f = glob.glob(os.path.join(REF, "environment", "controller", "solved", "nn_old_solved_128_32000_*.pth"))[0]
+    sd = torch.load(f, map_location="cpu")
+    W = {k.replace(".", "_"): v.to(torch.float32).numpy() for k, v in sd.items() if k.startswith("actor.")}
+    # reference closed-loop episode, ppo_quad_eval.py:32-66 protocol (training=False, T=5, fp32 forward)
+    sys.path.insert(0, REF)
+    from environment.controller.dl_auxiliary import dl_in_gen
+    env = quiet_quad(ref, 0.01, 500, training=False, euler=0, direct_control=1, T=5)
+    aux = dl_in_gen(5, 13, 4)
+    init, _ = qo.sample_reset_state(99, np.arange(1), 0)
+    state, action = env.reset(init[0].copy())
+    aux.reset()
+    in_nn = aux.dl_input(state, action)
+
+    def actor(x):
+        h = np.tanh(W["actor_0_weight"] @ x + W["actor_0_bias"])
+        h = np.tanh(W["actor_2_weight"] @ h + W["actor_2_bias"])
+        return np.tanh(W["actor_4_weight"] @ h + W["actor_4_bias"])
+
+    model = torch.nn.Sequential(torch.nn.Linear(75, 128), torch.nn.Tanh(), torch.nn.Linear(128, 128), torch.nn.Tanh(),
+                                torch.nn.Linear(128, 4), torch.nn.Tanh())
+    model.load_state_dict({k.replace("actor.", ""): v.float() for k, v in sd.items() if k.startswith("actor.")})
+    steps = 300
+    obs = np.zeros((steps, 14)); acts = np.zeros((steps, 4)); nn_in = np.zeros((steps, 75), np.float32)
+    states = np.zeros((steps, 13))
+    for t in range(steps):
+        nn_in[t] = in_nn
+        a = model(torch.FloatTensor(in_nn)).detach().numpy()
+        s, _, _ = env.step(a)
+        in_nn = aux.dl_input(s, np.array([a]))
+        obs[t] = s[0]; acts[t] = a; states[t] = env.state
+    np.savez_compressed(os.path.join(OUT, "actor_128.npz"), init=init[0], reset_obs=state, obs=obs, actions=acts,
+                        nn_in=nn_in, states=states, **W)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = ref_import.load_reference()
+    ref_u = ref_import.load_reference_utility()
+    rng = np.random.default_rng(20261017)
+    gen_utility(ref_u, rng)
+    gen_drone_eq(ref, rng)
+    gen_steps(ref, rng)
+    gen_logs(ref)
+    gen_actor(ref)
+    for f in sorted(os.listdir(OUT)):
+        print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,565 @@
+"""TEST INFRASTRUCTURE ONLY — CPU (NumPy, float64) restatement of the reference hot path.
+
+This file is the *checker* for the CUDA path.  Only ``tests/``,
+``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of
+``bench.py`` may import it.  The product package never does.
+
+Parity status: PINNED.  The restatement is checked (tests/test_oracle_*.py) against
+  * the unmodified reference imported in the build container (``oracle/ref_import.py``),
+  * fixtures generated from the reference by ``oracle/gen_golden.py`` (tests/golden/*.npz),
+  * the reference's own shipped trajectory logs (``environment/controller/
+    classical_controller_results/{lqr,pid}_log_same_start.npy``; a slice is committed
+    under tests/golden/).
+
+Every function is batched over a leading env axis N and cites the reference lines it
+follows (paths relative to the reference root; ``scipy/`` = the SciPy the reference
+calls for its integrator, algorithm unchanged since the pinned scipy==1.6.0).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# --------------------------------------------------------------------------------------
+# constants — environment/quadrotor_env.py:30-80
+# --------------------------------------------------------------------------------------
+BB_POS = 5
+BB_VEL = 10
+BB_ANG = np.pi / 2
+M, G = 1.03, 9.82
+RHO = 1.2041
+C_D = 1.1
+K_F = 1.435e-5
+K_M = 2.4086e-7
+I_R = 5e-5
+T2WR = 2
+J_DIAG = np.array([16.83e-3, 16.83e-3, 28.34e-3])
+D = 0.26
+BEAM_THICKNESS = 0.05
+A_X = BEAM_THICKNESS * 2 * D
+A_Y = BEAM_THICKNESS * 2 * D
+A_Z = BEAM_THICKNESS * 2 * D * 2
+AREA = np.array([A_X, A_Y, A_Z])
+SOLVED_REWARD = 20
+BROKEN_REWARD = -20
+SHAPING_WEIGHT = 5
+SHAPING_INTERNAL_WEIGHTS = [15, 4, 1]
+P_C = 0.003
+TR = [0.005, 0.01, 0.1]
+TR_P = [3, 2, 1]
+
+# quad.__init__ :139-143
+BB_COND = np.array([BB_VEL, BB_VEL, BB_VEL, BB_ANG, BB_ANG, 3 / 4 * np.pi,
+                    BB_VEL * 2, BB_VEL * 2, BB_VEL * 2], dtype=np.float64)
+# quad.__init__ :178-180
+D_XX = np.linspace(0, D, 10)
+
+# Dormand–Prince 5(4) tableau — scipy/integrate/_ivp/rk.py (class RK45: C, A, B, E)
+RK45_C = np.array([0, 1 / 5, 3 / 10, 4 / 5, 8 / 9, 1])
+RK45_A = np.array([
+    [0, 0, 0, 0, 0],
+    [1 / 5, 0, 0, 0, 0],
+    [3 / 40, 9 / 40, 0, 0, 0],
+    [44 / 45, -56 / 15, 32 / 9, 0, 0],
+    [19372 / 6561, -25360 / 2187, 64448 / 6561, -212 / 729, 0],
+    [9017 / 3168, -355 / 33, 46732 / 5247, 49 / 176, -5103 / 18656],
+])
+RK45_B = np.array([35 / 384, 0, 500 / 1113, 125 / 192, -2187 / 6784, 11 / 84])
+RK45_E = np.array([-71 / 57600, 0, 71 / 16695, -71 / 1920, 17253 / 339200, -22 / 525, 1 / 40])
+RK_SAFETY, RK_MIN_FACTOR, RK_MAX_FACTOR = 0.9, 0.2, 10.0
+RK45_RTOL, RK45_ATOL = 1e-3, 1e-6  # solve_ivp defaults, scipy/integrate/_ivp/ivp.py (solve_ivp signature)
+
+
+# --------------------------------------------------------------------------------------
+# environment/quaternion_euler_utility.py
+# --------------------------------------------------------------------------------------
+def euler_quat(ang):
+    """(N,3) 3-2-1 Euler -> (N,4) unit quaternion. quaternion_euler_utility.py:17-36."""
+    ang = np.asarray(ang, dtype=np.float64)
+    phi, theta, psi = ang[..., 0], ang[..., 1], ang[..., 2]
+    cp, sp = np.cos(phi / 2), np.sin(phi / 2)
+    ct, st = np.cos(theta / 2), np.sin(theta / 2)
+    cps, sps = np.cos(psi / 2), np.sin(psi / 2)
+    q = np.stack([cp * ct * cps + sp * st * sps,
+                  sp * ct * cps - cp * st * sps,
+                  cp * st * cps + sp * ct * sps,
+                  cp * ct * sps - sp * st * cps], axis=-1)
+    return q / np.linalg.norm(q, axis=-1, keepdims=True)
+
+
+def quat_euler(q):
+    """(N,4) quaternion -> (N,3) Euler. quaternion_euler_utility.py:39-48 (no asin clamp: NaN propagates)."""
+    q = np.asarray(q, dtype=np.float64)
+    q0, q1, q2, q3 = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    with np.errstate(invalid="ignore"):
+        phi = np.arctan2(2 * (q0 * q1 + q2 * q3), 1 - 2 * (q1 ** 2 + q2 ** 2))
+        theta = np.arcsin(2 * (q0 * q2 - q3 * q1))
+        psi = np.arctan2(2 * (q0 * q3 + q1 * q2), 1 - 2 * (q2 ** 2 + q3 ** 2))
+    return np.stack([phi, theta, psi], axis=-1)
+
+
+def deriv_quat(w, q):
+    """(N,3),(N,4) -> (N,4) quaternion derivative 1/2*Omega(w)*q. quaternion_euler_utility.py:58-69."""
+    wx, wy, wz = w[..., 0], w[..., 1], w[..., 2]
+    q0, q1, q2, q3 = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    z = np.zeros_like(wx)
+    # rows of omega (:63-66) dotted with q
+    d0 = z * q0 + (-wx) * q1 + (-wy) * q2 + (-wz) * q3
+    d1 = wx * q0 + z * q1 + wz * q2 + (-wy) * q3
+    d2 = wy * q0 + (-wz) * q1 + z * q2 + wx * q3
+    d3 = wz * q0 + wy * q1 + (-wx) * q2 + z * q3
+    return 1 / 2 * np.stack([d0, d1, d2, d3], axis=-1)
+
+
+def quat_rot_mat(q):
+    """(N,4) -> (N,3,3). quaternion_euler_utility.py:71-80."""
+    a, b, c, d = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    R = np.empty(q.shape[:-1] + (3, 3), dtype=np.float64)
+    R[..., 0, 0] = a ** 2 + b ** 2 - c ** 2 - d ** 2
+    R[..., 0, 1] = 2 * b * c - 2 * a * d
+    R[..., 0, 2] = 2 * b * d + 2 * a * c
+    R[..., 1, 0] = 2 * b * c + 2 * a * d
+    R[..., 1, 1] = a ** 2 - b ** 2 + c ** 2 - d ** 2
+    R[..., 1, 2] = 2 * c * d - 2 * a * b
+    R[..., 2, 0] = 2 * b * d - 2 * a * c
+    R[..., 2, 1] = 2 * c * d + 2 * a * b
+    R[..., 2, 2] = a ** 2 - b ** 2 - c ** 2 + d ** 2
+    return R
+
+
+# --------------------------------------------------------------------------------------
+# rotor / mixer maps
+# --------------------------------------------------------------------------------------
+def f2F(f_action):
+    """Direct mode: normalised rotor commands (N,4) -> w(N,4), F(N), M(N,3). quadrotor_env.py:247-272."""
+    f = (f_action + 1) * T2WR * M * G / 8
+    with np.errstate(invalid="ignore"):
+        w = np.sqrt(f / K_F)
+    F_new = f[:, 0] + f[:, 1] + f[:, 2] + f[:, 3]
+    M_new = np.stack([(f[:, 2] - f[:, 0]) * D,
+                      (f[:, 1] - f[:, 3]) * D,
+                      (-f[:, 0] + f[:, 1] - f[:, 2] + f[:, 3]) * K_M / K_F], axis=-1)
+    return w, F_new, M_new
+
+
+_MIXER = np.array([[K_F, K_F, K_F, K_F],
+                   [-D * K_F, 0, D * K_F, 0],
+                   [0, D * K_F, 0, -D * K_F],
+                   [-K_M, +K_M, -K_M, +K_M]])
+
+
+def f2w(f, m, clipped=True):
+    """Indirect mode mixer: F(N), M(N,3) -> step_effort(N,4), w(N,4), F_new(N), M_new(N,3).
+    quadrotor_env.py:197-245 (np.linalg.solve of the 4x4 mixer, clip or signed sqrt, FM_new = x.u)."""
+    y = np.concatenate([np.asarray(f, dtype=np.float64)[:, None], np.asarray(m, dtype=np.float64)], axis=1)
+    u = np.linalg.solve(_MIXER, y.T).T
+    if clipped:
+        u = np.clip(u, 0, T2WR * M * G / 4 / K_F)
+        w = np.sqrt(u)
+    else:
+        w = np.sqrt(np.abs(u)) * np.where(u < 0, -1.0, 1.0)
+    FM_new = u @ _MIXER.T
+    step_effort = (u * K_F / (T2WR * M * G / 4) * 2) - 1
+    return step_effort, w, FM_new[:, 0], FM_new[:, 1:4]
+
+
+# --------------------------------------------------------------------------------------
+# drone_eq — environment/quadrotor_env.py:274-406
+# --------------------------------------------------------------------------------------
+def drone_eq(x, F, Mact, w_rotor, want_aux=False):
+    """RHS of the 13-state ODE, batched.
+
+    x (N,13) = [x,vx,y,vy,z,vz,q0..q3,wx,wy,wz]; F (N) body thrust; Mact (N,3) body moments;
+    w_rotor (N,4) rotor speeds (for the gyroscopic term, :345).  Returns dx (N,13) and, if
+    ``want_aux``, a dict with the side-effect attributes the reference leaves behind
+    (V_q :392, accel :368, mat_rot :315, accelerometer_read :371).
+    """
+    vel = x[:, 1:6:2]
+    q = x[:, 6:10]
+    W = x[:, 10:13]
+    with np.errstate(invalid="ignore", divide="ignore"):
+        q = q / np.linalg.norm(q, axis=1, keepdims=True)                       # :311-312
+    R = quat_rot_mat(q)                                                       # :315
+    v_body = np.einsum("nji,nj->ni", R, vel)                                  # :322  R^T v
+    f_drag = -0.5 * RHO * C_D * AREA[None, :] * (np.abs(v_body) * v_body)     # :323
+    m_drag = np.zeros_like(W)
+    for xx in D_XX:                                                           # :328-334
+        m_drag[:, 0] += -RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 0]) * (xx * W[:, 0])) * xx
+        m_drag[:, 1] += -RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 1]) * (xx * W[:, 1])) * xx
+        m_drag[:, 2] += -2 * RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 2]) * (xx * W[:, 2])) * xx
+    omega_r = (-w_rotor[:, 0] + w_rotor[:, 1] - w_rotor[:, 2] + w_rotor[:, 3]) * I_R   # :345
+    m_gyro = np.stack([-W[:, 0] * omega_r, W[:, 1] * omega_r, np.zeros_like(omega_r)], axis=1)  # :347-349
+    f_body = f_drag.copy()
+    f_body[:, 2] += F                                                         # :352-353
+    f_inertial = np.einsum("nij,nj->ni", R, f_body)                           # :357
+    accel = f_inertial / M                                                    # :365-367
+    accel[:, 2] -= G
+    JW = W * J_DIAG[None, :]
+    m_in = Mact + m_gyro + m_drag - np.cross(W, JW)                           # :378
+    accel_ang = m_in * (1.0 / J_DIAG)[None, :]                                # :384-388 (J diagonal)
+    V_q = deriv_quat(W, q)                                                    # :392
+    out = np.empty_like(x)
+    out[:, 0:6:2] = vel
+    out[:, 1:6:2] = accel
+    out[:, 6:10] = V_q
+    out[:, 10:13] = accel_ang
+    if want_aux:
+        acc_read = np.einsum("nji,nj->ni", R, accel + np.array([0, 0, -G])[None, :])   # :371
+        return out, dict(V_q=V_q, accel=accel, mat_rot=R, accelerometer_read=acc_read)
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# integrators
+# --------------------------------------------------------------------------------------
+def _rms(x):
+    """scipy/integrate/_ivp/common.py:63-65  norm(x) = ||x||_2 / sqrt(n)."""
+    return np.linalg.norm(x, axis=1) / x.shape[1] ** 0.5
+
+
+def rk45_solve(fun, y0, t_bound, rtol=RK45_RTOL, atol=RK45_ATOL, max_attempts=10000):
+    """Per-env replica of ``solve_ivp(fun,(0,t_bound),y0)`` with all defaults (RK45), batched with masks.
+
+    Follows scipy/integrate/_ivp/rk.py:85-105 (RungeKutta.__init__), common.py:68-134
+    (select_initial_step), rk.py:111-183 (_step_impl), rk.py:14-70 (rk_step), base.py:179-210 (step).
+    ``fun(y, idx)`` evaluates the RHS for env subset ``idx``.
+    Returns y_final (N,13), nfev (N), n_accepted (N).
+    """
+    N, n = y0.shape
+    all_idx = np.arange(N)
+    t = np.zeros(N)
+    y = y0.astype(np.float64).copy()
+    f = fun(y, all_idx)
+    nfev = np.ones(N, dtype=np.int64)
+    nacc = np.zeros(N, dtype=np.int64)
+    # --- select_initial_step
+    with np.errstate(all="ignore"):
+        scale = atol + np.abs(y) * rtol
+        d0 = _rms(y / scale)
+        d1 = _rms(f / scale)
+        h0 = np.where((d0 < 1e-5) | (d1 < 1e-5), 1e-6, 0.01 * d0 / d1)
+        h0 = np.minimum(h0, t_bound)
+        y1 = y + h0[:, None] * f
+        f1 = fun(y1, all_idx)
+        nfev += 1
+        d2 = _rms((f1 - f) / scale) / h0
+        h1 = np.where((d1 <= 1e-15) & (d2 <= 1e-15), np.maximum(1e-6, h0 * 1e-3),
+                      (0.01 / np.maximum(d1, d2)) ** (1 / 5))
+        h_abs = np.minimum(np.minimum(100 * h0, h1), t_bound)
+    running = np.ones(N, dtype=bool)
+    new_step = np.ones(N, dtype=bool)          # entering _step_impl afresh
+    rejected = np.zeros(N, dtype=bool)
+    min_step = np.zeros(N)
+    K = np.zeros((N, 7, n))
+    for _ in range(max_attempts):
+        idx = np.nonzero(running)[0]
+        if idx.size == 0:
+            break
+        with np.errstate(all="ignore"):
+            # _step_impl prologue (only when a new solver.step() begins)
+            ns = idx[new_step[idx]]
+            if ns.size:
+                min_step[ns] = 10 * np.abs(np.nextafter(t[ns], np.inf) - t[ns])
+                h_abs[ns] = np.where(h_abs[ns] < min_step[ns], min_step[ns], h_abs[ns])
+                rejected[ns] = False
+                new_step[ns] = False
+            # too-small step -> solver fails, solve_ivp stops with the last accepted y
+            fail = idx[h_abs[idx] < min_step[idx]]
+            if fail.size:
+                running[fail] = False
+                idx = np.nonzero(running)[0]
+                if idx.size == 0:
+                    break
+            ti, yi, fi = t[idx], y[idx], f[idx]
+            t_new = ti + h_abs[idx]
+            t_new = np.where(t_new - t_bound > 0, t_bound, t_new)
+            h = t_new - ti
+            ha = np.abs(h)
+            # rk_step
+            Ki = K[idx]
+            Ki[:, 0] = fi
+            for s in range(1, 6):
+                dy = np.einsum("nsk,s->nk", Ki[:, :s], RK45_A[s, :s]) * h[:, None]
+                Ki[:, s] = fun(yi + dy, idx)
+            y_new = yi + h[:, None] * np.einsum("nsk,s->nk", Ki[:, :6], RK45_B)
+            f_new = fun(y_new, idx)
+            Ki[:, 6] = f_new
+            nfev[idx] += 6
+            scale = atol + np.maximum(np.abs(yi), np.abs(y_new)) * rtol
+            err = _rms(np.einsum("nsk,s->nk", Ki, RK45_E) * h[:, None] / scale)
+            acc = err < 1
+            # NaN error norm: `error_norm < 1` is False -> rejection path with NaN factor; the
+            # reference then loops until h_abs<min_step is False forever (NaN) -> we stop these envs.
+            nanerr = np.isnan(err)
+            factor_acc = np.where(err == 0, RK_MAX_FACTOR,
+                                  np.minimum(RK_MAX_FACTOR, RK_SAFETY * err ** -0.2))
+            factor_acc = np.where(rejected[idx], np.minimum(1.0, factor_acc), factor_acc)
+            factor_rej = np.maximum(RK_MIN_FACTOR, RK_SAFETY * err ** -0.2)
+            h_abs[idx] = np.where(acc, ha * factor_acc, ha * factor_rej)
+            K[idx] = Ki
+            a = idx[acc]
+            if a.size:
+                t[a] = t_new[acc]
+                y[a] = y_new[acc]
+                f[a] = f_new[acc]
+                nacc[a] += 1
+                new_step[a] = True
+                running[a] = ~(t[a] - t_bound >= 0)
+            r = idx[~acc]
+            rejected[r] = True
+            if nanerr.any():
+                # poisoned env: take the NaN state (what the caller would eventually see is undefined)
+                bad = idx[nanerr]
+                y[bad] = y_new[nanerr]
+                running[bad] = False
+    return y, nfev, nacc
+
+
+def rk4_solve(fun, y0, t_bound, substeps=1):
+    """Classical fixed-step RK4 with ``substeps`` equal sub-intervals (the FP32 production integrator)."""
+    N = y0.shape[0]
+    idx = np.arange(N)
+    y = y0.astype(np.float64).copy()
+    h = t_bound / substeps
+    for _ in range(substeps):
+        k1 = fun(y, idx)
+        k2 = fun(y + 0.5 * h * k1, idx)
+        k3 = fun(y + 0.5 * h * k2, idx)
+        k4 = fun(y + h * k3, idx)
+        y = y + (h / 6.0) * (k1 + 2 * k2 + 2 * k3 + k4)
+    return y
+
+
+# --------------------------------------------------------------------------------------
+# Philox4x32-10 (counter-based RNG used by the CUDA reset / noise sub-passes)
+# --------------------------------------------------------------------------------------
+_PHILOX_M0 = np.uint64(0xD2511F53)
+_PHILOX_M1 = np.uint64(0xCD9E8D57)
+_PHILOX_W0 = np.uint32(0x9E3779B9)
+_PHILOX_W1 = np.uint32(0xBB67AE85)
+
+
+def philox4x32_10(counter, key):
+    """counter (N,4) uint32, key (N,2) uint32 -> (N,4) uint32.  Salmon et al. 2011, 10 rounds
+    (integer work: the CUDA implementation must match bit-exactly)."""
+    c = np.array(counter, dtype=np.uint32).reshape(-1, 4).copy()
+    k = np.array(key, dtype=np.uint32).reshape(-1, 2).copy()
+    mask = np.uint64(0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        for _ in range(10):
+            p0 = _PHILOX_M0 * c[:, 0].astype(np.uint64)
+            p1 = _PHILOX_M1 * c[:, 2].astype(np.uint64)
+            hi0, lo0 = (p0 >> np.uint64(32)).astype(np.uint32), (p0 & mask).astype(np.uint32)
+            hi1, lo1 = (p1 >> np.uint64(32)).astype(np.uint32), (p1 & mask).astype(np.uint32)
+            c = np.stack([hi1 ^ c[:, 1] ^ k[:, 0], lo1, hi0 ^ c[:, 3] ^ k[:, 1], lo0], axis=1)
+            k = np.stack([k[:, 0] + _PHILOX_W0, k[:, 1] + _PHILOX_W1], axis=1)
+    return c
+
+
+def u32_to_unit(u):
+    """uint32 -> float64 in (0,1):  (u + 0.5) * 2^-32  (same map as the CUDA side)."""
+    return (u.astype(np.float64) + 0.5) * (1.0 / 4294967296.0)
+
+
+def box_muller(u1, u2):
+    r = np.sqrt(-2.0 * np.log(u1))
+    return r * np.cos(2 * np.pi * u2), r * np.sin(2 * np.pi * u2)
+
+
+# stream ids for the Philox counter word 3 (shared with csrc/philox.cuh)
+STREAM_RESET = 0
+STREAM_SENSOR = 1
+STREAM_ACTION = 2
+STREAM_POLICY = 3
+
+
+def philox_block(seed, env_id, episode, block, stream):
+    """counter = (env_id, episode, block, stream), key = (seed_lo, seed_hi)."""
+    env_id = np.asarray(env_id, dtype=np.uint32)
+    n = env_id.shape[0]
+    ctr = np.stack([env_id,
+                    np.broadcast_to(np.asarray(episode, dtype=np.uint32), (n,)),
+                    np.broadcast_to(np.asarray(block, dtype=np.uint32), (n,)),
+                    np.full(n, stream, dtype=np.uint32)], axis=1)
+    key = np.stack([np.full(n, seed & 0xFFFFFFFF, dtype=np.uint32),
+                    np.full(n, (seed >> 32) & 0xFFFFFFFF, dtype=np.uint32)], axis=1)
+    return philox4x32_10(ctr, key)
+
+
+def sample_reset_state(seed, env_id, episode):
+    """Device-side restatement of the random branch of quad.reset (quadrotor_env.py:439-445) with
+    Philox in place of NumPy's MT19937 (which a counter-based generator cannot reproduce):
+      ang ~ U(-0.5,0.5)^3; pos ~ clip(N(0,2),+-2.5); vel ~ clip(N(0,2),+-5); w ~ clip(N(0,2),-15,+7.5).
+    Draw order (fixed, shared with csrc): block0 -> u(ang0..2), u_spare; blocks 1..3 -> 4 uniforms each ->
+    2 Box-Muller pairs each: normals n0..n11; pos=n0..2, vel=n3..5, w=n6..8.
+    Returns state (N,13) float64 and ang (N,3).
+    """
+    b0 = u32_to_unit(philox_block(seed, env_id, episode, 0, STREAM_RESET))
+    ang = b0[:, 0:3] - 0.5
+    normals = []
+    for blk in (1, 2, 3):
+        u = u32_to_unit(philox_block(seed, env_id, episode, blk, STREAM_RESET))
+        a, b = box_muller(u[:, 0], u[:, 1])
+        c, d = box_muller(u[:, 2], u[:, 3])
+        normals += [a, b, c, d]
+    nrm = np.stack(normals, axis=1)
+    st = np.zeros((len(env_id), 13))
+    st[:, 0:5:2] = np.clip(nrm[:, 0:3] * 2, -BB_POS / 2, BB_POS / 2)
+    st[:, 1:6:2] = np.clip(nrm[:, 3:6] * 2, -BB_VEL / 2, BB_VEL / 2)
+    st[:, 6:10] = euler_quat(ang)
+    st[:, 10:13] = np.clip(nrm[:, 6:9] * 2, -BB_VEL * 1.5, BB_POS * 1.5)
+    return st, ang
+
+
+# --------------------------------------------------------------------------------------
+# the environment: N independent copies of `quad`, advanced in lock-step
+# --------------------------------------------------------------------------------------
+class BatchQuadOracle:
+    """N independent reference ``quad`` environments (quadrotor_env.py:111-577), vectorised.
+
+    integrator: "rk45" = replica of the reference's solve_ivp call (:483); "rk4" = fixed-step RK4.
+    """
+
+    def __init__(self, n_envs, t_step, n, training=True, direct_control=1, T=1, clipped=True,
+                 integrator="rk45", substeps=1):
+        self.N = n_envs
+        self.t_step = t_step
+        self.T = T
+        self.n = n + T                                                        # :157
+        self.training = bool(training)
+        self.direct = bool(direct_control)
+        self.clipped = clipped
+        self.integrator = integrator
+        self.substeps = substeps
+        self.zero_control = (np.ones(4) * (2 / T2WR - 1)) if self.direct else np.array([M * G, 0, 0, 0])  # :164-167
+        self.ang_vel = np.zeros((n_envs, 3))
+        self.prev_ang = np.zeros((n_envs, 3))                                 # :171-172 (never cleared by reset)
+        self.ang = np.zeros((n_envs, 3))
+        self.abs_sum = np.zeros(n_envs)
+        self.done = np.ones(n_envs, dtype=bool)                               # :154
+        self.solved = np.zeros(n_envs, dtype=np.int64)
+        self.i = np.zeros(n_envs, dtype=np.int64)
+        self.prev_shaping = np.zeros(n_envs)
+        self.has_prev_shaping = np.zeros(n_envs, dtype=bool)
+        self.previous_state = np.zeros((n_envs, 13))
+        self.state = np.zeros((n_envs, 13))
+        self.nfev = np.zeros(n_envs, dtype=np.int64)
+
+    # -- reset :408-454
+    def reset(self, det_state, mask=None):
+        """Deterministic-state reset for envs in ``mask`` (all if None), then T hover steps.
+        Returns obs_hist (T,N,14), act_hist (T,N,4) (rows of non-reset envs are whatever step produced)."""
+        m = np.ones(self.N, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+        self.solved[m] = 0
+        self.done[m] = False
+        self.i[m] = 0
+        self.has_prev_shaping[m] = False
+        self.abs_sum[m] = 0
+        self.previous_state[m] = np.asarray(det_state, dtype=np.float64)[m]
+        self.ang[m] = quat_euler(self.previous_state[m, 6:10])                # :437-438
+        obs_h, act_h = [], []
+        for _ in range(self.T):
+            a = np.broadcast_to(self.zero_control, (self.N, 4)).copy()
+            obs, _, _ = self.step(a, mask=m)
+            obs_h.append(obs)
+            act_h.append(a)
+        return np.array(obs_h), np.array(act_h)
+
+    # -- step :458-498
+    def step(self, action, mask=None):
+        m = np.ones(self.N, dtype=bool) if mask is None else np.asarray(mask, dtype=bool)
+        idx_all = np.nonzero(m)[0]
+        action = np.asarray(action, dtype=np.float64)
+        self.i[m] += 1
+        if self.direct:
+            act = np.clip(action, -1, 1)                                      # :470
+            self.action = act
+            self.clipped_action = act
+            step_effort = act
+            w, F, Mact = f2F(act)
+        else:
+            self.action = action
+            step_effort, w, F, Mact = f2w(action[:, 0], action[:, 1:4], self.clipped)   # :476
+            self.clipped_action = np.concatenate([F[:, None], Mact], axis=1)
+        self.w = w
+
+        def fun(y, idx):
+            g = idx_all[idx]
+            return drone_eq(y, F[g], Mact[g], w[g])
+
+        y0 = self.previous_state[m]
+        if self.integrator == "rk45":
+            y, nfev, _ = rk45_solve(fun, y0, self.t_step)
+            self.nfev[m] = nfev
+        else:
+            y = rk4_solve(fun, y0, self.t_step, self.substeps)
+        _, aux = drone_eq(y, F[m], Mact[m], w[m], want_aux=True)             # FSAL stage f(t+h,y_new): last drone_eq call
+        state = self.state.copy()
+        state[m] = y
+        self.state = state
+        V_q = np.zeros((self.N, 4))
+        V_q[m] = aux["V_q"]
+        self.V_q = V_q
+        self.accel = np.zeros((self.N, 3)); self.accel[m] = aux["accel"]
+        self.accelerometer_read = np.zeros((self.N, 3)); self.accelerometer_read[m] = aux["accelerometer_read"]
+        self.mat_rot = np.zeros((self.N, 3, 3)); self.mat_rot[m] = aux["mat_rot"]
+        self.f_in = F
+        quat_state = np.concatenate([self.state[:, 0:10], V_q], axis=1)       # :486
+        with np.errstate(invalid="ignore", divide="ignore"):
+            q = self.state[:, 6:10] / np.linalg.norm(self.state[:, 6:10], axis=1, keepdims=True)   # :488-489
+        ang = quat_euler(q)
+        self.ang = np.where(m[:, None], ang, self.ang)
+        self.ang_vel = np.where(m[:, None], (self.ang - self.prev_ang) / self.t_step, self.ang_vel)  # :492
+        self.prev_ang = np.where(m[:, None], self.ang, self.prev_ang)
+        self.previous_state = np.where(m[:, None], self.state, self.previous_state)
+        self.step_effort = step_effort
+        self._done_condition(m)
+        reward = self._reward_function(m)
+        self.abs_sum = np.where(m, self.abs_sum + np.sqrt(np.sum(np.square(step_effort), axis=1)), self.abs_sum)  # :575-577
+        self.reward = reward
+        return quat_state, reward, self.done.copy()
+
+    # -- done_condition :500-509
+    def _done_condition(self, m):
+        cond_x = np.concatenate([self.state[:, 1:6:2], self.ang, self.state[:, 10:13]], axis=1)
+        with np.errstate(invalid="ignore"):
+            hit = np.any(np.abs(cond_x) >= BB_COND[None, :], axis=1)
+        self.done = np.where(m, self.done | hit, self.done)
+
+    # -- reward_function :511-573
+    def _reward_function(self, m):
+        velocity = self.state[:, 1:6:2]
+        euler = self.ang
+        psi = self.ang[:, 2]
+        body_ang_vel = self.state[:, 10:13]
+        sw = SHAPING_INTERNAL_WEIGHTS
+        shaping = -SHAPING_WEIGHT / np.sum(sw) * (sw[0] * np.linalg.norm(velocity / BB_VEL, axis=1)
+                                                  + sw[1] * np.abs(psi / 4)
+                                                  + sw[2] * np.linalg.norm(euler[:, 0:2] / BB_ANG, axis=1))
+        r_state = np.concatenate([velocity, psi[:, None]], axis=1)
+        nr = np.linalg.norm(r_state, axis=1)
+        ne = np.linalg.norm(euler[:, 0:2], axis=1)
+        taken = np.zeros(self.N, dtype=bool)
+        with np.errstate(invalid="ignore"):
+            for TR_i, TR_Pi in zip(TR, TR_P):                                  # :535-542
+                c1 = (nr < np.linalg.norm(np.ones(4) * TR_i)) & ~taken
+                c2 = c1 & (ne < np.linalg.norm(np.ones(2) * TR_i * 4))
+                shaping = shaping + np.where(c1, TR_Pi, 0) + np.where(c2, TR_Pi, 0)
+                taken |= c1
+        reward = np.where(self.has_prev_shaping, shaping - self.prev_shaping, 0.0)     # :545-547
+        self.prev_shaping = np.where(m, shaping, self.prev_shaping)
+        self.has_prev_shaping = self.has_prev_shaping | m
+        reward = reward + (-np.sum(np.square(self.action - self.zero_control[None, :]), axis=1) * P_C)   # :553-554
+        target_state = 9 * (TR[0] ** 2)                                        # :557
+        current_state = np.sum(np.square(np.concatenate([velocity, euler, body_ang_vel], axis=1)), axis=1)
+        self.current_state = current_state
+        with np.errstate(invalid="ignore"):
+            is_solved = current_state < target_state
+        timeout = ~is_solved & (self.i >= self.n)
+        broken = ~is_solved & ~timeout & self.done
+        reward = reward + np.where(is_solved, SOLVED_REWARD, 0.0) + np.where(broken, BROKEN_REWARD, 0.0)
+        # :563-573  solved=1 | (timeout or broken) solved=0 | otherwise unchanged
+        solved_new = np.where(is_solved, 1, np.where(timeout | broken, 0, self.solved))
+        self.solved = np.where(m, solved_new, self.solved)
+        new_done = self.done | timeout | (is_solved & self.training)
+        self.done = np.where(m, new_done, self.done)
+        return np.where(m, reward, 0.0)
