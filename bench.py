@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/sec of the batched quadrotor hot path (BASELINE.json metric) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          # our arm (CUDA)
+    python bench.py --impl reference [--gpus N] ...              # the reference's algorithm on the host cores
+
+A "step" is one lock-step env step (quad.step) of every environment of the workload:
+  N=1  : BASELINE.json configs[2] — 1,048,576 envs, FP32 RK4, auto-reset, T=5, random actions read from HBM
+  N>1  : BASELINE.json configs[3] — 2,097,152 envs per GPU sharded by global env id (16,777,216 at N=8),
+         with an NCCL all-reduce of the episode statistics every 128 steps.
+`value` = env-steps/s with the actions already resident in HBM; `e2e` = the same through the C-ABI entry
+point qs_step_host with pinned HOST buffers (H2D of actions, D2H of obs/reward/done inside the timed region).
+One JSON line is printed by rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (RK4, FP32)"
+UNIT = "env-steps/s"
+ALGO_BYTES_PER_ENV_STEP = 181          # state 13 in + 13 out, action 4 in, obs 14 + reward 1 out (fp32), done 1 B
+FLOPS_PER_ENV_STEP = lambda S: 701 * S + 180
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20000)
+    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="0 = 1,048,576 at N=1, 2,097,152 at N>1")
+    ap.add_argument("--substeps", type=int, default=1)
+    ap.add_argument("--T", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=100)
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg (N=1, rank 0)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sensor-noise", type=int, default=1)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU legs (the only places bench.py may execute oracle/)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_reference_run(n_envs, steps, warmup, T, threads=0):
+    """The reference's algorithm (SciPy-RK45 replica + drone_eq + done/reward, oracle/quad_oracle.c) on the host."""
+    import numpy as np
+    from oracle.c_oracle import COracle
+    from oracle import quad_oracle as qo
+    env = COracle(n_envs, 0.01, 10 ** 9, training=False, direct_control=1, T=T, integrator="rk45", threads=threads)
+    cores = env.lib.qo_max_threads() if threads == 0 else threads
+    init, _ = qo.sample_reset_state(0, np.arange(n_envs), 0)
+    env.reset(init)
+    rng = np.random.default_rng(0)
+    acts = [rng.uniform(-1, 1, (n_envs, 4)) for _ in range(4)]
+    for w in range(warmup):
+        env.step(acts[w % 4])
+    t0 = time.perf_counter()
+    for k in range(steps):
+        env.step(acts[k % 4])
+        if k % 16 == 15:                               # keep envs alive: re-seed the ones that left the box
+            bad = env.done.astype(bool) | ~np.isfinite(env.state).all(axis=1)
+            if bad.any():
+                env.state[bad] = init[bad]; env.flags[bad] = 0; env.step_i[bad] = 0
+    dt = time.perf_counter() - t0
+    return n_envs * steps / dt, dt, cores
+
+
+def cpu_baseline(seconds, T):
+    n = 8192
+    rate, _, cores = cpu_reference_run(n, 4, 1, T)
+    steps = max(4, int(rate * seconds / n))
+    rate, dt, cores = cpu_reference_run(n, steps, 2, T)
+    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d envs x %d steps (%.1f s) of the FP64 SciPy-RK45-replica step the reference runs "
+                      "(oracle/quad_oracle.c, OpenMP); the Python reference itself measured 678 env-steps/s/core "
+                      "(BASELINE.md)" % (n, steps, dt)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_gpu_envs = args.envs_per_gpu or (1 << 20 if args.gpus == 1 else 1 << 21)
+    probe_n = 4096
+    rate, _, cores = cpu_reference_run(probe_n, 4, 1, args.T)
+    budget_s = 90.0
+    n = int(max(256, min(65536, rate * budget_s / max(1, args.steps + args.warmup))))
+    t0 = time.perf_counter()
+    rate, dt, cores = cpu_reference_run(n, args.steps, args.warmup, args.T)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "bounded sample (%d envs per step) of the %d-env lock-step workload, reference algorithm "
+                               "(FP64 RK45 rtol 1e-3) on host cores" % (n, n_gpu_envs * args.gpus), "T": args.T},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "%d envs x %d steps, oracle/quad_oracle.c with OpenMP" % (n, args.steps)},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.rows.append((time.perf_counter(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, ln in self.rows:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                if t0 <= ts <= t1 + 0.1:
+                    sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            if t0 <= ts <= t1 + 0.1:
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+    import torch
+    from autonomous_quadrotor_environment_b200 import BatchedQuad, _lib as L
+    from autonomous_quadrotor_environment_b200.sharding import init_distributed, allreduce_stats
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    rank, world, local = init_distributed()
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    N = args.envs_per_gpu or (1 << 20 if world == 1 else 1 << 21)
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
+                      substeps=args.substeps, auto_reset=True, sensor_noise=bool(args.sensor_noise), seed=0,
+                      env_id_offset=rank * N, device=dev)
+    env.reset()
+    P = 16                                               # action pool: 16 x (4,N) fp32 = 256 MB at 1M envs (> 126 MB L2)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    acts = [(torch.rand(4, N, device=dev, generator=g) * 2 - 1).contiguous() for _ in range(P)]
+    ptrs = [C.c_void_p(a.data_ptr()) for a in acts]
+    lib, h = env.lib, env._h
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    stats_buf = torch.zeros(8, dtype=torch.float64, device=dev)
+
+    def step(k):
+        rc = lib.qs_step(h, ptrs[k % P], None, None, None, None, stream)
+        if rc != 0:
+            L.check(rc)
+        if world > 1 and k % 128 == 127:                 # the path's only collective: episode statistics
+            stats_buf.copy_(env.stats_tensor())
+            allreduce_stats(stats_buf)
+
+    for w in range(args.warmup):
+        step(w)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]) if rank == 0 else None
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    ev0.record()
+    for k in range(args.steps):
+        step(k)
+    ev1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop(t0, t1) if sampler else None
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max = float(tmax.item())
+    total_envs = N * world
+    value = total_envs * args.steps / (ms_max * 1e-3)
+
+    # ---- e2e: qs_step_host with pinned host buffers (H2D actions, D2H obs/reward/done inside the timed region)
+    e2e_steps = max(1, args.e2e_steps)
+    a_host = [torch.empty(4, N).uniform_(-1, 1).pin_memory() for _ in range(2)]
+    obs_h = torch.empty(14, N).pin_memory(); rew_h = torch.empty(N).pin_memory()
+    done_h = torch.empty(N, dtype=torch.uint8).pin_memory()
+    for w in range(3):
+        L.check(lib.qs_step_host(h, a_host[w % 2].data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr(), stream))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    te0 = time.perf_counter()
+    for k in range(e2e_steps):
+        L.check(lib.qs_step_host(h, a_host[k % 2].data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr(), stream))
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - te0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_envs * e2e_steps / float(te.item())
+    h2d = 4 * N * 4
+    d2h = 14 * N * 4 + N * 4 + N
+
+    # ---- roofs
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(peaks_path):
+        hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    kernel_ms = ms / args.steps                          # one launch of step_kernel per step, back to back on one stream
+    achieved_gbs = ALGO_BYTES_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tp):
+        try:
+            traffic = json.load(open(tp)).get("step_kernel_f32_rk4_direct_bytes_per_launch")
+        except Exception:
+            traffic = None
+    probe_ms = C.c_float(0)
+    blocks, threads, iters = 148 * 8, 256, 1 << 16
+    L.check(lib.qs_fp32_peak_probe(blocks, threads, iters, C.byref(probe_ms), stream))
+    fp32_peak = 2.0 * blocks * threads * iters / (probe_ms.value * 1e-3) / 1e12
+    flops = FLOPS_PER_ENV_STEP(args.substeps) * N / (kernel_ms * 1e-3) / 1e12
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "%d envs/GPU x %d GPU lock-step quad.step, FP32 RK4 x%d substeps, auto-reset, T=%d, "
+                                   "sensor_noise=%d, U(-1,1) actions read from a %d-buffer HBM pool"
+                                   % (N, world, args.substeps, args.T, int(bool(args.sensor_noise)), P),
+                       "envs_per_gpu": N, "substeps": args.substeps, "T": args.T,
+                       "l2": "working set %.0f MB/step > 126 MB L2 (state+obs rows %d B/env + rotating action pool)"
+                             % (N * 200 / 1e6, 200)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "qs_step_host (pinned host buffers)"},
+            "gpu_launches": args.steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "step_kernel<float,RK4,direct>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                         "kernel_ms": kernel_ms},
+            "fp32": {"achieved_tflops": flops, "peak_tflops_probe": fp32_peak, "frac": flops / fp32_peak,
+                     "flops_per_env_step": FLOPS_PER_ENV_STEP(args.substeps),
+                     "note": "algorithmic FLOPs (SURVEY.md 8(d)) vs an in-run dependent-FFMA probe"},
+            "stats": env.stats(all_reduce=False),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.T)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

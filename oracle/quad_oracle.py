@@ -563,3 +563,37 @@ class BatchQuadOracle:
         new_done = self.done | timeout | (is_solved & self.training)
         self.done = np.where(m, new_done, self.done)
         return np.where(m, reward, 0.0)
+
+    # -- lock-step auto-reset (restatement of the CUDA kernel's predicated reset sub-pass) ---------------
+    def step_autoreset(self, action, seed, env_id_offset=0):
+        """step(); envs that are done are re-sampled with Philox (episode counter + 1) and warmed up for T hover
+        steps, exactly like the in-kernel sub-pass.  Returns (obs after reset, terminal reward, terminal done)."""
+        if not hasattr(self, "episode"):
+            self.episode = np.zeros(self.N, dtype=np.int64)
+            self.ep_return = np.zeros(self.N)
+            self.stats = dict(sum_return=0.0, sum_length=0.0, n_episodes=0, n_solved=0, n_broken=0, n_timeout=0,
+                              sum_effort=0.0)
+        was_done = self.done.copy()
+        obs, rew, done = self.step(action)
+        self.ep_return += rew
+        ended = done & ~was_done
+        if ended.any():
+            s = self.stats
+            s["sum_return"] += float(self.ep_return[ended].sum())
+            s["sum_length"] += float((self.i[ended] - self.T).sum())
+            s["n_episodes"] += int(ended.sum())
+            s["n_solved"] += int(self.solved[ended].sum())
+            timeout = ended & (self.solved == 0) & (self.i >= self.n)
+            s["n_timeout"] += int(timeout.sum())
+            s["n_broken"] += int((ended & (self.solved == 0) & ~timeout).sum())
+            s["sum_effort"] += float(self.abs_sum[ended].sum())
+        if done.any():
+            self.episode[done] += 1
+            ids = np.arange(self.N) + env_id_offset
+            st, _ = sample_reset_state(seed, ids[done], self.episode[done])
+            full = np.zeros((self.N, 13))
+            full[done] = st
+            oh, _ = self.reset(full, mask=done)
+            obs = np.where(done[:, None], oh[-1], obs)
+            self.ep_return[done] = 0.0
+        return obs, rew, done
