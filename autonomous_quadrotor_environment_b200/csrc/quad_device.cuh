@@ -126,11 +126,17 @@ __device__ __forceinline__ void deriv_quat(const R w[3], const R q[4], R dq[4]) 
     dq[3] = R(0.5) * (w[2] * q[0] + w[1] * q[1] - w[0] * q[2]);
 }
 
-// quat_euler :39-48 (no asin clamp: NaN propagates like the reference)
+// quat_euler :39-48.  FP64 (parity mode): no asin clamp, NaN propagates exactly like the reference.
+// FP32 (production mode): the argument is clamped to [-1,1] — rounding of a unit quaternion can push it one
+// ulp past 1 near gimbal lock, and a NaN pitch would poison reward/done for the rest of the episode
+// (SURVEY.md §5.3); with the clamp theta = +-pi/2 trips the bounding box (:500-509) instead.
+template <typename R> __device__ __forceinline__ R asin_arg(R s) { return s; }
+template <> __device__ __forceinline__ float asin_arg<float>(float s) { return fminf(fmaxf(s, -1.f), 1.f); }
+
 template <typename R>
 __device__ __forceinline__ void quat_euler(const R q[4], R ang[3]) {
     ang[0] = M_<R>::atan2(R(2) * (q[0] * q[1] + q[2] * q[3]), R(1) - R(2) * (q[1] * q[1] + q[2] * q[2]));
-    ang[1] = M_<R>::asin(R(2) * (q[0] * q[2] - q[3] * q[1]));
+    ang[1] = M_<R>::asin(asin_arg<R>(R(2) * (q[0] * q[2] - q[3] * q[1])));
     ang[2] = M_<R>::atan2(R(2) * (q[0] * q[3] + q[1] * q[2]), R(1) - R(2) * (q[2] * q[2] + q[3] * q[3]));
 }
 

@@ -415,13 +415,26 @@ template <typename R> struct StepIO {
 };
 
 // quad.step for every env of the shard.  One thread per env, grid-stride.
+//
+// Resets are a predicated, COMPACTED sub-pass: an env that finishes is not reset in its own lane (a reset is
+// T serial hover steps; with ~2 % of the lanes finishing per step that would make about half of all warps
+// execute T extra steps for one or two lanes).  Instead the lane appends its env index to a shared-memory
+// queue; after the block's main pass the queue is drained with one env per thread, i.e. with full warps.
+// A block owns at most kResetQueueCap envs (see grid_for), so the queue cannot overflow.
+constexpr int kResetQueueCap = 4096;
+
 template <typename R, int INTEG, bool DIRECT>
 __global__ void __launch_bounds__(kBlock)
 step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
             const __grid_constant__ StepIO<R> io) {
+    __shared__ int s_queue[kResetQueueCap];
+    __shared__ int s_qn;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
     LocalStats ls;
     ls.clear();
     bool any_end = false;
+    const bool auto_reset = (p.flags & F_AUTO_RESET) != 0;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
         Env<R> e;
@@ -434,27 +447,39 @@ step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimV
         Ctrl<R> c;
         step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
         e.ep_return += o.reward;
-        const R reward = o.reward;
-        const bool done = o.done, solved = o.solved;
-        if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+        if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
         if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
-        if ((p.flags & F_AUTO_RESET) && done) {
-            e.episode += 1;
-            reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
-        }
+        if (auto_reset && o.done) s_queue[atomicAdd(&s_qn, 1)] = (int)n;
         store_env(v, n, e, o.vq);
-        v.reward[n] = reward;
-        v.done[n] = done;
-        v.solved[n] = solved;
+        v.reward[n] = o.reward;
+        v.done[n] = o.done;
+        v.solved[n] = o.solved;
         if (io.obs) {
 #pragma unroll
             for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
 #pragma unroll
             for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
         }
-        if (io.reward) io.reward[n] = reward;
-        if (io.done) io.done[n] = done;
-        if (io.solved) io.solved[n] = solved;
+        if (io.reward) io.reward[n] = o.reward;
+        if (io.done) io.done[n] = o.done;
+        if (io.solved) io.solved[n] = o.solved;
+    }
+    __syncthreads();                       // queue complete; the block's global stores are visible to the block
+    const int qn = s_qn;
+    for (int q = threadIdx.x; q < qn; q += blockDim.x) {
+        const int64_t n = s_queue[q];
+        Env<R> e;
+        load_env(v, n, e);
+        e.episode += 1;
+        StepOut<R> o;
+        reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+        store_env(v, n, e, o.vq);
+        if (io.obs) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
+        }
     }
     flush_stats(ls, any_end, v.stats);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N);
@@ -559,7 +584,9 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
 // ------------------------------------------------------------------------------------------------
 static int grid_for(const qs_sim* s, int64_t n) {
     int64_t blocks = (n + kBlock - 1) / kBlock;
-    int64_t cap = (int64_t)s->sm_count * 16;          // grid-stride beyond 16 resident-CTA-equivalents per SM
+    int64_t cap = (int64_t)s->sm_count * 8;           // grid-stride beyond 8 CTAs per SM ...
+    int64_t need = (n + kResetQueueCap - 1) / kResetQueueCap;   // ... but a block never owns more envs than its reset queue holds
+    if (cap < need) cap = need;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;

@@ -259,9 +259,9 @@ def main():
         except Exception:
             traffic = None
     probe_ms = C.c_float(0)
-    blocks, threads, iters = 148 * 8, 256, 1 << 16
+    blocks, threads, iters = 148 * 8, 256, 1 << 14
     L.check(lib.qs_fp32_peak_probe(blocks, threads, iters, C.byref(probe_ms), stream))
-    fp32_peak = 2.0 * blocks * threads * iters / (probe_ms.value * 1e-3) / 1e12
+    fp32_peak = 2.0 * 8 * blocks * threads * iters / (probe_ms.value * 1e-3) / 1e12
     flops = FLOPS_PER_ENV_STEP(args.substeps) * N / (kernel_ms * 1e-3) / 1e12
 
     if rank == 0:

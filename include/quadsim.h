@@ -220,8 +220,9 @@ int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, u
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* qs_last_error(void);
 int qs_version(void);
-/* peak-FP32 micro-benchmark (dependent FFMA chains); returns elapsed ms for `iters` FFMA per thread
- * over blocks*threads threads via *ms_out, so that bench.py can state the FP32 roof it compares with. */
+/* peak-FP32 micro-benchmark: every thread runs 8 independent chains of `iters` dependent FFMAs
+ * (FLOPs = 2 * 8 * iters * blocks * threads); *ms_out = elapsed ms of one launch, so that bench.py can
+ * state the FP32 roof it compares with. */
 int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_out, void* stream);
 
 #ifdef __cplusplus

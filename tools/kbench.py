@@ -1,0 +1,73 @@
+"""Kernel micro-benchmarks (developer tool; prints one JSON line per case).  Usage on the GPU box:
+    python tools/kbench.py [case ...]      cases: step, rollout, all
+Times with CUDA events on the launching stream after warm-up."""
+import ctypes as C
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from autonomous_quadrotor_environment_b200 import BatchedQuad, _lib as L
+
+DEV = torch.device("cuda", 0)
+
+
+def time_ms(fn, iters, warm=20):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def case_step(N=1 << 20, iters=300, **kw):
+    cfg = dict(T=5, auto_reset=True, precision="f32", integrator="rk4", substeps=1, n=1000, act_scale=1.0)
+    cfg.update(kw)
+    env = BatchedQuad(N, 0.01, cfg["n"], training=True, direct_control=1, T=cfg["T"], precision=cfg["precision"],
+                      integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"],
+                      sensor_noise=cfg.get("sensor_noise", False), seed=0, device=DEV)
+    env.reset()
+    acts = [((torch.rand(4, N, device=DEV, dtype=env.dtype) * 2 - 1) * cfg["act_scale"]).contiguous() for _ in range(8)]
+    st = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    k = [0]
+
+    def fn():
+        L.check(env.lib.qs_step(env._h, C.c_void_p(acts[k[0] % 8].data_ptr()), None, None, None, None, st))
+        k[0] += 1
+
+    ms = time_ms(fn, iters, warm=60)
+    s = env.stats()
+    print(json.dumps({"case": "step", "N": N, **cfg, "ms": ms, "steps_per_s": N / ms * 1e3,
+                      "mean_len": s["mean_length"], "episodes_per_step": s["n_episodes"] / max(1, s["n_steps"] / N) / N}), flush=True)
+
+
+def case_rollout(N=1 << 20, K=32, iters=10, **kw):
+    cfg = dict(T=5, auto_reset=True, precision="f32", integrator="rk4", substeps=1, n=1000)
+    cfg.update(kw)
+    env = BatchedQuad(N, 0.01, cfg["n"], training=True, direct_control=1, T=cfg["T"], precision=cfg["precision"],
+                      integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"], seed=0, device=DEV)
+    env.reset()
+    ms = time_ms(lambda: env.rollout(K), iters, warm=3)
+    print(json.dumps({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3}), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["all"]
+    if "step" in which or "all" in which:
+        case_step(auto_reset=False, n=10 ** 9, act_scale=0.05)       # pure step, nobody finishes
+        case_step(auto_reset=True, T=1)
+        case_step(auto_reset=True, T=5)
+        case_step(auto_reset=True, T=5, substeps=4)
+        case_step(N=1 << 21, auto_reset=True, T=5)
+        case_step(N=1 << 18, auto_reset=True, T=5)
+        case_step(N=1 << 16, iters=100, precision="f64", integrator="rk45", auto_reset=True, T=5)
+    if "rollout" in which or "all" in which:
+        case_rollout(auto_reset=False, n=10 ** 9)
+        case_rollout(auto_reset=True, T=5)
+        case_rollout(auto_reset=True, T=1)
