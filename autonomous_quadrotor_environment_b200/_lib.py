@@ -20,6 +20,7 @@ QS_FLAG_TRAINING = 0x04
 QS_FLAG_AUTO_RESET = 0x08
 QS_FLAG_SENSOR_NOISE = 0x10
 QS_FLAG_AUX = 0x20
+QS_FLAG_ASYNC_RESET = 0x40
 QS_ACT_BUFFER, QS_ACT_PHILOX_UNIFORM = 0, 1
 QS_STATS_DIM = 8
 QS_SENSOR_STATE_DIM = 28

@@ -26,7 +26,7 @@ class BatchedQuad:
     def __init__(self, n_envs: int, t_step: float = 0.01, n: int = 1000, training: bool = True, euler: int = 0,
                  direct_control: int = 1, T: int = 1, clipped: bool = True, *, precision: str = "f32",
                  integrator: Optional[str] = None, substeps: int = 1, auto_reset: bool = False,
-                 sensor_noise: bool = False, aux: bool = False, seed: int = 0, device=None,
+                 async_reset: bool = False, sensor_noise: bool = False, aux: bool = False, seed: int = 0, device=None,
                  env_id_offset: int = 0, params: Optional[dict] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedQuad needs a CUDA device: the simulator has no CPU fallback")
@@ -54,6 +54,7 @@ class BatchedQuad:
         flags |= L.QS_FLAG_CLIPPED if clipped else 0
         flags |= L.QS_FLAG_TRAINING if training else 0
         flags |= L.QS_FLAG_AUTO_RESET if auto_reset else 0
+        flags |= L.QS_FLAG_ASYNC_RESET if async_reset else 0
         flags |= L.QS_FLAG_SENSOR_NOISE if sensor_noise else 0
         flags |= L.QS_FLAG_AUX if aux else 0
         cfg.flags = flags
@@ -222,8 +223,19 @@ class BatchedQuad:
         return self._field(L.QS_FIELD_REWARD)[0]
 
     @property
-    def done(self):
+    def done_flags(self):
+        """Raw done byte: bit0 = done, bit1 = asynchronous warm-up step (async_reset=True only)."""
         return self._field(L.QS_FIELD_DONE)[0]
+
+    @property
+    def done(self):
+        d = self._field(L.QS_FIELD_DONE)[0]
+        return (d & 1) if (self.flags & L.QS_FLAG_ASYNC_RESET) else d
+
+    @property
+    def warmup(self):
+        """1 where the last step was one of the T hover steps of an asynchronous reset (transition to ignore)."""
+        return (self._field(L.QS_FIELD_DONE)[0] >> 1) & 1
 
     @property
     def solved(self):

@@ -12,6 +12,40 @@
 namespace qs {
 
 // --------------------------------------------------------------------------------------------
+// TMA (1-D bulk async copy) + mbarrier primitives used to stage state / action tiles in shared memory
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// global -> shared bulk copy (TMA engine, SASS UBLKCP); bytes % 16 == 0, both addresses 16-byte aligned;
+// completion is signalled on `bar` as transaction bytes.
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// --------------------------------------------------------------------------------------------
 // math dispatch
 // --------------------------------------------------------------------------------------------
 template <typename R> struct M_;
@@ -51,9 +85,9 @@ template <> struct M_<double> {
 // --------------------------------------------------------------------------------------------
 enum : uint32_t {
     F_DIRECT = 0x01u, F_CLIPPED = 0x02u, F_TRAINING = 0x04u, F_AUTO_RESET = 0x08u,
-    F_SENSOR = 0x10u, F_AUX = 0x20u
+    F_SENSOR = 0x10u, F_AUX = 0x20u, F_ASYNC_RESET = 0x40u
 };
-enum : uint32_t { EF_DONE = 1u, EF_HAS_SHAPING = 2u, EF_SOLVED = 4u };
+enum : uint32_t { EF_DONE = 1u, EF_HAS_SHAPING = 2u, EF_SOLVED = 4u, EF_WARM_SHIFT = 3u, EF_LOW = 7u };
 
 template <typename R> struct DevParams {
     // rotor map (f2F :247-272, f2w :197-245)
@@ -572,10 +606,34 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
     } else if (done) {                                           // :571-573
         reward += p.broken_reward; solved = false; broken = true;
     }
-    e.flags = (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u);
+    e.flags = (e.flags & ~EF_LOW) | (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u);
     e.abs_sum += M_<R>::sqrt(o.effort[0] * o.effort[0] + o.effort[1] * o.effort[1] + o.effort[2] * o.effort[2] +
                              o.effort[3] * o.effort[3]);         // :575-577
     o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
+}
+
+// QS_FLAG_ASYNC_RESET: start-of-step hook.  An env whose sticky done flag is set begins a new episode now
+// (Philox-sampled initial state, bookkeeping cleared, T warm-up steps owed); an env that still owes warm-up
+// steps gets the neutral action (:448) for this step.  Returns true if this step is a warm-up step.
+template <typename R>
+__device__ __forceinline__ bool async_reset_prologue(const DevParams<R>& p, uint64_t seed, uint32_t env_id, Env<R>& e,
+                                                     R a[4]) {
+    if (e.flags & EF_DONE) {
+        e.episode += 1;
+        R ang[3];
+        sample_reset_state(p, seed, env_id, e.episode, e.y, ang);
+        e.flags = (uint32_t)p.T << EF_WARM_SHIFT;      // solved=0, done=False, prev_shaping=None
+        e.i = 0;
+        e.abs_sum = R(0);
+        e.ep_return = R(0);
+    }
+    if (e.flags >> EF_WARM_SHIFT) {
+        e.flags -= (1u << EF_WARM_SHIFT);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = p.zero_control[k];
+        return true;
+    }
+    return false;
 }
 
 // head of quad.reset :428-438 for one env (state already chosen); the T warm-up steps follow in the caller

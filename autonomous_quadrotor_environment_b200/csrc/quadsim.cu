@@ -13,6 +13,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -207,7 +208,9 @@ static int validate(const qs_config* c) {
     if (c->n_envs + c->env_id_offset > 0xFFFFFFFFll || c->env_id_offset < 0)
         return fail(QS_EINVAL, "global env ids must fit in 32 bits");
     if (!(c->t_step > 0)) return fail(QS_EINVAL, "t_step must be > 0");
-    if (c->T < 1 || c->T > 64) return fail(QS_EINVAL, "T must be in [1,64]");
+    if (c->T < 1 || c->T > 31) return fail(QS_EINVAL, "T must be in [1,31]");
+    if ((c->flags & QS_FLAG_AUTO_RESET) && (c->flags & QS_FLAG_ASYNC_RESET))
+        return fail(QS_EINVAL, "QS_FLAG_AUTO_RESET and QS_FLAG_ASYNC_RESET are mutually exclusive");
     if (c->substeps < 1) return fail(QS_EINVAL, "substeps must be >= 1");
     if (c->precision != QS_F32 && c->precision != QS_F64) return fail(QS_EINVAL, "bad precision");
     if (c->integrator != QS_RK4 && c->integrator != QS_RK45) return fail(QS_EINVAL, "bad integrator");
@@ -217,7 +220,7 @@ static int validate(const qs_config* c) {
 
 static size_t layout(const qs_config* c, qs_sim* s /*nullable*/) {
     const int rs = c->precision == QS_F64 ? 8 : 4;
-    const int64_t ld = (int64_t)align_up((size_t)c->n_envs, 32);
+    const int64_t ld = (int64_t)align_up((size_t)c->n_envs, 256);   // whole 256-env tiles: TMA row segments never run off a row
     size_t off = 0;
     for (int r = 0; r < kNumRows; ++r) {
         const RowSpec& rw = kRows[r];
@@ -414,45 +417,127 @@ template <typename R> struct StepIO {
     uint8_t* solved;     // [N] or NULL
 };
 
-// quad.step for every env of the shard.  One thread per env, grid-stride.
+// quad.step for every env of the shard: persistent CTAs, one thread per env, 256-env tiles.
 //
-// Resets are a predicated, COMPACTED sub-pass: an env that finishes is not reset in its own lane (a reset is
-// T serial hover steps; with ~2 % of the lanes finishing per step that would make about half of all warps
-// execute T extra steps for one or two lanes).  Instead the lane appends its env index to a shared-memory
-// queue; after the block's main pass the queue is drained with one env per thread, i.e. with full warps.
+// Staging.  Each tile's 22 SoA row segments (13 state + 3 prev_ang + prev_shaping + abs_sum + ep_return reals,
+// step_i, episode, flags) and — when aligned — its 4 action row segments are fetched by the TMA engine
+// (cp.async.bulk, one elected thread issues, completion counted on an mbarrier) into a double-buffered
+// shared-memory stage, one tile ahead of the arithmetic, so the ~1 us HBM latency of the loads is hidden
+// behind the previous tile's RK4 instead of stalling the 16 resident warps per SM.
+//
+// Resets (QS_FLAG_AUTO_RESET, strict lock-step) are a predicated, COMPACTED sub-pass: an env that finishes is
+// not reset in its own lane (a reset is T serial hover steps; with ~2 % of the lanes finishing per step about
+// half of all warps would run T extra steps for one or two lanes).  The lane appends its env index to a
+// shared-memory queue which is drained after the block's main pass with one env per thread, i.e. full warps.
 // A block owns at most kResetQueueCap envs (see grid_for), so the queue cannot overflow.
+// QS_FLAG_ASYNC_RESET needs no sub-pass at all (see async_reset_prologue).
 constexpr int kResetQueueCap = 4096;
+constexpr int kTile = kBlock;
+constexpr int kStageRealRows = 19 + 4;      // 13 state, 3 prev_ang, prev_shaping, abs_sum, ep_return, 4 action
+
+template <typename R> struct Stage {
+    R real[kStageRealRows][kTile];
+    int32_t step_i[kTile];
+    uint32_t episode[kTile];
+    uint8_t flags[kTile];
+    uint8_t pad_[kTile * 3];                 // keeps sizeof(Stage) a multiple of 1 KB
+};
+
+template <typename R>
+__device__ __forceinline__ void issue_tile(const SimView<R>& v, const R* action, bool act_bulk, int64_t tile,
+                                           Stage<R>* st, uint64_t* bar) {
+    const int64_t n0 = tile * kTile;
+    const bool act_now = act_bulk && (n0 + kTile <= v.N);
+    const uint32_t rb = kTile * sizeof(R);
+    mbar_expect_tx(bar, (19 + (act_now ? 4 : 0)) * rb + kTile * 9);
+#pragma unroll
+    for (int k = 0; k < 10; ++k) tma_load_1d(st->real[k], v.obs17 + k * v.ld + n0, rb, bar);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tma_load_1d(st->real[10 + k], v.obs17 + (14 + k) * v.ld + n0, rb, bar);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tma_load_1d(st->real[13 + k], v.prev_ang + k * v.ld + n0, rb, bar);
+    tma_load_1d(st->real[16], v.prev_shaping + n0, rb, bar);
+    tma_load_1d(st->real[17], v.abs_sum + n0, rb, bar);
+    tma_load_1d(st->real[18], v.ep_return + n0, rb, bar);
+    tma_load_1d(st->step_i, v.step_i + n0, kTile * 4, bar);
+    tma_load_1d(st->episode, v.episode + n0, kTile * 4, bar);
+    tma_load_1d(st->flags, v.flags + n0, kTile, bar);
+    if (act_now) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tma_load_1d(st->real[19 + k], action + k * v.N + n0, rb, bar);
+    }
+}
 
 template <typename R, int INTEG, bool DIRECT>
 __global__ void __launch_bounds__(kBlock)
 step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
             const __grid_constant__ StepIO<R> io) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Stage<R>* stages = reinterpret_cast<Stage<R>*>(smem_raw);
+    __shared__ uint64_t s_bar[2];
     __shared__ int s_queue[kResetQueueCap];
     __shared__ int s_qn;
-    if (threadIdx.x == 0) s_qn = 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        s_qn = 0;
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        mbar_fence_init();
+    }
     __syncthreads();
     LocalStats ls;
     ls.clear();
     bool any_end = false;
     const bool auto_reset = (p.flags & F_AUTO_RESET) != 0;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
+    const bool act_bulk = ((reinterpret_cast<uintptr_t>(io.action) & 15) == 0) && ((v.N * sizeof(R)) % 16 == 0);
+    const int64_t n_tiles = (v.N + kTile - 1) / kTile;
+    int64_t tile = blockIdx.x;
+    if (tid == 0 && tile < n_tiles) issue_tile(v, io.action, act_bulk, tile, &stages[0], &s_bar[0]);
+    for (int j = 0; tile < n_tiles; tile += gridDim.x, ++j) {
+        const int s = j & 1;
+        const int64_t next = tile + gridDim.x;
+        // stage s^1 was last read in iteration j-1, and every thread has passed that iteration's barrier
+        if (tid == 0 && next < n_tiles) issue_tile(v, io.action, act_bulk, next, &stages[s ^ 1], &s_bar[s ^ 1]);
+        mbar_wait(&s_bar[s], (j >> 1) & 1);
+        const Stage<R>& st = stages[s];
+        const int64_t n0 = tile * kTile;
+        const int64_t n = n0 + tid;
+        const bool active = n < v.N;
         Env<R> e;
-        load_env(v, n, e);
-        R a[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] = io.action[k * v.N + n];
+        for (int k = 0; k < 13; ++k) e.y[k] = st.real[k][tid];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) e.prev_ang[k] = st.real[13 + k][tid];
+        e.prev_shaping = st.real[16][tid];
+        e.abs_sum = st.real[17][tid];
+        e.ep_return = st.real[18][tid];
+        e.i = st.step_i[tid];
+        e.episode = st.episode[tid];
+        e.flags = st.flags[tid];
+        R a[4];
+        if (act_bulk && (n0 + kTile <= v.N)) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = st.real[19 + k][tid];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[k] = active ? io.action[k * v.N + n] : R(0);
+        }
+        __syncthreads();                   // all reads of stage s done -> it may be refilled next iteration
+        if (!active) continue;
+        bool warm = false;
+        if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
         const bool was_done = (e.flags & EF_DONE) != 0;
         StepOut<R> o;
         Ctrl<R> c;
         step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
-        e.ep_return += o.reward;
+        if (warm) o.reward = R(0); else e.ep_return += o.reward;
         if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
         if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
         if (auto_reset && o.done) s_queue[atomicAdd(&s_qn, 1)] = (int)n;
+        const uint8_t done_byte = (uint8_t)((o.done ? 1 : 0) | (warm ? 2 : 0));
         store_env(v, n, e, o.vq);
         v.reward[n] = o.reward;
-        v.done[n] = o.done;
+        v.done[n] = done_byte;
         v.solved[n] = o.solved;
         if (io.obs) {
 #pragma unroll
@@ -461,12 +546,12 @@ step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimV
             for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
         }
         if (io.reward) io.reward[n] = o.reward;
-        if (io.done) io.done[n] = o.done;
+        if (io.done) io.done[n] = done_byte;
         if (io.solved) io.solved[n] = o.solved;
     }
     __syncthreads();                       // queue complete; the block's global stores are visible to the block
     const int qn = s_qn;
-    for (int q = threadIdx.x; q < qn; q += blockDim.x) {
+    for (int q = tid; q < qn; q += blockDim.x) {
         const int64_t n = s_queue[q];
         Env<R> e;
         load_env(v, n, e);
@@ -482,7 +567,7 @@ step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimV
         }
     }
     flush_stats(ls, any_end, v.stats);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N);
 }
 
 // quad.reset for the masked envs (det_state given or Philox-sampled).
@@ -534,7 +619,7 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
         load_env(v, n, e);
         StepOut<R> o;
         R reward = R(0);
-        bool done = false, solved = false;
+        bool done = false, solved = false, warm_last = false;
         for (int t = 0; t < io.horizon; ++t) {
             R a[4];
             if (io.action_source == QS_ACT_PHILOX_UNIFORM) {
@@ -546,10 +631,12 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
 #pragma unroll
                 for (int k = 0; k < 4; ++k) a[k] = at[k * v.N + n];
             }
+            bool warm = false;
+            if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
             step_core<R, INTEG, DIRECT>(p, e, a, o, nullptr);
-            e.ep_return += o.reward;
-            reward = o.reward; done = o.done; solved = o.solved;
+            if (warm) o.reward = R(0); else e.ep_return += o.reward;
+            reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
             if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
             if ((p.flags & F_AUTO_RESET) && done) {
                 e.episode += 1;
@@ -568,11 +655,11 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
                 for (int k = 0; k < 4; ++k) at[k * v.N + n] = a[k];
             }
             if (io.reward_out) io.reward_out[(int64_t)t * v.N + n] = reward;
-            if (io.done_out) io.done_out[(int64_t)t * v.N + n] = done;
+            if (io.done_out) io.done_out[(int64_t)t * v.N + n] = (uint8_t)((done ? 1 : 0) | (warm ? 2 : 0));
         }
         store_env(v, n, e, o.vq);
         v.reward[n] = reward;
-        v.done[n] = done;
+        v.done[n] = (uint8_t)((done ? 1 : 0) | (warm_last ? 2 : 0));
         v.solved[n] = solved;
     }
     flush_stats(ls, any_end, v.stats);
@@ -590,6 +677,24 @@ static int grid_for(const qs_sim* s, int64_t n) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+// persistent grid of the staged step kernel: a few CTAs per SM, each looping over 256-env tiles
+static int grid_step(const qs_sim* s) {
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        const char* e = getenv("QS_STEP_CTAS_PER_SM");
+        ctas_per_sm = e ? atoi(e) : 4;
+        if (ctas_per_sm < 1) ctas_per_sm = 4;
+    }
+    const int64_t tiles = (s->N + kTile - 1) / kTile;
+    int64_t g = (int64_t)s->sm_count * ctas_per_sm;
+    if (s->cfg.flags & QS_FLAG_AUTO_RESET) {            // a block never owns more envs than its reset queue holds
+        const int64_t need = (s->N + kResetQueueCap - 1) / kResetQueueCap;
+        if (g < need) g = need;
+    }
+    if (g > tiles) g = tiles;
+    return (int)(g < 1 ? 1 : g);
 }
 
 #define QS_DISPATCH(s, FN, ...)                                                                          \
@@ -613,7 +718,13 @@ template <typename R, int INTEG, bool DIRECT>
 static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
                         cudaStream_t st) {
     StepIO<R> io{(const R*)action, (R*)obs, (R*)reward, done, solved};
-    step_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+    constexpr size_t smem = 2 * sizeof(Stage<R>);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(step_kernel<R, INTEG, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    step_kernel<R, INTEG, DIRECT><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
 
 template <typename R, int INTEG, bool DIRECT>
@@ -649,7 +760,7 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
     s->N = cfg->n_envs;
-    s->ld = (int64_t)align_up((size_t)cfg->n_envs, 32);
+    s->ld = (int64_t)align_up((size_t)cfg->n_envs, 256);
     s->rs = cfg->precision == QS_F64 ? 8 : 4;
     s->seed = cfg->seed;
     s->ws_bytes = layout(cfg, nullptr);

@@ -177,7 +177,7 @@ def main():
     torch.cuda.set_device(dev)
     N = args.envs_per_gpu or (1 << 20 if world == 1 else 1 << 21)
     env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
-                      substeps=args.substeps, auto_reset=True, sensor_noise=bool(args.sensor_noise), seed=0,
+                      substeps=args.substeps, async_reset=True, sensor_noise=bool(args.sensor_noise), seed=0,
                       env_id_offset=rank * N, device=dev)
     env.reset()
     P = 16                                               # action pool: 16 x (4,N) fp32 = 256 MB at 1M envs (> 126 MB L2)
@@ -269,7 +269,7 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "%d envs/GPU x %d GPU lock-step quad.step, FP32 RK4 x%d substeps, auto-reset, T=%d, "
+            "config": {"workload": "%d envs/GPU x %d GPU lock-step quad.step, FP32 RK4 x%d substeps, auto-reset (async warm-up), T=%d, "
                                    "sensor_noise=%d, U(-1,1) actions read from a %d-buffer HBM pool"
                                    % (N, world, args.substeps, args.T, int(bool(args.sensor_noise)), P),
                        "envs_per_gpu": N, "substeps": args.substeps, "T": args.T,

@@ -58,6 +58,11 @@ extern "C" {
 #define QS_FLAG_AUTO_RESET     0x08u /* re-sample + T warm-up steps inside the step kernel when done          */
 #define QS_FLAG_SENSOR_NOISE   0x10u /* run the `sensor` model (quadrotor_env.py:579-724) each step           */
 #define QS_FLAG_AUX            0x20u /* also store ang_vel, step_effort, w, accel, mat_rot, accelerometer_read */
+#define QS_FLAG_ASYNC_RESET    0x40u /* auto-reset with ASYNCHRONOUS warm-up (production mode): an env that returned  */
+                                     /* done is re-sampled at the start of its NEXT step, and the T hover steps of    */
+                                     /* quad.reset (:447-453) run as its next T ordinary lock-step steps (caller's     */
+                                     /* action ignored, reward 0, bit1 of the done byte set).  Per-env sequences are   */
+                                     /* exactly those of reset()+step(); no lane ever runs T serial steps.             */
 
 /* Physical / reward constants.  Defaults (qs_default_config) = environment/quadrotor_env.py:30-80. */
 typedef struct qs_params {
@@ -108,14 +113,16 @@ typedef enum qs_field {
     QS_FIELD_STEP_EFFORT = 4, /* [4][N]  real  (AUX)                                     :474,:476,:243  */
     QS_FIELD_W = 5,           /* [4][N]  real  rotor speeds rad/s (AUX)                  :288,:476       */
     QS_FIELD_REWARD = 6,      /* [N]     real  reward of the last step                   :511-573        */
-    QS_FIELD_DONE = 7,        /* [N]     u8    done returned by the last step            :498            */
+    QS_FIELD_DONE = 7,        /* [N]     u8    bit0 = done returned by the last step (:498); bit1 = the step was an  */
+                              /*               asynchronous warm-up step (QS_FLAG_ASYNC_RESET only)                  */
     QS_FIELD_SOLVED = 8,      /* [N]     u8    quad.solved                               :564            */
     QS_FIELD_I = 9,           /* [N]     i32   quad.i step counter                       :467            */
     QS_FIELD_ABS_SUM = 10,    /* [N]     real  accumulated control effort                :575-577        */
     QS_FIELD_PREV_SHAPING = 11,/*[N]     real  reward shaping memory                     :545-547        */
     QS_FIELD_EP_RETURN = 12,  /* [N]     real  sum of rewards since the last reset                        */
     QS_FIELD_EPISODE = 13,    /* [N]     u32   episode counter (Philox counter word)                      */
-    QS_FIELD_FLAGS = 14,      /* [N]     u8    bit0 sticky done (:509), bit1 prev_shaping valid, bit2 solved */
+    QS_FIELD_FLAGS = 14,      /* [N]     u8    bit0 sticky done (:509), bit1 prev_shaping valid, bit2 solved,        */
+                              /*               bits 3..7 warm-up steps still owed (QS_FLAG_ASYNC_RESET)               */
     QS_FIELD_ACCEL = 15,      /* [3][N]  real  inertial acceleration (AUX)               :368            */
     QS_FIELD_ACC_READ = 16,   /* [3][N]  real  accelerometer_read (AUX)                  :371            */
     QS_FIELD_MAT_ROT = 17,    /* [9][N]  real  body->inertial rotation, row-major (AUX)  :315            */

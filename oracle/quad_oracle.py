@@ -597,3 +597,48 @@ class BatchQuadOracle:
             obs = np.where(done[:, None], oh[-1], obs)
             self.ep_return[done] = 0.0
         return obs, rew, done
+
+    # -- asynchronous warm-up (restatement of QS_FLAG_ASYNC_RESET) ---------------------------------------
+    def step_async(self, action, seed, env_id_offset=0):
+        """An env whose sticky done flag is set begins a new episode at the START of this step (Philox-sampled
+        state, episode counter + 1) and owes T warm-up steps; a warm-up step applies zero_control instead of the
+        caller's action and returns reward 0.  Returns (obs, reward, done, warm)."""
+        if not hasattr(self, "episode"):
+            self.episode = np.zeros(self.N, dtype=np.int64)
+            self.ep_return = np.zeros(self.N)
+            self.stats = dict(sum_return=0.0, sum_length=0.0, n_episodes=0, n_solved=0, n_broken=0, n_timeout=0,
+                              sum_effort=0.0)
+        if not hasattr(self, "warm"):
+            self.warm = np.zeros(self.N, dtype=np.int64)
+        begin = self.done.copy()
+        if begin.any():
+            self.episode[begin] += 1
+            ids = np.arange(self.N) + env_id_offset
+            st, _ = sample_reset_state(seed, ids[begin], self.episode[begin])
+            self.previous_state[begin] = st
+            self.solved[begin] = 0
+            self.done[begin] = False
+            self.i[begin] = 0
+            self.has_prev_shaping[begin] = False
+            self.abs_sum[begin] = 0
+            self.ep_return[begin] = 0
+            self.warm[begin] = self.T
+        w = self.warm > 0
+        a = np.where(w[:, None], self.zero_control[None, :], np.asarray(action, dtype=np.float64))
+        self.warm[w] -= 1
+        was_done = self.done.copy()
+        obs, rew, done = self.step(a)
+        rew = np.where(w, 0.0, rew)
+        self.ep_return += rew
+        ended = done & ~was_done
+        if ended.any():
+            s = self.stats
+            s["sum_return"] += float(self.ep_return[ended].sum())
+            s["sum_length"] += float((self.i[ended] - self.T).sum())
+            s["n_episodes"] += int(ended.sum())
+            s["n_solved"] += int(self.solved[ended].sum())
+            timeout = ended & (self.solved == 0) & (self.i >= self.n)
+            s["n_timeout"] += int(timeout.sum())
+            s["n_broken"] += int((ended & (self.solved == 0) & ~timeout).sum())
+            s["sum_effort"] += float(self.abs_sum[ended].sum())
+        return obs, rew, done, w

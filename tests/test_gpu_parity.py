@@ -172,6 +172,48 @@ def test_f64_auto_reset_matches_oracle():
     assert s["n_steps"] == N * steps
 
 
+def test_f64_async_reset_matches_oracle():
+    """QS_FLAG_ASYNC_RESET: warm-up steps run as ordinary lock-step steps; done / warm-up flags bit-exact."""
+    N, steps, seed, off = 512, 160, 43, 77
+    env = BatchedQuad(N, 0.01, 60, training=True, direct_control=1, T=5, precision="f64", integrator="rk45",
+                      async_reset=True, seed=seed, env_id_offset=off, device=DEV)
+    ora = qo.BatchQuadOracle(N, 0.01, 60, training=True, direct_control=1, T=5, integrator="rk45")
+    init, _ = qo.sample_reset_state(seed, np.arange(N) + off, 0)
+    env.reset(T64(init)); ora.reset(init)
+    rng = np.random.default_rng(10)
+    worst, resets, warms = 0.0, 0, 0
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (N, 4)) * 0.6
+        obs, rew, done = env.step(T64(a))
+        o_ref, r_ref, d_ref, w_ref = ora.step_async(a, seed, off)
+        assert np.array_equal(done.cpu().numpy().astype(bool), d_ref), "done differs at step %d" % t
+        assert np.array_equal(env.warmup.cpu().numpy().astype(bool), w_ref), "warm-up mask differs at step %d" % t
+        worst = max(worst, rel_err(npy(obs), o_ref), rel_err(npy(rew), r_ref))
+        resets += int(d_ref.sum()); warms += int(w_ref.sum())
+    assert resets > N and warms >= 5 * (resets - N)
+    assert worst < 1e-9, worst
+    assert np.array_equal(env.episode.cpu().numpy(), ora.episode)
+    s = env.stats()
+    for k in ("n_episodes", "n_solved", "n_broken", "n_timeout"):
+        assert s[k] == ora.stats[k], k
+    assert abs(s["sum_return"] - ora.stats["sum_return"]) < 1e-3 * max(1, abs(ora.stats["sum_return"]))
+
+
+def test_async_rollout_equals_async_steps():
+    N, K, seed = 3000, 40, 6
+    mk = lambda: BatchedQuad(N, 0.01, 30, T=3, precision="f32", async_reset=True, seed=seed, device=DEV)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    acts = (torch.rand(K, 4, N, device=DEV) * 2 - 1)
+    rec = a.rollout(K, actions=acts, record_obs=True, record_reward=True, record_done=True)
+    for t in range(K):
+        obs, rew, done = b.step_soa(acts[t].contiguous())
+        assert torch.equal(b.done_flags, rec["done"][t])
+        assert torch.allclose(obs.t(), rec["obs"][t], rtol=1e-6, atol=1e-6)
+        assert torch.allclose(rew, rec["reward"][t], rtol=1e-5, atol=1e-5)
+    assert torch.equal(a.episode, b.episode) and int(a.episode.max()) > 1
+
+
 def test_random_reset_on_device_matches_oracle_sampler():
     N, seed = 2048, 77
     for prec, tol in (("f64", 1e-12), ("f32", 2e-5)):

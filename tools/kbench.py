@@ -27,11 +27,11 @@ def time_ms(fn, iters, warm=20):
 
 
 def case_step(N=1 << 20, iters=300, **kw):
-    cfg = dict(T=5, auto_reset=True, precision="f32", integrator="rk4", substeps=1, n=1000, act_scale=1.0)
+    cfg = dict(T=5, auto_reset=False, async_reset=False, precision="f32", integrator="rk4", substeps=1, n=1000, act_scale=1.0)
     cfg.update(kw)
     env = BatchedQuad(N, 0.01, cfg["n"], training=True, direct_control=1, T=cfg["T"], precision=cfg["precision"],
                       integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"],
-                      sensor_noise=cfg.get("sensor_noise", False), seed=0, device=DEV)
+                      async_reset=cfg["async_reset"], sensor_noise=cfg.get("sensor_noise", False), seed=0, device=DEV)
     env.reset()
     acts = [((torch.rand(4, N, device=DEV, dtype=env.dtype) * 2 - 1) * cfg["act_scale"]).contiguous() for _ in range(8)]
     st = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
@@ -48,10 +48,11 @@ def case_step(N=1 << 20, iters=300, **kw):
 
 
 def case_rollout(N=1 << 20, K=32, iters=10, **kw):
-    cfg = dict(T=5, auto_reset=True, precision="f32", integrator="rk4", substeps=1, n=1000)
+    cfg = dict(T=5, auto_reset=False, async_reset=False, precision="f32", integrator="rk4", substeps=1, n=1000)
     cfg.update(kw)
     env = BatchedQuad(N, 0.01, cfg["n"], training=True, direct_control=1, T=cfg["T"], precision=cfg["precision"],
-                      integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"], seed=0, device=DEV)
+                      integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"],
+                      async_reset=cfg["async_reset"], seed=0, device=DEV)
     env.reset()
     ms = time_ms(lambda: env.rollout(K), iters, warm=3)
     print(json.dumps({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3}), flush=True)
@@ -59,15 +60,18 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
 
 if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]
+    if "prof" in which:                                              # short run for ncu
+        case_step(async_reset=True, T=5, iters=20)
     if "step" in which or "all" in which:
-        case_step(auto_reset=False, n=10 ** 9, act_scale=0.05)       # pure step, nobody finishes
-        case_step(auto_reset=True, T=1)
+        case_step(n=10 ** 9, act_scale=0.05)                         # pure step, nobody finishes
+        case_step(async_reset=True, T=5)
+        case_step(async_reset=True, T=1)
         case_step(auto_reset=True, T=5)
-        case_step(auto_reset=True, T=5, substeps=4)
-        case_step(N=1 << 21, auto_reset=True, T=5)
-        case_step(N=1 << 18, auto_reset=True, T=5)
-        case_step(N=1 << 16, iters=100, precision="f64", integrator="rk45", auto_reset=True, T=5)
+        case_step(async_reset=True, T=5, substeps=4)
+        case_step(N=1 << 21, async_reset=True, T=5)
+        case_step(N=1 << 18, async_reset=True, T=5)
+        case_step(N=1 << 16, iters=100, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "rollout" in which or "all" in which:
-        case_rollout(auto_reset=False, n=10 ** 9)
-        case_rollout(auto_reset=True, T=5)
-        case_rollout(auto_reset=True, T=1)
+        case_rollout(n=10 ** 9)
+        case_rollout(async_reset=True, T=5)
+        case_rollout(async_reset=True, T=5, K=128)
