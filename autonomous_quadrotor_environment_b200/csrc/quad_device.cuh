@@ -25,6 +25,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n\t"
@@ -49,18 +52,70 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
 // math dispatch
 // --------------------------------------------------------------------------------------------
 template <typename R> struct M_;
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double fma_(double a, double b, double c) { return ::fma(a, b, c); }
+// FP32 production-mode math: branch-free, MUFU-based, a few ulp — far inside the FP32 parity bound
+// (1e-4 relative + 1e-5 absolute) and ~3x fewer instructions than the IEEE-exact libdevice routines.
+__device__ __forceinline__ float fast_sqrtf(float x) {            // max rel. error 2^-23 (PTX ISA)
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fast_rcpf(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// atan on [0,1]: odd minimax polynomial (max error ~1.5 ulp), then octant reconstruction.
+__device__ __forceinline__ float fast_atan2f(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float a = mn * fast_rcpf(mx);
+    a = (mx == 0.f) ? 0.f : a;                                    // atan2(0,0) = 0 like numpy
+    const float s = a * a;
+    float r = 0.0027856871f;
+    r = fmaf(r, s, -0.0158660002f);
+    r = fmaf(r, s, 0.042472221f);
+    r = fmaf(r, s, -0.0749753043f);
+    r = fmaf(r, s, 0.106448799f);
+    r = fmaf(r, s, -0.142070308f);
+    r = fmaf(r, s, 0.199934542f);
+    r = fmaf(r, s, -0.333331466f);
+    r = r * s;
+    r = fmaf(r, a, a);
+    r = (ay > ax) ? (1.57079637f - r) : r;
+    r = (x < 0.f) ? (3.14159274f - r) : r;
+    return copysignf(r, y);
+}
+// asin on [-1,1]: |x|<=0.5 -> x + x^3 P(x^2); else pi/2 - 2 asin(sqrt((1-|x|)/2))  (Cephes asinf coefficients)
+__device__ __forceinline__ float fast_asinf(float x) {
+    const float ax = fabsf(x);
+    const bool big = ax > 0.5f;
+    const float z = big ? fmaf(-0.5f, ax, 0.5f) : ax * ax;
+    const float s = big ? fast_sqrtf(z) : ax;
+    float pz = 4.2163199048e-2f;
+    pz = fmaf(pz, z, 2.4181311049e-2f);
+    pz = fmaf(pz, z, 4.5470025998e-2f);
+    pz = fmaf(pz, z, 7.4953002686e-2f);
+    pz = fmaf(pz, z, 1.6666752422e-1f);
+    float r = fmaf(s * z, pz, s);
+    r = big ? fmaf(-2.f, r, 1.57079637f) : r;
+    r = (ax > 1.f) ? __int_as_float(0x7fc00000) : r;              // NaN outside the domain, like asin
+    return copysignf(r, x);
+}
+
 template <> struct M_<float> {
     static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
-    static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+    static __device__ __forceinline__ float sqrt(float x) { return fast_sqrtf(x); }
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
-    static __device__ __forceinline__ float atan2(float y, float x) { return atan2f(y, x); }
-    static __device__ __forceinline__ float asin(float x) { return asinf(x); }
+    static __device__ __forceinline__ float atan2(float y, float x) { return fast_atan2f(y, x); }
+    static __device__ __forceinline__ float asin(float x) { return fast_asinf(x); }
     static __device__ __forceinline__ float pow(float x, float y) { return powf(x, y); }
-    static __device__ __forceinline__ float log(float x) { return logf(x); }
+    static __device__ __forceinline__ float log(float x) { return __logf(x); }
     static __device__ __forceinline__ float fmin(float a, float b) { return fminf(a, b); }
     static __device__ __forceinline__ float fmax(float a, float b) { return fmaxf(a, b); }
-    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { sincosf(x, s, c); }
-    static __device__ __forceinline__ void sincospi(float x, float* s, float* c) { sincospif(x, s, c); }
+    static __device__ __forceinline__ void sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
+    static __device__ __forceinline__ void sincospi(float x, float* s, float* c) { __sincosf(3.14159274f * x, s, c); }
     static __device__ __forceinline__ float next_up(float x) { return nextafterf(x, CUDART_INF_F); }
     static __device__ __forceinline__ float inf() { return CUDART_INF_F; }
 };
@@ -107,7 +162,7 @@ template <typename R> struct DevParams {
     R inv_j[3];
     R cross_j[3];    // (Jz-Jy)/Jx, (Jx-Jz)/Jy, (Jy-Jx)/Jz
     // stepping
-    R dt, h_sub;     // env step, RK4 sub-interval
+    R dt, h_sub, inv_dt;   // env step, RK4 sub-interval, 1/dt
     R bb[9];         // bb_cond :139-143
     // reward (:511-573)
     R sh_v, sh_psi, sh_ang;          // shaping weights folded with SHAPING_WEIGHT/sum and the normalisers
@@ -272,24 +327,26 @@ __device__ __forceinline__ void drone_rhs(const DevParams<R>& p, const Ctrl<R>& 
 // --------------------------------------------------------------------------------------------
 // integrators
 // --------------------------------------------------------------------------------------------
-// Fixed-step classical RK4, S sub-intervals of length p.h_sub.
+// Fixed-step classical RK4, S sub-intervals of length p.h_sub.  The four stages are a ROLLED loop (one copy of
+// the RHS in the instruction stream instead of four): the kernel is instruction-issue bound and the unrolled
+// form overflowed the instruction cache (ncu: stall_no_instructions) — the cost is 13 dead FMAs per substep.
 template <typename R>
 __device__ __forceinline__ void integrate_rk4(const DevParams<R>& p, const Ctrl<R>& c, R y[13]) {
     const R h = p.h_sub, hh = p.h_sub * R(0.5), h6 = p.h_sub * R(1.0 / 6.0);
     for (int s = 0; s < p.substeps; ++s) {
         R k[13], acc[13], yt[13];
-        drone_rhs(p, c, y, k);
 #pragma unroll
-        for (int j = 0; j < 13; ++j) { acc[j] = k[j]; yt[j] = y[j] + hh * k[j]; }
-        drone_rhs(p, c, yt, k);
+        for (int j = 0; j < 13; ++j) { acc[j] = R(0); yt[j] = y[j]; }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            drone_rhs(p, c, yt, k);
+            const R wgt = (st == 0 || st == 3) ? R(1) : R(2);
+            const R cc = (st < 2) ? hh : h;
 #pragma unroll
-        for (int j = 0; j < 13; ++j) { acc[j] += R(2) * k[j]; yt[j] = y[j] + hh * k[j]; }
-        drone_rhs(p, c, yt, k);
+            for (int j = 0; j < 13; ++j) { acc[j] = fma_(wgt, k[j], acc[j]); yt[j] = fma_(cc, k[j], y[j]); }
+        }
 #pragma unroll
-        for (int j = 0; j < 13; ++j) { acc[j] += R(2) * k[j]; yt[j] = y[j] + h * k[j]; }
-        drone_rhs(p, c, yt, k);
-#pragma unroll
-        for (int j = 0; j < 13; ++j) { y[j] += h6 * (acc[j] + k[j]); }
+        for (int j = 0; j < 13; ++j) y[j] = fma_(h6, acc[j], y[j]);
     }
 }
 
@@ -467,6 +524,13 @@ template <typename R> __device__ __forceinline__ void box_muller(R u1, R u2, R* 
     M_<R>::sincospi(R(2) * u2, &s, &c);
     *n0 = r * c; *n1 = r * s;
 }
+// FP32: MUFU sin/cos are most accurate on [-pi,pi] -> evaluate at 2*pi*(u2-1/2) and flip both signs.
+template <> __device__ __forceinline__ void box_muller<float>(float u1, float u2, float* n0, float* n1) {
+    float r = fast_sqrtf(-2.f * __logf(u1));
+    float s, c;
+    __sincosf(6.28318548f * (u2 - 0.5f), &s, &c);
+    *n0 = -r * c; *n1 = -r * s;
+}
 
 template <typename R> __device__ __forceinline__ R clampr(R v, R lo, R hi) {
     return M_<R>::fmin(M_<R>::fmax(v, lo), hi);
@@ -503,6 +567,9 @@ __device__ __forceinline__ void sample_reset_state(const DevParams<R>& p, uint64
 // --------------------------------------------------------------------------------------------
 // one environment, in registers
 // --------------------------------------------------------------------------------------------
+__device__ __forceinline__ float div_dt(float x, const DevParams<float>& p) { return x * p.inv_dt; }
+__device__ __forceinline__ double div_dt(double x, const DevParams<double>& p) { return x / p.dt; }
+
 template <typename R> struct Env {
     R y[13];
     R prev_ang[3];       // quad.prev_ang — NOT cleared by reset (reference quirk, :171-172/:492-493)
@@ -561,7 +628,7 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
     quat_euler(qn, o.ang);                                       // :491
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        o.ang_vel[k] = (o.ang[k] - e.prev_ang[k]) / p.dt;        // :492
+        o.ang_vel[k] = div_dt(o.ang[k] - e.prev_ang[k], p);      // :492
         e.prev_ang[k] = o.ang[k];                                // :493
     }
     // done_condition :500-509 (>=, sticky; NaN compares false)

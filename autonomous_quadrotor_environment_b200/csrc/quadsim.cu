@@ -113,7 +113,7 @@ template <typename R> static DevParams<R> make_params(const qs_config& c) {
     p.cross_j[0] = R((q.j[2] - q.j[1]) / q.j[0]);
     p.cross_j[1] = R((q.j[0] - q.j[2]) / q.j[1]);
     p.cross_j[2] = R((q.j[1] - q.j[0]) / q.j[2]);
-    p.dt = R(c.t_step); p.h_sub = R(c.t_step / c.substeps);
+    p.dt = R(c.t_step); p.h_sub = R(c.t_step / c.substeps); p.inv_dt = R(1.0 / c.t_step);
     const double bb[9] = {q.bb_vel, q.bb_vel, q.bb_vel, q.bb_ang, q.bb_ang, 3.0 / 4 * M_PI,
                           q.bb_vel * 2, q.bb_vel * 2, q.bb_vel * 2};                       // :139-143
     for (int k = 0; k < 9; ++k) p.bb[k] = R(bb[k]);
@@ -314,8 +314,8 @@ __device__ __forceinline__ void store_env(const SimView<R>& v, int64_t n, const 
 // AUX attributes the single-env compatibility class exposes (quad.ang_vel, step_effort, w, accel,
 // accelerometer_read, mat_rot); evaluated at the new state like the reference's trailing drone_eq call.
 template <typename R>
-__device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R>& e,
-                                       const StepOut<R>& o, const Ctrl<R>& c) {
+__device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
+                                       const StepOut<R> o, const Ctrl<R> c) {   // by VALUE: callers' structs stay in registers
 #pragma unroll
     for (int k = 0; k < 3; ++k) v.ang_vel[k * v.ld + n] = o.ang_vel[k];
 #pragma unroll
@@ -468,37 +468,133 @@ __device__ __forceinline__ void issue_tile(const SimView<R>& v, const R* action,
     }
 }
 
+// quad.step for one env held in registers + all of its stores (shared by both loader variants).
 template <typename R, int INTEG, bool DIRECT>
-__global__ void __launch_bounds__(kBlock)
-step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
-            const __grid_constant__ StepIO<R> io) {
+__device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io, int64_t n,
+                                            Env<R>& e, R a[4], LocalStats& ls, bool& any_end, int* s_queue, int* s_qn) {
+    bool warm = false;
+    if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
+    const bool was_done = (e.flags & EF_DONE) != 0;
+    StepOut<R> o;
+    Ctrl<R> c;
+    step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
+    if (warm) o.reward = R(0); else e.ep_return += o.reward;
+    if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+    if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
+    if ((p.flags & F_AUTO_RESET) && o.done) s_queue[atomicAdd(s_qn, 1)] = (int)n;
+    const uint8_t done_byte = (uint8_t)((o.done ? 1 : 0) | (warm ? 2 : 0));
+    store_env(v, n, e, o.vq);
+    v.reward[n] = o.reward;
+    v.done[n] = done_byte;
+    v.solved[n] = o.solved;
+    if (io.obs) {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
+    }
+    if (io.reward) io.reward[n] = o.reward;
+    if (io.done) io.done[n] = done_byte;
+    if (io.solved) io.solved[n] = o.solved;
+}
+
+// compacted strict-reset sub-pass + statistics flush (common tail of both step kernels)
+template <typename R, int INTEG, bool DIRECT>
+__device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io,
+                                              const LocalStats& ls, bool any_end, const int* s_queue, const int* s_qn) {
+    __syncthreads();                       // queue complete; the block's global stores are visible to the block
+    const int qn = *s_qn;
+    for (int q = threadIdx.x; q < qn; q += blockDim.x) {
+        const int64_t n = s_queue[q];
+        Env<R> e;
+        load_env(v, n, e);
+        e.episode += 1;
+        StepOut<R> o;
+        reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+        store_env(v, n, e, o.vq);
+        if (io.obs) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
+        }
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N);
+}
+
+// Loader A — direct: every thread issues its 27 coalesced LDGs up front (one 128-byte line per warp request).
+template <typename R, int INTEG, bool DIRECT>
+__global__ void __launch_bounds__(kBlock, 2)
+step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
+                   const __grid_constant__ StepIO<R> io) {
+    __shared__ int s_queue[kResetQueueCap];
+    __shared__ int s_qn;
+    if (threadIdx.x == 0) s_qn = 0;
+    __syncthreads();
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < v.N; n += stride) {
+        Env<R> e;
+        load_env(v, n, e);
+        R a[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a[k] = io.action[k * v.N + n];
+        process_env<R, INTEG, DIRECT>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
+    }
+    step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
+}
+
+// Loader B — TMA: 3-stage shared-memory ring filled by cp.async.bulk two tiles ahead of the arithmetic.
+// full[s]  : tx-count mbarrier completed by the TMA engine when tile data has landed;
+// empty[s] : arrive-count mbarrier (one arrival per warp) completed when every warp has copied its slice of the
+//            stage into registers.  There is NO block-wide barrier in the loop: warps drift freely (a warp whose
+//            lanes re-sample an episode is ~30 % slower that iteration) and only the issuing thread ever waits.
+constexpr int kStages = 3;
+
+template <typename R, int INTEG, bool DIRECT>
+__global__ void __launch_bounds__(kBlock, 2)
+step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
+                const __grid_constant__ StepIO<R> io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     Stage<R>* stages = reinterpret_cast<Stage<R>*>(smem_raw);
-    __shared__ uint64_t s_bar[2];
+    __shared__ uint64_t s_full[kStages], s_empty[kStages];
     __shared__ int s_queue[kResetQueueCap];
     __shared__ int s_qn;
     const int tid = threadIdx.x;
     if (tid == 0) {
         s_qn = 0;
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(&s_full[s], 1); mbar_init(&s_empty[s], kBlock / 32); }
         mbar_fence_init();
     }
     __syncthreads();
     LocalStats ls;
     ls.clear();
     bool any_end = false;
-    const bool auto_reset = (p.flags & F_AUTO_RESET) != 0;
     const bool act_bulk = ((reinterpret_cast<uintptr_t>(io.action) & 15) == 0) && ((v.N * sizeof(R)) % 16 == 0);
     const int64_t n_tiles = (v.N + kTile - 1) / kTile;
-    int64_t tile = blockIdx.x;
-    if (tid == 0 && tile < n_tiles) issue_tile(v, io.action, act_bulk, tile, &stages[0], &s_bar[0]);
+    const int64_t tile0 = blockIdx.x;
+    if (tid == 0) {
+        for (int d = 0; d < kStages - 1; ++d) {
+            const int64_t t = tile0 + (int64_t)d * gridDim.x;
+            if (t < n_tiles) issue_tile(v, io.action, act_bulk, t, &stages[d], &s_full[d]);
+        }
+    }
+    int64_t tile = tile0;
     for (int j = 0; tile < n_tiles; tile += gridDim.x, ++j) {
-        const int s = j & 1;
-        const int64_t next = tile + gridDim.x;
-        // stage s^1 was last read in iteration j-1, and every thread has passed that iteration's barrier
-        if (tid == 0 && next < n_tiles) issue_tile(v, io.action, act_bulk, next, &stages[s ^ 1], &s_bar[s ^ 1]);
-        mbar_wait(&s_bar[s], (j >> 1) & 1);
+        const int s = j % kStages;
+        if (tid == 0) {                    // refill the stage that tile j-1 used with tile j+kStages-1
+            const int jn = j + kStages - 1;
+            const int64_t tn = tile0 + (int64_t)jn * gridDim.x;
+            if (tn < n_tiles) {
+                const int sn = jn % kStages, use = jn / kStages;
+                if (use > 0) mbar_wait(&s_empty[sn], (use - 1) & 1);
+                issue_tile(v, io.action, act_bulk, tn, &stages[sn], &s_full[sn]);
+            }
+        }
+        mbar_wait(&s_full[s], (j / kStages) & 1);
         const Stage<R>& st = stages[s];
         const int64_t n0 = tile * kTile;
         const int64_t n = n0 + tid;
@@ -522,52 +618,11 @@ step_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimV
 #pragma unroll
             for (int k = 0; k < 4; ++k) a[k] = active ? io.action[k * v.N + n] : R(0);
         }
-        __syncthreads();                   // all reads of stage s done -> it may be refilled next iteration
-        if (!active) continue;
-        bool warm = false;
-        if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
-        const bool was_done = (e.flags & EF_DONE) != 0;
-        StepOut<R> o;
-        Ctrl<R> c;
-        step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
-        if (warm) o.reward = R(0); else e.ep_return += o.reward;
-        if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
-        if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
-        if (auto_reset && o.done) s_queue[atomicAdd(&s_qn, 1)] = (int)n;
-        const uint8_t done_byte = (uint8_t)((o.done ? 1 : 0) | (warm ? 2 : 0));
-        store_env(v, n, e, o.vq);
-        v.reward[n] = o.reward;
-        v.done[n] = done_byte;
-        v.solved[n] = o.solved;
-        if (io.obs) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
-        }
-        if (io.reward) io.reward[n] = o.reward;
-        if (io.done) io.done[n] = done_byte;
-        if (io.solved) io.solved[n] = o.solved;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);     // this warp's slice of stage s is in registers
+        if (active) process_env<R, INTEG, DIRECT>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
     }
-    __syncthreads();                       // queue complete; the block's global stores are visible to the block
-    const int qn = s_qn;
-    for (int q = tid; q < qn; q += blockDim.x) {
-        const int64_t n = s_queue[q];
-        Env<R> e;
-        load_env(v, n, e);
-        e.episode += 1;
-        StepOut<R> o;
-        reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
-        store_env(v, n, e, o.vq);
-        if (io.obs) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) io.obs[k * v.N + n] = e.y[k];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + n] = o.vq[k];
-        }
-    }
-    flush_stats(ls, any_end, v.stats);
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N);
+    step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
 
 // quad.reset for the masked envs (det_state given or Philox-sampled).
@@ -607,7 +662,7 @@ template <typename R> struct RolloutIO {
 };
 
 template <typename R, int INTEG, bool DIRECT>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 2)
 rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                const __grid_constant__ RolloutIO<R> io) {
     LocalStats ls;
@@ -679,6 +734,13 @@ static int grid_for(const qs_sim* s, int64_t n) {
     return (int)blocks;
 }
 
+// QS_STEP_LOADER=0 direct LDG loads, 1 (default) TMA-staged ring
+static int step_loader() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 // persistent grid of the staged step kernel: a few CTAs per SM, each looping over 256-env tiles
 static int grid_step(const qs_sim* s) {
     static int ctas_per_sm = 0;
@@ -718,13 +780,17 @@ template <typename R, int INTEG, bool DIRECT>
 static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
                         cudaStream_t st) {
     StepIO<R> io{(const R*)action, (R*)obs, (R*)reward, done, solved};
-    constexpr size_t smem = 2 * sizeof(Stage<R>);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(step_kernel<R, INTEG, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
+    if (step_loader() == 1) {
+        constexpr size_t smem = kStages * sizeof(Stage<R>);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(step_kernel_tma<R, INTEG, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        step_kernel_tma<R, INTEG, DIRECT><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
+    } else {
+        step_kernel_direct<R, INTEG, DIRECT><<<grid_step(s), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
     }
-    step_kernel<R, INTEG, DIRECT><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
 
 template <typename R, int INTEG, bool DIRECT>
