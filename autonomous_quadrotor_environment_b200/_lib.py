@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libquadsim.so")
+LIB_PATH = os.environ.get("QUADSIM_LIB") or os.path.join(_HERE, "_C", "libquadsim.so")   # override: tuning builds only
 
 QS_OK, QS_EINVAL, QS_ECUDA, QS_ENOMEM, QS_ESTATE = 0, -1, -2, -3, -4
 QS_F32, QS_F64 = 0, 1

@@ -679,21 +679,10 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
     o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
 }
 
-// QS_FLAG_ASYNC_RESET: start-of-step hook.  An env whose sticky done flag is set begins a new episode now
-// (Philox-sampled initial state, bookkeeping cleared, T warm-up steps owed); an env that still owes warm-up
-// steps gets the neutral action (:448) for this step.  Returns true if this step is a warm-up step.
+// QS_FLAG_ASYNC_RESET, start of a step: an env that still owes warm-up steps gets the neutral action (:448)
+// for this step.  Returns true if this step is a warm-up step.
 template <typename R>
-__device__ __forceinline__ bool async_reset_prologue(const DevParams<R>& p, uint64_t seed, uint32_t env_id, Env<R>& e,
-                                                     R a[4]) {
-    if (e.flags & EF_DONE) {
-        e.episode += 1;
-        R ang[3];
-        sample_reset_state(p, seed, env_id, e.episode, e.y, ang);
-        e.flags = (uint32_t)p.T << EF_WARM_SHIFT;      // solved=0, done=False, prev_shaping=None
-        e.i = 0;
-        e.abs_sum = R(0);
-        e.ep_return = R(0);
-    }
+__device__ __forceinline__ bool async_warmup_prologue(const DevParams<R>& p, Env<R>& e, R a[4]) {
     if (e.flags >> EF_WARM_SHIFT) {
         e.flags -= (1u << EF_WARM_SHIFT);
 #pragma unroll
@@ -701,6 +690,21 @@ __device__ __forceinline__ bool async_reset_prologue(const DevParams<R>& p, uint
         return true;
     }
     return false;
+}
+
+// QS_FLAG_ASYNC_RESET, end of the step that returned done: begin the next episode — Philox-sampled initial
+// state (random branch of quad.reset :439-445), bookkeeping cleared (:428-433), T warm-up steps owed.
+// vq receives V_q of the initial state so that the observation rows are the new episode's first observation.
+template <typename R>
+__device__ __forceinline__ void async_resample(const DevParams<R>& p, uint64_t seed, uint32_t env_id, Env<R>& e, R vq[4]) {
+    e.episode += 1;
+    R ang[3];
+    sample_reset_state(p, seed, env_id, e.episode, e.y, ang);
+    e.flags = (uint32_t)p.T << EF_WARM_SHIFT;          // solved=0, done=False, prev_shaping=None
+    e.i = 0;
+    e.abs_sum = R(0);
+    e.ep_return = R(0);
+    deriv_quat(&e.y[10], &e.y[6], vq);                 // euler_quat returns a unit quaternion
 }
 
 // head of quad.reset :428-438 for one env (state already chosen); the T warm-up steps follow in the caller

@@ -275,7 +275,16 @@ template <typename R> static SimView<R> make_view(const qs_sim* s) {
 // ------------------------------------------------------------------------------------------------
 // kernels
 // ------------------------------------------------------------------------------------------------
-constexpr int kBlock = 256;
+#ifndef QS_BLOCK
+#define QS_BLOCK 256          // threads (= envs) per CTA tile
+#endif
+#ifndef QS_MIN_CTAS
+#define QS_MIN_CTAS 2         // resident CTAs per SM the step / rollout kernels are compiled for
+#endif
+#ifndef QS_STAGES
+#define QS_STAGES 3           // depth of the TMA staging ring
+#endif
+constexpr int kBlock = QS_BLOCK;
 
 template <typename R>
 __device__ __forceinline__ void load_env(const SimView<R>& v, int64_t n, Env<R>& e) {
@@ -429,7 +438,7 @@ template <typename R> struct StepIO {
 // not reset in its own lane (a reset is T serial hover steps; with ~2 % of the lanes finishing per step about
 // half of all warps would run T extra steps for one or two lanes).  The lane appends its env index to a
 // shared-memory queue which is drained after the block's main pass with one env per thread, i.e. full warps.
-// A block owns at most kResetQueueCap envs (see grid_for), so the queue cannot overflow.
+// If more than kResetQueueCap envs of one block finish in the same step the surplus is reset in-lane.
 // QS_FLAG_ASYNC_RESET needs no sub-pass at all (see async_reset_prologue).
 constexpr int kResetQueueCap = 4096;
 constexpr int kTile = kBlock;
@@ -473,7 +482,7 @@ template <typename R, int INTEG, bool DIRECT>
 __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io, int64_t n,
                                             Env<R>& e, R a[4], LocalStats& ls, bool& any_end, int* s_queue, int* s_qn) {
     bool warm = false;
-    if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
+    if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
     const bool was_done = (e.flags & EF_DONE) != 0;
     StepOut<R> o;
     Ctrl<R> c;
@@ -481,7 +490,24 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
     if (warm) o.reward = R(0); else e.ep_return += o.reward;
     if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
     if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
-    if ((p.flags & F_AUTO_RESET) && o.done) s_queue[atomicAdd(s_qn, 1)] = (int)n;
+    if ((p.flags & (F_AUTO_RESET | F_ASYNC_RESET)) && o.done) {
+        const int slot = atomicAdd(s_qn, 1);
+        if (slot < kResetQueueCap) {
+            s_queue[slot] = (int)n;
+        } else {                            // queue full (e.g. a whole block timing out at once): reset in this lane
+            Env<R> te = e;                  // copies: only this cold path touches local memory
+            StepOut<R> to;
+            if (p.flags & F_ASYNC_RESET) {
+                async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, te, to.vq);
+            } else {
+                te.episode += 1;
+                reset_env<R, INTEG, DIRECT>(p, v, n, te, true, to, nullptr, nullptr);
+            }
+            e = te;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) o.vq[k] = to.vq[k];
+        }
+    }
     const uint8_t done_byte = (uint8_t)((o.done ? 1 : 0) | (warm ? 2 : 0));
     store_env(v, n, e, o.vq);
     v.reward[n] = o.reward;
@@ -503,14 +529,18 @@ template <typename R, int INTEG, bool DIRECT>
 __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io,
                                               const LocalStats& ls, bool any_end, const int* s_queue, const int* s_qn) {
     __syncthreads();                       // queue complete; the block's global stores are visible to the block
-    const int qn = *s_qn;
+    const int qn = (*s_qn < kResetQueueCap) ? *s_qn : kResetQueueCap;
     for (int q = threadIdx.x; q < qn; q += blockDim.x) {
         const int64_t n = s_queue[q];
         Env<R> e;
         load_env(v, n, e);
-        e.episode += 1;
         StepOut<R> o;
-        reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+        if (p.flags & F_ASYNC_RESET) {
+            async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+        } else {
+            e.episode += 1;
+            reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+        }
         store_env(v, n, e, o.vq);
         if (io.obs) {
 #pragma unroll
@@ -525,7 +555,7 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
 
 // Loader A — direct: every thread issues its 27 coalesced LDGs up front (one 128-byte line per warp request).
 template <typename R, int INTEG, bool DIRECT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                    const __grid_constant__ StepIO<R> io) {
     __shared__ int s_queue[kResetQueueCap];
@@ -552,10 +582,10 @@ step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant
 // empty[s] : arrive-count mbarrier (one arrival per warp) completed when every warp has copied its slice of the
 //            stage into registers.  There is NO block-wide barrier in the loop: warps drift freely (a warp whose
 //            lanes re-sample an episode is ~30 % slower that iteration) and only the issuing thread ever waits.
-constexpr int kStages = 3;
+constexpr int kStages = QS_STAGES;
 
 template <typename R, int INTEG, bool DIRECT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                 const __grid_constant__ StepIO<R> io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -662,7 +692,7 @@ template <typename R> struct RolloutIO {
 };
 
 template <typename R, int INTEG, bool DIRECT>
-__global__ void __launch_bounds__(kBlock, 2)
+__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                const __grid_constant__ RolloutIO<R> io) {
     LocalStats ls;
@@ -687,12 +717,13 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
                 for (int k = 0; k < 4; ++k) a[k] = at[k * v.N + n];
             }
             bool warm = false;
-            if (p.flags & F_ASYNC_RESET) warm = async_reset_prologue(p, v.seed, v.env_id_offset + (uint32_t)n, e, a);
+            if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
             step_core<R, INTEG, DIRECT>(p, e, a, o, nullptr);
             if (warm) o.reward = R(0); else e.ep_return += o.reward;
             reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
             if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+            if ((p.flags & F_ASYNC_RESET) && done) async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
             if ((p.flags & F_AUTO_RESET) && done) {
                 e.episode += 1;
                 reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
@@ -746,15 +777,11 @@ static int grid_step(const qs_sim* s) {
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
         const char* e = getenv("QS_STEP_CTAS_PER_SM");
-        ctas_per_sm = e ? atoi(e) : 4;
-        if (ctas_per_sm < 1) ctas_per_sm = 4;
+        ctas_per_sm = e ? atoi(e) : QS_MIN_CTAS;
+        if (ctas_per_sm < 1) ctas_per_sm = QS_MIN_CTAS;
     }
     const int64_t tiles = (s->N + kTile - 1) / kTile;
     int64_t g = (int64_t)s->sm_count * ctas_per_sm;
-    if (s->cfg.flags & QS_FLAG_AUTO_RESET) {            // a block never owns more envs than its reset queue holds
-        const int64_t need = (s->N + kResetQueueCap - 1) / kResetQueueCap;
-        if (g < need) g = need;
-    }
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
 }

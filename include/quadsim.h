@@ -58,11 +58,12 @@ extern "C" {
 #define QS_FLAG_AUTO_RESET     0x08u /* re-sample + T warm-up steps inside the step kernel when done          */
 #define QS_FLAG_SENSOR_NOISE   0x10u /* run the `sensor` model (quadrotor_env.py:579-724) each step           */
 #define QS_FLAG_AUX            0x20u /* also store ang_vel, step_effort, w, accel, mat_rot, accelerometer_read */
-#define QS_FLAG_ASYNC_RESET    0x40u /* auto-reset with ASYNCHRONOUS warm-up (production mode): an env that returned  */
-                                     /* done is re-sampled at the start of its NEXT step, and the T hover steps of    */
-                                     /* quad.reset (:447-453) run as its next T ordinary lock-step steps (caller's     */
-                                     /* action ignored, reward 0, bit1 of the done byte set).  Per-env sequences are   */
-                                     /* exactly those of reset()+step(); no lane ever runs T serial steps.             */
+#define QS_FLAG_ASYNC_RESET    0x40u /* auto-reset with ASYNCHRONOUS warm-up (production mode): an env that returns   */
+                                     /* done is re-sampled at the end of that step (the observation returned with done */
+                                     /* is the new episode's initial observation), and the T hover steps of quad.reset */
+                                     /* (:447-453) run as its next T ordinary lock-step steps (caller's action         */
+                                     /* ignored, reward 0, bit1 of the done byte set).  Per-env sequences are exactly  */
+                                     /* those of reset()+step(); no lane ever runs T serial steps.                     */
 
 /* Physical / reward constants.  Defaults (qs_default_config) = environment/quadrotor_env.py:30-80. */
 typedef struct qs_params {

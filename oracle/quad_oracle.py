@@ -600,9 +600,10 @@ class BatchQuadOracle:
 
     # -- asynchronous warm-up (restatement of QS_FLAG_ASYNC_RESET) ---------------------------------------
     def step_async(self, action, seed, env_id_offset=0):
-        """An env whose sticky done flag is set begins a new episode at the START of this step (Philox-sampled
-        state, episode counter + 1) and owes T warm-up steps; a warm-up step applies zero_control instead of the
-        caller's action and returns reward 0.  Returns (obs, reward, done, warm)."""
+        """A warm-up step applies zero_control instead of the caller's action and returns reward 0.  An env that
+        returns done begins its next episode at the END of that step: Philox-sampled state (episode counter + 1),
+        bookkeeping cleared, T warm-up steps owed; the observation returned with done is the new episode's initial
+        observation [s0[0:10], V_q(s0)].  Returns (obs, reward, done, warm)."""
         if not hasattr(self, "episode"):
             self.episode = np.zeros(self.N, dtype=np.int64)
             self.ep_return = np.zeros(self.N)
@@ -610,19 +611,6 @@ class BatchQuadOracle:
                               sum_effort=0.0)
         if not hasattr(self, "warm"):
             self.warm = np.zeros(self.N, dtype=np.int64)
-        begin = self.done.copy()
-        if begin.any():
-            self.episode[begin] += 1
-            ids = np.arange(self.N) + env_id_offset
-            st, _ = sample_reset_state(seed, ids[begin], self.episode[begin])
-            self.previous_state[begin] = st
-            self.solved[begin] = 0
-            self.done[begin] = False
-            self.i[begin] = 0
-            self.has_prev_shaping[begin] = False
-            self.abs_sum[begin] = 0
-            self.ep_return[begin] = 0
-            self.warm[begin] = self.T
         w = self.warm > 0
         a = np.where(w[:, None], self.zero_control[None, :], np.asarray(action, dtype=np.float64))
         self.warm[w] -= 1
@@ -641,4 +629,19 @@ class BatchQuadOracle:
             s["n_timeout"] += int(timeout.sum())
             s["n_broken"] += int((ended & (self.solved == 0) & ~timeout).sum())
             s["sum_effort"] += float(self.abs_sum[ended].sum())
+        if done.any():
+            self.episode[done] += 1
+            ids = np.arange(self.N) + env_id_offset
+            st, _ = sample_reset_state(seed, ids[done], self.episode[done])
+            self.previous_state[done] = st
+            self.state[done] = st
+            self.solved[done] = 0
+            self.done[done] = False
+            self.i[done] = 0
+            self.has_prev_shaping[done] = False
+            self.abs_sum[done] = 0
+            self.ep_return[done] = 0
+            self.warm[done] = self.T
+            obs = obs.copy()
+            obs[done] = np.concatenate([st[:, 0:10], deriv_quat(st[:, 10:13], st[:, 6:10])], axis=1)
         return obs, rew, done, w

@@ -214,6 +214,23 @@ def test_async_rollout_equals_async_steps():
     assert torch.equal(a.episode, b.episode) and int(a.episode.max()) > 1
 
 
+def test_reset_queue_overflow_falls_back_in_lane():
+    """Every env of a never-reset handle is done (quad.__init__ :154), so the first step finishes 2M episodes at
+    once: far more than the per-block reset queue holds.  All of them must still be re-sampled correctly."""
+    N, seed = 1 << 21, 17
+    env = BatchedQuad(N, 0.01, 1000, T=3, precision="f32", async_reset=True, seed=seed, device=DEV)
+    obs, rew, done = env.step_soa(torch.zeros(4, N, device=DEV))
+    assert bool(done.all())
+    assert torch.equal(env.episode, torch.ones_like(env.episode)) and int(env.i.abs().max()) == 0
+    assert torch.equal(env.env_flags, torch.full_like(env.env_flags, 3 << 3))
+    idx = np.concatenate([np.arange(0, 4096), np.arange(N - 4096, N), np.arange(1_000_000, 1_004_096)])
+    st, _ = qo.sample_reset_state(seed, idx, 1)
+    got = npy(env.state)[idx]
+    assert np.max(np.abs(got - st) / (1 + np.abs(st))) < 2e-5
+    obs2, _, done2 = env.step_soa(torch.zeros(4, N, device=DEV))
+    assert int(done2.sum()) == 0 and bool(env.warmup.all())
+
+
 def test_random_reset_on_device_matches_oracle_sampler():
     N, seed = 2048, 77
     for prec, tol in (("f64", 1e-12), ("f32", 2e-5)):
