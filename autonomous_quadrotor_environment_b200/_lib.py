@@ -23,7 +23,7 @@ QS_FLAG_AUX = 0x20
 QS_FLAG_ASYNC_RESET = 0x40
 QS_ACT_BUFFER, QS_ACT_PHILOX_UNIFORM = 0, 1
 QS_STATS_DIM = 8
-QS_SENSOR_STATE_DIM = 28
+QS_SENSOR_STATE_DIM = 20
 
 (QS_FIELD_OBS, QS_FIELD_STATE, QS_FIELD_ANG, QS_FIELD_ANG_VEL, QS_FIELD_STEP_EFFORT, QS_FIELD_W, QS_FIELD_REWARD,
  QS_FIELD_DONE, QS_FIELD_SOLVED, QS_FIELD_I, QS_FIELD_ABS_SUM, QS_FIELD_PREV_SHAPING, QS_FIELD_EP_RETURN,

@@ -10,6 +10,7 @@
 // A warp reads/writes 32 consecutive envs of one row = one 128-byte line per request (FP32).
 #include "../../include/quadsim.h"
 #include "quad_device.cuh"
+#include "sensor_device.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -141,6 +142,19 @@ template <typename R> static DevParams<R> make_params(const qs_config& c) {
     p.s_gyro_std = R(q.gyro_std); p.s_gyro_drift = R(q.gyro_bias_drift);
     p.s_mag_std = R(q.magnet_std); p.s_mag_drift = R(q.magnet_bias_drift);
     p.s_gps_p = R(q.gps_std_p); p.s_gps_v = R(q.gps_std_v);
+    {   // sensor.triad :650-651,:682-691 — inertial triad of (gravity, magnetic field of Santo Andre in mG)
+        const double mv[3] = {-4047 * 0.01, 12911 * 0.01, -9899 * 0.01};
+        const double mn = std::sqrt(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]);
+        const double gv[3] = {0, 0, -1}, m1[3] = {mv[0] / mn, mv[1] / mn, mv[2] / mn};
+        double t2[3] = {gv[1] * m1[2] - gv[2] * m1[1], gv[2] * m1[0] - gv[0] * m1[2], gv[0] * m1[1] - gv[1] * m1[0]};
+        const double n2 = std::sqrt(t2[0] * t2[0] + t2[1] * t2[1] + t2[2] * t2[2]);
+        for (int k = 0; k < 3; ++k) t2[k] /= n2;
+        double t3[3] = {gv[1] * t2[2] - gv[2] * t2[1], gv[2] * t2[0] - gv[0] * t2[2], gv[0] * t2[1] - gv[1] * t2[0]};
+        const double n3 = std::sqrt(t3[0] * t3[0] + t3[1] * t3[1] + t3[2] * t3[2]);
+        for (int k = 0; k < 3; ++k) {
+            p.s_mag[k] = R(mv[k]); p.s_ti[k] = R(gv[k]); p.s_ti[3 + k] = R(t2[k]); p.s_ti[6 + k] = R(t3[k] / n3);
+        }
+    }
     p.n_limit = c.n_max + c.T;                                                             // :157
     p.T = c.T;
     p.substeps = c.substeps;
@@ -347,6 +361,41 @@ __device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& 
     for (int k = 0; k < 9; ++k) v.mat_rot[k * v.ld + n] = r[k];
 }
 
+// Sensor sub-pass for one env (QS_FLAG_SENSOR_NOISE).  mode 0: one step of the sensor model; mode 1: sensor.reset
+// from the true state (end of an episode's warm-up) and pass the true observation through; mode 2: pass-through only.
+template <typename R>
+__device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
+                                           const Ctrl<R> c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
+    R obs[14];
+    if (mode == 0) {
+        R s[kSensorStateDim], z[32], dy[13], qn[4], rot[9];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) s[k] = v.sensor_state[k * v.ld + n];
+        drone_rhs(p, c, e.y, dy);                                  // trailing drone_eq call: accel at the new state
+        quat_normalize(&e.y[6], qn);
+        quat_rot_mat(qn, rot);
+        const R g[3] = {dy[1], dy[3], dy[5] - p.g};               // :371
+        const R acc_read[3] = {rot[0] * g[0] + rot[3] * g[1] + rot[6] * g[2], rot[1] * g[0] + rot[4] * g[1] + rot[7] * g[2],
+                               rot[2] * g[0] + rot[5] * g[1] + rot[8] * g[2]};
+        sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, z);
+        sensor_step(p, z, e.y, acc_read, rot, c.f_m, s, obs);
+#pragma unroll
+        for (int k = 0; k < kSensorStateDim; ++k) v.sensor_state[k * v.ld + n] = s[k];
+    } else {
+        if (mode == 1) {
+            R s[kSensorStateDim];
+            sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)n, e.episode, e.y, s);
+#pragma unroll
+            for (int k = 0; k < kSensorStateDim; ++k) v.sensor_state[k * v.ld + n] = s[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) obs[k] = e.y[k];
+        obs[10] = vq0; obs[11] = vq1; obs[12] = vq2; obs[13] = vq3;
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) v.sensed_obs[k * v.ld + n] = obs[k];
+}
+
 // quad.reset (:408-454) for one env held in registers: (optionally) sample the initial state with Philox,
 // clear the episode bookkeeping, then take T hover steps.  obs_hist/act_hist: [T][14][N] / [T][4][N] or NULL.
 template <typename R, int INTEG, bool DIRECT>
@@ -373,6 +422,7 @@ __device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& 
             for (int k = 0; k < 4; ++k) ah[k * v.N + n] = p.zero_control[k];
         }
         if ((p.flags & F_AUX) && t == p.T - 1) store_aux(p, v, n, e, o, c);
+        if ((p.flags & F_SENSOR) && t == p.T - 1) sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], 1);
     }
     e.ep_return = R(0);
 }
@@ -490,6 +540,8 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
     if (warm) o.reward = R(0); else e.ep_return += o.reward;
     if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
     if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
+    if (p.flags & F_SENSOR)                 // warm-up steps bypass the sensor; the last one re-initialises it (sensor.reset)
+        sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
     if ((p.flags & (F_AUTO_RESET | F_ASYNC_RESET)) && o.done) {
         const int slot = atomicAdd(s_qn, 1);
         if (slot < kResetQueueCap) {
@@ -537,6 +589,12 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
         StepOut<R> o;
         if (p.flags & F_ASYNC_RESET) {
             async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+            if (p.flags & F_SENSOR) {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) v.sensed_obs[k * v.ld + n] = e.y[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v.sensed_obs[(10 + k) * v.ld + n] = o.vq[k];
+            }
         } else {
             e.episode += 1;
             reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
@@ -928,7 +986,8 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
     if (args->action_source == QS_ACT_BUFFER && !args->actions) return fail(QS_EINVAL, "qs_rollout: actions is NULL");
     if (args->action_source != QS_ACT_BUFFER && args->action_source != QS_ACT_PHILOX_UNIFORM)
         return fail(QS_EINVAL, "qs_rollout: bad action_source");
-    if (h->cfg.flags & QS_FLAG_AUX) return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX");
+    if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE))
+        return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_SENSOR_NOISE");
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_rollout, h, args, st);
     QS_CUDA(cudaGetLastError());

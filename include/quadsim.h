@@ -134,7 +134,7 @@ typedef enum qs_field {
     QS_FIELD_COUNT_
 } qs_field;
 
-#define QS_SENSOR_STATE_DIM 28
+#define QS_SENSOR_STATE_DIM 20
 
 typedef struct qs_field_desc {
     int32_t channels;     /* C of [C][N]                                             */

@@ -10,6 +10,7 @@ Fixtures (all float64 unless noted):
   lqr_log.npz           slice of the reference's SHIPPED log classical_controller_results/lqr_log_same_start.npy
                         (written by the author's 2021 run) + the LQR gains of lqr_quad.py:25-111 + initial states
   pid_log.npz           same for pid_log_same_start.npy (first episodes)
+  sensor_stats.npz      noise statistics of the reference `sensor` class at hover (canonical call order)
   actor_128.npz         float32 weights of solved/nn_old_solved_128_32000_*.pth (actor only) and a reference
                         closed-loop episode driven by it (ppo_quad_eval.py protocol)
 """
@@ -230,6 +231,33 @@ def gen_actor(ref):
                         nn_in=nn_in, states=states, **W)
 
 
+def gen_sensor_stats(ref):
+    """Statistics of the reference `sensor` class at hover in the canonical call order (rl_worker.py:164-175):
+    the Philox-driven model cannot match NumPy's MT19937 draws, so distributions are compared instead."""
+    sys.path.insert(0, REF)
+    from environment.quaternion_euler_utility import deriv_quat
+    qv_std, dv_std, pos_end = [], [], []
+    for seed in range(4):
+        env = quiet_quad(ref, 0.01, 10 ** 6, training=False, direct_control=1, T=1)
+        np.random.seed(seed)
+        init = np.zeros(13); init[6] = 1
+        env.reset(init.copy())
+        sen = ref.sensor(env)
+        env.state = env.state.copy()
+        sen.reset()
+        # neutralise the aliasing of sensor.reset (:636-638) so that the TRUE state is not perturbed
+        sen.quaternion_t0 = sen.quaternion_t0.copy(); sen.position_t0 = sen.position_t0.copy(); sen.velocity_t0 = sen.velocity_t0.copy()
+        obs = []
+        for t in range(1500):
+            env.step(np.zeros(4))
+            _, v, p = sen.accel_int(); qg = sen.gyro_int().copy(); w = sen.gyro(); qv = deriv_quat(w, qg); sen.gps(); sen.triad()
+            obs.append(np.concatenate([[p[0], v[0], p[1], v[1], p[2], v[2]], qg, qv]))
+        obs = np.array(obs)
+        qv_std.append(obs[:, 11:14].std(0)); dv_std.append(np.diff(obs[:, [1, 3, 5]], axis=0).std(0)); pos_end.append(obs[-1, [0, 2, 4]])
+    np.savez_compressed(os.path.join(OUT, "sensor_stats.npz"), qv_std=np.array(qv_std), dv_std=np.array(dv_std),
+                        pos_end=np.array(pos_end), steps=1500)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load_reference()
@@ -240,6 +268,7 @@ def main():
     gen_steps(ref, rng)
     gen_logs(ref)
     gen_actor(ref)
+    gen_sensor_stats(ref)
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

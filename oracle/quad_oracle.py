@@ -645,3 +645,102 @@ class BatchQuadOracle:
             obs = obs.copy()
             obs[done] = np.concatenate([st[:, 0:10], deriv_quat(st[:, 10:13], st[:, 6:10])], axis=1)
         return obs, rew, done, w
+
+
+# --------------------------------------------------------------------------------------
+# sensor model — environment/quadrotor_env.py:579-724 in the canonical call order
+# accel_int -> gyro_int -> gyro -> gps -> triad (visual_landing/rl_worker.py:164-175)
+# --------------------------------------------------------------------------------------
+MAGNET_VEC = np.array([-4047, 12911, -9899]) * 0.01          # :651
+
+
+def sensor_normals(seed, env_id, episode, step):
+    """27(+5 spare) normals per env step from 4 Philox blocks; every 32-bit word gives two 16-bit uniforms
+    (one Box-Muller pair) — the same mapping as csrc/sensor_device.cuh."""
+    env_id = np.asarray(env_id)
+    z = np.zeros((env_id.shape[0], 32))
+    step = np.asarray(step, dtype=np.uint32)
+    for b in range(4):
+        w = philox_block(seed, env_id, episode, step * np.uint32(4) + np.uint32(b), STREAM_SENSOR)
+        for k in range(4):
+            u1 = ((w[:, k] & np.uint32(0xFFFF)).astype(np.float64) + 0.5) / 65536.0
+            u2 = ((w[:, k] >> np.uint32(16)).astype(np.float64) + 0.5) / 65536.0
+            z[:, 8 * b + 2 * k], z[:, 8 * b + 2 * k + 1] = box_muller(u1, u2)
+    return z
+
+
+def _unit(a):
+    return a / np.linalg.norm(a, axis=-1, keepdims=True)
+
+
+def _triad_inertial():
+    gv = _unit(np.array([0, 0, -G], dtype=np.float64))
+    mv = _unit(MAGNET_VEC)
+    t2 = _unit(np.cross(gv, mv))
+    t3 = _unit(np.cross(gv, t2))
+    return np.vstack((gv, t2, t3)).T                           # ti, :691
+
+
+def _triad(grav_body, mag_body):
+    """sensor.triad :664-693 -> R (N,3,3)."""
+    g = _unit(grav_body)
+    m = _unit(mag_body)
+    t2 = _unit(np.cross(g, m))
+    t3 = _unit(np.cross(g, t2))
+    tb = np.stack((g, t2, t3), axis=2)                         # columns
+    return tb @ _triad_inertial().T
+
+
+class SensorOracle:
+    def __init__(self, n_envs, t_step, accel_std=0.1, accel_bias_drift=0.0005, gyro_std=0.035, gyro_bias_drift=0.00015,
+                 magnet_std=15):
+        self.N, self.dt = n_envs, t_step
+        self.a_std, self.a_drift, self.g_std, self.g_drift, self.m_std = accel_std, accel_bias_drift, gyro_std, gyro_bias_drift, magnet_std
+        self.a_b = np.zeros(n_envs); self.g_b = np.zeros(n_envs)
+        self.a_b_d = np.zeros(n_envs); self.g_b_d = np.zeros(n_envs)
+        self.vel = np.zeros((n_envs, 3)); self.pos = np.zeros((n_envs, 3)); self.quat = np.zeros((n_envs, 4))
+        self.Rc2 = np.tile(np.array([0.0, 0.0, 1.0]), (n_envs, 1))
+
+    def reset(self, seed, env_id, episode, y, mask=None):
+        """sensor.reset :630-640 + bias_reset :600-608 for the masked envs."""
+        m = np.ones(self.N, bool) if mask is None else np.asarray(mask, bool)
+        u = u32_to_unit(philox_block(seed, np.asarray(env_id)[m], np.asarray(episode)[m], 0xFFFFFFF0, STREAM_SENSOR))
+        self.a_b[m] = 0; self.g_b[m] = 0
+        self.a_b_d[m] = (u[:, 0] - 0.5) * 2 * self.a_drift
+        self.g_b_d[m] = (u[:, 1] - 0.5) * 2 * self.g_drift
+        self.vel[m] = y[m][:, 1:6:2]; self.pos[m] = y[m][:, 0:5:2]; self.quat[m] = y[m][:, 6:10]
+        self.Rc2[m] = np.array([0.0, 0.0, 1.0])
+
+    def step(self, z, y, acc_read, rot, f_m, mask=None):
+        """One env step of the sensor model for the masked envs; returns the 14-float sensed observation (N,14)."""
+        m = np.ones(self.N, bool) if mask is None else np.asarray(mask, bool)
+        dt = self.dt
+        a_b, g_b = self.a_b.copy(), self.g_b.copy()
+        a_b += self.a_b_d * dt                                                          # accel_int -> accel()
+        acc1 = acc_read + a_b[:, None] + self.a_std * z[:, 0:3]
+        a_b += self.a_b_d * dt                                                          # triad -> accel()
+        ind = G * self.Rc2.copy(); ind[:, 2] += f_m
+        gb = acc_read + a_b[:, None] + self.a_std * z[:, 3:6] - ind
+        mb = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 6:9])
+        Rm = _triad(gb, mb)
+        a_in = np.einsum("nji,nj->ni", Rm, acc1) + np.array([0, 0, G])
+        vel = self.vel + a_in * dt
+        pos = self.pos + vel * dt
+        g_b += self.g_b_d * dt                                                          # gyro_int -> gyro()
+        w1 = y[:, 10:13] + g_b[:, None] + self.g_std * z[:, 9:12]
+        qg = self.quat + deriv_quat(w1, self.quat) * dt
+        quat = qg / np.linalg.norm(qg, axis=1, keepdims=True)
+        g_b += self.g_b_d * dt                                                          # gyro()
+        w2 = y[:, 10:13] + g_b[:, None] + self.g_std * z[:, 12:15]
+        qv = deriv_quat(w2, qg)
+        a_b += self.a_b_d * dt                                                          # triad -> accel()  (gps: z[15:21])
+        ind2 = G * Rm[:, :, 2].copy(); ind2[:, 2] += f_m
+        gb2 = acc_read + a_b[:, None] + self.a_std * z[:, 21:24] - ind2
+        mb2 = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 24:27])
+        R2 = _triad(gb2, mb2)
+        obs = np.concatenate([np.stack([pos[:, 0], vel[:, 0], pos[:, 1], vel[:, 1], pos[:, 2], vel[:, 2]], axis=1), qg, qv], axis=1)
+        self.a_b = np.where(m, a_b, self.a_b); self.g_b = np.where(m, g_b, self.g_b)
+        self.vel = np.where(m[:, None], vel, self.vel); self.pos = np.where(m[:, None], pos, self.pos)
+        self.quat = np.where(m[:, None], quat, self.quat)
+        self.Rc2 = np.where(m[:, None], R2[:, :, 2], self.Rc2)
+        return obs

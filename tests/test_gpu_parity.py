@@ -309,6 +309,58 @@ def test_f32_closed_loop_1000_steps_with_trained_actor():
 
 
 # ----------------------------------------------------------------------------------------------------
+# sensor model (A13): same Philox -> normal mapping on both sides, so the comparison is deterministic
+# ----------------------------------------------------------------------------------------------------
+def test_sensor_model_matches_oracle_f64():
+    N, steps, seed, off = 256, 60, 5, 9
+    env = BatchedQuad(N, 0.01, 1000, training=False, direct_control=1, T=2, precision="f64", integrator="rk45",
+                      sensor_noise=True, seed=seed, env_id_offset=off, device=DEV)
+    ora = qo.BatchQuadOracle(N, 0.01, 1000, training=False, direct_control=1, T=2, integrator="rk45")
+    sen = qo.SensorOracle(N, 0.01)
+    init = np.zeros((N, 13)); init[:, 6] = 1
+    rng = np.random.default_rng(3)
+    init[:, 1:6:2] = rng.normal(0, 0.3, (N, 3)); init[:, 10:13] = rng.normal(0, 0.3, (N, 3))
+    env.reset(T64(init)); ora.reset(init)
+    ids = np.arange(N) + off
+    ep = np.zeros(N, dtype=np.int64)
+    sen.reset(seed, ids, ep, ora.state)                       # sensor.reset after quad.reset's warm-up steps
+    assert rel_err(npy(env.sensed_obs), np.concatenate([ora.state[:, 0:10], ora.V_q], axis=1)) < 1e-9
+    worst = 0.0
+    for t in range(steps):
+        a = rng.uniform(-0.2, 0.2, (N, 4))
+        env.step(T64(a))
+        ora.step(a)
+        z = qo.sensor_normals(seed, ids, ep, ora.i)
+        ref = sen.step(z, ora.state, ora.accelerometer_read, ora.mat_rot, ora.f_in / qo.M)
+        worst = max(worst, rel_err(npy(env.sensed_obs), ref))
+    assert worst < 1e-8, worst
+    # the noise is really there: sensed attitude rate differs from the true one at the gyro-noise scale
+    d = npy(env.sensed_obs)[:, 10:14] - npy(env.obs)[:, 10:14]
+    assert 0.005 < d.std() < 0.05
+
+
+def test_sensor_model_f32_statistics_and_async_reset():
+    N, seed = 1 << 16, 8
+    env = BatchedQuad(N, 0.01, 200, T=3, precision="f32", async_reset=True, sensor_noise=True, seed=seed, device=DEV)
+    env.reset()
+    acts = torch.zeros(4, N, device=DEV)
+    gyro_dev = []
+    for t in range(120):
+        env.step_soa(acts)
+        if t % 10 == 9:
+            alive = (env.i > env.T + 1)
+            so, to = env.sensed_obs[alive], env.obs[alive]
+            assert torch.isfinite(so).all()
+            gyro_dev.append((so[:, 10:14] - to[:, 10:14]).std().item())
+    # 1/2*Omega(w_noise)*q with sigma_gyro = 0.035 rad/s -> ~0.5*0.035*sqrt(3)/2 per component, plus INS attitude drift
+    assert 0.008 < np.mean(gyro_dev) < 0.04, gyro_dev
+    # warm-up steps pass the true observation through
+    w = env.warmup.bool()
+    if w.any():
+        assert torch.equal(env.sensed_obs[w], env.obs[w])
+
+
+# ----------------------------------------------------------------------------------------------------
 # structure: rollout fusion, sharding, checkpoint, host-buffer entry point
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("prec,integ", [("f32", "rk4"), ("f64", "rk45")])

@@ -130,3 +130,27 @@ def test_reset_sampler_distribution():
     # different episodes / envs give different streams
     st2, _ = qo.sample_reset_state(3, np.arange(20000), 1)
     assert np.abs(st - st2).max() > 1
+
+
+def test_sensor_oracle_statistics_match_reference_sensor():
+    """The Philox-driven sensor restatement has the noise statistics of the reference `sensor` class at hover."""
+    g = load_golden("sensor_stats.npz")
+    init = np.zeros((4, 13)); init[:, 6] = 1
+    o = qo.BatchQuadOracle(4, 0.01, 10 ** 6, training=False, T=1, integrator="rk4")
+    o.reset(init)
+    s = qo.SensorOracle(4, 0.01)
+    ids, ep = np.arange(4), np.zeros(4, dtype=np.int64)
+    s.reset(0, ids, ep, o.state)
+    obs = []
+    for t in range(int(g["steps"])):
+        o.step(np.zeros((4, 4)))
+        z = qo.sensor_normals(0, ids, ep, o.i)
+        obs.append(s.step(z, o.state, o.accelerometer_read, o.mat_rot, o.f_in / qo.M))
+    obs = np.array(obs)                                   # (steps, 4, 14)
+    qv_std = obs[:, :, 11:14].std(axis=0).mean()
+    dv_std = np.diff(obs[:, :, [1, 3, 5]], axis=0).std(axis=0).mean()
+    assert abs(qv_std / g["qv_std"].mean() - 1) < 0.06, (qv_std, g["qv_std"].mean())
+    assert abs(dv_std / g["dv_std"].mean() - 1) < 0.06, (dv_std, g["dv_std"].mean())
+    # dead-reckoning drift after 15 s is a random walk of the same scale (well inside 4x of the reference's spread)
+    ref_scale = np.abs(g["pos_end"]).mean()
+    assert 0.2 * ref_scale < np.abs(obs[-1][:, [0, 2, 4]]).mean() < 5 * ref_scale
