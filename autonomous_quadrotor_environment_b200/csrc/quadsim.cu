@@ -364,8 +364,8 @@ __device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& 
 // Sensor sub-pass for one env (QS_FLAG_SENSOR_NOISE).  mode 0: one step of the sensor model; mode 1: sensor.reset
 // from the true state (end of an episode's warm-up) and pass the true observation through; mode 2: pass-through only.
 template <typename R>
-__device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
-                                           const Ctrl<R> c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
+__device__ __forceinline__ void sensor_update_inl(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R>& e,
+                                                  const Ctrl<R>& c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
     R obs[14];
     if (mode == 0) {
         R s[kSensorStateDim], z[32], dy[13], qn[4], rot[9];
@@ -394,6 +394,13 @@ __device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<
     }
 #pragma unroll
     for (int k = 0; k < 14; ++k) v.sensed_obs[k * v.ld + n] = obs[k];
+}
+
+// out-of-line variant for cold paths (explicit / strict resets): arguments by value, callers' structs stay in registers
+template <typename R>
+__device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
+                                           const Ctrl<R> c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
+    sensor_update_inl(p, v, n, e, c, vq0, vq1, vq2, vq3, mode);
 }
 
 // quad.reset (:408-454) for one env held in registers: (optionally) sample the initial state with Philox,
@@ -528,7 +535,7 @@ __device__ __forceinline__ void issue_tile(const SimView<R>& v, const R* action,
 }
 
 // quad.step for one env held in registers + all of its stores (shared by both loader variants).
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io, int64_t n,
                                             Env<R>& e, R a[4], LocalStats& ls, bool& any_end, int* s_queue, int* s_qn) {
     bool warm = false;
@@ -540,8 +547,8 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
     if (warm) o.reward = R(0); else e.ep_return += o.reward;
     if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
     if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
-    if (p.flags & F_SENSOR)                 // warm-up steps bypass the sensor; the last one re-initialises it (sensor.reset)
-        sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
+    if (SENSOR)                             // warm-up steps bypass the sensor; the last one re-initialises it (sensor.reset)
+        sensor_update_inl(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
     if ((p.flags & (F_AUTO_RESET | F_ASYNC_RESET)) && o.done) {
         const int slot = atomicAdd(s_qn, 1);
         if (slot < kResetQueueCap) {
@@ -612,7 +619,7 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
 }
 
 // Loader A — direct: every thread issues its 27 coalesced LDGs up front (one 128-byte line per warp request).
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 __global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                    const __grid_constant__ StepIO<R> io) {
@@ -630,7 +637,7 @@ step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant
         R a[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] = io.action[k * v.N + n];
-        process_env<R, INTEG, DIRECT>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
+        process_env<R, INTEG, DIRECT, SENSOR>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
     }
     step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
@@ -642,7 +649,7 @@ step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant
 //            lanes re-sample an episode is ~30 % slower that iteration) and only the issuing thread ever waits.
 constexpr int kStages = QS_STAGES;
 
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 __global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                 const __grid_constant__ StepIO<R> io) {
@@ -708,7 +715,7 @@ step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ 
         }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(&s_empty[s]);     // this warp's slice of stage s is in registers
-        if (active) process_env<R, INTEG, DIRECT>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
+        if (active) process_env<R, INTEG, DIRECT, SENSOR>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
     }
     step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
@@ -861,21 +868,27 @@ template <typename R> static const DevParams<R>& params_of(const qs_sim* s);
 template <> const DevParams<float>& params_of<float>(const qs_sim* s) { return s->pf; }
 template <> const DevParams<double>& params_of<double>(const qs_sim* s) { return s->pd; }
 
-template <typename R, int INTEG, bool DIRECT>
-static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
-                        cudaStream_t st) {
-    StepIO<R> io{(const R*)action, (R*)obs, (R*)reward, done, solved};
+template <typename R, int INTEG, bool DIRECT, bool SENSOR>
+static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
     if (step_loader() == 1) {
         constexpr size_t smem = kStages * sizeof(Stage<R>);
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(step_kernel_tma<R, INTEG, DIRECT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(step_kernel_tma<R, INTEG, DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             attr_set = true;
         }
-        step_kernel_tma<R, INTEG, DIRECT><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
+        step_kernel_tma<R, INTEG, DIRECT, SENSOR><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
     } else {
-        step_kernel_direct<R, INTEG, DIRECT><<<grid_step(s), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+        step_kernel_direct<R, INTEG, DIRECT, SENSOR><<<grid_step(s), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
     }
+}
+
+template <typename R, int INTEG, bool DIRECT>
+static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved,
+                        cudaStream_t st) {
+    StepIO<R> io{(const R*)action, (R*)obs, (R*)reward, done, solved};
+    if (s->cfg.flags & QS_FLAG_SENSOR_NOISE) launch_step_v<R, INTEG, DIRECT, true>(s, io, st);
+    else launch_step_v<R, INTEG, DIRECT, false>(s, io, st);
 }
 
 template <typename R, int INTEG, bool DIRECT>

@@ -62,6 +62,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]
     if "prof" in which:                                              # short run for ncu
         case_step(async_reset=True, T=5, iters=20)
+    if "sensor" in which:
+        case_step(async_reset=True, T=5)
+        case_step(async_reset=True, T=5, sensor_noise=True)
+        case_step(n=10 ** 9, act_scale=0.05, sensor_noise=True)
     if "step" in which or "all" in which:
         case_step(n=10 ** 9, act_scale=0.05)                         # pure step, nobody finishes
         case_step(async_reset=True, T=5)
