@@ -13,6 +13,17 @@ from autonomous_quadrotor_environment_b200 import BatchedQuad, _lib as L
 DEV = torch.device("cuda", 0)
 
 
+def emit(d):
+    """one compact line per case (full JSON with KBENCH_JSON=1)"""
+    if os.environ.get("KBENCH_JSON"):
+        print(json.dumps(d), flush=True)
+        return
+    tag = "%s N=%d %s/%s S=%d T=%d%s%s%s%s" % (d["case"], d["N"], d["precision"], d["integrator"], d["substeps"], d["T"],
+                                              " strict-reset" if d.get("auto_reset") else "", " async-reset" if d.get("async_reset") else "",
+                                              " sensor" if d.get("sensor_noise") else "", " K=%d" % d["K"] if "K" in d else "")
+    print("%-62s %8.2f us/step  %.3e env-steps/s" % (tag, d["ms"] * 1e3 / d.get("K", 1), d["steps_per_s"]), flush=True)
+
+
 def time_ms(fn, iters, warm=20):
     for _ in range(warm):
         fn()
@@ -43,8 +54,8 @@ def case_step(N=1 << 20, iters=300, **kw):
 
     ms = time_ms(fn, iters, warm=60)
     s = env.stats()
-    print(json.dumps({"case": "step", "N": N, **cfg, "ms": ms, "steps_per_s": N / ms * 1e3,
-                      "mean_len": s["mean_length"], "episodes_per_step": s["n_episodes"] / max(1, s["n_steps"] / N) / N}), flush=True)
+    emit({"case": "step", "N": N, **cfg, "ms": ms, "steps_per_s": N / ms * 1e3,
+          "mean_len": s["mean_length"], "episodes_per_step": s["n_episodes"] / max(1, s["n_steps"] / N) / N})
 
 
 def case_rollout(N=1 << 20, K=32, iters=10, **kw):
@@ -55,7 +66,7 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
                       async_reset=cfg["async_reset"], seed=0, device=DEV)
     env.reset()
     ms = time_ms(lambda: env.rollout(K), iters, warm=3)
-    print(json.dumps({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3}), flush=True)
+    emit({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
 
 
 if __name__ == "__main__":
