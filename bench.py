@@ -250,12 +250,17 @@ def main():
     else:
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     kernel_ms = ms / args.steps                          # one launch of step_kernel per step, back to back on one stream
-    achieved_gbs = ALGO_BYTES_PER_ENV_STEP * N / (kernel_ms * 1e-3) / 1e9
+    sensor = int(bool(args.sensor_noise))
+    kernel_name = "step_kernel_tma<float,RK4,direct,sensor=%d>" % sensor
+    # algorithmic bytes per env-step: 181 B; the sensor model adds its 17-float state in + out and the
+    # 14-float sensed observation out
+    algo_bytes = ALGO_BYTES_PER_ENV_STEP + (192 if sensor else 0)
+    achieved_gbs = algo_bytes * N / (kernel_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tp):
+    if os.path.isfile(tp) and N == (1 << 20):
         try:
-            traffic = json.load(open(tp)).get("step_kernel_f32_rk4_direct_bytes_per_launch")
+            traffic = json.load(open(tp)).get(kernel_name)
         except Exception:
             traffic = None
     probe_ms = C.c_float(0)
@@ -281,7 +286,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": "step_kernel<float,RK4,direct>", "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                         "kernel": kernel_name, "algorithmic_bytes_per_env_step": algo_bytes,
                          "kernel_ms": kernel_ms},
             "fp32": {"achieved_tflops": flops, "peak_tflops_probe": fp32_peak, "frac": flops / fp32_peak,
                      "flops_per_env_step": FLOPS_PER_ENV_STEP(args.substeps),
