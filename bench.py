@@ -54,8 +54,10 @@ def cpu_reference_run(n_envs, steps, warmup, T, threads=0):
     import numpy as np
     from oracle.c_oracle import COracle
     from oracle import quad_oracle as qo
+    if threads == 0:                                   # all host cores (torchrun pins OMP_NUM_THREADS=1: ask explicitly)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     env = COracle(n_envs, 0.01, 10 ** 9, training=False, direct_control=1, T=T, integrator="rk45", threads=threads)
-    cores = env.lib.qo_max_threads() if threads == 0 else threads
+    cores = threads
     init, _ = qo.sample_reset_state(0, np.arange(n_envs), 0)
     env.reset(init)
     rng = np.random.default_rng(0)
