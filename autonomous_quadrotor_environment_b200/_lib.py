@@ -33,9 +33,9 @@ QS_SENSOR_STATE_DIM = 20
 # every symbol include/quadsim.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
-    "qs_rollout", "qs_step_host", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
+    "qs_rollout", "qs_policy_rollout", "qs_step_host", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
-    "qs_last_error", "qs_version", "qs_fp32_peak_probe",
+    "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest",
 ]
 
 
@@ -81,6 +81,17 @@ class qs_rollout_args(C.Structure):
                 ("done_out", C.c_void_p)]
 
 
+class qs_actor(C.Structure):
+    _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
+                ("b3", C.c_void_p), ("hidden", C.c_int32), ("in_dim", C.c_int32), ("action_std", C.c_float),
+                ("reserved", C.c_int32)]
+
+
+class qs_policy_rollout_args(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32), ("obs_out", C.c_void_p), ("action_out", C.c_void_p),
+                ("logprob_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("hist", C.c_void_p)]
+
+
 class QuadSimError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libquadsim error %d: %s" % (code, msg))
@@ -111,6 +122,7 @@ def load_library():
         "qs_reset": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "qs_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
         "qs_rollout": (C.c_int, [vp, P(qs_rollout_args), vp]),
+        "qs_policy_rollout": (C.c_int, [vp, P(qs_actor), P(qs_policy_rollout_args), vp]),
         "qs_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "qs_field_info": (C.c_int, [vp, C.c_int, P(qs_field_desc)]),
         "qs_get": (C.c_int, [vp, C.c_int, vp, vp]),
@@ -127,6 +139,7 @@ def load_library():
         "qs_last_error": (C.c_char_p, []),
         "qs_version": (C.c_int, []),
         "qs_fp32_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_float), vp]),
+        "qs_umma_selftest": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

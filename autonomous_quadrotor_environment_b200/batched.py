@@ -209,6 +209,62 @@ class BatchedQuad:
         L.check(self.lib.qs_rollout(self._h, C.byref(a), self._stream()))
         return out
 
+    # ------------------------------------------------------------------ fused actor rollout (config 5)
+    def load_actor(self, source, action_std: float = 0.1):
+        """Prepare the reference's actor (environment/controller/model.py:27-34) for policy_rollout.
+        source: path to a solved/*.pth state dict, a state dict, or a dict/npz with keys actor_{0,2,4}_{weight,bias}."""
+        if isinstance(source, (str, bytes)):
+            source = torch.load(source, map_location="cpu")
+
+        def get(i, kind):
+            for key in ("actor.%d.%s" % (i, kind), "actor_%d_%s" % (i, kind), "%d.%s" % (i, kind)):
+                if key in source:
+                    return torch.as_tensor(source[key]).to(device=self.device, dtype=torch.float32).contiguous()
+            raise KeyError("actor layer %d %s not found" % (i, kind))
+
+        w = {"w1": get(0, "weight"), "b1": get(0, "bias"), "w2": get(2, "weight"), "b2": get(2, "bias"),
+             "w3": get(4, "weight"), "b3": get(4, "bias")}
+        if w["w1"].shape != (128, 75) or w["w2"].shape != (128, 128) or w["w3"].shape != (4, 128):
+            raise ValueError("only the 75-128-128-4 actor is supported by the fused kernel")
+        a = L.qs_actor()
+        for k, t in w.items():
+            setattr(a, k, t.data_ptr())
+        a.hidden, a.in_dim, a.action_std = 128, 75, float(action_std)
+        self._actor = (a, w)                                    # keep the tensors alive
+        return self
+
+    @property
+    def history(self) -> torch.Tensor:
+        """(N,75) view of dl_in_gen.deep_learning_input per env (oldest entry first); persists across policy_rollout calls."""
+        if getattr(self, "_hist", None) is None:
+            self._hist = torch.zeros(75, self.N, dtype=torch.float32, device=self.device)
+        return self._hist.t()
+
+    def policy_rollout(self, horizon: int, record_obs=False, record_actions=True, record_logprob=True,
+                       record_reward=True, record_done=True):
+        """K fused steps of  history -> actor MLP (tcgen05) -> Normal sample -> quad.step -> history push  in ONE launch
+        (the loop of environment/controller/ppo.py:238-257).  Returns the recorded (K,C,N) buffers."""
+        if getattr(self, "_actor", None) is None:
+            raise RuntimeError("call load_actor() first")
+        _ = self.history
+        a = L.qs_policy_rollout_args()
+        a.horizon = int(horizon)
+        a.hist = self._hist.data_ptr()
+        out = {}
+        f32 = torch.float32
+        if record_obs:
+            out["obs"] = torch.empty(horizon, 14, self.N, dtype=f32, device=self.device); a.obs_out = out["obs"].data_ptr()
+        if record_actions:
+            out["actions"] = torch.empty(horizon, 4, self.N, dtype=f32, device=self.device); a.action_out = out["actions"].data_ptr()
+        if record_logprob:
+            out["logprob"] = torch.empty(horizon, 4, self.N, dtype=f32, device=self.device); a.logprob_out = out["logprob"].data_ptr()
+        if record_reward:
+            out["reward"] = torch.empty(horizon, self.N, dtype=f32, device=self.device); a.reward_out = out["reward"].data_ptr()
+        if record_done:
+            out["done"] = torch.empty(horizon, self.N, dtype=torch.uint8, device=self.device); a.done_out = out["done"].data_ptr()
+        L.check(self.lib.qs_policy_rollout(self._h, C.byref(self._actor[0]), C.byref(a), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ attributes of the reference `quad`
     @property
     def obs(self):            # quat_state :486

@@ -1,0 +1,357 @@
+// actor_rollout.cuh — the reference's actor MLP (environment/controller/model.py:27-34: Linear(75,H)-Tanh-Linear(H,H)-
+// Tanh-Linear(H,4)-Tanh) and its observation-history input (environment/controller/dl_auxiliary.py:15-32) fused into
+// the K-step rollout: per CTA 128 envs = one UMMA M=128 tile; the three layers are tcgen05.mma (BF16 operands staged
+// in shared memory in the canonical K-major layout, FP32 accumulators in TMEM), the epilogues read TMEM with
+// tcgen05.ld, apply bias + tanh and write the next layer's A operand back to shared memory; the dynamics run on the
+// same 128 threads (thread = env = TMEM lane) with the env state in registers.
+// Included at the end of quadsim.cu (single translation unit).
+#pragma once
+#include "umma.cuh"
+
+// ---------------------------------------------------------------------------------------------------------------
+// self-test: D[128][N] = A[128][K] * B[N][K]^T through the same operand layout / descriptors / TMEM path
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_umma_selftest(int N, int K, const float* A, const float* B, float* D) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 128 * K * 2;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int k = 0; k < K; k += 8) {
+        uint4 v;
+        v.x = pack_bf16x2(A[tid * K + k + 0], A[tid * K + k + 1]);
+        v.y = pack_bf16x2(A[tid * K + k + 2], A[tid * K + k + 3]);
+        v.z = pack_bf16x2(A[tid * K + k + 4], A[tid * K + k + 5]);
+        v.w = pack_bf16x2(A[tid * K + k + 6], A[tid * K + k + 7]);
+        *reinterpret_cast<uint4*>(sA + umma_canon_offset(tid, k, K)) = v;
+        if (tid < N) {
+            v.x = pack_bf16x2(B[tid * K + k + 0], B[tid * K + k + 1]);
+            v.y = pack_bf16x2(B[tid * K + k + 2], B[tid * K + k + 3]);
+            v.z = pack_bf16x2(B[tid * K + k + 4], B[tid * K + k + 5]);
+            v.w = pack_bf16x2(B[tid * K + k + 6], B[tid * K + k + 7]);
+            *reinterpret_cast<uint4*>(sB + umma_canon_offset(tid, k, K)) = v;
+        }
+    }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 128);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    if (tid == 0) {
+        umma_gemm_k(tmem_base, smem_u32(sA), K, 0, smem_u32(sB), K, 0, K, N, false);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        for (int i = 0; i < 16; ++i) D[tid * N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+extern "C" int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, void* stream) {
+    if (N < 16 || N > 128 || (N % 16) || K < 16 || K > 128 || (K % 16) || !A || !B || !D)
+        return fail(QS_EINVAL, "qs_umma_selftest: need 16 <= N,K <= 128, multiples of 16");
+    const size_t smem = (size_t)(128 + N) * K * 2;
+    QS_CUDA(cudaFuncSetAttribute(k_umma_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fused policy rollout (BASELINE.json configs[4]: 1M envs x 128-step horizon with the actor MLP on tensor cores)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPM = 128;        // envs per CTA = UMMA M
+constexpr int kPH = 128;        // hidden width of the shipped actors (solved/nn_*_128_*.pth)
+constexpr int kPSlots = 5;      // history length T of dl_in_gen (ppo.py:306, T = 5)
+constexpr int kPSlotK = 16;     // 15 floats per history entry [action(4), v(3), q(4), dq(4)] padded to one UMMA K block
+constexpr int kPKin = kPSlots * kPSlotK;   // 80
+
+struct ActorView {
+    const float *w1, *b1, *w2, *b2, *w3, *b3;   // PyTorch Linear layout [out][in]: (128,75) (128,128) (4,128)
+    float action_std;                            // sigma of the fixed-std Normal policy (model.py:62); <= 0: deterministic
+};
+struct PolicyIO {
+    int32_t horizon;
+    float* obs_out;       // [K][14][N] or NULL
+    float* action_out;    // [K][4][N]  or NULL  (the sampled, unclipped action PPO stores, model.py:64-68)
+    float* logprob_out;   // [K][4][N]  or NULL  (per-dimension log-prob, model.py:66)
+    float* reward_out;    // [K][N]     or NULL
+    uint8_t* done_out;    // [K][N]     or NULL  (bit0 done, bit1 warm-up step)
+    float* hist;          // [75][N] in/out: dl_in_gen.deep_learning_input per env (oldest entry first), or NULL
+};
+
+struct PolicySmem {
+    static constexpr int kX = 0;
+    static constexpr int kHd = kX + kPM * kPKin * 2;
+    static constexpr int kW1 = kHd + kPM * kPH * 2;
+    static constexpr int kW2 = kW1 + kPH * kPKin * 2;
+    static constexpr int kW3 = kW2 + kPH * kPH * 2;
+    static constexpr int kB = kW3 + 16 * kPH * 2;
+    static constexpr int kBytes = kB + (kPH + kPH + 16) * 4;
+};
+
+// bias + tanh epilogue of one hidden layer: TMEM accumulators (thread = row) -> BF16 A operand of the next layer
+__device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, const float* bias, unsigned char* sH, int row) {
+#pragma unroll 1
+    for (int c = 0; c < kPH; c += 32) {
+        float acc[32];
+        tmem_ld_32x32b_x32(lane_addr + (uint32_t)c, acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c + 8 * j);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 8 * j + 4);
+            uint4 o;
+            o.x = pack_bf16x2(tanh_fast(acc[8 * j + 0] + b0.x), tanh_fast(acc[8 * j + 1] + b0.y));
+            o.y = pack_bf16x2(tanh_fast(acc[8 * j + 2] + b0.z), tanh_fast(acc[8 * j + 3] + b0.w));
+            o.z = pack_bf16x2(tanh_fast(acc[8 * j + 4] + b1.x), tanh_fast(acc[8 * j + 5] + b1.y));
+            o.w = pack_bf16x2(tanh_fast(acc[8 * j + 6] + b1.z), tanh_fast(acc[8 * j + 7] + b1.w));
+            *reinterpret_cast<uint4*>(sH + umma_canon_offset(row, c + 8 * j, kPH)) = o;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kPM, 2)
+policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
+                      const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sX = smem + PolicySmem::kX;
+    unsigned char* sH = smem + PolicySmem::kHd;
+    unsigned char* sW1 = smem + PolicySmem::kW1;
+    unsigned char* sW2 = smem + PolicySmem::kW2;
+    unsigned char* sW3 = smem + PolicySmem::kW3;
+    float* sB = reinterpret_cast<float*>(smem + PolicySmem::kB);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+
+    // ---- one-time: weights fp32 (global) -> bf16 canonical K-major operand tiles (shared)
+    for (int idx = tid; idx < kPH * kPKin; idx += kPM) {             // W1: input j = 15*slot + e  ->  K index 16*slot + e
+        const int n = idx / kPKin, kk = idx % kPKin, a = kk / kPSlotK, e = kk % kPSlotK;
+        const float w = (e < 15) ? act.w1[n * 75 + a * 15 + e] : 0.f;
+        *reinterpret_cast<__nv_bfloat16*>(sW1 + umma_canon_offset(n, kk, kPKin)) = __float2bfloat16(w);
+    }
+    for (int idx = tid; idx < kPH * kPH; idx += kPM) {
+        const int n = idx / kPH, kk = idx % kPH;
+        *reinterpret_cast<__nv_bfloat16*>(sW2 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(act.w2[n * kPH + kk]);
+    }
+    for (int idx = tid; idx < 16 * kPH; idx += kPM) {
+        const int n = idx / kPH, kk = idx % kPH;
+        *reinterpret_cast<__nv_bfloat16*>(sW3 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(n < 4 ? act.w3[n * kPH + kk] : 0.f);
+    }
+    sB[tid] = act.b1[tid];
+    sB[kPH + tid] = act.b2[tid];
+    if (tid < 16) sB[2 * kPH + tid] = tid < 4 ? act.b3[tid] : 0.f;
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase = 0;
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const float sigma = act.action_std;
+    const float log_norm = (sigma > 0.f) ? (-__logf(sigma) - 0.918938533f) : 0.f;
+
+    const int64_t n_tiles = (v.N + kPM - 1) / kPM;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t n = tile * kPM + tid;
+        const bool active = n < v.N;
+        Env<float> e;
+        if (active) {
+            load_env(v, n, e);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 13; ++k) e.y[k] = 0.f;
+            e.y[6] = 1.f;
+            e.prev_ang[0] = e.prev_ang[1] = e.prev_ang[2] = 0.f;
+            e.prev_shaping = e.abs_sum = e.ep_return = 0.f;
+            e.i = 0; e.flags = 0; e.episode = 0;
+        }
+        // history -> A operand: physical slot s holds age s at tile start (head = 0 is the OLDEST entry)
+#pragma unroll
+        for (int s = 0; s < kPSlots; ++s) {
+            float h[16];
+#pragma unroll
+            for (int q = 0; q < 15; ++q) h[q] = (active && io.hist) ? io.hist[(int64_t)(s * 15 + q) * v.N + n] : 0.f;
+            h[15] = 0.f;
+            uint4 lo, hi;
+            lo.x = pack_bf16x2(h[0], h[1]); lo.y = pack_bf16x2(h[2], h[3]); lo.z = pack_bf16x2(h[4], h[5]); lo.w = pack_bf16x2(h[6], h[7]);
+            hi.x = pack_bf16x2(h[8], h[9]); hi.y = pack_bf16x2(h[10], h[11]); hi.z = pack_bf16x2(h[12], h[13]); hi.w = pack_bf16x2(h[14], h[15]);
+            *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, s * kPSlotK, kPKin)) = lo;
+            *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, s * kPSlotK + 8, kPKin)) = hi;
+        }
+        int head = 0;
+        StepOut<float> o;
+        float reward = 0.f;
+        bool done = false, solved = false, warm_last = false;
+        for (int t = 0; t < io.horizon; ++t) {
+            // ---------------- layer 1: [128 x 80] x W1^T, one K=16 MMA per history slot, oldest first
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int a = 0; a < kPSlots; ++a) {
+                    int s = head + a; s = s >= kPSlots ? s - kPSlots : s;
+                    umma_gemm_k(tmem_base, smem_u32(sX), kPKin, s * kPSlotK, smem_u32(sW1), kPKin, a * kPSlotK, kPSlotK, kPH, a > 0);
+                }
+                umma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+            actor_hidden_epilogue(lane_addr, sB, sH, tid);
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+            // ---------------- layer 2: [128 x 128] x W2^T
+            if (tid == 0) {
+                tc_fence_after();
+                umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW2), kPH, 0, kPH, kPH, false);
+                umma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+            actor_hidden_epilogue(lane_addr, sB + kPH, sH, tid);      // MMA 2 has finished reading sH: reuse it
+            tc_fence_before();
+            fence_proxy_async_smem();
+            __syncthreads();
+            // ---------------- layer 3: [128 x 128] x W3^T (N padded 4 -> 16)
+            if (tid == 0) {
+                tc_fence_after();
+                umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW3), kPH, 0, kPH, 16, false);
+                umma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+            float mean[4];
+            {
+                float acc[16];
+                tmem_ld_32x32b_x16(lane_addr, acc);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(acc[k] + sB[2 * kPH + k]);
+            }
+            tc_fence_before();
+            // ---------------- a ~ Normal(mean, sigma)  (model.py:60-66), per-dimension log-prob
+            float a[4], logp[4];
+            if (sigma > 0.f) {
+                const uint4 u = philox_block(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, RNG_POLICY);
+                float z[4];
+                box_muller(u32_to_unit<float>(u.x), u32_to_unit<float>(u.y), &z[0], &z[1]);
+                box_muller(u32_to_unit<float>(u.z), u32_to_unit<float>(u.w), &z[2], &z[3]);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a[k] = fmaf(sigma, z[k], mean[k]); logp[k] = fmaf(-0.5f * z[k], z[k], log_norm); }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { a[k] = mean[k]; logp[k] = 0.f; }
+            }
+            // ---------------- quad.step (same code path as rollout_kernel)
+            bool warm = false;
+            if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
+            const bool was_done = (e.flags & EF_DONE) != 0;
+            step_core<float, 0, true>(p, e, a, o, nullptr);
+            if (warm) o.reward = 0.f; else e.ep_return += o.reward;
+            reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
+            if (active && done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
+            if ((p.flags & F_ASYNC_RESET) && done) async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+            if (active) {
+                if (io.obs_out) {
+                    float* ot = io.obs_out + (int64_t)t * 14 * v.N;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) ot[k * v.N + n] = e.y[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ot[(10 + k) * v.N + n] = o.vq[k];
+                }
+                if (io.action_out) {
+                    float* at = io.action_out + (int64_t)t * 4 * v.N;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) at[k * v.N + n] = a[k];
+                }
+                if (io.logprob_out) {
+                    float* lt = io.logprob_out + (int64_t)t * 4 * v.N;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) lt[k * v.N + n] = logp[k];
+                }
+                if (io.reward_out) io.reward_out[(int64_t)t * v.N + n] = reward;
+                if (io.done_out) io.done_out[(int64_t)t * v.N + n] = (uint8_t)((done ? 1 : 0) | (warm ? 2 : 0));
+            }
+            // ---------------- dl_in_gen.dl_input (dl_auxiliary.py:25-32): the new entry replaces the oldest slot
+            {
+                uint4 lo, hi;
+                lo.x = pack_bf16x2(a[0], a[1]); lo.y = pack_bf16x2(a[2], a[3]);
+                lo.z = pack_bf16x2(e.y[1], e.y[3]); lo.w = pack_bf16x2(e.y[5], e.y[6]);
+                hi.x = pack_bf16x2(e.y[7], e.y[8]); hi.y = pack_bf16x2(e.y[9], o.vq[0]);
+                hi.z = pack_bf16x2(o.vq[1], o.vq[2]); hi.w = pack_bf16x2(o.vq[3], 0.f);
+                *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK, kPKin)) = lo;
+                *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK + 8, kPKin)) = hi;
+                head = head + 1 == kPSlots ? 0 : head + 1;
+            }
+        }
+        if (active) {
+            store_env(v, n, e, o.vq);
+            v.reward[n] = reward;
+            v.done[n] = (uint8_t)((done ? 1 : 0) | (warm_last ? 2 : 0));
+            v.solved[n] = solved;
+            if (io.hist) {                                           // back to oldest-first order
+#pragma unroll
+                for (int a = 0; a < kPSlots; ++a) {
+                    int s = head + a; s = s >= kPSlots ? s - kPSlots : s;
+                    const uint4 lo = *reinterpret_cast<const uint4*>(sX + umma_canon_offset(tid, s * kPSlotK, kPKin));
+                    const uint4 hi = *reinterpret_cast<const uint4*>(sX + umma_canon_offset(tid, s * kPSlotK + 8, kPKin));
+                    const uint32_t w[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                    for (int q = 0; q < 15; ++q) {
+                        const uint32_t bits = (q & 1) ? (w[q >> 1] & 0xFFFF0000u) : (w[q >> 1] << 16);
+                        io.hist[(int64_t)(a * 15 + q) * v.N + n] = __uint_as_float(bits);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                             // sX is re-initialised by the next tile
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_policy_rollout_args* args, void* stream) {
+    if (!h || !actor || !args) return fail(QS_EINVAL, "qs_policy_rollout: NULL argument");
+    if (args->horizon < 1) return fail(QS_EINVAL, "qs_policy_rollout: horizon must be >= 1");
+    if (actor->hidden != kPH || actor->in_dim != 75)
+        return fail(QS_EINVAL, "qs_policy_rollout: only the 75-128-128-4 actor (history T=5) is supported");
+    if (!actor->w1 || !actor->b1 || !actor->w2 || !actor->b2 || !actor->w3 || !actor->b3)
+        return fail(QS_EINVAL, "qs_policy_rollout: NULL weight pointer");
+    const uint32_t f = h->cfg.flags;
+    if (h->cfg.precision != QS_F32 || h->cfg.integrator != QS_RK4 || !(f & QS_FLAG_DIRECT_CONTROL))
+        return fail(QS_ESTATE, "qs_policy_rollout: needs an FP32 / RK4 / direct-control handle");
+    if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET))
+        return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / strict AUTO_RESET (use ASYNC_RESET)");
+    ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std};
+    PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
+                (float*)args->reward_out, args->done_out, (float*)args->hist};
+    static bool attr_set = false;
+    if (!attr_set) {
+        QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PolicySmem::kBytes));
+        attr_set = true;
+    }
+    const int64_t tiles = (h->N + kPM - 1) / kPM;
+    int64_t grid = (int64_t)h->sm_count * 2;
+    if (grid > tiles) grid = tiles;
+    policy_rollout_kernel<<<(int)grid, kPM, PolicySmem::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}

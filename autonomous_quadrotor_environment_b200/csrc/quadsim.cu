@@ -1264,3 +1264,5 @@ extern "C" int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }
+
+#include "actor_rollout.cuh"

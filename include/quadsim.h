@@ -171,6 +171,33 @@ typedef struct qs_rollout_args {
     uint8_t* done_out;           /* [K][N] or NULL                                                 */
 } qs_rollout_args;
 
+/* Actor of the reference's PPO controller (environment/controller/model.py:27-34): Linear(in_dim,H)-Tanh-Linear(H,H)-
+ * Tanh-Linear(H,4)-Tanh with a fixed-sigma diagonal Normal (model.py:60-66).  FP32 device pointers, PyTorch Linear
+ * layout [out][in] (the keys actor.{0,2,4}.{weight,bias} of the shipped solved/*.pth files). */
+typedef struct qs_actor {
+    const float* w1; const float* b1;   /* [hidden][in_dim], [hidden] */
+    const float* w2; const float* b2;   /* [hidden][hidden], [hidden] */
+    const float* w3; const float* b3;   /* [4][hidden], [4]           */
+    int32_t hidden;                     /* 128 */
+    int32_t in_dim;                     /* 75 = 15 floats x history T=5 (environment/controller/dl_auxiliary.py:15-23) */
+    float   action_std;                 /* sigma; <= 0 -> deterministic (evaluation, ppo_quad_eval.py:53) */
+    int32_t reserved;
+} qs_actor;
+
+/* Fused PPO rollout (BASELINE.json configs[4]): per step  history -> actor MLP (tcgen05 tensor cores, BF16 operands,
+ * FP32 accumulate) -> a ~ N(mean, sigma) (Philox) -> quad.step -> history push, K steps per launch with the env state in
+ * registers.  Replaces the per-step loop of environment/controller/ppo.py:238-257.  Output buffers are [K][C][N]. */
+typedef struct qs_policy_rollout_args {
+    int32_t horizon;
+    int32_t reserved;
+    void* obs_out;        /* [K][14][N] float or NULL */
+    void* action_out;     /* [K][4][N]  float or NULL : sampled (unclipped) actions                     */
+    void* logprob_out;    /* [K][4][N]  float or NULL : per-dimension log-probabilities (model.py:66)   */
+    void* reward_out;     /* [K][N]     float or NULL */
+    uint8_t* done_out;    /* [K][N]     or NULL : bit0 done, bit1 warm-up step                          */
+    void* hist;           /* [75][N] float in/out: dl_in_gen.deep_learning_input per env, oldest first; NULL = zeros */
+} qs_policy_rollout_args;
+
 /* ---- lifecycle ----------------------------------------------------------------------------- */
 /* Fill *cfg with the reference defaults (constants quadrotor_env.py:30-80; quad() keyword defaults :112). */
 int qs_default_config(qs_config* cfg);
@@ -193,6 +220,8 @@ int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_
 int qs_step(qs_handle h, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved, void* stream);
 /* K fused env steps (see qs_rollout_args). */
 int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream);
+/* K fused policy steps (see qs_policy_rollout_args); FP32 / RK4 / direct-control handles only. */
+int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_policy_rollout_args* args, void* stream);
 /* Same contract as qs_step but with HOST buffers (pinned or pageable): H2D of the actions, the step
  * kernel and D2H of obs/reward/done are enqueued on `stream` and the call returns after they finish. */
 int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);
@@ -224,6 +253,10 @@ int qs_f2w(int precision, const qs_params* p, int64_t n, int clipped, const void
 /* Philox4x32-10 raw blocks: out[4][n] u32 for counter (env_id0+i, episode, block, stream_id). */
 int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, uint32_t block, uint32_t stream_id,
                   uint32_t* out /*[4][n]*/, void* stream);
+
+/* tcgen05 self-test: D[128][N] = A[128][K] * B[N][K]^T with BF16 operands / FP32 accumulation through the same
+ * shared-memory operand layout, descriptors and TMEM read-back the fused actor rollout uses (row-major fp32 in/out). */
+int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* qs_last_error(void);

@@ -427,6 +427,79 @@ def test_step_host_entry_point():
 
 
 # ----------------------------------------------------------------------------------------------------
+# A14: actor MLP on tcgen05 tensor cores fused into the rollout (BASELINE.json configs[4])
+# ----------------------------------------------------------------------------------------------------
+def test_umma_selftest_gemm():
+    lib = L.load_library()
+    torch.manual_seed(0)
+    for N, K in [(16, 16), (128, 80), (128, 128), (16, 128)]:
+        A = torch.randn(128, K, device=DEV); B = torch.randn(N, K, device=DEV); D = torch.zeros(128, N, device=DEV)
+        L.check(lib.qs_umma_selftest(N, K, A.data_ptr(), B.data_ptr(), D.data_ptr(), None))
+        ref = A.bfloat16().float() @ B.bfloat16().float().t()
+        assert (D - ref).abs().max().item() < 1e-3
+
+
+def _torch_actor(W, x):
+    h = torch.tanh(x @ W["actor_0_weight"].t() + W["actor_0_bias"])
+    h = torch.tanh(h @ W["actor_2_weight"].t() + W["actor_2_bias"])
+    return torch.tanh(h @ W["actor_4_weight"].t() + W["actor_4_bias"])
+
+
+def test_fused_actor_rollout_deterministic():
+    """sigma = 0: (1) every recorded action equals the FP32 torch actor evaluated on the history rebuilt from the
+    kernel's own recorded (action, obs) stream, up to BF16-operand error; (2) replaying the recorded actions through
+    the plain rollout kernel reproduces the recorded observations bit-for-bit (same dynamics code path)."""
+    g = load_golden("actor_128.npz")
+    W = {k: torch.as_tensor(v, device=DEV) for k, v in g.items() if k.startswith("actor_")}
+    N, K, seed = 1000, 48, 12                                   # N not a multiple of 128: ragged last tile
+    mk = lambda: BatchedQuad(N, 0.01, 300, training=False, direct_control=1, T=5, precision="f32", async_reset=True,
+                             seed=seed, device=DEV)
+    env, ref = mk(), mk()
+    oh, ah = env.reset(); ref.reset()
+    hist = torch.zeros(N, 75, device=DEV)
+    for k in range(5):                                          # dl_in_gen.dl_input over the T warm-up pairs
+        s = torch.cat([ah[k], oh[k][:, 1:6:2], oh[k][:, 6:14]], dim=1)
+        hist = torch.cat([hist[:, 15:], s], dim=1)
+    env.history.copy_(hist)
+    env.load_actor(g, action_std=0.0)
+    rec = env.policy_rollout(K, record_obs=True)
+    worst = 0.0
+    for t in range(K):
+        mean = _torch_actor(W, hist.bfloat16().float())         # the kernel's A operand is the BF16-rounded history
+        worst = max(worst, (rec["actions"][t].t() - mean).abs().max().item())
+        a_t, o_t = rec["actions"][t].t(), rec["obs"][t].t()
+        warm = ((rec["done"][t] >> 1) & 1).bool()
+        a_hist = torch.where(warm[:, None], torch.zeros_like(a_t), a_t)
+        # what the kernel pushed: the action it applied (zero_control on warm-up steps) and the observation it returned
+        hist = torch.cat([hist[:, 15:], torch.cat([a_hist, o_t[:, 1:6:2], o_t[:, 6:14]], dim=1)], dim=1)
+        rec["actions"][t][:, warm] = 0.0
+    assert worst < 0.03, worst                                  # BF16 weights/activations, MUFU tanh
+    assert torch.allclose(env.history, hist.bfloat16().float(), atol=0, rtol=0)
+    replay = ref.rollout(K, actions=rec["actions"].contiguous(), record_obs=True, record_done=True)
+    assert torch.equal(replay["done"], rec["done"])
+    assert torch.equal(replay["obs"], rec["obs"])
+    assert torch.equal(ref.state, env.state)
+
+
+def test_fused_actor_rollout_closed_loop_solves_and_samples():
+    g = load_golden("actor_128.npz")
+    N = 8192
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=3, device=DEV)
+    env.reset()
+    env.load_actor(g, action_std=0.1)
+    rec = None
+    for _ in range(6):
+        rec = env.policy_rollout(128)
+    s = env.stats()
+    # the shipped controller solves ~95 % of the training episodes (training_log/log_128_*.csv); BF16 MLP + noise sigma=0.1
+    assert s["n_episodes"] > N // 2 and s["solved_frac"] > 0.85, s
+    # log-prob of a fixed-sigma Normal: -z^2/2 - log(sigma) - log(sqrt(2 pi)), z ~ N(0,1)
+    lp = rec["logprob"][:, :, :].flatten()
+    z2 = -2 * (lp + np.log(0.1) + 0.5 * np.log(2 * np.pi))
+    assert abs(z2.mean().item() - 1.0) < 0.02 and z2.min().item() > -1e-4
+
+
+# ----------------------------------------------------------------------------------------------------
 # the reference's own shipped log through the drop-in `quad` class
 # ----------------------------------------------------------------------------------------------------
 def test_dropin_quad_reproduces_shipped_lqr_log():
