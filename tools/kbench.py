@@ -69,10 +69,27 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
     emit({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
 
 
+def case_policy(N=1 << 20, K=128, iters=3, sigma=0.1, record=True):
+    import numpy as np
+    g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "actor_128.npz")))
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=0, device=DEV)
+    env.reset()
+    env.load_actor(g, action_std=sigma)
+    kw = dict(record_obs=record, record_actions=record, record_logprob=record, record_reward=record, record_done=record)
+    ms = time_ms(lambda: env.policy_rollout(K, **kw), iters, warm=2)
+    s = env.stats()
+    print("policy_rollout N=%d K=%d sigma=%.2f record=%d   %8.2f us/step  %.3e env-steps/s   (%.1f ms per %d-step rollout; solved %.3f, mean len %.0f)"
+          % (N, K, sigma, record, ms * 1e3 / K, N * K / ms * 1e3, ms, K, s["solved_frac"], s["mean_length"]), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]
     if "prof" in which:                                              # short run for ncu
         case_step(async_reset=True, T=5, iters=20)
+    if "policy" in which:
+        case_policy()
+        case_policy(record=False)
+        case_policy(N=1 << 18)
     if "sensor" in which:
         case_step(async_reset=True, T=5)
         case_step(async_reset=True, T=5, sensor_noise=True)
