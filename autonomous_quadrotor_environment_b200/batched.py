@@ -142,6 +142,11 @@ class BatchedQuad:
             return x.contiguous()
         raise ValueError("expected shape (%d,%d) or (%d,%d), got %s" % (self.N, channels, channels, self.N, tuple(x.shape)))
 
+    def set_step_loader(self, loader: int):
+        """Pick the qs_step implementation (0 plain loads, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline); A/B testing."""
+        L.check(self.lib.qs_set_step_loader(self._h, int(loader)))
+        return self
+
     # ------------------------------------------------------------------ reference API
     def seed(self, seed: int):
         """quad.seed (quadrotor_env.py:189-193): re-keys the Philox streams."""

@@ -85,6 +85,7 @@ struct qs_sim {
     DevParams<double> pd;
     int sm_count;
     uint64_t seed;
+    int step_loader;        // 0 direct LDG, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline (FP32 RK4 default)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -197,9 +198,9 @@ static const RowSpec kRows[] = {
     {QS_FIELD_PREV_SHAPING, 1, 0, 0},
     {QS_FIELD_ABS_SUM, 1, 0, 0},
     {QS_FIELD_EP_RETURN, 1, 0, 0},
-    {QS_FIELD_REWARD, 1, 0, 0},
     {QS_FIELD_I, 1, 4, 0},
     {QS_FIELD_EPISODE, 1, 4, 0},
+    {QS_FIELD_REWARD, 1, 0, 0},          // rows 0..25 of an FP32 handle form one [26][ld] matrix of 4-byte elements (step_warp.cuh)
     {QS_FIELD_FLAGS, 1, 1, 0},
     {QS_FIELD_DONE, 1, 1, 0},
     {QS_FIELD_SOLVED, 1, 1, 0},
@@ -720,6 +721,8 @@ step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ 
     step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
 
+#include "step_warp.cuh"
+
 // quad.reset for the masked envs (det_state given or Philox-sampled).
 template <typename R, int INTEG, bool DIRECT>
 __global__ void __launch_bounds__(kBlock)
@@ -830,10 +833,10 @@ static int grid_for(const qs_sim* s, int64_t n) {
     return (int)blocks;
 }
 
-// QS_STEP_LOADER=0 direct LDG loads, 1 (default) TMA-staged ring
-static int step_loader() {
+// QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 (default) per-warp cp.async pipeline
+static int default_step_loader() {
     static int v = -1;
-    if (v < 0) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : 1; }
+    if (v < 0) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : 2; }
     return v;
 }
 
@@ -868,9 +871,30 @@ template <typename R> static const DevParams<R>& params_of(const qs_sim* s);
 template <> const DevParams<float>& params_of<float>(const qs_sim* s) { return s->pf; }
 template <> const DevParams<double>& params_of<double>(const qs_sim* s) { return s->pd; }
 
+// the per-warp pipeline exists for the production configuration only: FP32, fixed-step RK4, no AUX rows, resets
+// either asynchronous or none (strict lock-step resets run T serial hover steps per env and keep the CTA-wide kernel)
+template <typename R, int INTEG> struct WarpKernelOk { static constexpr bool value = false; };
+template <> struct WarpKernelOk<float, 0> { static constexpr bool value = true; };
+
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
-    if (step_loader() == 1) {
+    if constexpr (WarpKernelOk<R, INTEG>::value) {
+        if (s->step_loader == 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
+            constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * 2 * (kBlock / 32);
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(step_kernel_warp<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = true;
+            }
+            const int64_t chunks = (s->N + 31) / 32;
+            int64_t g = (int64_t)s->sm_count * QS_MIN_CTAS;
+            const int64_t need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
+            if (g > need) g = need;
+            step_kernel_warp<DIRECT, SENSOR><<<(int)(g < 1 ? 1 : g), kBlock, smem, st>>>(s->pf, make_view<float>(s), io);
+            return;
+        }
+    }
+    if (s->step_loader >= 1) {
         constexpr size_t smem = kStages * sizeof(Stage<R>);
         static bool attr_set = false;
         if (!attr_set) {
@@ -945,6 +969,16 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
     cudaDeviceProp prop;
     cudaError_t e1 = cudaGetDeviceProperties(&prop, cfg->device);
     s->sm_count = (e1 == cudaSuccess) ? prop.multiProcessorCount : 148;
+    s->step_loader = default_step_loader();
+    if (s->rs == 4) {       // the per-warp pipeline addresses the 4-byte rows as one matrix: make sure the row table still says so
+        const char* b = (const char*)s->obs17;
+        const size_t rb = (size_t)s->ld * 4;
+        const bool ok = (char*)s->slot[QS_FIELD_ANG].ptr == b + 17 * rb && (char*)s->slot[QS_FIELD_PREV_SHAPING].ptr == b + 20 * rb &&
+                        (char*)s->slot[QS_FIELD_ABS_SUM].ptr == b + 21 * rb && (char*)s->slot[QS_FIELD_EP_RETURN].ptr == b + 22 * rb &&
+                        (char*)s->slot[QS_FIELD_I].ptr == b + 23 * rb && (char*)s->slot[QS_FIELD_EPISODE].ptr == b + 24 * rb &&
+                        (char*)s->slot[QS_FIELD_REWARD].ptr == b + 25 * rb;
+        if (!ok && s->step_loader == 2) s->step_loader = 1;
+    }
     cudaError_t e2 = cudaMemset(s->ws, 0, s->ws_bytes);
     if (e2 == cudaSuccess) {
         // quad.__init__ leaves done=True (:154): flags = EF_DONE, done out = 1, quaternion undefined until reset
@@ -970,6 +1004,13 @@ extern "C" int qs_destroy(qs_handle h) {
 extern "C" int qs_seed(qs_handle h, uint64_t seed) {
     if (!h) return fail(QS_EINVAL, "qs_seed: NULL handle");
     h->seed = seed;
+    return QS_OK;
+}
+
+extern "C" int qs_set_step_loader(qs_handle h, int loader) {
+    if (!h) return fail(QS_EINVAL, "qs_set_step_loader: NULL handle");
+    if (loader < 0 || loader > 2) return fail(QS_EINVAL, "qs_set_step_loader: loader must be 0, 1 or 2");
+    h->step_loader = loader;
     return QS_OK;
 }
 

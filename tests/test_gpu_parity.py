@@ -363,6 +363,63 @@ def test_sensor_model_f32_statistics_and_async_reset():
 # ----------------------------------------------------------------------------------------------------
 # structure: rollout fusion, sharding, checkpoint, host-buffer entry point
 # ----------------------------------------------------------------------------------------------------
+# ----------------------------------------------------------------------------------------------------
+# the three implementations of qs_step (plain loads, CTA-wide TMA ring, per-warp cp.async pipeline) are the same function
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,sensor,direct,ext", [(5000, False, 1, False), (4099, True, 1, True), (1 << 16, True, 1, False),
+                                                 (2500, False, 0, True), (31, False, 1, True), (33, True, 1, False)])
+def test_step_loaders_agree(N, sensor, direct, ext):
+    """Same inputs through loader 2 (per-warp pipeline, 16-byte vector loads/stores, opportunistic reset drains) and loader 1
+    (CTA-wide ring, scalar stores), teacher-forced (handle b restarts every step from a's workspace): every field must agree
+    after every step — floats to FP32 rounding (the two kernels are compiled separately, so FMA contraction may differ by an
+    ulp), integer/byte fields exactly except where a threshold comparison sits within that ulp — including ragged sizes
+    (N % 32 != 0, N % 4 != 0), the sensor rows, indirect control and caller-provided output arrays."""
+    seed, K = 11, 60
+    mk = lambda ld: BatchedQuad(N, 0.01, 25, T=3, precision="f32", direct_control=direct, async_reset=True,
+                                sensor_noise=sensor, seed=seed, device=DEV).set_step_loader(ld)
+    a, b = mk(2), mk(1)
+    a.reset(); b.reset()
+    g = torch.Generator(device=DEV); g.manual_seed(5)
+    ffields = [L.QS_FIELD_OBS, L.QS_FIELD_ANG, L.QS_FIELD_REWARD, L.QS_FIELD_ABS_SUM, L.QS_FIELD_PREV_SHAPING, L.QS_FIELD_EP_RETURN]
+    ifields = [L.QS_FIELD_DONE, L.QS_FIELD_SOLVED, L.QS_FIELD_I, L.QS_FIELD_EPISODE, L.QS_FIELD_FLAGS]
+    if sensor:
+        ffields += [L.QS_FIELD_SENSED_OBS, L.QS_FIELD_SENSOR_STATE]
+    outs = []
+    for env in (a, b):
+        outs.append((torch.full((14, N), -7.0, device=DEV), torch.full((N,), -7.0, device=DEV),
+                     torch.full((N,), 9, dtype=torch.uint8, device=DEV), torch.full((N,), 9, dtype=torch.uint8, device=DEV)))
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    flips = 0
+    for t in range(K):
+        b._ws.copy_(a._ws)
+        if direct:
+            act = (torch.rand(4, N, device=DEV, generator=g) * 2 - 1).contiguous()
+        else:
+            act = torch.stack([torch.rand(N, device=DEV, generator=g) * 20, *(torch.rand(3, N, device=DEV, generator=g) - 0.5)]).contiguous()
+        for env, (o, r, d, sv) in zip((a, b), outs):
+            if ext:
+                L.check(env.lib.qs_step(env._h, C.c_void_p(act.data_ptr()), C.c_void_p(o.data_ptr()), C.c_void_p(r.data_ptr()),
+                                        C.c_void_p(d.data_ptr()), C.c_void_p(sv.data_ptr()), st))
+            else:
+                env.step_soa(act)
+        same = torch.ones(N, dtype=torch.bool, device=DEV)
+        for f in ifields:
+            same &= (a._field(f) == b._field(f)).all(dim=0)
+        flips += int((~same).sum())
+        for f in ffields:
+            fa, fb = a._field(f)[:, same], b._field(f)[:, same]
+            assert torch.allclose(fa, fb, rtol=2e-5, atol=2e-5, equal_nan=True), (t, f, float((fa - fb).abs().max()))
+        if ext:     # the caller's arrays hold exactly what the handle's own rows hold
+            o, r, d, sv = outs[0]
+            assert torch.equal(o, a._field(L.QS_FIELD_OBS)) and torch.equal(r, a._field(L.QS_FIELD_REWARD)[0])
+            assert torch.equal(d, a._field(L.QS_FIELD_DONE)[0]) and torch.equal(sv, a._field(L.QS_FIELD_SOLVED)[0])
+            o, r, d, sv = outs[1]
+            assert torch.equal(o, b._field(L.QS_FIELD_OBS)) and torch.equal(d, b._field(L.QS_FIELD_DONE)[0])
+    assert flips <= 2 + N * K // 100000, flips
+    sa = a.stats()
+    assert sa["n_episodes"] > 0 and int(a.episode.max()) >= 2
+
+
 @pytest.mark.parametrize("prec,integ", [("f32", "rk4"), ("f64", "rk45")])
 def test_rollout_kernel_equals_repeated_steps(prec, integ):
     N, K, seed = 3000, 24, 5

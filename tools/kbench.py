@@ -86,6 +86,10 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["all"]
     if "prof" in which:                                              # short run for ncu
         case_step(async_reset=True, T=5, iters=20)
+    if "profsensor" in which:
+        case_step(async_reset=True, T=5, iters=20, sensor_noise=True)
+    if "profpolicy" in which:
+        case_policy(N=1 << 18, K=32, iters=1)
     if "policy" in which:
         case_policy()
         case_policy(record=False)
