@@ -253,7 +253,9 @@ def main():
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     kernel_ms = ms / args.steps                          # one launch of step_kernel per step, back to back on one stream
     sensor = int(bool(args.sensor_noise))
-    kernel_name = "step_kernel_tma<float,RK4,direct,sensor=%d>" % sensor
+    loader = int(os.environ.get("QS_STEP_LOADER", "2"))    # libquadsim's default step kernel for FP32/RK4 handles
+    kernel_name = {0: "step_kernel_direct<float,RK4,direct,sensor=%d>", 1: "step_kernel_tma<float,RK4,direct,sensor=%d>",
+                   2: "step_kernel_warp<direct,sensor=%d>"}[loader] % sensor
     # algorithmic bytes per env-step: 181 B; the sensor model adds its 17-float state in + out and the
     # 14-float sensed observation out
     algo_bytes = ALGO_BYTES_PER_ENV_STEP + (192 if sensor else 0)
