@@ -143,9 +143,18 @@ class BatchedQuad:
         raise ValueError("expected shape (%d,%d) or (%d,%d), got %s" % (self.N, channels, channels, self.N, tuple(x.shape)))
 
     def set_step_loader(self, loader: int):
-        """Pick the qs_step implementation (0 plain loads, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline); A/B testing."""
+        """Pick the qs_step implementation (0 plain loads, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline, 3 per-warp
+        pipeline with two envs per lane on the packed FP32 pipe); A/B testing."""
         L.check(self.lib.qs_set_step_loader(self._h, int(loader)))
         return self
+
+    @property
+    def step_loader(self) -> int:
+        """The qs_step implementation this handle launches (see set_step_loader)."""
+        r = int(self.lib.qs_get_step_loader(self._h))
+        if r < 0:
+            L.check(r)
+        return r
 
     # ------------------------------------------------------------------ reference API
     def seed(self, seed: int):

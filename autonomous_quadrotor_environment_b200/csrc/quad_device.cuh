@@ -61,6 +61,11 @@ __device__ __forceinline__ float fast_sqrtf(float x) {            // max rel. er
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float fast_rsqrtf(float x) {           // MUFU.RSQ without the denormal pre-scaling of rsqrtf()
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float fast_rcpf(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -105,7 +110,7 @@ __device__ __forceinline__ float fast_asinf(float x) {
 }
 
 template <> struct M_<float> {
-    static __device__ __forceinline__ float rsqrt(float x) { return rsqrtf(x); }
+    static __device__ __forceinline__ float rsqrt(float x) { return fast_rsqrtf(x); }
     static __device__ __forceinline__ float sqrt(float x) { return fast_sqrtf(x); }
     static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
     static __device__ __forceinline__ float atan2(float y, float x) { return fast_atan2f(y, x); }
@@ -597,12 +602,15 @@ template <typename R> struct StepOut {
     bool broken, timeout;
 };
 
-// quad.step :458-498 for one env.  `a_in` = action as given by the caller.
-template <typename R, int INTEG, bool DIRECT>
-__device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o,
-                                          Ctrl<R>* ctrl_out = nullptr) {
+// quad.step :458-498 for one env, in three phases so that kernels which integrate two envs per thread with the packed
+// FP32 instructions (step_pair.cuh) share the scalar action map and the done/reward evaluation with every other kernel.
+// `a_in` = action as given by the caller.
+//
+// phase 1 — :467-477: step counter, action clip, rotor map (f2F / f2w) -> rotor command held constant over the RK stages
+template <typename R, bool DIRECT>
+__device__ __forceinline__ Ctrl<R> step_pre(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o, R act[4]) {
     e.i += 1;                                                    // :467
-    R act[4], fm[4];
+    R fm[4];
     if (DIRECT) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {                            // np.clip(action,-1,1) :470
@@ -619,10 +627,12 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { o.fm[k] = fm[k]; o.clipped[k] = DIRECT ? act[k] : fm[k]; }
-    Ctrl<R> c = make_ctrl(p, fm, o.w);
-    if (ctrl_out) *ctrl_out = c;
-    if (INTEG == 1) integrate_rk45(p, c, e.y);                   // :483
-    else integrate_rk4(p, c, e.y);
+    return make_ctrl(p, fm, o.w);
+}
+
+// phase 3 — :486-498 after the integration: observation tail, Euler angles, done_condition, reward_function, control_effort
+template <typename R>
+__device__ __forceinline__ void step_post(const DevParams<R>& p, Env<R>& e, const R act[4], StepOut<R>& o) {
     // observation tail: V_q = 1/2 Omega(w_new) normalize(q_new)  (:392 evaluated at the FSAL stage)
     R qn[4];
     quat_normalize(&e.y[6], qn);                                 // :488-489
@@ -633,12 +643,14 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
         o.ang_vel[k] = div_dt(o.ang[k] - e.prev_ang[k], p);      // :492
         e.prev_ang[k] = o.ang[k];                                // :493
     }
-    // done_condition :500-509 (>=, sticky; NaN compares false)
+    // done_condition :500-509 (>=, sticky; NaN compares false).  Everything from here on is written without
+    // short-circuit operators or if/else bodies so that it compiles to straight-line predicated code: kernels that
+    // instantiate this phase for two envs per thread get both dependency chains into one basic block.
     bool done = (e.flags & EF_DONE) != 0;
     {
         const R cx[9] = {e.y[1], e.y[3], e.y[5], o.ang[0], o.ang[1], o.ang[2], e.y[10], e.y[11], e.y[12]};
 #pragma unroll
-        for (int k = 0; k < 9; ++k) done = done || (M_<R>::abs(cx[k]) >= p.bb[k]);
+        for (int k = 0; k < 9; ++k) done = done | (M_<R>::abs(cx[k]) >= p.bb[k]);
     }
     // reward_function :511-573
     R v2 = e.y[1] * e.y[1] + e.y[3] * e.y[3] + e.y[5] * e.y[5];
@@ -651,11 +663,11 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
         bool taken = false;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {                            // cascade :535-542
-            bool c1 = !taken && (nr < p.tr_r[k]);
-            bool c2 = c1 && (ne < p.tr_e[k]);
+            const bool c1 = (!taken) & (nr < p.tr_r[k]);
+            const bool c2 = c1 & (ne < p.tr_e[k]);
             shaping += c1 ? p.tr_p[k] : R(0);
             shaping += c2 ? p.tr_p[k] : R(0);
-            taken = taken || c1;
+            taken = taken | c1;
         }
     }
     R reward = (e.flags & EF_HAS_SHAPING) ? (shaping - e.prev_shaping) : R(0);       // :545-547
@@ -665,33 +677,39 @@ __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, cons
     for (int k = 0; k < 4; ++k) { R d = act[k] - p.zero_control[k]; pen += d * d; }
     reward += -pen * p.p_c;                                      // :553-554
     R cur = v2 + (e2 + psi * psi) + (e.y[10] * e.y[10] + e.y[11] * e.y[11] + e.y[12] * e.y[12]);   // :558
-    bool solved = (e.flags & EF_SOLVED) != 0;
-    bool broken = false, timeout = false;
-    if (cur < p.target_state) {                                  // :562-566
-        reward += p.solved_reward; solved = true;
-        if (p.flags & F_TRAINING) done = true;
-    } else if (e.i >= p.n_limit) {                               // :567-570
-        solved = false; done = true; timeout = true;
-    } else if (done) {                                           // :571-573
-        reward += p.broken_reward; solved = false; broken = true;
-    }
+    // :562-573  precedence solved > time limit > broken
+    const bool is_solved = cur < p.target_state;
+    const bool timeout = (!is_solved) & (e.i >= p.n_limit);
+    const bool broken = (!is_solved) & (!timeout) & done;
+    reward = is_solved ? reward + p.solved_reward : (broken ? reward + p.broken_reward : reward);
+    const bool solved = is_solved | (((e.flags & EF_SOLVED) != 0) & (!timeout) & (!broken));
+    done = done | (is_solved & ((p.flags & F_TRAINING) != 0)) | timeout;
     e.flags = (e.flags & ~EF_LOW) | (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u);
     e.abs_sum += M_<R>::sqrt(o.effort[0] * o.effort[0] + o.effort[1] * o.effort[1] + o.effort[2] * o.effort[2] +
                              o.effort[3] * o.effort[3]);         // :575-577
     o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
 }
 
+template <typename R, int INTEG, bool DIRECT>
+__device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o,
+                                          Ctrl<R>* ctrl_out = nullptr) {
+    R act[4];
+    const Ctrl<R> c = step_pre<R, DIRECT>(p, e, a_in, o, act);
+    if (ctrl_out) *ctrl_out = c;
+    if (INTEG == 1) integrate_rk45(p, c, e.y);                   // :483
+    else integrate_rk4(p, c, e.y);
+    step_post(p, e, act, o);
+}
+
 // QS_FLAG_ASYNC_RESET, start of a step: an env that still owes warm-up steps gets the neutral action (:448)
 // for this step.  Returns true if this step is a warm-up step.
 template <typename R>
 __device__ __forceinline__ bool async_warmup_prologue(const DevParams<R>& p, Env<R>& e, R a[4]) {
-    if (e.flags >> EF_WARM_SHIFT) {
-        e.flags -= (1u << EF_WARM_SHIFT);
+    const bool warm = (e.flags >> EF_WARM_SHIFT) != 0u;
+    e.flags -= warm ? (1u << EF_WARM_SHIFT) : 0u;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) a[k] = p.zero_control[k];
-        return true;
-    }
-    return false;
+    for (int k = 0; k < 4; ++k) a[k] = warm ? p.zero_control[k] : a[k];
+    return warm;
 }
 
 // QS_FLAG_ASYNC_RESET, end of the step that returned done: begin the next episode — Philox-sampled initial

@@ -85,7 +85,7 @@ struct qs_sim {
     DevParams<double> pd;
     int sm_count;
     uint64_t seed;
-    int step_loader;        // 0 direct LDG, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline (FP32 RK4 default)
+    int step_loader;        // 0 direct LDG, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline, 3 per-warp pipeline with env pairs (packed FP32)
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -722,6 +722,7 @@ step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ 
 }
 
 #include "step_warp.cuh"
+#include "step_pair.cuh"
 
 // quad.reset for the masked envs (det_state given or Philox-sampled).
 template <typename R, int INTEG, bool DIRECT>
@@ -833,11 +834,15 @@ static int grid_for(const qs_sim* s, int64_t n) {
     return (int)blocks;
 }
 
-// QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 (default) per-warp cp.async pipeline
-static int default_step_loader() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : 2; }
-    return v;
+// QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 per-warp cp.async pipeline (one env per lane),
+// 3 per-warp pipeline with two envs per lane on the packed FP32 pipe.  Unset = per handle: 3 without the sensor model
+// (49 vs 57 us per step of 1,048,576 envs), 2 with it (the sensor phase needs ~250 registers for an env pair, which
+// halves the resident warps and cancels the gain: 110 us either way).
+static int default_step_loader(uint32_t flags) {
+    static int v = -2;
+    if (v == -2) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : -1; }
+    if (v >= 0) return v;
+    return (flags & QS_FLAG_SENSOR_NOISE) ? 2 : 3;
 }
 
 // persistent grid of the staged step kernel: a few CTAs per SM, each looping over 256-env tiles
@@ -879,7 +884,23 @@ template <> struct WarpKernelOk<float, 0> { static constexpr bool value = true; 
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
     if constexpr (WarpKernelOk<R, INTEG>::value) {
-        if (s->step_loader == 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
+        if (s->step_loader == 3 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
+            constexpr int threads = SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain;
+            constexpr int warps = threads / 32;
+            constexpr size_t smem = (size_t)(SENSOR ? pr::kRowsSensor : pr::kRowsPlain) * 256 * warps;
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaFuncSetAttribute(step_kernel_pair<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                attr_set = true;
+            }
+            const int64_t chunks = (s->N + 63) / 64;
+            int64_t g = (int64_t)s->sm_count;
+            const int64_t need = (chunks + warps - 1) / warps;
+            if (g > need) g = need;
+            step_kernel_pair<DIRECT, SENSOR><<<(int)(g < 1 ? 1 : g), threads, smem, st>>>(s->pf, make_view<float>(s), io);
+            return;
+        }
+        if (s->step_loader >= 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
             constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * 2 * (kBlock / 32);
             static bool attr_set = false;
             if (!attr_set) {
@@ -969,7 +990,7 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
     cudaDeviceProp prop;
     cudaError_t e1 = cudaGetDeviceProperties(&prop, cfg->device);
     s->sm_count = (e1 == cudaSuccess) ? prop.multiProcessorCount : 148;
-    s->step_loader = default_step_loader();
+    s->step_loader = default_step_loader(cfg->flags);
     if (s->rs == 4) {       // the per-warp pipeline addresses the 4-byte rows as one matrix: make sure the row table still says so
         const char* b = (const char*)s->obs17;
         const size_t rb = (size_t)s->ld * 4;
@@ -977,7 +998,7 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
                         (char*)s->slot[QS_FIELD_ABS_SUM].ptr == b + 21 * rb && (char*)s->slot[QS_FIELD_EP_RETURN].ptr == b + 22 * rb &&
                         (char*)s->slot[QS_FIELD_I].ptr == b + 23 * rb && (char*)s->slot[QS_FIELD_EPISODE].ptr == b + 24 * rb &&
                         (char*)s->slot[QS_FIELD_REWARD].ptr == b + 25 * rb;
-        if (!ok && s->step_loader == 2) s->step_loader = 1;
+        if (!ok && s->step_loader >= 2) s->step_loader = 1;
     }
     cudaError_t e2 = cudaMemset(s->ws, 0, s->ws_bytes);
     if (e2 == cudaSuccess) {
@@ -1009,9 +1030,16 @@ extern "C" int qs_seed(qs_handle h, uint64_t seed) {
 
 extern "C" int qs_set_step_loader(qs_handle h, int loader) {
     if (!h) return fail(QS_EINVAL, "qs_set_step_loader: NULL handle");
-    if (loader < 0 || loader > 2) return fail(QS_EINVAL, "qs_set_step_loader: loader must be 0, 1 or 2");
+    if (loader < 0 || loader > 3) return fail(QS_EINVAL, "qs_set_step_loader: loader must be 0, 1, 2 or 3");
     h->step_loader = loader;
     return QS_OK;
+}
+
+extern "C" int qs_get_step_loader(qs_handle h) {
+    if (!h) return fail(QS_EINVAL, "qs_get_step_loader: NULL handle");
+    const bool warp_ok = h->cfg.precision == QS_F32 && h->cfg.integrator == QS_RK4 &&
+                         !(h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET));
+    return (h->step_loader >= 2 && !warp_ok) ? 1 : h->step_loader;
 }
 
 extern "C" int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_hist, void* act_hist,

@@ -1,0 +1,376 @@
+// step_pair.cuh — quad.step for every env of the shard, FP32 production kernel with TWO environments per lane (loader 3).
+//
+// A warp owns 64-env chunks and lane l the ADJACENT pair (n0+2l, n0+2l+1):
+//   * every quantity of the pair is one aligned 64-bit register pair {A, B}: one LDS.64 reads it from the warp's
+//     shared-memory stage, one STG.64 writes it back to its SoA row (a warp-wide STG.64 = 256 contiguous bytes);
+//   * the RK4 stages of drone_eq run on FFMA2/FMUL2/FADD2 (packed_device.cuh): half the issue slots per env;
+//   * the scalar phases (action map, Euler angles, done/reward, sensor model) are instantiated once per half: two
+//     independent dependency chains per thread where the one-env kernel stalls on its single chain (ncu: 3-5x more
+//     warp-time per instruction outside the RK loop than inside), and the per-chunk bookkeeping (addresses, loop,
+//     queue) is paid once per 64 envs.
+// Pipeline per warp (no synchronisation between warps inside the loop):
+//   wait(chunk j) -> LDS the whole chunk into registers -> __syncwarp -> cp.async (LDGSTS, 16 B per lane: two 256-byte row
+//   segments per instruction) of chunk j+1 into the SAME stage, which has the whole arithmetic of chunk j to land ->
+//   quad.step x2 -> STG.64 of the results straight from registers.
+// One stage per warp is 26 rows x 256 B (46 with the sensor state), so 16 warps x 2 envs per SM fit (104 KB).
+// Resets: same per-CTA queue and opportunistic full-warp drains as step_warp.cuh.
+#pragma once
+#include "packed_device.cuh"
+
+namespace pr {
+
+using wp::cp16; using wp::cp4; using wp::cp_commit; using wp::cp_wait; using wp::Ext;
+
+// stage rows (64 floats each): 0..9 = matrix rows 0..9 (x vx y vy z vz q0..q3), 10..20 = matrix rows 14..24 (w, ang,
+// prev_shaping, abs_sum, ep_return, step_i, episode), 21..24 = the 4 action rows, 25 = flag bytes [0,64),
+// 26..45 = sensor_state (SENSOR only)
+constexpr int kSW = 10;              // stage row of matrix row 14
+constexpr int kRowAct = 21;
+constexpr int kRowBytes = 25;
+constexpr int kRowSensor = 26;
+constexpr int kRowsPlain = 26;
+constexpr int kRowsSensor = 46;
+#ifndef QS_PAIR_THREADS
+#define QS_PAIR_THREADS 384
+#endif
+#ifndef QS_PAIR_THREADS_SENSOR
+#define QS_PAIR_THREADS_SENSOR 256
+#endif
+#ifndef QS_PAIR_SENSOR_ROLLED
+#define QS_PAIR_SENSOR_ROLLED 1
+#endif
+constexpr int kThreadsPlain = QS_PAIR_THREADS;
+constexpr int kThreadsSensor = QS_PAIR_THREADS_SENSOR;
+constexpr int kQueueCapPlain = 2048;
+constexpr int kQueueCapSensor = 1024;
+
+typedef float Row[64];
+
+template <int H> __device__ __forceinline__ float half_of(const qs::P2& x) { return H == 0 ? x.v.x : x.v.y; }
+template <int H> __device__ __forceinline__ float half_of(const float2& x) { return H == 0 ? x.x : x.y; }
+
+__device__ __forceinline__ float2 lds2(const Row* st, int row, int lane) { return reinterpret_cast<const float2*>(st[row])[lane]; }
+__device__ __forceinline__ void sts2(Row* st, int row, int lane, float a, float b) { reinterpret_cast<float2*>(st[row])[lane] = make_float2(a, b); }
+
+// issue the loads of one chunk (envs n0 .. n0+63) into the warp's stage; every lane executes the same number of commits
+template <bool SENSOR>
+__device__ __forceinline__ void prefetch(const SimView<float>& v, const float* __restrict__ action, const Ext& x,
+                                         int64_t n0, Row* st, int lane) {
+    const int r2 = lane >> 4, c4 = (lane & 15) << 2;       // 16-byte pieces: 2 rows x 16 lanes
+    const int64_t ld = v.ld;
+    const float* g = v.obs17 + (int64_t)r2 * ld + n0 + c4;
+    const uint32_t s = smem_u32(&st[r2][c4]);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cp16(s + 2 * k * 256, g + (int64_t)(2 * k) * ld);                      // matrix rows 0..9
+#pragma unroll
+    for (int k = 0; k < 5; ++k) cp16(s + (kSW + 2 * k) * 256, g + (int64_t)(14 + 2 * k) * ld);         // matrix rows 14..23
+    if (r2 == 0) cp16(s + (kSW + 10) * 256, g + (int64_t)24 * ld);                                     // matrix row 24 (episode)
+    if (lane < 4) cp16(smem_u32(reinterpret_cast<unsigned char*>(st[kRowBytes]) + 16 * lane), v.flags + n0 + 16 * lane);
+    const bool full = n0 + 64 <= v.N;
+    if (x.act_vec && full) {
+        const float* ga = action + (int64_t)r2 * v.N + n0 + c4;
+        cp16(s + kRowAct * 256, ga);
+        cp16(s + (kRowAct + 2) * 256, ga + 2 * v.N);
+    } else {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int col = lane + 32 * hf;
+            if (n0 + col < v.N) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) cp4(smem_u32(&st[kRowAct + k][col]), action + (int64_t)k * v.N + n0 + col);
+            }
+        }
+    }
+    if (SENSOR) {
+        const float* gs = v.sensor_state + (int64_t)r2 * ld + n0 + c4;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) cp16(s + (kRowSensor + 2 * k) * 256, gs + (int64_t)(2 * k) * ld);
+    }
+    cp_commit();
+}
+
+// row k of a [rows][ld] 4-byte matrix, columns n0+2*lane, n0+2*lane+1 <- {a, b}; g2 = (float2*)(matrix + n0) + lane, ld2 = ld / 2
+__device__ __forceinline__ void stg2(float2* g2, int64_t ld2, int k, float a, float b) { g2[(int64_t)k * ld2] = make_float2(a, b); }
+
+}  // namespace pr
+
+template <bool DIRECT, bool SENSOR>
+__global__ void __launch_bounds__(SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain, 1)
+step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
+                 const __grid_constant__ StepIO<float> io) {
+    using namespace pr;
+    constexpr int kRows = SENSOR ? kRowsSensor : kRowsPlain;
+    constexpr int kQueueCap = SENSOR ? kQueueCapSensor : kQueueCapPlain;
+    constexpr int kThreads = SENSOR ? kThreadsSensor : kThreadsPlain;
+    constexpr int kWarps = kThreads / 32;
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t s_queue[kQueueCap];
+    __shared__ int s_qn, s_qhead;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    Row* st = reinterpret_cast<Row*>(smem_raw) + (size_t)w * kRows;
+    for (int i = tid; i < kQueueCap; i += kThreads) s_queue[i] = 0xFFFFFFFFu;
+    if (tid == 0) { s_qn = 0; s_qhead = 0; }
+    __syncthreads();
+
+    Ext x;
+    const bool n2 = (v.N & 1) == 0, n4 = (v.N & 3) == 0;
+    x.act_vec = n4 && ((reinterpret_cast<uintptr_t>(io.action) & 15) == 0);
+    x.obs_vec = n2 && ((reinterpret_cast<uintptr_t>(io.obs) & 7) == 0);         // 8-byte pair stores into the caller's arrays
+    x.rew_vec = n2 && ((reinterpret_cast<uintptr_t>(io.reward) & 7) == 0);
+    x.done_vec = n2 && ((reinterpret_cast<uintptr_t>(io.done) & 1) == 0);       // 2-byte pair stores
+    x.solved_vec = n2 && ((reinterpret_cast<uintptr_t>(io.solved) & 1) == 0);
+    const bool async_reset = (p.flags & F_ASYNC_RESET) != 0;
+    const int64_t ld2 = v.ld >> 1, N2 = v.N >> 1;
+
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const int64_t n_chunks = (v.N + 63) >> 6;
+    const int64_t stride = (int64_t)gridDim.x * kWarps;
+    int64_t c = (int64_t)blockIdx.x * kWarps + w;
+    if (c < n_chunks) prefetch<SENSOR>(v, io.action, x, c << 6, st, lane);
+    for (; c < n_chunks; c += stride) {
+        cp_wait<0>();
+        __syncwarp();
+        const int64_t n0 = c << 6;
+        const int64_t nA = n0 + 2 * lane;                       // env A; env B = nA + 1
+        const bool act_[2] = {nA < v.N, nA + 1 < v.N};
+        // ---- stage -> registers: the state stays packed {A, B} from the LDS.64 to the end of the integration
+        P2 y[13];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) y[k].v = lds2(st, k, lane);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) y[10 + k].v = lds2(st, kSW + k, lane);
+        float2 pa[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) pa[k] = lds2(st, kSW + 3 + k, lane);
+        const float2 sh = lds2(st, kSW + 6, lane), as = lds2(st, kSW + 7, lane), er = lds2(st, kSW + 8, lane);
+        const float2 si = lds2(st, kSW + 9, lane), ep = lds2(st, kSW + 10, lane);
+        const uint32_t fl = reinterpret_cast<const uint16_t*>(st[kRowBytes])[lane];
+        float2 a2[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a2[k] = lds2(st, kRowAct + k, lane);
+        float2 s2[SENSOR ? kSensorStateDim : 1];
+        if (SENSOR) {
+#pragma unroll
+            for (int k = 0; k < kSensorStateDim; ++k) s2[k] = lds2(st, kRowSensor + k, lane);
+        }
+        __syncwarp();                          // every lane has read its pair: the stage is free for the next chunk
+        if (c + stride < n_chunks) prefetch<SENSOR>(v, io.action, x, (c + stride) << 6, st, lane);
+
+        Env<float> e[2];
+        StepOut<float> o[2];
+        Ctrl<float> ctl[2];
+        float act[2][4];
+        bool warm[2], was_done[2], push[2];
+        // ---- phase 1 per env: warm-up override, action clip, rotor map
+#define QS_PAIR_PRE(H)                                                                                        \
+        {                                                                                                     \
+            _Pragma("unroll") for (int k = 0; k < 3; ++k) e[H].prev_ang[k] = half_of<H>(pa[k]);              \
+            e[H].prev_shaping = half_of<H>(sh); e[H].abs_sum = half_of<H>(as); e[H].ep_return = half_of<H>(er); \
+            e[H].i = __float_as_int(half_of<H>(si)); e[H].episode = __float_as_uint(half_of<H>(ep));          \
+            e[H].flags = (fl >> (8 * H)) & 0xffu;                                                             \
+            float a[4];                                                                                       \
+            _Pragma("unroll") for (int k = 0; k < 4; ++k) a[k] = half_of<H>(a2[k]);                           \
+            warm[H] = async_reset ? async_warmup_prologue(p, e[H], a) : false;                                \
+            was_done[H] = (e[H].flags & EF_DONE) != 0;                                                        \
+            ctl[H] = step_pre<float, DIRECT>(p, e[H], a, o[H], act[H]);                                       \
+        }
+        QS_PAIR_PRE(0)
+        QS_PAIR_PRE(1)
+#undef QS_PAIR_PRE
+        // ---- phase 2: both envs through the RK4 stages on the packed pipe
+        const Ctrl2 c2 = pack_ctrl(ctl[0], ctl[1]);
+        integrate_rk4_2(p, c2, y);
+        // ---- phase 3 per env: observation tail, Euler angles, done, reward
+#define QS_PAIR_POST(H)                                                                                       \
+        {                                                                                                     \
+            _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);                      \
+            step_post(p, e[H], act[H], o[H]);                                                                 \
+            o[H].reward = warm[H] ? 0.f : o[H].reward;                                                        \
+            e[H].ep_return += o[H].reward;                                                                    \
+            push[H] = async_reset & act_[H] & o[H].done;                                                      \
+        }
+        QS_PAIR_POST(0)
+        QS_PAIR_POST(1)
+        if (act_[0] && o[0].done && !was_done[0]) { count_episode(ls, p, e[0], o[0]); any_end = true; }
+        if (act_[1] && o[1].done && !was_done[1]) { count_episode(ls, p, e[1], o[1]); any_end = true; }
+#undef QS_PAIR_POST
+        // ---- results -> HBM straight from the register pairs (rows of the handle are padded to whole chunks)
+        {
+            float2* g2 = reinterpret_cast<float2*>(v.obs17 + n0) + lane;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) g2[(int64_t)k * ld2] = y[k].v;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stg2(g2, ld2, 10 + k, o[0].vq[k], o[1].vq[k]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) g2[(int64_t)(14 + k) * ld2] = y[10 + k].v;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) stg2(g2, ld2, wp::kMAng + k, e[0].prev_ang[k], e[1].prev_ang[k]);
+            stg2(g2, ld2, wp::kMShaping, e[0].prev_shaping, e[1].prev_shaping);
+            stg2(g2, ld2, wp::kMAbsSum, e[0].abs_sum, e[1].abs_sum);
+            stg2(g2, ld2, wp::kMEpRet, e[0].ep_return, e[1].ep_return);
+            stg2(g2, ld2, wp::kMStepI, __int_as_float(e[0].i), __int_as_float(e[1].i));
+            stg2(g2, ld2, wp::kMEpisode, __uint_as_float(e[0].episode), __uint_as_float(e[1].episode));
+            stg2(g2, ld2, wp::kMReward, o[0].reward, o[1].reward);
+            const uint16_t bf = (uint16_t)((e[0].flags & 0xffu) | ((e[1].flags & 0xffu) << 8));
+            const uint16_t bd = (uint16_t)(((o[0].done ? 1u : 0u) | (warm[0] ? 2u : 0u)) | (((o[1].done ? 1u : 0u) | (warm[1] ? 2u : 0u)) << 8));
+            const uint16_t bs = (uint16_t)((o[0].solved ? 1u : 0u) | ((o[1].solved ? 1u : 0u) << 8));
+            reinterpret_cast<uint16_t*>(v.flags + n0)[lane] = bf;
+            reinterpret_cast<uint16_t*>(v.done + n0)[lane] = bd;
+            reinterpret_cast<uint16_t*>(v.solved + n0)[lane] = bs;
+            if (io.obs) {
+                if (x.obs_vec && act_[1]) {
+                    float2* q2 = reinterpret_cast<float2*>(io.obs + n0) + lane;
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) q2[(int64_t)k * N2] = y[k].v;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) stg2(q2, N2, 10 + k, o[0].vq[k], o[1].vq[k]);
+                } else {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        if (act_[hf]) {
+#pragma unroll
+                            for (int k = 0; k < 10; ++k) io.obs[k * v.N + nA + hf] = hf ? y[k].v.y : y[k].v.x;
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) io.obs[(10 + k) * v.N + nA + hf] = o[hf].vq[k];
+                        }
+                    }
+                }
+            }
+            if (io.reward) {
+                if (x.rew_vec && act_[1]) reinterpret_cast<float2*>(io.reward + n0)[lane] = make_float2(o[0].reward, o[1].reward);
+                else {
+                    if (act_[0]) io.reward[nA] = o[0].reward;
+                    if (act_[1]) io.reward[nA + 1] = o[1].reward;
+                }
+            }
+            if (io.done) {
+                if (x.done_vec && act_[1]) reinterpret_cast<uint16_t*>(io.done + n0)[lane] = bd;
+                else {
+                    if (act_[0]) io.done[nA] = (uint8_t)(bd & 0xff);
+                    if (act_[1]) io.done[nA + 1] = (uint8_t)(bd >> 8);
+                }
+            }
+            if (io.solved) {
+                if (x.solved_vec && act_[1]) reinterpret_cast<uint16_t*>(io.solved + n0)[lane] = bs;
+                else {
+                    if (act_[0]) io.solved[nA] = (uint8_t)(bs & 0xff);
+                    if (act_[1]) io.solved[nA + 1] = (uint8_t)(bs >> 8);
+                }
+            }
+        }
+        if (SENSOR) {
+            // trailing drone_eq call at the new state for both envs at once: acceleration and rotation matrix
+            P2 dy[13], rot[9];
+            drone_rhs2<true>(p, c2, y, dy, rot);
+#if QS_PAIR_SENSOR_ROLLED
+            // The sensor model (~900 instructions, ~60 live values) runs once per half in a ROLLED loop: one copy in the
+            // instruction stream and one env's worth of registers, so that more warps fit; each half writes its own
+            // columns (4-byte stores, the two halves of a 32-byte sector arrive within the same chunk).
+            float* gs = v.sensor_state + nA;
+            float* go = v.sensed_obs + nA;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                const bool hb = h != 0;
+                const bool wm = hb ? warm[1] : warm[0];
+                const uint32_t fl_h = hb ? e[1].flags : e[0].flags, ep_h = hb ? e[1].episode : e[0].episode;
+                const uint32_t i_h = (uint32_t)(hb ? e[1].i : e[0].i);
+                const float fm_h = hb ? ctl[1].f_m : ctl[0].f_m;
+                float z[32], rt[9], yh[13], sn[kSensorStateDim], s_new[kSensorStateDim], so[14], vq[4];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) yh[k] = hb ? y[k].v.y : y[k].v.x;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vq[k] = hb ? o[1].vq[k] : o[0].vq[k];
+#pragma unroll
+                for (int k = 0; k < kSensorStateDim; ++k) { sn[k] = hb ? s2[k].y : s2[k].x; s_new[k] = sn[k]; }
+#pragma unroll
+                for (int k = 0; k < 9; ++k) rt[k] = hb ? rot[k].v.y : rot[k].v.x;
+                const float g[3] = {hb ? dy[1].v.y : dy[1].v.x, hb ? dy[3].v.y : dy[3].v.x, (hb ? dy[5].v.y : dy[5].v.x) - p.g};
+                const float acc_read[3] = {rt[0] * g[0] + rt[3] * g[1] + rt[6] * g[2], rt[1] * g[0] + rt[4] * g[1] + rt[7] * g[2],
+                                           rt[2] * g[0] + rt[5] * g[1] + rt[8] * g[2]};
+                const uint32_t gid = v.env_id_offset + (uint32_t)(nA + h);
+                sensor_normals(v.seed, gid, ep_h, i_h, z);
+                sensor_step(p, z, yh, acc_read, rt, fm_h, s_new, so);
+#pragma unroll
+                for (int k = 0; k < kSensorStateDim; ++k) sn[k] = wm ? sn[k] : s_new[k];
+                if (wm && (fl_h >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, gid, ep_h, yh, sn);
+#pragma unroll
+                for (int k = 0; k < kSensorStateDim; ++k) gs[(int64_t)k * v.ld + h] = sn[k];
+#pragma unroll
+                for (int k = 0; k < 10; ++k) go[(int64_t)k * v.ld + h] = wm ? yh[k] : so[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) go[(int64_t)(10 + k) * v.ld + h] = wm ? vq[k] : so[10 + k];
+            }
+#else
+            float sobs[2][14], sn[2][kSensorStateDim];
+            // The model runs for both envs unconditionally (straight-line code, the two chains interleave); warm-up
+            // steps bypass it afterwards (select) and the last warm-up step re-initialises it (sensor.reset, rare branch).
+#define QS_PAIR_SENSOR(H)                                                                                     \
+            {                                                                                                 \
+                float z[32], rt[9], s_new[kSensorStateDim], so[14];                                           \
+                _Pragma("unroll") for (int k = 0; k < kSensorStateDim; ++k) { sn[H][k] = half_of<H>(s2[k]); s_new[k] = sn[H][k]; } \
+                _Pragma("unroll") for (int k = 0; k < 9; ++k) rt[k] = half_of<H>(rot[k]);                     \
+                const float g[3] = {half_of<H>(dy[1]), half_of<H>(dy[3]), half_of<H>(dy[5]) - p.g};           \
+                const float acc_read[3] = {rt[0] * g[0] + rt[3] * g[1] + rt[6] * g[2],                        \
+                                           rt[1] * g[0] + rt[4] * g[1] + rt[7] * g[2],                        \
+                                           rt[2] * g[0] + rt[5] * g[1] + rt[8] * g[2]};                       \
+                sensor_normals(v.seed, v.env_id_offset + (uint32_t)(nA + H), e[H].episode, (uint32_t)e[H].i, z); \
+                sensor_step(p, z, e[H].y, acc_read, rt, ctl[H].f_m, s_new, so);                               \
+                _Pragma("unroll") for (int k = 0; k < kSensorStateDim; ++k) sn[H][k] = warm[H] ? sn[H][k] : s_new[k]; \
+                _Pragma("unroll") for (int k = 0; k < 10; ++k) sobs[H][k] = warm[H] ? e[H].y[k] : so[k];      \
+                _Pragma("unroll") for (int k = 0; k < 4; ++k) sobs[H][10 + k] = warm[H] ? o[H].vq[k] : so[10 + k]; \
+            }
+            QS_PAIR_SENSOR(0)
+            QS_PAIR_SENSOR(1)
+#undef QS_PAIR_SENSOR
+            if (warm[0] && (e[0].flags >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)nA, e[0].episode, e[0].y, sn[0]);
+            if (warm[1] && (e[1].flags >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)(nA + 1), e[1].episode, e[1].y, sn[1]);
+            float2* gs2 = reinterpret_cast<float2*>(v.sensor_state + n0) + lane;
+#pragma unroll
+            for (int k = 0; k < kSensorStateDim; ++k) stg2(gs2, ld2, k, sn[0][k], sn[1][k]);
+            float2* go2 = reinterpret_cast<float2*>(v.sensed_obs + n0) + lane;
+#pragma unroll
+            for (int k = 0; k < 14; ++k) stg2(go2, ld2, k, sobs[0][k], sobs[1][k]);
+#endif
+        }
+        // ---- resets: push finished envs, claim 32 queued ones if available
+        if (async_reset) {
+            if (__any_sync(kFull, push[0] || push[1])) {
+                __threadfence_block();         // this warp's stores of the finished envs precede the re-sampler's
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    if (push[hf]) {
+                        const int slot = atomicAdd(&s_qn, 1);
+                        if (slot < kQueueCap) *reinterpret_cast<volatile uint32_t*>(&s_queue[slot]) = (uint32_t)(nA + hf);
+                        else wp::resample_env<SENSOR>(p, v, io, nA + hf);   // queue exhausted (e.g. a whole shard timing out at once)
+                    }
+                }
+            }
+            int take = -1;
+            if (lane == 0) {
+                const int head = *reinterpret_cast<volatile int*>(&s_qhead);
+                int qn = *reinterpret_cast<volatile int*>(&s_qn);
+                qn = qn < kQueueCap ? qn : kQueueCap;
+                if (qn - head >= 32 && atomicCAS(&s_qhead, head, head + 32) == head) take = head;
+            }
+            take = __shfl_sync(kFull, take, 0);
+            if (take >= 0) {
+                uint32_t ent;
+                do { ent = *reinterpret_cast<volatile uint32_t*>(&s_queue[take + lane]); } while (ent == 0xFFFFFFFFu);
+                __threadfence_block();
+                wp::resample_env<SENSOR>(p, v, io, (int64_t)ent);
+            }
+        }
+    }
+    __syncthreads();                           // every push of this CTA has been made
+    if (async_reset) {
+        const int head = s_qhead;
+        const int qn = s_qn < kQueueCap ? s_qn : kQueueCap;
+        __threadfence_block();
+        for (int q = head + tid; q < qn; q += kThreads) wp::resample_env<SENSOR>(p, v, io, (int64_t)s_queue[q]);
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N);
+}

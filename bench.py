@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg (N=1, rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sensor-noise", type=int, default=1)
+    ap.add_argument("--variant-steps", type=int, default=2000, help="timed steps of the sensor_noise=0 variant (0 = skip)")
     return ap.parse_args()
 
 
@@ -253,9 +254,8 @@ def main():
         hbm_peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
     kernel_ms = ms / args.steps                          # one launch of step_kernel per step, back to back on one stream
     sensor = int(bool(args.sensor_noise))
-    loader = int(os.environ.get("QS_STEP_LOADER", "2"))    # libquadsim's default step kernel for FP32/RK4 handles
     kernel_name = {0: "step_kernel_direct<float,RK4,direct,sensor=%d>", 1: "step_kernel_tma<float,RK4,direct,sensor=%d>",
-                   2: "step_kernel_warp<direct,sensor=%d>"}[loader] % sensor
+                   2: "step_kernel_warp<direct,sensor=%d>", 3: "step_kernel_pair<direct,sensor=%d>"}[env.step_loader] % sensor
     # algorithmic bytes per env-step: 181 B; the sensor model adds its 17-float state in + out and the
     # 14-float sensed observation out
     algo_bytes = ALGO_BYTES_PER_ENV_STEP + (192 if sensor else 0)
@@ -272,6 +272,38 @@ def main():
     L.check(lib.qs_fp32_peak_probe(blocks, threads, iters, C.byref(probe_ms), stream))
     fp32_peak = 2.0 * 8 * blocks * threads * iters / (probe_ms.value * 1e-3) / 1e12
     flops = FLOPS_PER_ENV_STEP(args.substeps) * N / (kernel_ms * 1e-3) / 1e12
+
+    # ---- the same workload without the sensor model (the kernel every non-sensor user of qs_step runs), reported
+    #      beside the headline so that both step kernels are measured by the same command (N=1 only)
+    variants = {}
+    if world == 1 and sensor and args.variant_steps > 0:
+        env2 = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
+                           substeps=args.substeps, async_reset=True, sensor_noise=False, seed=0, env_id_offset=rank * N, device=dev)
+        env2.reset()
+        for w in range(max(3, args.warmup)):
+            L.check(lib.qs_step(env2._h, ptrs[w % P], None, None, None, None, stream))
+        torch.cuda.synchronize(dev)
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for k in range(args.variant_steps):
+            L.check(lib.qs_step(env2._h, ptrs[k % P], None, None, None, None, stream))
+        v1.record()
+        torch.cuda.synchronize(dev)
+        vms = v0.elapsed_time(v1) / args.variant_steps
+        vname = {0: "step_kernel_direct<float,RK4,direct,sensor=0>", 1: "step_kernel_tma<float,RK4,direct,sensor=0>",
+                 2: "step_kernel_warp<direct,sensor=0>", 3: "step_kernel_pair<direct,sensor=0>"}[env2.step_loader]
+        vgbs = ALGO_BYTES_PER_ENV_STEP * N / (vms * 1e-3) / 1e9
+        vtraffic = None
+        try:
+            vtraffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(vname) if N == (1 << 20) else None
+        except Exception:
+            pass
+        variants["sensor_noise=0"] = {
+            "value": N / (vms * 1e-3), "unit": UNIT, "steps": args.variant_steps, "kernel_ms": vms,
+            "roofline": {"bound": "hbm", "achieved": vgbs, "peak": hbm_peak, "unit": "GB/s", "frac": vgbs / hbm_peak,
+                         "traffic": vtraffic, "kernel": vname, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP},
+            "fp32_frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (vms * 1e-3) / 1e12 / fp32_peak}
+        del env2
 
     if rank == 0:
         line = {
@@ -297,6 +329,8 @@ def main():
                      "note": "algorithmic FLOPs (SURVEY.md 8(d)) vs an in-run dependent-FFMA probe"},
             "stats": env.stats(all_reduce=False),
         }
+        if variants:
+            line["variants"] = variants
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.T)
         print(json.dumps(line), flush=True)

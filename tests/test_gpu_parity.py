@@ -366,9 +366,11 @@ def test_sensor_model_f32_statistics_and_async_reset():
 # ----------------------------------------------------------------------------------------------------
 # the three implementations of qs_step (plain loads, CTA-wide TMA ring, per-warp cp.async pipeline) are the same function
 # ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("loader", [2, 3])
 @pytest.mark.parametrize("N,sensor,direct,ext", [(5000, False, 1, False), (4099, True, 1, True), (1 << 16, True, 1, False),
-                                                 (2500, False, 0, True), (31, False, 1, True), (33, True, 1, False)])
-def test_step_loaders_agree(N, sensor, direct, ext):
+                                                 (2500, False, 0, True), (31, False, 1, True), (33, True, 1, False),
+                                                 (65, False, 1, True), (4160, True, 0, True)])
+def test_step_loaders_agree(N, sensor, direct, ext, loader):
     """Same inputs through loader 2 (per-warp pipeline, 16-byte vector loads/stores, opportunistic reset drains) and loader 1
     (CTA-wide ring, scalar stores), teacher-forced (handle b restarts every step from a's workspace): every field must agree
     after every step — floats to FP32 rounding (the two kernels are compiled separately, so FMA contraction may differ by an
@@ -377,7 +379,7 @@ def test_step_loaders_agree(N, sensor, direct, ext):
     seed, K = 11, 60
     mk = lambda ld: BatchedQuad(N, 0.01, 25, T=3, precision="f32", direct_control=direct, async_reset=True,
                                 sensor_noise=sensor, seed=seed, device=DEV).set_step_loader(ld)
-    a, b = mk(2), mk(1)
+    a, b = mk(loader), mk(1)
     a.reset(); b.reset()
     g = torch.Generator(device=DEV); g.manual_seed(5)
     ffields = [L.QS_FIELD_OBS, L.QS_FIELD_ANG, L.QS_FIELD_REWARD, L.QS_FIELD_ABS_SUM, L.QS_FIELD_PREV_SHAPING, L.QS_FIELD_EP_RETURN]
