@@ -85,6 +85,10 @@ struct qs_sim {
     DevParams<double> pd;
     int sm_count;
     uint64_t seed;
+    int64_t slice_begin, slice_count;   // env range the step launchers address (whole shard except inside qs_step_host's pipeline)
+    cudaStream_t host_streams[4];       // qs_step_host: slices of the shard flow H2D -> step -> D2H on these, overlapping both PCIe directions
+    cudaEvent_t host_ev[5];
+    bool host_pipe_ready;
     int step_loader;        // 0 direct LDG, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline, 3 per-warp pipeline with env pairs (packed FP32)
 };
 
@@ -284,6 +288,15 @@ template <typename R> static SimView<R> make_view(const qs_sim* s) {
     v.stats = s->stats;
     v.seed = s->seed;
     v.env_id_offset = (uint32_t)s->cfg.env_id_offset;
+    if (s->slice_begin != 0 || s->slice_count != s->N) {       // a 256-aligned sub-range of the shard: same rows, shifted columns
+        const int64_t b = s->slice_begin;
+        R** real_rows[] = {&v.obs17, &v.prev_ang, &v.prev_shaping, &v.abs_sum, &v.ep_return, &v.reward, &v.ang_vel, &v.step_effort,
+                           &v.w, &v.accel, &v.acc_read, &v.mat_rot, &v.clipped_action, &v.fm, &v.sensed_obs, &v.sensor_state};
+        for (R** r : real_rows) if (*r) *r += b;
+        v.step_i += b; v.episode += b; v.flags += b; v.done += b; v.solved += b;
+        v.N = s->slice_count;
+        v.env_id_offset += (uint32_t)b;
+    }
     return v;
 }
 
@@ -853,7 +866,7 @@ static int grid_step(const qs_sim* s) {
         ctas_per_sm = e ? atoi(e) : QS_MIN_CTAS;
         if (ctas_per_sm < 1) ctas_per_sm = QS_MIN_CTAS;
     }
-    const int64_t tiles = (s->N + kTile - 1) / kTile;
+    const int64_t tiles = (s->slice_count + kTile - 1) / kTile;
     int64_t g = (int64_t)s->sm_count * ctas_per_sm;
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
@@ -893,7 +906,7 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
                 cudaFuncSetAttribute(step_kernel_pair<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 attr_set = true;
             }
-            const int64_t chunks = (s->N + 63) / 64;
+            const int64_t chunks = (s->slice_count + 63) / 64;
             int64_t g = (int64_t)s->sm_count;
             const int64_t need = (chunks + warps - 1) / warps;
             if (g > need) g = need;
@@ -907,7 +920,7 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
                 cudaFuncSetAttribute(step_kernel_warp<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 attr_set = true;
             }
-            const int64_t chunks = (s->N + 31) / 32;
+            const int64_t chunks = (s->slice_count + 31) / 32;
             int64_t g = (int64_t)s->sm_count * QS_MIN_CTAS;
             const int64_t need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
             if (g > need) g = need;
@@ -969,6 +982,7 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
     memset(s, 0, sizeof(*s));
     s->cfg = *cfg;
     s->N = cfg->n_envs;
+    s->slice_begin = 0; s->slice_count = cfg->n_envs; s->host_pipe_ready = false;
     s->ld = (int64_t)align_up((size_t)cfg->n_envs, 256);
     s->rs = cfg->precision == QS_F64 ? 8 : 4;
     s->seed = cfg->seed;
@@ -1017,6 +1031,10 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
 
 extern "C" int qs_destroy(qs_handle h) {
     if (!h) return QS_OK;
+    if (h->host_pipe_ready) {
+        for (cudaStream_t q : h->host_streams) cudaStreamDestroy(q);
+        for (cudaEvent_t ev : h->host_ev) cudaEventDestroy(ev);
+    }
     if (h->owns_ws && h->ws) cudaFree(h->ws);
     delete h;
     return QS_OK;
@@ -1076,20 +1094,62 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
     return QS_OK;
 }
 
+// Shards of >= 2 slices x 65,536 envs are pipelined: slice i's actions go up while slice i-1 steps and slice i-2's
+// results come down, so both PCIe directions and the SMs are busy at once (the D2H of 61 B/env is the floor).
 extern "C" int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host,
                             uint8_t* done_host, void* stream) {
     if (!h || !action_host) return fail(QS_EINVAL, "qs_step_host: NULL argument");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t rs = (size_t)h->rs, N = (size_t)h->N, ld = (size_t)h->ld;
-    QS_CUDA(cudaMemcpyAsync(h->action_stage, action_host, 4 * N * rs, cudaMemcpyHostToDevice, st));
-    int rc = qs_step(h, h->action_stage, nullptr, nullptr, nullptr, nullptr, stream);
+    constexpr size_t kSliceMin = 65536;
+    size_t n_slices = N / kSliceMin;
+    if (n_slices > 8) n_slices = 8;
+    if (n_slices < 2) {
+        QS_CUDA(cudaMemcpyAsync(h->action_stage, action_host, 4 * N * rs, cudaMemcpyHostToDevice, st));
+        int rc = qs_step(h, h->action_stage, nullptr, nullptr, nullptr, nullptr, stream);
+        if (rc != QS_OK) return rc;
+        if (obs_host)
+            QS_CUDA(cudaMemcpy2DAsync(obs_host, N * rs, h->obs17, ld * rs, N * rs, 14, cudaMemcpyDeviceToHost, st));
+        if (reward_host)
+            QS_CUDA(cudaMemcpyAsync(reward_host, h->slot[QS_FIELD_REWARD].ptr, N * rs, cudaMemcpyDeviceToHost, st));
+        if (done_host)
+            QS_CUDA(cudaMemcpyAsync(done_host, h->slot[QS_FIELD_DONE].ptr, N, cudaMemcpyDeviceToHost, st));
+        QS_CUDA(cudaStreamSynchronize(st));
+        return QS_OK;
+    }
+    if (!h->host_pipe_ready) {
+        for (cudaStream_t& q : h->host_streams) QS_CUDA(cudaStreamCreateWithFlags(&q, cudaStreamNonBlocking));
+        for (cudaEvent_t& ev : h->host_ev) QS_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        h->host_pipe_ready = true;
+    }
+    const size_t per = ((N + n_slices - 1) / n_slices + 255) / 256 * 256;      // slices start on 256-env boundaries
+    QS_CUDA(cudaEventRecord(h->host_ev[4], st));                               // everything queued on `stream` so far comes first
+    for (cudaStream_t q : h->host_streams) QS_CUDA(cudaStreamWaitEvent(q, h->host_ev[4], 0));
+    int rc = QS_OK;
+    int k = 0;
+    for (size_t b = 0; b < N && rc == QS_OK; b += per, ++k) {
+        const size_t cnt = (N - b < per) ? N - b : per;
+        cudaStream_t q = h->host_streams[k & 3];
+        char* stage = (char*)h->action_stage + 4 * b * rs;                     // contiguous [4][cnt] block of this slice
+        QS_CUDA(cudaMemcpy2DAsync(stage, cnt * rs, (const char*)action_host + b * rs, N * rs, cnt * rs, 4, cudaMemcpyHostToDevice, q));
+        h->slice_begin = (int64_t)b; h->slice_count = (int64_t)cnt;
+        rc = qs_step(h, stage, nullptr, nullptr, nullptr, nullptr, (void*)q);
+        h->slice_begin = 0; h->slice_count = h->N;
+        if (rc != QS_OK) break;
+        if (obs_host)
+            QS_CUDA(cudaMemcpy2DAsync((char*)obs_host + b * rs, N * rs, (const char*)h->obs17 + b * rs, ld * rs, cnt * rs, 14,
+                                      cudaMemcpyDeviceToHost, q));
+        if (reward_host)
+            QS_CUDA(cudaMemcpyAsync((char*)reward_host + b * rs, (const char*)h->slot[QS_FIELD_REWARD].ptr + b * rs, cnt * rs,
+                                    cudaMemcpyDeviceToHost, q));
+        if (done_host)
+            QS_CUDA(cudaMemcpyAsync(done_host + b, (const uint8_t*)h->slot[QS_FIELD_DONE].ptr + b, cnt, cudaMemcpyDeviceToHost, q));
+    }
+    for (int i = 0; i < 4; ++i) {                                              // later work on `stream` is ordered after the pipeline
+        cudaEventRecord(h->host_ev[i], h->host_streams[i]);
+        cudaStreamWaitEvent(st, h->host_ev[i], 0);
+    }
     if (rc != QS_OK) return rc;
-    if (obs_host)
-        QS_CUDA(cudaMemcpy2DAsync(obs_host, N * rs, h->obs17, ld * rs, N * rs, 14, cudaMemcpyDeviceToHost, st));
-    if (reward_host)
-        QS_CUDA(cudaMemcpyAsync(reward_host, h->slot[QS_FIELD_REWARD].ptr, N * rs, cudaMemcpyDeviceToHost, st));
-    if (done_host)
-        QS_CUDA(cudaMemcpyAsync(done_host, h->slot[QS_FIELD_DONE].ptr, N, cudaMemcpyDeviceToHost, st));
     QS_CUDA(cudaStreamSynchronize(st));
     return QS_OK;
 }

@@ -469,20 +469,28 @@ def test_checkpoint_resume():
     assert torch.equal(a.state, b.state) and torch.equal(a.episode, b.episode)
 
 
-def test_step_host_entry_point():
-    N = 2048
-    a = BatchedQuad(N, 0.01, 1000, T=1, precision="f32", device=DEV)
-    b = BatchedQuad(N, 0.01, 1000, T=1, precision="f32", device=DEV)
-    init, _ = qo.sample_reset_state(2, np.arange(N), 0)
-    a.reset(T32(init)); b.reset(T32(init))
-    act = torch.rand(4, N) * 2 - 1
-    act_p = act.pin_memory()
+@pytest.mark.parametrize("N,sensor", [(2048, False), (3 * 65536 + 777, False), (1 << 18, True)])
+def test_step_host_entry_point(N, sensor):
+    """qs_step_host (host buffers in, host buffers out) == qs_step on device tensors, bit for bit — also when the shard is
+    large enough for the sliced H2D -> step -> D2H pipeline (>= 2 x 65,536 envs; ragged last slice), over several steps with
+    auto-reset so that the slices' Philox streams (global env ids) are exercised too."""
+    mk = lambda: BatchedQuad(N, 0.01, 20, T=2, precision="f32", async_reset=True, sensor_noise=sensor, seed=9, device=DEV)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
     obs_h = torch.empty(14, N).pin_memory(); rew_h = torch.empty(N).pin_memory()
     done_h = torch.empty(N, dtype=torch.uint8).pin_memory()
-    torch.cuda.synchronize()
-    L.check(a.lib.qs_step_host(a._h, act_p.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr(), None))
-    obs, rew, done = b.step_soa(act.to(DEV))
-    assert torch.equal(obs.t().cpu(), obs_h) and torch.equal(rew.cpu(), rew_h) and torch.equal(done.cpu(), done_h)
+    g = torch.Generator(); g.manual_seed(3)
+    for t in range(30):
+        act = torch.rand(4, N, generator=g) * 2 - 1
+        act_p = act.pin_memory()
+        torch.cuda.synchronize()
+        L.check(a.lib.qs_step_host(a._h, act_p.data_ptr(), obs_h.data_ptr(), rew_h.data_ptr(), done_h.data_ptr(), None))
+        obs, rew, done = b.step_soa(act.to(DEV))
+        assert torch.equal(obs.t().cpu(), obs_h), t
+        assert torch.equal(rew.cpu(), rew_h) and torch.equal(b.done_flags.cpu(), done_h), t      # raw byte: bit1 = warm-up step
+    assert torch.equal(a.state, b.state) and torch.equal(a.episode, b.episode)
+    sa, sb = a.stats(), b.stats()
+    assert sa["n_episodes"] == sb["n_episodes"] > 0 and sa["n_steps"] == sb["n_steps"]
 
 
 # ----------------------------------------------------------------------------------------------------
