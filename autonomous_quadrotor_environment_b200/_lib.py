@@ -33,7 +33,7 @@ QS_SENSOR_STATE_DIM = 20
 # every symbol include/quadsim.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
-    "qs_rollout", "qs_policy_rollout", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
+    "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
     "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest",
 ]
@@ -92,6 +92,21 @@ class qs_policy_rollout_args(C.Structure):
                 ("logprob_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("hist", C.c_void_p)]
 
 
+class qs_controller(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("reserved", C.c_int32), ("k_t", (C.c_double * 6) * 3), ("k_att", (C.c_double * 6) * 4),
+                ("pid_xy", C.c_double * 3), ("pid_z", C.c_double * 3), ("pid_att", C.c_double * 3), ("pid_psi", C.c_double * 3),
+                ("target_vel", C.c_double * 3), ("target_psi", C.c_double), ("pid_ts", C.c_double)]
+
+
+class qs_control_rollout_args(C.Structure):
+    _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32), ("ctrl_state", C.c_void_p), ("obs_out", C.c_void_p),
+                ("action_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("aux_out", C.c_void_p)]
+
+
+QS_CTRL_LQR, QS_CTRL_PID = 0, 1
+QS_CTRL_STATE_DIM = 22
+
+
 class QuadSimError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__("libquadsim error %d: %s" % (code, msg))
@@ -124,6 +139,8 @@ def load_library():
         "qs_rollout": (C.c_int, [vp, P(qs_rollout_args), vp]),
         "qs_policy_rollout": (C.c_int, [vp, P(qs_actor), P(qs_policy_rollout_args), vp]),
         "qs_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
+        "qs_default_controller": (C.c_int, [P(qs_controller), C.c_int, C.c_int]),
+        "qs_control_rollout": (C.c_int, [vp, P(qs_controller), P(qs_control_rollout_args), vp]),
         "qs_set_step_loader": (C.c_int, [vp, C.c_int]),
         "qs_get_step_loader": (C.c_int, [vp]),
         "qs_field_info": (C.c_int, [vp, C.c_int, P(qs_field_desc)]),

@@ -279,6 +279,40 @@ class BatchedQuad:
         L.check(self.lib.qs_policy_rollout(self._h, C.byref(self._actor[0]), C.byref(a), self._stream()))
         return out
 
+    def controller_state(self) -> torch.Tensor:
+        """Fresh controller memory (QS_CTRL_STATE_DIM, N): zeros, pending PID action = hover [M*G,0,0,0]
+        (pid_vel_control.py:143-144).  Pass it to control_rollout(ctrl_state=...) to continue a controller across launches."""
+        cs = torch.zeros(L.QS_CTRL_STATE_DIM, self.N, dtype=self.dtype, device=self.device)
+        cs[18] = float(self._cfg.params.mass * self._cfg.params.gravity)
+        return cs
+
+    def control_rollout(self, controller, horizon: int, ctrl_state=None, record_obs=False, record_actions=False,
+                        record_reward=False, record_done=False, record_aux=False):
+        """K fused env steps driven by an in-kernel classical control law (controllers.lqr_controller / pid_controller:
+        environment/controller/lqr_quad.py:129-157, pid_vel_control.py:29-127) in ONE launch.  Needs direct_control=0.
+        record_aux -> (K,10,N): ang(3), ang_vel(3), step_effort(4), i.e. with obs[:, (1,3,5)] the 13 columns of the reference's
+        classical_controller_results logs.  Returns the recorded buffers."""
+        a = L.qs_control_rollout_args()
+        a.horizon = int(horizon)
+        if ctrl_state is not None:
+            if ctrl_state.shape != (L.QS_CTRL_STATE_DIM, self.N) or ctrl_state.dtype != self.dtype or not ctrl_state.is_contiguous():
+                raise ValueError("ctrl_state must be a contiguous (%d,N) %s tensor" % (L.QS_CTRL_STATE_DIM, self.dtype))
+            a.ctrl_state = ctrl_state.data_ptr()
+        out = {}
+        mk = lambda c: torch.empty(horizon, c, self.N, dtype=self.dtype, device=self.device)
+        if record_obs:
+            out["obs"] = mk(14); a.obs_out = out["obs"].data_ptr()
+        if record_actions:
+            out["actions"] = mk(4); a.action_out = out["actions"].data_ptr()
+        if record_aux:
+            out["aux"] = mk(10); a.aux_out = out["aux"].data_ptr()
+        if record_reward:
+            out["reward"] = torch.empty(horizon, self.N, dtype=self.dtype, device=self.device); a.reward_out = out["reward"].data_ptr()
+        if record_done:
+            out["done"] = torch.empty(horizon, self.N, dtype=torch.uint8, device=self.device); a.done_out = out["done"].data_ptr()
+        L.check(self.lib.qs_control_rollout(self._h, C.byref(controller), C.byref(a), self._stream()))
+        return out
+
     # ------------------------------------------------------------------ attributes of the reference `quad`
     @property
     def obs(self):            # quat_state :486

@@ -1394,4 +1394,5 @@ extern "C" int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_
     return QS_OK;
 }
 
+#include "controller_rollout.cuh"
 #include "actor_rollout.cuh"

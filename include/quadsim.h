@@ -198,6 +198,38 @@ typedef struct qs_policy_rollout_args {
     void* hist;           /* [75][N] float in/out: dl_in_gen.deep_learning_input per env, oldest first; NULL = zeros */
 } qs_policy_rollout_args;
 
+/* Classical comparison controllers of the reference as in-kernel control laws: LQR
+ * (environment/controller/lqr_quad.py:129-157) and the cascaded velocity/attitude PID (environment/controller/
+ * pid_vel_control.py:29-127).  Both command [F, Mx, My, Mz]: indirect-control (direct_control=0) handles only. */
+#define QS_CTRL_LQR 0
+#define QS_CTRL_PID 1
+typedef struct qs_controller {
+    int32_t kind;              /* QS_CTRL_*                                                                     */
+    int32_t reserved;
+    double k_t[3][6];          /* LQR translational gain K_t   lqr_quad.py:107-111 (solution of an ARE: computed by the host) */
+    double k_att[4][6];        /* LQR attitude gain K_att      lqr_quad.py:82-86                                 */
+    double pid_xy[3], pid_z[3], pid_att[3], pid_psi[3];   /* P, I, D of the velocity / attitude loops  pid_vel_control.py:17-27 */
+    double target_vel[3];      /* velocity set-point xd        pid_vel_control.py:150                            */
+    double target_psi;         /* yaw set-point psd                                                              */
+    double pid_ts;             /* time step of class pid (its default argument, 0.01, :114); <= 0 -> 0.01        */
+} qs_controller;
+
+/* Controller memory per env, [QS_CTRL_STATE_DIM][N]: rows 0..2 quad.ang_vel as of the last step (the LQR's rate feedback),
+ * 3..8 x_old and 9..14 ix of the six scalar PIDs [vx, vy, vz, phi, theta, psi], 15..17 ang_d_ant, 18..21 the PID action
+ * computed after the previous step and applied at the next (pid_vel_control.py:144-153; [M*G,0,0,0] for a fresh controller). */
+#define QS_CTRL_STATE_DIM 22
+typedef struct qs_control_rollout_args {
+    int32_t horizon;
+    int32_t reserved;
+    void* ctrl_state;          /* [QS_CTRL_STATE_DIM][N] in/out, or NULL = fresh controller, ang_vel = 0, not written back */
+    void* obs_out;             /* [K][14][N] or NULL */
+    void* action_out;          /* [K][4][N]  or NULL : the [F,Mx,My,Mz] command applied at step t               */
+    void* reward_out;          /* [K][N]     or NULL */
+    uint8_t* done_out;         /* [K][N]     or NULL */
+    void* aux_out;             /* [K][10][N] or NULL : ang(3), ang_vel(3), step_effort(4) — with the velocities of obs_out the */
+                               /*                      13 columns of the reference's classical_controller_results logs         */
+} qs_control_rollout_args;
+
 /* ---- lifecycle ----------------------------------------------------------------------------- */
 /* Fill *cfg with the reference defaults (constants quadrotor_env.py:30-80; quad() keyword defaults :112). */
 int qs_default_config(qs_config* cfg);
@@ -222,6 +254,13 @@ int qs_step(qs_handle h, const void* action, void* obs, void* reward, uint8_t* d
 int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream);
 /* K fused policy steps (see qs_policy_rollout_args); FP32 / RK4 / direct-control handles only. */
 int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_policy_rollout_args* args, void* stream);
+/* PID gains of pid_vel_control.py:17-27 (clipped / not clipped); the LQR gains are left zero (host computes the AREs). */
+int qs_default_controller(qs_controller* c, int kind, int clipped);
+/* K fused steps driven by an in-kernel control law (see qs_controller); resets: none, or QS_FLAG_ASYNC_RESET (the
+ * controller memory is cleared after every reset like `controller = pid_control(drone)`, pid_vel_control.py:143).
+ * On QS_FLAG_AUX handles quad.ang_vel is read from / written back to the handle's ANG_VEL row (rows 0..2 of ctrl_state are
+ * then ignored on input), so reset() -> control_rollout() behaves like the reference scripts. */
+int qs_control_rollout(qs_handle h, const qs_controller* c, const qs_control_rollout_args* args, void* stream);
 /* Same contract as qs_step but with HOST buffers (pinned or pageable): H2D of the actions, the step
  * kernel and D2H of obs/reward/done are enqueued on `stream` and the call returns after they finish. */
 int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);

@@ -744,3 +744,96 @@ class SensorOracle:
         self.quat = np.where(m[:, None], quat, self.quat)
         self.Rc2 = np.where(m[:, None], R2[:, :, 2], self.Rc2)
         return obs
+
+
+# --------------------------------------------------------------------------------------
+# classical controllers the reference compares against PPO — batched restatements
+# --------------------------------------------------------------------------------------
+def lqr_gains(clipped=True):
+    """Gains exactly as environment/controller/lqr_quad.py:25-111 computes them (two continuous-time AREs)."""
+    from scipy.linalg import solve_continuous_are as solve_lqr
+    if clipped:                                                               # :25-43
+        Q_att = np.diag([5, 1, 5, 1, 0.05, 0.01]) * 50.0
+        R_att = np.diag(np.ones(4)) * 40.0
+        Q_t = np.diag([1e-08, 1, 1e-08, 1, 1e-08, 0.8]) * 10.0
+        R_t = np.diag(np.ones(3)) * 10.0
+    else:                                                                     # :44-62
+        Q_att = np.diag([5, 0.3, 5, 0.3, 2, 0.3]) * 160.0
+        R_att = np.diag(np.ones(4)) * 40.0
+        Q_t = np.diag([1e-08, 1, 1e-08, 1, 1e-08, 0.5]) * 60.0
+        R_t = np.diag(np.ones(3)) * 5.0
+    A = np.zeros((6, 6)); A[0, 1] = A[2, 3] = A[4, 5] = 1.0                   # :67-72, :88-93 (same chain of integrators)
+    B_att = np.zeros((6, 4)); B_att[1, 1] = 1 / J_DIAG[0]; B_att[3, 2] = 1 / J_DIAG[1]; B_att[5, 3] = 1 / J_DIAG[2]   # :74-79
+    B_t = np.zeros((6, 3)); B_t[1, 0] = B_t[3, 1] = B_t[5, 2] = 1 / M         # :98-103
+    K_att = -np.dot(np.linalg.inv(R_att), np.dot(B_att.T, solve_lqr(A, B_att, Q_att, R_att)))     # :82-86
+    K_t = -np.dot(np.linalg.inv(R_t), np.dot(B_t.T, solve_lqr(A, B_t, Q_t, R_t)))                 # :107-111
+    return K_t, K_att
+
+
+def lqr_law(K_t, K_att, state, ang, ang_vel):
+    """environment/controller/lqr_quad.py:129-157 for N envs: state (N,13), ang (N,3), ang_vel (N,3) -> action (N,4) =
+    [F, Mx, My, Mz] for an indirect-control quad.  (deuler_t, :148, is computed by the script but never used.)"""
+    z = np.zeros(len(state))
+    state_t = np.stack([z, state[:, 1], z, state[:, 3], z, state[:, 5]], axis=1)                 # :129
+    F = state_t @ K_t.T                                                                           # :130
+    theta_t = np.arctan2(F[:, 0], F[:, 2] + G)                                                    # :135
+    phi_t = np.arctan2(-F[:, 1] * np.cos(theta_t), F[:, 2] + G)                                   # :137
+    U_1 = M * (F[:, 2] + G) / (np.cos(theta_t) * np.cos(phi_t))                                   # :141
+    euler = ang - np.stack([phi_t, theta_t, z], axis=1)                                           # :139,:144
+    state_att = np.stack([euler[:, 0], ang_vel[:, 0], euler[:, 1], ang_vel[:, 1], euler[:, 2], ang_vel[:, 2]], axis=1)  # :152
+    action = state_att @ K_att.T                                                                  # :153
+    action[:, 0] = U_1                                                                            # :154
+    return action
+
+
+PID_GAINS_CLIPPED = dict(xy=(1, -0.0, 0), z=(0.4, -0.0, 0), att=(20, 0, 20), psi=(5, 0, 5))       # pid_vel_control.py:18-22
+PID_GAINS_NOT_CLIPPED = dict(xy=(2, -0.0, 0), z=(1, -0.0, 0), att=(180, 0, 50), psi=(40, 0, 20))  # :24-27
+
+
+class PidControllerOracle:
+    """environment/controller/pid_vel_control.py:29-127 (class pid_control + class pid) for N envs.
+    Controller memory per env: x_old(6), ix(6) of the six scalar PIDs [x, y, z, phi, theta, psi] and ang_d_ant(3)."""
+
+    def __init__(self, n_envs, t_step=0.01, gains=PID_GAINS_CLIPPED):
+        self.N, self.ts = n_envs, t_step
+        g = gains
+        self.p = np.array([g["xy"][0], g["xy"][0], g["z"][0], g["att"][0], g["att"][0], g["psi"][0]], dtype=np.float64)
+        self.i = np.array([g["xy"][1], g["xy"][1], g["z"][1], g["att"][1], g["att"][1], g["psi"][1]], dtype=np.float64)
+        self.d = np.array([g["xy"][2], g["xy"][2], g["z"][2], g["att"][2], g["att"][2], g["psi"][2]], dtype=np.float64)
+        self.reset()
+
+    def reset(self, mask=None):
+        if mask is None:
+            self.x_old = np.zeros((self.N, 6)); self.ix = np.zeros((self.N, 6)); self.ang_d_ant = np.zeros((self.N, 3))
+        else:
+            self.x_old[mask] = 0; self.ix[mask] = 0; self.ang_d_ant[mask] = 0
+
+    def _pid(self, k, x, x_d, dx_d):                                           # class pid :114-127 (the dx argument is overwritten)
+        dx = (x - self.x_old[:, k]) / 0.01                                     # pid.ts defaults to 0.01 (:115)
+        self.x_old[:, k] = x
+        self.ix[:, k] = self.ix[:, k] + (x_d - x) * 0.01
+        return self.p[k] * (x_d - x) + self.d[k] * (dx_d - dx) - self.i[k] * self.ix[:, k]
+
+    def control(self, state, ang, xd, psd):
+        """pid_control.control :97-110: state (N,13), ang (N,3), velocity set-point xd (3,), yaw set-point psd."""
+        z = np.zeros(self.N)
+        u_1 = self._pid(0, state[:, 1], xd[0] + z, z)                          # lower_control :48-63
+        u_2 = self._pid(1, state[:, 3], xd[1] + z, z)
+        u_3 = self._pid(2, state[:, 5], xd[2] + z, z)
+        theta_d = np.arctan2(u_1, u_3 + G)
+        phi_d = np.arctan2(-u_2 * np.cos(theta_d), u_3 + G)
+        U_1 = M * (u_3 + G) / (np.cos(theta_d) * np.cos(phi_d))
+        ang_d = np.stack([phi_d, theta_d, psd + z], axis=1)                    # :103
+        v_ang_d = (ang_d - self.ang_d_ant) / self.ts                           # :104
+        u_5 = self._pid(3, ang[:, 0], ang_d[:, 0], v_ang_d[:, 0])              # upper_control :66-95
+        u_6 = self._pid(4, ang[:, 1], ang_d[:, 1], v_ang_d[:, 1])
+        u_7 = self._pid(5, ang[:, 2], ang_d[:, 2], v_ang_d[:, 2])
+        sp, cp = np.sin(ang[:, 0]), np.cos(ang[:, 0])
+        ct, tt = np.cos(ang[:, 1]), np.tan(ang[:, 1])
+        Mm = np.zeros((self.N, 3, 3))
+        Mm[:, 0, 0] = 1 / J_DIAG[0]; Mm[:, 0, 1] = tt * sp / J_DIAG[1]; Mm[:, 0, 2] = tt * cp / J_DIAG[2]
+        Mm[:, 1, 1] = cp / J_DIAG[1]; Mm[:, 1, 2] = -sp / J_DIAG[2]
+        Mm[:, 2, 1] = sp / ct / J_DIAG[1]; Mm[:, 2, 2] = cp / ct / J_DIAG[2]
+        U = np.einsum("nij,nj->ni", np.linalg.inv(Mm), np.stack([u_5, u_6, u_7], axis=1))    # :93
+        self.ang_d_ant = ang_d                                                 # :106
+        return np.concatenate([U_1[:, None], U], axis=1)                       # :107

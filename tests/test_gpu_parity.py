@@ -594,6 +594,97 @@ def test_dropin_quad_reproduces_shipped_lqr_log():
 
 
 # ----------------------------------------------------------------------------------------------------
+# the reference's classical comparison controllers as in-kernel control laws
+# ----------------------------------------------------------------------------------------------------
+def _log_rows(rec):
+    """(K,N,13) = [vel(3), ang(3), ang_vel(3), step_effort(4)]: the columns of classical_controller_results/*.npy"""
+    obs, aux = rec["obs"].cpu().numpy(), rec["aux"].cpu().numpy()
+    return np.concatenate([obs[:, (1, 3, 5)], aux], axis=1).transpose(0, 2, 1)
+
+
+@pytest.mark.parametrize("kind", ["lqr", "pid"])
+def test_control_rollout_reproduces_shipped_controller_logs(kind):
+    """FP64 + RK45 replica, one env per logged episode, ONE launch of 500 fused steps with the control law in-kernel vs the
+    logs the reference ships (written by the author's 2021 run).  Episodes ran back to back in the scripts, so prev_ang of
+    episode k is the last Euler angle of episode k-1 (never cleared by reset, quadrotor_env.py:171-172)."""
+    from autonomous_quadrotor_environment_b200 import controllers as ctl
+    g = load_golden("%s_log.npz" % kind)
+    E = g["log"].shape[0]
+    T = 1 if kind == "lqr" else 5                        # lqr_quad.py:114, pid_vel_control.py:132
+    env = BatchedQuad(E, 0.01, 500, training=True, direct_control=0, T=T, clipped=True, precision="f64", aux=True, device=DEV)
+    env.prev_ang[1:] = T64(g["log"][:E - 1, -1, 3:6])
+    env.reset(T64(g["inits"][:E]))
+    c = ctl.lqr_controller(K_t=g["K_t"], K_att=g["K_att"]) if kind == "lqr" else ctl.pid_controller()
+    rec = env.control_rollout(c, 500, record_obs=True, record_aux=True)
+    rows = _log_rows(rec)                                # (500, E, 13)
+    for ep in range(E):
+        n_steps = 60 if (kind == "lqr" and ep == 0) else 300     # LQR episode 0 diverges chaotically (reference re-run: 5e-7)
+        err = np.abs(rows[:n_steps, ep] - g["log"][ep, :n_steps]).max()
+        assert err < 1e-8, (kind, ep, err)
+    # the AUX attributes of the handle are those of the last step, like the reference object's
+    assert np.allclose(env.ang_vel.cpu().numpy(), rows[-1][:, 6:9], rtol=0, atol=1e-12)
+    assert np.allclose(env.step_effort.cpu().numpy(), rows[-1][:, 9:13], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["lqr", "pid"])
+def test_control_rollout_f64_vs_oracle_random_states(kind):
+    """256 envs from the reset distribution, 120 closed-loop steps: in-kernel law + RK45 replica vs the oracle driven by the
+    restated law, every step within 1e-9 (relative to max(|x|, 1e-3)); controller memory round-trips through ctrl_state."""
+    from autonomous_quadrotor_environment_b200 import controllers as ctl
+    N, K = 256, 120
+    init, _ = qo.sample_reset_state(21, np.arange(N), 0)
+    env = BatchedQuad(N, 0.01, 500, training=False, direct_control=0, T=2, clipped=True, precision="f64", aux=True, device=DEV)
+    ora = qo.BatchQuadOracle(N, 0.01, 500, training=False, direct_control=0, T=2, clipped=True, integrator="rk45")
+    env.reset(T64(init)); ora.reset(init)
+    K_t, K_att = qo.lqr_gains()
+    c = ctl.lqr_controller() if kind == "lqr" else ctl.pid_controller(target_vel=(0.3, -0.2, 0.1), target_psi=0.05)
+    pid = qo.PidControllerOracle(N)
+    cs = env.controller_state()
+    recs = [env.control_rollout(c, K // 2, ctrl_state=cs, record_obs=True, record_aux=True, record_actions=True) for _ in range(2)]
+    rows = np.concatenate([_log_rows(r) for r in recs])
+    acts = np.concatenate([r["actions"].cpu().numpy() for r in recs]).transpose(0, 2, 1)
+    action = np.tile(np.array([9.82 * 1.03, 0, 0, 0]), (N, 1))
+    worst = 0.0
+    for t in range(K):
+        if kind == "lqr":
+            action = qo.lqr_law(K_t, K_att, ora.state, ora.ang, ora.ang_vel)
+        worst = max(worst, float(rel_err(acts[t], action)))
+        ora.step(action)
+        if kind == "pid":
+            action = pid.control(ora.state, ora.ang, np.array([0.3, -0.2, 0.1]), 0.05)
+        ref = np.concatenate([ora.state[:, 1:6:2], ora.ang, ora.ang_vel, ora.step_effort], axis=1)
+        worst = max(worst, float(rel_err(rows[t], ref)))
+    assert worst < 1e-9, worst
+
+
+def test_control_rollout_f32_million_env_comparison():
+    """The README's controller comparison at scale: FP32 RK4, 262,144 envs from the reset distribution, 400 fused steps of
+    each law.  Property checks (size-independent): both laws stabilise (the median speed at least halves within 4 s),
+    nothing becomes non-finite, and FP32 agrees with the FP64 kernel on a sub-sample within the closed-loop FP32 bound."""
+    from autonomous_quadrotor_environment_b200 import controllers as ctl
+    N, K = 1 << 18, 400
+    for c in (ctl.lqr_controller(), ctl.pid_controller()):
+        env = BatchedQuad(N, 0.01, 10 ** 6, training=False, direct_control=0, T=1, clipped=True, precision="f32", seed=4, device=DEV)
+        env.reset()
+        st0 = env.state.clone()
+        env.control_rollout(c, K)
+        st = env.state
+        assert bool(torch.isfinite(st).all())
+        v0, v1 = st0[:, (1, 3, 5)].norm(dim=1).median(), st[:, (1, 3, 5)].norm(dim=1).median()
+        assert float(v1) < 0.5 * float(v0), (float(v0), float(v1))
+        sub = 512
+        e64 = BatchedQuad(sub, 0.01, 10 ** 6, training=False, direct_control=0, T=1, clipped=True, precision="f64", integrator="rk4",
+                          seed=4, device=DEV)
+        e64.reset(st0[:sub].double())
+        e32 = BatchedQuad(sub, 0.01, 10 ** 6, training=False, direct_control=0, T=1, clipped=True, precision="f32", seed=4, device=DEV)
+        e32.reset(st0[:sub])
+        e64.control_rollout(c, 100); e32.control_rollout(c, 100)
+        a, b = e32.state.double()[:, 1:].cpu().numpy(), e64.state[:, 1:].cpu().numpy()     # positions integrate the error: skip x
+        ok = np.abs(a - b) <= 2e-3 + 2e-3 * np.abs(b)
+        assert ok.mean() > 0.999, ok.mean()
+
+
+# ----------------------------------------------------------------------------------------------------
 # BASELINE.json full size (configs[2]): size-independent properties
 # ----------------------------------------------------------------------------------------------------
 def test_full_size_properties_1M_envs():

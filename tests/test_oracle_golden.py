@@ -154,3 +154,37 @@ def test_sensor_oracle_statistics_match_reference_sensor():
     # dead-reckoning drift after 15 s is a random walk of the same scale (well inside 4x of the reference's spread)
     ref_scale = np.abs(g["pos_end"]).mean()
     assert 0.2 * ref_scale < np.abs(obs[-1][:, [0, 2, 4]]).mean() < 5 * ref_scale
+
+
+def test_shipped_pid_log_and_lqr_gains():
+    """Controller restatements are pinned by the reference's own shipped logs: the cascaded PID of
+    pid_vel_control.py:29-127 driving the oracle reproduces classical_controller_results/pid_log_same_start.npy
+    (T=5, 500 steps, episodes back to back -> prev_ang carried over), and lqr_gains() equals the gains the script computes."""
+    g = load_golden("lqr_log.npz")
+    K_t, K_att = qo.lqr_gains()
+    assert np.abs(K_t - g["K_t"]).max() < 1e-12 and np.abs(K_att - g["K_att"]).max() < 1e-12
+    gp = load_golden("pid_log.npz")
+    E = 3
+    env = qo.BatchQuadOracle(E, 0.01, 500, training=True, direct_control=0, T=5, clipped=True, integrator="rk45")
+    env.prev_ang[1:] = gp["log"][:E - 1, -1, 3:6]
+    env.reset(gp["inits"][:E])
+    ctl = qo.PidControllerOracle(E)
+    action = np.tile(np.array([9.82 * 1.03, 0, 0, 0]), (E, 1))                # pid_vel_control.py:144
+    worst = 0.0
+    for j in range(300):
+        env.step(action)
+        action = ctl.control(env.state, env.ang, np.zeros(3), 0.0)
+        row = np.concatenate([env.state[:, 1:6:2], env.ang, env.ang_vel, env.step_effort], axis=1)
+        worst = max(worst, float(np.abs(row - gp["log"][:E, j]).max()))
+    assert worst < 1e-9, worst
+
+
+def test_lqr_law_equals_script_restatement():
+    """The batched lqr_law equals the per-env restatement used to pin the oracle against the shipped LQR log."""
+    g = load_golden("lqr_log.npz")
+    rng = np.random.default_rng(0)
+    st = rng.normal(size=(64, 13)); ang = rng.uniform(-1, 1, (64, 3)); av = rng.normal(size=(64, 3))
+    a = qo.lqr_law(g["K_t"], g["K_att"], st, ang, av)
+    for n in range(64):
+        ref, _ = lqr_action(g["K_t"], g["K_att"], st[n], ang[n], av[n], None)
+        assert np.allclose(a[n], ref, rtol=1e-13, atol=1e-13)
