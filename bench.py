@@ -235,6 +235,8 @@ def run_policy_workload(args):
 
 def main():
     args = parse()
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner on stdout before the JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference_arm(args)
         return
