@@ -33,7 +33,7 @@ QS_SENSOR_STATE_DIM = 20
 # every symbol include/quadsim.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
-    "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
+    "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_gae", "qs_adv_normalize", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
     "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest",
 ]
@@ -141,6 +141,8 @@ def load_library():
         "qs_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp]),
         "qs_default_controller": (C.c_int, [P(qs_controller), C.c_int, C.c_int]),
         "qs_control_rollout": (C.c_int, [vp, P(qs_controller), P(qs_control_rollout_args), vp]),
+        "qs_gae": (C.c_int, [i64, C.c_int32, C.c_float, C.c_float, vp, vp, vp, vp, vp, vp, vp]),
+        "qs_adv_normalize": (C.c_int, [i64, vp, vp, vp, vp, vp]),
         "qs_set_step_loader": (C.c_int, [vp, C.c_int]),
         "qs_get_step_loader": (C.c_int, [vp]),
         "qs_field_info": (C.c_int, [vp, C.c_int, P(qs_field_desc)]),

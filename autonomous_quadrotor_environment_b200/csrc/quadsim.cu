@@ -1395,4 +1395,5 @@ extern "C" int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_
 }
 
 #include "controller_rollout.cuh"
+#include "ppo_kernels.cuh"
 #include "actor_rollout.cuh"

@@ -1,0 +1,170 @@
+"""On-device PPO iteration around the fused rollout — host-side mirror of the reference trainer
+`environment/controller/ppo.py` (class PPO :80-209, model.py ActorCritic) for the batched simulator:
+
+    rollout   BatchedQuad.policy_rollout   history -> actor (tcgen05) -> Normal sample -> quad.step, K steps per launch
+    values    critic over the recorded network inputs (torch / cuBLAS GEMMs, chunked over envs)
+    GAE       qs_gae / qs_adv_normalize    hand-written backward scan + masked normalisation on the [K][N] buffers
+    update    K_epochs full-batch clipped-surrogate steps (ppo.py:164-206), gradients accumulated over env chunks and
+              all-reduced across ranks (the path's second collective: ~0.2 MB per step), Adam
+
+Nothing of the 1M x 128 rollout leaves the GPU.  PyTorch supplies autograd, Adam and the GEMMs of the update; the rollout,
+the simulator and the scans are the CUDA kernels of libquadsim.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from . import _lib as L
+
+
+class ActorCritic(nn.Module):
+    """model.py:19-47 — actor Linear-Tanh-Linear-Tanh-Linear-Tanh, critic Linear-Tanh-Linear-Tanh-Linear, fixed std."""
+
+    def __init__(self, hidden: int = 128, state_dim: int = 75, action_dim: int = 4, action_std: float = 0.1):
+        super().__init__()
+        self.actor = nn.Sequential(nn.Linear(state_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(),
+                                   nn.Linear(hidden, action_dim), nn.Tanh())
+        self.critic = nn.Sequential(nn.Linear(state_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh(),
+                                    nn.Linear(hidden, 1))
+        # model.py:42 keeps std as a float32 Parameter and Normal(mean, ones(4)*std) keeps a float32 scale: its square and
+        # its log are rounded to float32 before they meet the (double) means — reproduced so that losses agree to 1e-12
+        s32 = torch.tensor(action_std, dtype=torch.float32)
+        self.std, self._var, self._log_std = float(s32), float(s32 * s32), float(torch.log(s32))
+        self._entropy = float(0.5 + 0.5 * math.log(2 * math.pi) + torch.log(s32))     # Normal.entropy() stays float32
+
+    def evaluate(self, state, action):
+        """model.py:74-88: per-dimension log-prob of `action` under Normal(actor(state), std), state value, entropy."""
+        mean = self.actor(state)
+        logp = -((action - mean) ** 2) / (2 * self._var) - self._log_std - math.log(math.sqrt(2 * math.pi))
+        entropy = torch.full_like(mean, self._entropy)
+        return logp, self.critic(state).squeeze(-1), entropy
+
+
+def ppo_loss(policy: ActorCritic, states, actions, old_logprobs, advantages, returns, weight=None, eps_clip: float = 0.2):
+    """The loss of PPO.update (ppo.py:183-201) on one batch; `weight` (0/1) drops warm-up transitions.  Returns the SUM over
+    the batch of the per-sample loss (divide by the global sample count: the reference takes loss.mean(), :203; its scalar
+    0.5*MSELoss term is the mean of 0.5*(V - R)^2, so it distributes over the samples)."""
+    logp, values, entropy = policy.evaluate(states, actions)
+    ratios = torch.exp(logp.sum(-1) - old_logprobs.sum(-1))                          # :187
+    surr1 = ratios * advantages                                                      # :192
+    surr2 = torch.clamp(ratios, 1 - eps_clip, 1 + eps_clip) * advantages             # :193
+    sq = (values - returns) ** 2
+    per = -torch.min(surr1, surr2) + 0.5 * sq - 0.006 * entropy.sum(-1)              # :194-200 (0.5*MSE enters every sample's loss)
+    if weight is not None:
+        per = per * weight
+    return per.sum()
+
+
+class BatchedPPO:
+    """class PPO (ppo.py:80-209) driving a BatchedQuad.  Hyper-parameters default to the reference's (:296-318)."""
+
+    def __init__(self, env, hidden: int = 128, action_std: float = 0.1, lr: float = 5e-4, betas=(0.9, 0.999), gamma: float = 0.99,
+                 lmbda: float = 0.99, K_epochs: int = 10, eps_clip: float = 0.2, chunk_envs: int = 16384, seed: int = 0,
+                 tf32: bool = True):
+        self.env = env
+        self.dev = env.device if env is not None else torch.device("cpu")     # env=None: update()-only use (tests on CPU / gloo)
+        torch.manual_seed(seed)
+        self.policy = ActorCritic(hidden, 75, 4, action_std).to(self.dev)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, betas=betas)
+        self.gamma, self.lmbda, self.K_epochs, self.eps_clip = gamma, lmbda, K_epochs, eps_clip
+        self.chunk = int(chunk_envs)
+        self.tf32 = bool(tf32)            # TF32 tensor-core GEMMs for the update's autograd (FP32 accumulate); False = IEEE FP32
+        self.moments = torch.zeros(3, dtype=torch.float64, device=self.dev)
+        self._sync_actor()
+
+    def _sync_actor(self):
+        """policy_old.load_state_dict(policy.state_dict()) (:206): the rollout kernel reads the actor weights."""
+        if self.env is None:
+            return
+        self.env.load_actor({"actor_%d_%s" % (i, k): getattr(self.policy.actor[i], k).detach() for i in (0, 2, 4) for k in ("weight", "bias")},
+                            action_std=self.policy.std)
+
+    # ---------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def history_entries(rec):
+        """(K,15,N) dl_in_gen entries [action(4), v(3), q(4), dq(4)] (dl_auxiliary.py:27-30) of a recorded rollout, rounded
+        to BF16 like the A operand the fused actor reads."""
+        obs, act = rec["obs"], rec["actions"]
+        e = torch.cat([act, obs[:, (1, 3, 5)], obs[:, 6:14]], dim=1)
+        return e.bfloat16().float()
+
+    def network_inputs(self, hist0, entries, n0, n1):
+        """Inputs the actor saw at every step for envs [n0,n1): (K, n, 75), oldest entry first (dl_auxiliary.py:25-32).
+        hist0 (75,N) = history at rollout start; entries (K,15,N)."""
+        K = entries.shape[0]
+        h = hist0[:, n0:n1].reshape(5, 15, n1 - n0)
+        seq = torch.cat([h, entries[:, :, n0:n1]], dim=0)                 # (5+K, 15, n): input of step t = seq[t:t+5]
+        x = seq.unfold(0, 5, 1)[:K + 1]                                   # (K+1, 15, n, 5)
+        return x.permute(0, 2, 3, 1).reshape(K + 1, n1 - n0, 75)          # [..., 15*slot + e]
+
+    @torch.no_grad()
+    def collect(self, horizon: int):
+        """One rollout + values + GAE.  Returns the batch dict (all tensors on the device, time-major)."""
+        env = self.env
+        hist0 = env.history.t().contiguous().clone()                      # (75, N)
+        rec = env.policy_rollout(horizon, record_obs=True, record_actions=True, record_logprob=True, record_reward=True,
+                                 record_done=True)
+        entries = self.history_entries(rec)
+        K, N = horizon, env.N
+        value = torch.empty(K + 1, N, dtype=torch.float32, device=self.dev)
+        for n0 in range(0, N, self.chunk):
+            n1 = min(N, n0 + self.chunk)
+            x = self.network_inputs(hist0, entries, n0, n1)
+            value[:, n0:n1] = self.policy.critic(x).squeeze(-1)
+        ret = torch.empty(K, N, dtype=torch.float32, device=self.dev)
+        adv = torch.empty(K, N, dtype=torch.float32, device=self.dev)
+        weight = torch.empty(K, N, dtype=torch.float32, device=self.dev)
+        self.moments.zero_()
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        L.check(env.lib.qs_gae(N, K, self.gamma, self.lmbda, rec["reward"].data_ptr(), value.data_ptr(), rec["done"].data_ptr(),
+                               ret.data_ptr(), adv.data_ptr(), self.moments.data_ptr(), st))
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.moments)                                 # normalise over the GLOBAL batch
+        L.check(env.lib.qs_adv_normalize(K * N, rec["done"].data_ptr(), self.moments.data_ptr(), adv.data_ptr(), weight.data_ptr(), st))
+        return dict(hist0=hist0, entries=entries, actions=rec["actions"], logprob=rec["logprob"], reward=rec["reward"],
+                    done=rec["done"], value=value, returns=ret, adv=adv, weight=weight, count=float(self.moments[0].item()))
+
+    def update(self, batch):
+        """PPO.update (:143-206): K_epochs full-batch steps (the reference's randperm does not change a full-batch mean)."""
+        K, N = batch["reward"].shape
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        count = batch["count"]                                            # global number of valid transitions
+        losses = []
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        if self.dev.type == "cuda":
+            torch.backends.cuda.matmul.allow_tf32 = self.tf32
+        for _ in range(self.K_epochs):
+            self.optimizer.zero_grad(set_to_none=False)
+            total = torch.zeros((), dtype=torch.float64, device=self.dev)
+            for n0 in range(0, N, self.chunk):
+                n1 = min(N, n0 + self.chunk)
+                x = self.network_inputs(batch["hist0"], batch["entries"], n0, n1)[:K]
+                loss = ppo_loss(self.policy, x, batch["actions"][:, :, n0:n1].permute(0, 2, 1), batch["logprob"][:, :, n0:n1].permute(0, 2, 1),
+                                batch["adv"][:, n0:n1], batch["returns"][:, n0:n1], batch["weight"][:, n0:n1], self.eps_clip)
+                (loss / count).backward()                                 # loss.mean().backward() over the global batch (:203)
+                total += loss.detach().double()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in self.policy.parameters() if p.grad is not None])
+                dist.all_reduce(flat)                                     # ~0.2 MB: sum of the per-rank partial gradients
+                o = 0
+                for p in self.policy.parameters():
+                    if p.grad is not None:
+                        n = p.grad.numel(); p.grad.copy_(flat[o:o + n].view_as(p.grad)); o += n
+                dist.all_reduce(total)
+            self.optimizer.step()
+            losses.append(float(total.item()) / count)
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+        self._sync_actor()
+        return losses
+
+    def iterate(self, horizon: int = 128):
+        batch = self.collect(horizon)
+        losses = self.update(batch)
+        r = batch["reward"]
+        return dict(mean_reward=float((r * batch["weight"]).sum().item() / max(1.0, batch["count"])), losses=losses,
+                    stats=self.env.stats(reset=True))

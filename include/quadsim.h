@@ -261,6 +261,15 @@ int qs_default_controller(qs_controller* c, int kind, int clipped);
  * On QS_FLAG_AUX handles quad.ang_vel is read from / written back to the handle's ANG_VEL row (rows 0..2 of ctrl_state are
  * then ignored on input), so reset() -> control_rollout() behaves like the reference scripts. */
 int qs_control_rollout(qs_handle h, const qs_controller* c, const qs_control_rollout_args* args, void* stream);
+/* PPO.get_advantages (environment/controller/ppo.py:125-141) on time-major rollout buffers: backward GAE scan per env.
+ * reward [K][N], value [K+1][N] (row K = bootstrap value of the state after the last step; the reference appends 0, :384),
+ * done u8 [K][N] (bit0 = done -> mask 0; bit1 = asynchronous warm-up step -> not a transition).  Writes returns [K][N] and the
+ * UNNORMALISED advantages [K][N], and ACCUMULATES {count, sum, sum of squares} of the valid advantages into moments[3]
+ * (device doubles, zeroed by the caller; all-reduce them across ranks before normalising).  FP32. */
+int qs_gae(int64_t n_envs, int32_t horizon, float gamma, float lambda, const float* reward, const float* value,
+           const uint8_t* done, float* returns_out, float* adv_out, double* moments, void* stream);
+/* ppo.py:141  adv <- (adv - mean) / (std + 1e-10) in place (population std), 0 for warm-up steps; weight (nullable) <- 1/0. */
+int qs_adv_normalize(int64_t total, const uint8_t* done, const double* moments, float* adv, float* weight, void* stream);
 /* Same contract as qs_step but with HOST buffers (pinned or pageable): H2D of the actions, the step
  * kernel and D2H of obs/reward/done are enqueued on `stream` and the call returns after they finish. */
 int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);

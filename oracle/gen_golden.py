@@ -258,6 +258,56 @@ def gen_sensor_stats(ref):
                         pos_end=np.array(pos_end), steps=1500)
 
 
+def gen_ppo_vectors():
+    """PPO.get_advantages and the loss of PPO.update (environment/controller/ppo.py:125-141, :183-201) evaluated by the
+    reference's own code: ppo.py is a script (argparse + training loop at import), so the two method bodies are lifted
+    out of its source with `ast` and executed unmodified against random rollouts."""
+    import ast
+    import torch
+    src = open(os.path.join(REF, "environment", "controller", "ppo.py")).read()
+    tree = ast.parse(src)
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ClassDef) and node.name == "PPO":
+            for f in node.body:
+                if isinstance(f, ast.FunctionDef) and f.name == "get_advantages":
+                    fn = f
+    assert fn is not None
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"np": np}
+    exec(compile(mod, "ppo.py:get_advantages", "exec"), ns)
+    rng = np.random.default_rng(77)
+    out = {}
+    for i, L_ in enumerate((37, 400)):
+        rewards = rng.normal(0, 1, L_)
+        values = np.concatenate([rng.normal(0, 2, L_), [0.0]])             # memory.values.append(0)  ppo.py:384
+        term = rng.random(L_) < 0.05
+        term[-1] = True                                                     # a worker only returns after `done` (:283)
+        ret, adv = ns["get_advantages"](None, torch.tensor(values), np.logical_not(term), rewards)
+        out.update({"rewards%d" % i: rewards, "values%d" % i: values, "terminals%d" % i: term, "returns%d" % i: ret, "adv%d" % i: adv})
+    # model.py:62-66,74-88 + ppo.py:183-201: loss of one update step on a random batch, by the reference's ActorCritic
+    sys.path.insert(0, REF)
+    from environment.controller.model import ActorCritic
+    torch.manual_seed(5)
+    pol = ActorCritic(32, 75, 4, 0.1, True).double()
+    B = 64
+    st = torch.randn(B, 1, 75, dtype=torch.double); ac = torch.randn(B, 1, 4, dtype=torch.double) * 0.3
+    old_lp = torch.randn(B, 1, 4, dtype=torch.double) * 0.1 + 1.0
+    adv_t = torch.randn(B, dtype=torch.double); ret_t = torch.randn(B, dtype=torch.double)
+    logprobs, state_values, dist_entropy = pol.evaluate(st, ac)
+    ratios = torch.exp(logprobs.sum(axis=2).flatten() - old_lp.sum(axis=2).detach().flatten())
+    surr1 = ratios * adv_t
+    surr2 = torch.clamp(ratios, 1 - 0.2, 1 + 0.2) * adv_t
+    critic_loss = 0.5 * torch.nn.MSELoss()(state_values, ret_t)
+    loss = (-torch.min(surr1, surr2) + critic_loss - 0.006 * dist_entropy.sum(axis=2).flatten()).mean()
+    loss.backward()
+    sd = {k.replace(".", "_"): v.detach().numpy() for k, v in pol.state_dict().items()}
+    grads = {"grad_" + k.replace(".", "_"): p_.grad.numpy() for k, p_ in pol.named_parameters() if p_.grad is not None}
+    out.update(dict(loss_states=st.numpy()[:, 0], loss_actions=ac.numpy()[:, 0], loss_old_logprobs=old_lp.numpy()[:, 0],
+                    loss_adv=adv_t.numpy(), loss_returns=ret_t.numpy(), loss_value=float(loss.detach()), **{"w_" + k: v for k, v in sd.items()}, **grads))
+    np.savez_compressed(os.path.join(OUT, "ppo_vectors.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load_reference()
@@ -269,6 +319,7 @@ def main():
     gen_logs(ref)
     gen_actor(ref)
     gen_sensor_stats(ref)
+    gen_ppo_vectors()
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -837,3 +837,38 @@ class PidControllerOracle:
         U = np.einsum("nij,nj->ni", np.linalg.inv(Mm), np.stack([u_5, u_6, u_7], axis=1))    # :93
         self.ang_d_ant = ang_d                                                 # :106
         return np.concatenate([U_1[:, None], U], axis=1)                       # :107
+
+
+# --------------------------------------------------------------------------------------
+# PPO.get_advantages — environment/controller/ppo.py:125-141
+# --------------------------------------------------------------------------------------
+def gae_advantages(values, masks, rewards, gamma=0.99, lmbda=0.99):
+    """Literal restatement for ONE concatenated sequence: values has len(rewards)+1 entries (ppo.py:384 appends 0),
+    masks = not terminal.  Returns (returns, normalised advantages)."""
+    values = np.asarray(values, dtype=np.float64)
+    returns = np.zeros(len(rewards))
+    gae = 0.0
+    for i in reversed(range(len(rewards))):
+        delta = rewards[i] + gamma * values[i + 1] * masks[i] - values[i]          # :135 (the `i == len(rewards)` branch is dead)
+        gae = delta + gamma * lmbda * masks[i] * gae                                # :136
+        returns[i] = gae + values[i]                                                # :137
+    adv = returns - values[:-1]                                                     # :139
+    return returns, (adv - np.mean(adv)) / (np.std(adv) + 1e-10)                    # :141
+
+
+def gae_batched(reward, value, done, gamma=0.99, lmbda=0.99):
+    """Time-major batched form the CUDA kernel implements: reward (K,N), value (K+1,N), done u8 (K,N) with bit0 = done and
+    bit1 = asynchronous warm-up step (not a transition).  Returns (returns (K,N), raw advantages (K,N), valid (K,N) bool,
+    normalised advantages (K,N) with zeros at invalid entries)."""
+    K, N = reward.shape
+    mask = ((done & 1) == 0).astype(np.float64)
+    valid = (done & 2) == 0
+    ret = np.zeros((K, N)); adv = np.zeros((K, N))
+    gae = np.zeros(N)
+    for t in reversed(range(K)):
+        delta = reward[t] + gamma * value[t + 1] * mask[t] - value[t]
+        gae = delta + gamma * lmbda * mask[t] * gae
+        ret[t] = gae + value[t]; adv[t] = gae
+    a = adv[valid]
+    norm = np.where(valid, (adv - a.mean()) / (a.std() + 1e-10), 0.0)
+    return ret, adv, valid, norm
