@@ -50,7 +50,7 @@ class qs_params(C.Structure):
         ("tr", C.c_double * 3), ("tr_p", C.c_double * 3),
         ("accel_std", C.c_double), ("accel_bias_drift", C.c_double), ("gyro_std", C.c_double),
         ("gyro_bias_drift", C.c_double), ("magnet_std", C.c_double), ("magnet_bias_drift", C.c_double),
-        ("gps_std_p", C.c_double), ("gps_std_v", C.c_double),
+        ("gps_std_p", C.c_double), ("gps_std_v", C.c_double), ("gps_blend", C.c_double),
     ]
 
 

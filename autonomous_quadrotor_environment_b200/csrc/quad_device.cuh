@@ -178,6 +178,7 @@ template <typename R> struct DevParams {
     R pos_clip, vel_clip, w_clip_lo, w_clip_hi;
     // sensor (:587-608)
     R s_accel_std, s_accel_drift, s_gyro_std, s_gyro_drift, s_mag_std, s_mag_drift, s_gps_p, s_gps_v;
+    R s_gps_blend;   // GPS_P in per cent (visual_landing/math_trajectory.py:71-77); 0 = off
     R s_mag[3];      // magnetic field vector, mG (:651)
     R s_ti[9];       // inertial TRIAD basis t1i,t2i,t3i (:682-691), constant
     int32_t n_limit; // n + T  :157

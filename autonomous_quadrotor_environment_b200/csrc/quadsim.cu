@@ -146,7 +146,7 @@ template <typename R> static DevParams<R> make_params(const qs_config& c) {
     p.s_accel_std = R(q.accel_std); p.s_accel_drift = R(q.accel_bias_drift);
     p.s_gyro_std = R(q.gyro_std); p.s_gyro_drift = R(q.gyro_bias_drift);
     p.s_mag_std = R(q.magnet_std); p.s_mag_drift = R(q.magnet_bias_drift);
-    p.s_gps_p = R(q.gps_std_p); p.s_gps_v = R(q.gps_std_v);
+    p.s_gps_p = R(q.gps_std_p); p.s_gps_v = R(q.gps_std_v); p.s_gps_blend = R(q.gps_blend);
     {   // sensor.triad :650-651,:682-691 — inertial triad of (gravity, magnetic field of Santo Andre in mG)
         const double mv[3] = {-4047 * 0.01, 12911 * 0.01, -9899 * 0.01};
         const double mn = std::sqrt(mv[0] * mv[0] + mv[1] * mv[1] + mv[2] * mv[2]);
@@ -190,7 +190,7 @@ extern "C" int qs_default_config(qs_config* cfg) {
     p.tr[0] = 0.005; p.tr[1] = 0.01; p.tr[2] = 0.1;
     p.tr_p[0] = 3; p.tr_p[1] = 2; p.tr_p[2] = 1;
     p.accel_std = 0.1; p.accel_bias_drift = 0.0005; p.gyro_std = 0.035; p.gyro_bias_drift = 0.00015;
-    p.magnet_std = 15; p.magnet_bias_drift = 0.075; p.gps_std_p = 1.71; p.gps_std_v = 0.5;
+    p.magnet_std = 15; p.magnet_bias_drift = 0.075; p.gps_std_p = 1.71; p.gps_std_v = 0.5; p.gps_blend = 0.0;
     return QS_OK;
 }
 

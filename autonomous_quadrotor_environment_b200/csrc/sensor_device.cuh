@@ -127,7 +127,19 @@ __device__ __forceinline__ void sensor_step(const DevParams<R>& p, const R z[32]
     const R w2[3] = {y[10] + s[1] + p.s_gyro_std * z[12], y[11] + s[1] + p.s_gyro_std * z[13], y[12] + s[1] + p.s_gyro_std * z[14]};
     R qv[4];
     deriv_quat(w2, qg, qv);                                                                // rl_worker.py:168
-    // ---- gps :642-647 consumes z[15..20]; its readings are not part of the observation
+    // ---- gps :642-647 consumes z[15..20].  Its readings enter only through the optional complementary blend of the landing
+    //      stack (visual_landing/math_trajectory.py:71-77, GPS_P per cent; off by default like the script's GPS = False),
+    //      which also writes the blended estimate back into the dead-reckoning integrators.
+    if (p.s_gps_blend > R(0)) {
+        const R wg = p.s_gps_blend, wa = R(100) - p.s_gps_blend;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const R pos_gps = y[2 * k] + p.s_gps_p * z[15 + k];
+            const R vel_gps = y[2 * k + 1] + p.s_gps_v * z[18 + k];
+            s[7 + k] = (wa * s[7 + k] + wg * pos_gps) / R(100);
+            s[4 + k] = (wa * s[4 + k] + wg * vel_gps) / R(100);
+        }
+    }
     // ---- triad :649-697 (updates self.R for the next step)
     {
         s[0] += s[2] * dt;

@@ -81,6 +81,8 @@ typedef struct qs_params {
     /* sensor model defaults: sensor.__init__ :587-591 */
     double accel_std, accel_bias_drift, gyro_std, gyro_bias_drift;
     double magnet_std, magnet_bias_drift, gps_std_p, gps_std_v;
+    double gps_blend;                  /* GPS_P of visual_landing/math_trajectory.py:71-77: per cent of the GPS reading blended into the
+                                          dead-reckoned position/velocity each step (and written back); 0 = off (the script's GPS = False) */
 } qs_params;
 
 /* Mirrors quad.__init__(t_step, n, training, euler, direct_control, T, clipped)  quadrotor_env.py:112 */

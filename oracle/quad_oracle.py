@@ -693,8 +693,9 @@ def _triad(grav_body, mag_body):
 
 class SensorOracle:
     def __init__(self, n_envs, t_step, accel_std=0.1, accel_bias_drift=0.0005, gyro_std=0.035, gyro_bias_drift=0.00015,
-                 magnet_std=15):
+                 magnet_std=15, gps_std_p=1.71, gps_std_v=0.5, gps_blend=0.0):
         self.N, self.dt = n_envs, t_step
+        self.gps_p, self.gps_v, self.gps_blend = gps_std_p, gps_std_v, gps_blend      # sensor.__init__ :591; math_trajectory.py:104-105
         self.a_std, self.a_drift, self.g_std, self.g_drift, self.m_std = accel_std, accel_bias_drift, gyro_std, gyro_bias_drift, magnet_std
         self.a_b = np.zeros(n_envs); self.g_b = np.zeros(n_envs)
         self.a_b_d = np.zeros(n_envs); self.g_b_d = np.zeros(n_envs)
@@ -733,7 +734,12 @@ class SensorOracle:
         g_b += self.g_b_d * dt                                                          # gyro()
         w2 = y[:, 10:13] + g_b[:, None] + self.g_std * z[:, 12:15]
         qv = deriv_quat(w2, qg)
-        a_b += self.a_b_d * dt                                                          # triad -> accel()  (gps: z[15:21])
+        if self.gps_blend > 0:                                                          # gps :642-647 + math_trajectory.py:71-77
+            pos_gps = y[:, 0:5:2] + self.gps_p * z[:, 15:18]
+            vel_gps = y[:, 1:6:2] + self.gps_v * z[:, 18:21]
+            pos = ((100 - self.gps_blend) * pos + self.gps_blend * pos_gps) / 100
+            vel = ((100 - self.gps_blend) * vel + self.gps_blend * vel_gps) / 100
+        a_b += self.a_b_d * dt                                                          # triad -> accel()
         ind2 = G * Rm[:, :, 2].copy(); ind2[:, 2] += f_m
         gb2 = acc_read + a_b[:, None] + self.a_std * z[:, 21:24] - ind2
         mb2 = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 24:27])

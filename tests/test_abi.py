@@ -32,8 +32,9 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header(tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include "quadsim.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %d\\n",'
+    prog.write_text('#include "quadsim.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
                     'sizeof(qs_params),sizeof(qs_config),sizeof(qs_field_desc),sizeof(qs_stats),sizeof(qs_rollout_args),'
+                    'sizeof(qs_controller),sizeof(qs_control_rollout_args),sizeof(qs_policy_rollout_args),sizeof(qs_actor),'
                     'offsetof(qs_config,params),offsetof(qs_config,workspace),(int)QS_FIELD_COUNT_);return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
@@ -44,9 +45,13 @@ def test_struct_layouts_match_header(tmp_path):
     assert sizes[2] == C.sizeof(L.qs_field_desc)
     assert sizes[3] == C.sizeof(L.qs_stats)
     assert sizes[4] == C.sizeof(L.qs_rollout_args)
-    assert sizes[5] == L.qs_config.params.offset
-    assert sizes[6] == L.qs_config.workspace.offset
-    assert sizes[7] == L.QS_FIELD_COUNT
+    assert sizes[5] == C.sizeof(L.qs_controller)
+    assert sizes[6] == C.sizeof(L.qs_control_rollout_args)
+    assert sizes[7] == C.sizeof(L.qs_policy_rollout_args)
+    assert sizes[8] == C.sizeof(L.qs_actor)
+    assert sizes[9] == L.qs_config.params.offset
+    assert sizes[10] == L.qs_config.workspace.offset
+    assert sizes[11] == L.QS_FIELD_COUNT
 
 
 def test_default_config_is_the_reference_constants():

@@ -311,12 +311,14 @@ def test_f32_closed_loop_1000_steps_with_trained_actor():
 # ----------------------------------------------------------------------------------------------------
 # sensor model (A13): same Philox -> normal mapping on both sides, so the comparison is deterministic
 # ----------------------------------------------------------------------------------------------------
-def test_sensor_model_matches_oracle_f64():
+@pytest.mark.parametrize("gps_blend", [0.0, 30.0])
+def test_sensor_model_matches_oracle_f64(gps_blend):
+    """gps_blend > 0: the complementary GPS blend of the landing stack (visual_landing/math_trajectory.py:71-77)."""
     N, steps, seed, off = 256, 60, 5, 9
     env = BatchedQuad(N, 0.01, 1000, training=False, direct_control=1, T=2, precision="f64", integrator="rk45",
-                      sensor_noise=True, seed=seed, env_id_offset=off, device=DEV)
+                      sensor_noise=True, seed=seed, env_id_offset=off, device=DEV, params={"gps_blend": gps_blend})
     ora = qo.BatchQuadOracle(N, 0.01, 1000, training=False, direct_control=1, T=2, integrator="rk45")
-    sen = qo.SensorOracle(N, 0.01)
+    sen = qo.SensorOracle(N, 0.01, gps_blend=gps_blend)
     init = np.zeros((N, 13)); init[:, 6] = 1
     rng = np.random.default_rng(3)
     init[:, 1:6:2] = rng.normal(0, 0.3, (N, 3)); init[:, 10:13] = rng.normal(0, 0.3, (N, 3))
