@@ -90,15 +90,24 @@ struct PolicyIO {
     float* hist;          // [75][N] in/out: dl_in_gen.deep_learning_input per env (oldest entry first), or NULL
 };
 
+#ifndef QS_POLICY_GROUPS
+#define QS_POLICY_GROUPS 3      // 128-env tiles in flight per CTA (one per group of 4 warps), sharing one copy of the weights
+#endif
+constexpr int kPG = QS_POLICY_GROUPS;
+
 struct PolicySmem {
+    static constexpr int kXH = kPM * kPKin * 2 + kPM * kPH * 2;          // per group: history/A tile + hidden tile
     static constexpr int kX = 0;
-    static constexpr int kHd = kX + kPM * kPKin * 2;
-    static constexpr int kW1 = kHd + kPM * kPH * 2;
+    static constexpr int kHd = kPM * kPKin * 2;
+    static constexpr int kW1 = kPG * kXH;
     static constexpr int kW2 = kW1 + kPH * kPKin * 2;
     static constexpr int kW3 = kW2 + kPH * kPH * 2;
     static constexpr int kB = kW3 + 16 * kPH * 2;
     static constexpr int kBytes = kB + (kPH + kPH + 16) * 4;
 };
+
+// barrier among the 128 threads of one group (ids 1..kPG; 0 is __syncthreads)
+__device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kPM) : "memory"); }
 
 // bias + tanh epilogue of one hidden layer: TMEM accumulators (thread = row) -> BF16 A operand of the next layer
 __device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, const float* bias, unsigned char* sH, int row) {
@@ -120,43 +129,45 @@ __device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, const 
     }
 }
 
-__global__ void __launch_bounds__(kPM, 2)
+__global__ void __launch_bounds__(kPM * kPG, 1)
 policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                       const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char* sX = smem + PolicySmem::kX;
-    unsigned char* sH = smem + PolicySmem::kHd;
+    const int tid_all = threadIdx.x, grp = tid_all / kPM, tid = tid_all % kPM, warp = tid >> 5;   // group-local thread / warp
+    unsigned char* sX = smem + grp * PolicySmem::kXH + PolicySmem::kX;
+    unsigned char* sH = smem + grp * PolicySmem::kXH + PolicySmem::kHd;
     unsigned char* sW1 = smem + PolicySmem::kW1;
     unsigned char* sW2 = smem + PolicySmem::kW2;
     unsigned char* sW3 = smem + PolicySmem::kW3;
     float* sB = reinterpret_cast<float*>(smem + PolicySmem::kB);
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bars[kPG];
     __shared__ uint32_t tmem_slot;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    uint64_t& bar = bars[grp];
 
-    // ---- one-time: weights fp32 (global) -> bf16 canonical K-major operand tiles (shared)
-    for (int idx = tid; idx < kPH * kPKin; idx += kPM) {             // W1: input j = 15*slot + e  ->  K index 16*slot + e
+    // ---- one-time: weights fp32 (global) -> bf16 canonical K-major operand tiles (shared, one copy per CTA)
+    for (int idx = tid_all; idx < kPH * kPKin; idx += kPM * kPG) {   // W1: input j = 15*slot + e  ->  K index 16*slot + e
         const int n = idx / kPKin, kk = idx % kPKin, a = kk / kPSlotK, e = kk % kPSlotK;
         const float w = (e < 15) ? act.w1[n * 75 + a * 15 + e] : 0.f;
         *reinterpret_cast<__nv_bfloat16*>(sW1 + umma_canon_offset(n, kk, kPKin)) = __float2bfloat16(w);
     }
-    for (int idx = tid; idx < kPH * kPH; idx += kPM) {
+    for (int idx = tid_all; idx < kPH * kPH; idx += kPM * kPG) {
         const int n = idx / kPH, kk = idx % kPH;
         *reinterpret_cast<__nv_bfloat16*>(sW2 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(act.w2[n * kPH + kk]);
     }
-    for (int idx = tid; idx < 16 * kPH; idx += kPM) {
+    for (int idx = tid_all; idx < 16 * kPH; idx += kPM * kPG) {
         const int n = idx / kPH, kk = idx % kPH;
         *reinterpret_cast<__nv_bfloat16*>(sW3 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(n < 4 ? act.w3[n * kPH + kk] : 0.f);
     }
-    sB[tid] = act.b1[tid];
-    sB[kPH + tid] = act.b2[tid];
-    if (tid < 16) sB[2 * kPH + tid] = tid < 4 ? act.b3[tid] : 0.f;
+    if (tid_all < kPH) { sB[tid_all] = act.b1[tid_all]; sB[kPH + tid_all] = act.b2[tid_all]; }
+    if (tid_all < 16) sB[2 * kPH + tid_all] = tid_all < 4 ? act.b3[tid_all] : 0.f;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
-    if (warp == 0) tmem_alloc(&tmem_slot, 128);
+    constexpr uint32_t kTmemCols = kPG * kPH <= 128 ? 128 : (kPG * kPH <= 256 ? 256 : 512);      // power of two >= 128 accumulator columns per group
+    if (tid_all < 32) tmem_alloc(&tmem_slot, kTmemCols);
     tc_fence_before();
+    fence_proxy_async_smem();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = tmem_slot;
+    const uint32_t tmem_base = tmem_slot + (uint32_t)(grp * kPH);
     const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
     uint32_t phase = 0;
     LocalStats ls;
@@ -166,7 +177,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
     const float log_norm = (sigma > 0.f) ? (-__logf(sigma) - 0.918938533f) : 0.f;
 
     const int64_t n_tiles = (v.N + kPM - 1) / kPM;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = (int64_t)blockIdx.x * kPG + grp; tile < n_tiles; tile += (int64_t)gridDim.x * kPG) {
         const int64_t n = tile * kPM + tid;
         const bool active = n < v.N;
         Env<float> e;
@@ -200,7 +211,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
         for (int t = 0; t < io.horizon; ++t) {
             // ---------------- layer 1: [128 x 80] x W1^T, one K=16 MMA per history slot, oldest first
             fence_proxy_async_smem();
-            __syncthreads();
+            group_sync(grp);
             if (tid == 0) {
                 tc_fence_after();
 #pragma unroll
@@ -215,7 +226,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             actor_hidden_epilogue(lane_addr, sB, sH, tid);
             tc_fence_before();
             fence_proxy_async_smem();
-            __syncthreads();
+            group_sync(grp);
             // ---------------- layer 2: [128 x 128] x W2^T
             if (tid == 0) {
                 tc_fence_after();
@@ -227,7 +238,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             actor_hidden_epilogue(lane_addr, sB + kPH, sH, tid);      // MMA 2 has finished reading sH: reuse it
             tc_fence_before();
             fence_proxy_async_smem();
-            __syncthreads();
+            group_sync(grp);
             // ---------------- layer 3: [128 x 128] x W3^T (N padded 4 -> 16)
             if (tid == 0) {
                 tc_fence_after();
@@ -319,13 +330,13 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
                 }
             }
         }
-        __syncthreads();                                             // sX is re-initialised by the next tile
+        group_sync(grp);                                             // sX is re-initialised by the next tile
     }
     flush_stats(ls, any_end, v.stats);
-    if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
+    if (blockIdx.x == 0 && tid_all == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, 128);
+    if (tid_all < 32) tmem_dealloc(tmem_slot, kTmemCols);
 }
 
 extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_policy_rollout_args* args, void* stream) {
@@ -349,9 +360,10 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
         attr_set = true;
     }
     const int64_t tiles = (h->N + kPM - 1) / kPM;
-    int64_t grid = (int64_t)h->sm_count * 2;
-    if (grid > tiles) grid = tiles;
-    policy_rollout_kernel<<<(int)grid, kPM, PolicySmem::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+    int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, kPG tiles in flight each
+    const int64_t need = (tiles + kPG - 1) / kPG;
+    if (grid > need) grid = need;
+    policy_rollout_kernel<<<(int)grid, kPM * kPG, PolicySmem::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }
