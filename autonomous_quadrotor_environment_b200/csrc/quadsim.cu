@@ -834,6 +834,8 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
 }
 
+#include "rollout_pair.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -959,6 +961,17 @@ template <typename R, int INTEG, bool DIRECT>
 static void launch_rollout(qs_sim* s, const qs_rollout_args* a, cudaStream_t st) {
     RolloutIO<R> io{a->horizon, a->action_source, (const R*)a->actions, (R*)a->obs_out, (R*)a->action_out,
                     (R*)a->reward_out, a->done_out};
+    if constexpr (WarpKernelOk<R, INTEG>::value) {
+        // production mode (FP32, RK4; no strict in-lane resets; even shard; 8-byte aligned caller buffers): two envs per thread
+        const bool use_pair = s->step_loader == 3;     // qs_set_step_loader(h, 0..2) selects the one-env-per-thread kernel
+        const uintptr_t al = (uintptr_t)a->actions | (uintptr_t)a->obs_out | (uintptr_t)a->action_out | (uintptr_t)a->reward_out;
+        if (use_pair && !(s->cfg.flags & QS_FLAG_AUTO_RESET) && (s->N & 1) == 0 && (al & 7) == 0 && ((uintptr_t)a->done_out & 1) == 0) {
+            int64_t g = (s->N / 2 + QS_ROLLOUT_PAIR_THREADS - 1) / QS_ROLLOUT_PAIR_THREADS;
+            if (g > (int64_t)s->sm_count * 8) g = (int64_t)s->sm_count * 8;
+            rollout_pair_kernel<DIRECT><<<(int)g, QS_ROLLOUT_PAIR_THREADS, 0, st>>>(s->pf, make_view<float>(s), io);
+            return;
+        }
+    }
     rollout_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
 

@@ -1,0 +1,133 @@
+// rollout_pair.cuh — K fused env steps per launch with TWO envs per thread (FP32 / RK4 production mode).
+//
+// Same contract as rollout_kernel (quadsim.cu): the env state stays in registers for the whole horizon, actions come from
+// a [K][4][N] buffer or are drawn in-kernel (Philox U(-1,1), BASELINE.json configs[2]), outputs are optional.  Thread t owns
+// the adjacent pair (2t, 2t+1) as aligned register pairs: the RK4 stages of drone_eq run on FFMA2/FMUL2/FADD2
+// (packed_device.cuh), the scalar phases are instantiated per half (two independent chains per thread), loads and stores
+// are 8 bytes per thread.  With no state traffic this is the kernel whose FP32 pipe utilisation the metric's
+// "% of FP32 FMA roofline" is about.
+#pragma once
+#include "packed_device.cuh"
+
+#ifndef QS_ROLLOUT_PAIR_THREADS
+#define QS_ROLLOUT_PAIR_THREADS 256
+#endif
+
+template <bool DIRECT>
+__global__ void __launch_bounds__(QS_ROLLOUT_PAIR_THREADS, 1)
+rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
+                    const __grid_constant__ RolloutIO<float> io) {
+    using pr::half_of;
+    LocalStats ls;
+    ls.clear();
+    bool any_end = false;
+    const bool async_reset = (p.flags & F_ASYNC_RESET) != 0;
+    const int64_t N2 = v.N >> 1, ld2 = v.ld >> 1;                   // v.N is even (checked by the launcher)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N2; m += stride) {
+        const int64_t nA = 2 * m;
+        const float2* g2 = reinterpret_cast<const float2*>(v.obs17) + m;
+        P2 y[13];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) y[k].v = g2[(int64_t)k * ld2];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) y[10 + k].v = g2[(int64_t)(14 + k) * ld2];
+        Env<float> e[2];
+        {
+            float2 t;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { t = g2[(int64_t)(wp::kMAng + k) * ld2]; e[0].prev_ang[k] = t.x; e[1].prev_ang[k] = t.y; }
+            t = g2[(int64_t)wp::kMShaping * ld2]; e[0].prev_shaping = t.x; e[1].prev_shaping = t.y;
+            t = g2[(int64_t)wp::kMAbsSum * ld2]; e[0].abs_sum = t.x; e[1].abs_sum = t.y;
+            t = g2[(int64_t)wp::kMEpRet * ld2]; e[0].ep_return = t.x; e[1].ep_return = t.y;
+            t = g2[(int64_t)wp::kMStepI * ld2]; e[0].i = __float_as_int(t.x); e[1].i = __float_as_int(t.y);
+            t = g2[(int64_t)wp::kMEpisode * ld2]; e[0].episode = __float_as_uint(t.x); e[1].episode = __float_as_uint(t.y);
+            const uint32_t fl = reinterpret_cast<const uint16_t*>(v.flags)[m];
+            e[0].flags = fl & 0xffu; e[1].flags = fl >> 8;
+        }
+        StepOut<float> o[2];
+        bool warm[2] = {false, false};
+        for (int t = 0; t < io.horizon; ++t) {
+            float a[2][4], act[2][4];
+            Ctrl<float> ctl[2];
+            bool was_done[2];
+            if (io.action_source == QS_ACT_PHILOX_UNIFORM) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const uint4 u = philox_block(v.seed, v.env_id_offset + (uint32_t)(nA + h), e[h].episode, (uint32_t)e[h].i, RNG_ACTION);
+                    a[h][0] = 2.f * u32_to_unit<float>(u.x) - 1.f; a[h][1] = 2.f * u32_to_unit<float>(u.y) - 1.f;
+                    a[h][2] = 2.f * u32_to_unit<float>(u.z) - 1.f; a[h][3] = 2.f * u32_to_unit<float>(u.w) - 1.f;
+                }
+            } else {
+                const float2* at = reinterpret_cast<const float2*>(io.actions + (int64_t)t * 4 * v.N) + m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 q = at[(int64_t)k * N2]; a[0][k] = q.x; a[1][k] = q.y; }
+            }
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                warm[h] = async_reset ? async_warmup_prologue(p, e[h], a[h]) : false;
+                was_done[h] = (e[h].flags & EF_DONE) != 0;
+                ctl[h] = step_pre<float, DIRECT>(p, e[h], a[h], o[h], act[h]);
+            }
+            const Ctrl2 c2 = pack_ctrl(ctl[0], ctl[1]);
+            integrate_rk4_2(p, c2, y);
+#define QS_RP_POST(H)                                                                                         \
+            {                                                                                                 \
+                _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);                  \
+                step_post(p, e[H], act[H], o[H]);                                                             \
+                o[H].reward = warm[H] ? 0.f : o[H].reward;                                                    \
+                e[H].ep_return += o[H].reward;                                                                \
+            }
+            QS_RP_POST(0)
+            QS_RP_POST(1)
+#undef QS_RP_POST
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (o[h].done && !was_done[h]) { count_episode(ls, p, e[h], o[h]); any_end = true; }
+                if (async_reset && o[h].done) {
+                    async_resample(p, v.seed, v.env_id_offset + (uint32_t)(nA + h), e[h], o[h].vq);
+#pragma unroll
+                    for (int k = 0; k < 13; ++k) { if (h == 0) y[k].v.x = e[0].y[k]; else y[k].v.y = e[1].y[k]; }
+                }
+            }
+            if (io.obs_out) {
+                float2* ot = reinterpret_cast<float2*>(io.obs_out + (int64_t)t * 14 * v.N) + m;
+#pragma unroll
+                for (int k = 0; k < 10; ++k) ot[(int64_t)k * N2] = y[k].v;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ot[(int64_t)(10 + k) * N2] = make_float2(o[0].vq[k], o[1].vq[k]);
+            }
+            if (io.action_out) {
+                float2* at = reinterpret_cast<float2*>(io.action_out + (int64_t)t * 4 * v.N) + m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) at[(int64_t)k * N2] = make_float2(a[0][k], a[1][k]);
+            }
+            if (io.reward_out) reinterpret_cast<float2*>(io.reward_out + (int64_t)t * v.N)[m] = make_float2(o[0].reward, o[1].reward);
+            if (io.done_out)
+                reinterpret_cast<uint16_t*>(io.done_out + (int64_t)t * v.N)[m] =
+                    (uint16_t)(((o[0].done ? 1u : 0u) | (warm[0] ? 2u : 0u)) | (((o[1].done ? 1u : 0u) | (warm[1] ? 2u : 0u)) << 8));
+        }
+        // ---- state back to the handle
+        float2* s2 = reinterpret_cast<float2*>(v.obs17) + m;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s2[(int64_t)k * ld2] = y[k].v;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s2[(int64_t)(10 + k) * ld2] = make_float2(o[0].vq[k], o[1].vq[k]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s2[(int64_t)(14 + k) * ld2] = y[10 + k].v;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) s2[(int64_t)(wp::kMAng + k) * ld2] = make_float2(e[0].prev_ang[k], e[1].prev_ang[k]);
+        s2[(int64_t)wp::kMShaping * ld2] = make_float2(e[0].prev_shaping, e[1].prev_shaping);
+        s2[(int64_t)wp::kMAbsSum * ld2] = make_float2(e[0].abs_sum, e[1].abs_sum);
+        s2[(int64_t)wp::kMEpRet * ld2] = make_float2(e[0].ep_return, e[1].ep_return);
+        s2[(int64_t)wp::kMStepI * ld2] = make_float2(__int_as_float(e[0].i), __int_as_float(e[1].i));
+        s2[(int64_t)wp::kMEpisode * ld2] = make_float2(__uint_as_float(e[0].episode), __uint_as_float(e[1].episode));
+        s2[(int64_t)wp::kMReward * ld2] = make_float2(o[0].reward, o[1].reward);
+        reinterpret_cast<uint16_t*>(v.flags)[m] = (uint16_t)((e[0].flags & 0xffu) | ((e[1].flags & 0xffu) << 8));
+        reinterpret_cast<uint16_t*>(v.done)[m] =
+            (uint16_t)(((o[0].done ? 1u : 0u) | (warm[0] ? 2u : 0u)) | (((o[1].done ? 1u : 0u) | (warm[1] ? 2u : 0u)) << 8));
+        reinterpret_cast<uint16_t*>(v.solved)[m] = (uint16_t)((o[0].solved ? 1u : 0u) | ((o[1].solved ? 1u : 0u) << 8));
+    }
+    flush_stats(ls, any_end, v.stats);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
+}

@@ -380,6 +380,25 @@ def main():
             "roofline": {"bound": "hbm", "achieved": vgbs, "peak": hbm_peak, "unit": "GB/s", "frac": vgbs / hbm_peak,
                          "traffic": vtraffic, "kernel": vname, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP},
             "fp32_frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (vms * 1e-3) / 1e12 / fp32_peak}
+        # BASELINE.json configs[2], "actions from Philox in-kernel, so no HBM read" variant: K fused steps per launch with the env
+        # state in registers (qs_rollout) — the kernel the metric's "% of FP32 FMA roofline" is about
+        KR = 32
+        for w in range(3):
+            env2.rollout(KR)
+        torch.cuda.synchronize(dev)
+        reps = max(1, args.variant_steps // (KR * 4))
+        v0.record()
+        for k in range(reps):
+            env2.rollout(KR)
+        v1.record()
+        torch.cuda.synchronize(dev)
+        rms = v0.elapsed_time(v1) / (reps * KR)
+        variants["rollout_philox_actions"] = {
+            "value": N / (rms * 1e-3), "unit": UNIT, "steps": reps * KR, "ms_per_env_step_of_all_envs": rms,
+            "kernel": "rollout_pair_kernel<direct>" if env2.step_loader == 3 else "rollout_kernel<float,RK4,direct>",
+            "fp32": {"achieved_tflops": FLOPS_PER_ENV_STEP(args.substeps) * N / (rms * 1e-3) / 1e12, "peak_tflops_probe": fp32_peak,
+                     "frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (rms * 1e-3) / 1e12 / fp32_peak},
+            "note": "K=%d steps per launch, async auto-reset, state in registers, no state/action traffic" % KR}
         del env2
 
     if rank == 0:

@@ -424,6 +424,32 @@ def test_step_loaders_agree(N, sensor, direct, ext, loader):
     assert sa["n_episodes"] > 0 and int(a.episode.max()) >= 2
 
 
+@pytest.mark.parametrize("N,src", [(4096, "philox"), (1002, "buffer"), (4096, "buffer")])
+def test_pair_rollout_equals_scalar_rollout(N, src):
+    """rollout_pair_kernel (two envs per thread, RK4 on FFMA2; the default of FP32 handles) vs rollout_kernel (one env per
+    thread) on the same envs, teacher-forced every K=4 steps (handle b restarts from a's workspace): all fields agree to FP32
+    rounding, integer fields exactly except threshold cases within that rounding; statistics and Philox streams identical."""
+    K, rounds, seed = 4, 12, 21
+    mk = lambda ld: BatchedQuad(N, 0.01, 25, T=3, precision="f32", async_reset=True, seed=seed, device=DEV).set_step_loader(ld)
+    a, b = mk(3), mk(2)
+    a.reset(); b.reset()
+    g = torch.Generator(device=DEV); g.manual_seed(5)
+    flips = 0
+    for r in range(rounds):
+        b._ws.copy_(a._ws)
+        acts = (torch.rand(K, 4, N, device=DEV, generator=g) * 2 - 1) if src == "buffer" else None
+        ra = a.rollout(K, actions=acts, record_obs=True, record_reward=True, record_done=True, record_actions=True)
+        rb = b.rollout(K, actions=acts, record_obs=True, record_reward=True, record_done=True, record_actions=True)
+        same = (ra["done"] == rb["done"]).all(dim=0) & (a.episode == b.episode) & (a.i == b.i)
+        flips += int((~same).sum())
+        assert torch.equal(ra["actions"][:, :, same], rb["actions"][:, :, same])             # same Philox draws / same buffer
+        assert torch.allclose(ra["obs"][:, :, same], rb["obs"][:, :, same], rtol=1e-4, atol=1e-4)
+        assert torch.allclose(ra["reward"][:, same], rb["reward"][:, same], rtol=1e-3, atol=2e-3)
+        assert torch.allclose(a.state[same], b.state[same], rtol=1e-4, atol=1e-4)
+    assert flips <= 2 + N * K * rounds // 50000, flips
+    assert a.stats()["n_episodes"] > 0
+
+
 @pytest.mark.parametrize("prec,integ", [("f32", "rk4"), ("f64", "rk45")])
 def test_rollout_kernel_equals_repeated_steps(prec, integ):
     N, K, seed = 3000, 24, 5
@@ -545,6 +571,7 @@ def test_fused_actor_rollout_deterministic():
     assert worst < 0.03, worst                                  # BF16 weights/activations, MUFU tanh
     assert n_warm > 0                                           # some envs broke and went through an async reset
     assert torch.allclose(env.history, hist.bfloat16().float(), atol=0, rtol=0)
+    ref.set_step_loader(2)                                      # one env per thread: the scalar step_core the policy kernel runs
     replay = ref.rollout(K, actions=rec["actions"].contiguous(), record_obs=True, record_done=True)
     assert torch.equal(replay["done"], rec["done"])
     assert torch.equal(replay["obs"], rec["obs"])
