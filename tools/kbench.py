@@ -88,6 +88,10 @@ if __name__ == "__main__":
         case_step(async_reset=True, T=5, iters=20)
     if "profsensor" in which:
         case_step(async_reset=True, T=5, iters=20, sensor_noise=True)
+    if "profrollout" in which:
+        case_rollout(n=10 ** 9, K=32, iters=2)
+    if "proff64" in which:
+        case_step(N=1 << 16, iters=5, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "profpolicy" in which:
         case_policy(N=1 << 18, K=32, iters=1)
     if "policy" in which:

@@ -12,7 +12,7 @@ want = ['Kernel Name', 'gpu__time_duration.sum', 'launch__registers_per_thread',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
         'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__inst_executed.sum', 'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active',
-        'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_alu.sum',
+        'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fp64.sum', 'sm__inst_executed_pipe_fma.sum', 'sm__inst_executed_pipe_xu.sum', 'sm__inst_executed_pipe_alu.sum',
         'sm__inst_executed_pipe_fmaheavy.sum', 'sm__inst_executed_pipe_fmalite.sum',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__cycles_elapsed.max',
         'smsp__thread_inst_executed_per_inst_executed.ratio', 'smsp__inst_executed_op_local_ld.sum',
