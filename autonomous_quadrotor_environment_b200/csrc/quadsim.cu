@@ -916,14 +916,14 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
             return;
         }
         if (s->step_loader >= 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
-            constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * 2 * (kBlock / 32);
+            constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * wp::kStagesW * (kBlock / 32);
             static bool attr_set = false;
             if (!attr_set) {
                 cudaFuncSetAttribute(step_kernel_warp<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 attr_set = true;
             }
             const int64_t chunks = (s->slice_count + 31) / 32;
-            int64_t g = (int64_t)s->sm_count * QS_MIN_CTAS;
+            int64_t g = (int64_t)s->sm_count * wp::kMinCtas;
             const int64_t need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
             if (g > need) g = need;
             step_kernel_warp<DIRECT, SENSOR><<<(int)(g < 1 ? 1 : g), kBlock, smem, st>>>(s->pf, make_view<float>(s), io);

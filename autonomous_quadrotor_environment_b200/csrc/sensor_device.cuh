@@ -70,6 +70,24 @@ __device__ __forceinline__ void triad(const DevParams<R>& p, const R grav_body_i
             Rm[3 * r + c] = g[r] * p.s_ti[c] + t2[r] * p.s_ti[3 + c] + t3[r] * p.s_ti[6 + c];   // :693  tb @ ti.T
 }
 
+// quad.mat_rot and quad.accelerometer_read (:315, :371) at state y, as the trailing drone_eq call of a step leaves them.
+// With accel = R f_b / M - G z^ (:364-367):  accelerometer_read = R^T (accel - G z^) = f_b / M - 2 G (r6, r7, r8),
+// which saves the two matrix-vector products of the literal form (used by the FP32 production kernels; the FP64 parity
+// path keeps the literal form).
+template <typename R>
+__device__ __forceinline__ void accel_read(const DevParams<R>& p, const Ctrl<R>& c, const R y[13], R rot[9], R acc[3]) {
+    R qn[4];
+    quat_normalize(&y[6], qn);
+    quat_rot_mat(qn, rot);
+    const R vbx = rot[0] * y[1] + rot[3] * y[3] + rot[6] * y[5];
+    const R vby = rot[1] * y[1] + rot[4] * y[3] + rot[7] * y[5];
+    const R vbz = rot[2] * y[1] + rot[5] * y[3] + rot[8] * y[5];
+    const R g2 = R(-2) * p.g;
+    acc[0] = g2 * rot[6] - p.kd_m[0] * (M_<R>::abs(vbx) * vbx);
+    acc[1] = g2 * rot[7] - p.kd_m[1] * (M_<R>::abs(vby) * vby);
+    acc[2] = g2 * rot[8] + (c.f_m - p.kd_m[2] * (M_<R>::abs(vbz) * vbz));
+}
+
 // sensor.reset :630-640 + bias_reset :600-608 (called once per episode, after quad.reset's warm-up steps)
 template <typename R>
 __device__ __forceinline__ void sensor_reset(const DevParams<R>& p, uint64_t seed, uint32_t env_id, uint32_t episode,

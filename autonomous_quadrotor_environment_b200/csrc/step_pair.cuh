@@ -4,18 +4,26 @@
 //   * every quantity of the pair is one aligned 64-bit register pair {A, B}: one LDS.64 reads it from the warp's
 //     shared-memory stage, one STG.64 writes it back to its SoA row (a warp-wide STG.64 = 256 contiguous bytes);
 //   * the RK4 stages of drone_eq run on FFMA2/FMUL2/FADD2 (packed_device.cuh): half the issue slots per env;
-//   * the scalar phases (action map, Euler angles, done/reward, sensor model) are instantiated once per half: two
-//     independent dependency chains per thread where the one-env kernel stalls on its single chain (ncu: 3-5x more
-//     warp-time per instruction outside the RK loop than inside), and the per-chunk bookkeeping (addresses, loop,
-//     queue) is paid once per 64 envs.
+//   * the scalar phases (action map, Euler angles, done/reward) are instantiated once per half: two independent
+//     dependency chains per thread where the one-env kernel stalls on its single chain (ncu: 3-5x more warp-time per
+//     instruction outside the RK loop than inside), and the per-chunk bookkeeping (addresses, loop, queue) is paid once
+//     per 64 envs;
+//   * the sensor model runs packed as well (sensor_pair.cuh).
 // Pipeline per warp (no synchronisation between warps inside the loop):
 //   wait(chunk j) -> LDS the whole chunk into registers -> __syncwarp -> cp.async (LDGSTS, 16 B per lane: two 256-byte row
 //   segments per instruction) of chunk j+1 into the SAME stage, which has the whole arithmetic of chunk j to land ->
 //   quad.step x2 -> STG.64 of the results straight from registers.
-// One stage per warp is 26 rows x 256 B (46 with the sensor state), so 16 warps x 2 envs per SM fit (104 KB).
+//
+// With the sensor model (256 threads, ~240 registers: dynamics + packed sensor model of an env pair in one thread) the
+// sensor_state rows travel as their own cp.async group: they are read after the dynamics and re-filled after the sensor
+// phase, so they never sit in registers during the RK4 stages.  Measured alternatives (1,048,576 envs, T=5, async resets,
+// us per step): this kernel 108-110; one env per lane (step_warp.cuh) 111; warp-specialised variant (6 dynamics + 6 sensor
+// warps per CTA at 168 registers, mbarrier hand-off through shared memory) 132 — stall_no_instructions 21 %: twelve warps
+// spread over ~96 KB of straight-line code thrash the instruction cache; Philox rounds rolled 115; IMAD.WIDE Philox 114.
 // Resets: same per-CTA queue and opportunistic full-warp drains as step_warp.cuh.
 #pragma once
 #include "packed_device.cuh"
+#include "sensor_pair.cuh"
 
 namespace pr {
 
@@ -23,7 +31,7 @@ using wp::cp16; using wp::cp4; using wp::cp_commit; using wp::cp_wait; using wp:
 
 // stage rows (64 floats each): 0..9 = matrix rows 0..9 (x vx y vy z vz q0..q3), 10..20 = matrix rows 14..24 (w, ang,
 // prev_shaping, abs_sum, ep_return, step_i, episode), 21..24 = the 4 action rows, 25 = flag bytes [0,64),
-// 26..45 = sensor_state (SENSOR only)
+// 26..45 = sensor_state (fused sensor mode only)
 constexpr int kSW = 10;              // stage row of matrix row 14
 constexpr int kRowAct = 21;
 constexpr int kRowBytes = 25;
@@ -35,9 +43,6 @@ constexpr int kRowsSensor = 46;
 #endif
 #ifndef QS_PAIR_THREADS_SENSOR
 #define QS_PAIR_THREADS_SENSOR 256
-#endif
-#ifndef QS_PAIR_SENSOR_ROLLED
-#define QS_PAIR_SENSOR_ROLLED 1
 #endif
 constexpr int kThreadsPlain = QS_PAIR_THREADS;
 constexpr int kThreadsSensor = QS_PAIR_THREADS_SENSOR;
@@ -53,7 +58,6 @@ __device__ __forceinline__ float2 lds2(const Row* st, int row, int lane) { retur
 __device__ __forceinline__ void sts2(Row* st, int row, int lane, float a, float b) { reinterpret_cast<float2*>(st[row])[lane] = make_float2(a, b); }
 
 // issue the loads of one chunk (envs n0 .. n0+63) into the warp's stage; every lane executes the same number of commits
-template <bool SENSOR>
 __device__ __forceinline__ void prefetch(const SimView<float>& v, const float* __restrict__ action, const Ext& x,
                                          int64_t n0, Row* st, int lane) {
     const int r2 = lane >> 4, c4 = (lane & 15) << 2;       // 16-byte pieces: 2 rows x 16 lanes
@@ -81,16 +85,111 @@ __device__ __forceinline__ void prefetch(const SimView<float>& v, const float* _
             }
         }
     }
-    if (SENSOR) {
-        const float* gs = v.sensor_state + (int64_t)r2 * ld + n0 + c4;
+    cp_commit();
+}
+
+// the sensor_state rows of one chunk as their own cp.async group: they are read, and therefore re-filled, later in the
+// iteration than the state rows
+__device__ __forceinline__ void prefetch_sensor(const SimView<float>& v, int64_t n0, Row* srows, int lane) {
+    const int r2 = lane >> 4, c4 = (lane & 15) << 2;
+    const float* gs = v.sensor_state + (int64_t)r2 * v.ld + n0 + c4;
+    const uint32_t s = smem_u32(&srows[r2][c4]);
 #pragma unroll
-        for (int k = 0; k < 10; ++k) cp16(s + (kRowSensor + 2 * k) * 256, gs + (int64_t)(2 * k) * ld);
-    }
+    for (int k = 0; k < 10; ++k) cp16(s + 2 * k * 256, gs + (int64_t)(2 * k) * v.ld);
     cp_commit();
 }
 
 // row k of a [rows][ld] 4-byte matrix, columns n0+2*lane, n0+2*lane+1 <- {a, b}; g2 = (float2*)(matrix + n0) + lane, ld2 = ld / 2
 __device__ __forceinline__ void stg2(float2* g2, int64_t ld2, int k, float a, float b) { g2[(int64_t)k * ld2] = make_float2(a, b); }
+
+// what the sensor phase needs to know about a stepped env pair
+struct PairMeta {
+    uint32_t episode[2], step_i[2], flags[2];     // after the step
+    bool warm[2];                                 // this step was a warm-up step of quad.reset
+};
+
+// Sensor phase of a pair, arithmetic only: trailing drone_eq evaluation at the new state (rotation matrix, accelerometer
+// reading), the packed sensor model, then the warm-up rules (warm-up steps bypass the model: state kept, true observation
+// passed through; the last one re-initialises it = sensor.reset).  srows = the pair's sensor_state rows in shared memory.
+__device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const SimView<float>& v, const Row* srows, int lane, int64_t nA,
+                                             const qs::P2 y[13], const qs::P2 vq[4], qs::P2 f_m, const PairMeta& m,
+                                             qs::P2 sn[qs::kSensorStateDim], qs::P2 so[14]) {
+    using namespace qs;
+    P2 rot[9], acc[3];
+    accel_read2(p, f_m, y, rot, acc);
+#pragma unroll
+    for (int k = 0; k < kSensorStateDim; ++k) sn[k].v = lds2(srows, k, lane);
+    SensorRng2 rng;
+    rng.seed = v.seed;
+    rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
+    rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
+    rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
+    sensor_step2(p, rng, y, acc, rot, f_m, sn, so);
+    const bool w0 = m.warm[0], w1 = m.warm[1];
+    if (__any_sync(0xffffffffu, w0 | w1)) {
+#pragma unroll
+        for (int k = 0; k < kSensorStateDim; ++k) { P2 old; old.v = lds2(srows, k, lane); sn[k] = psel(w0, w1, old, sn[k]); }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) so[k] = psel(w0, w1, y[k], so[k]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) so[10 + k] = psel(w0, w1, vq[k], so[10 + k]);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            if (m.warm[hf] && (m.flags[hf] >> EF_WARM_SHIFT) == 0) {
+                float yh[13], sh_[kSensorStateDim];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) yh[k] = hf ? y[k].v.y : y[k].v.x;
+                sensor_reset(p, v.seed, rng.id[hf], rng.ep[hf], yh, sh_);
+#pragma unroll
+                for (int k = 0; k < kSensorStateDim; ++k) { if (hf) sn[k].v.y = sh_[k]; else sn[k].v.x = sh_[k]; }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void sensor_store(const SimView<float>& v, int64_t n0, int lane, const qs::P2 sn[qs::kSensorStateDim],
+                                             const qs::P2 so[14]) {
+    const int64_t ld2 = v.ld >> 1;
+    float2* gs2 = reinterpret_cast<float2*>(v.sensor_state + n0) + lane;
+#pragma unroll
+    for (int k = 0; k < qs::kSensorStateDim; ++k) gs2[(int64_t)k * ld2] = sn[k].v;
+    float2* go2 = reinterpret_cast<float2*>(v.sensed_obs + n0) + lane;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) go2[(int64_t)k * ld2] = so[k].v;
+}
+
+// QS_FLAG_ASYNC_RESET, once per chunk: push the finished envs of this lane's pair on the CTA's queue (AFTER all of their
+// rows have been stored), then claim 32 queued envs if available and re-sample them with all lanes busy
+template <bool SENSOR, int kQueueCap>
+__device__ __forceinline__ void reset_queue_step(const DevParams<float>& p, const SimView<float>& v, const StepIO<float>& io,
+                                                 uint32_t* s_queue, int* s_qn, int* s_qhead, int lane, int64_t nA, bool push0, bool push1) {
+    constexpr unsigned kFull = 0xffffffffu;
+    if (__any_sync(kFull, push0 || push1)) {
+        __threadfence_block();                 // this warp's stores of the finished envs precede the re-sampler's
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            if (hf ? push1 : push0) {
+                const int slot = atomicAdd(s_qn, 1);
+                if (slot < kQueueCap) *reinterpret_cast<volatile uint32_t*>(&s_queue[slot]) = (uint32_t)(nA + hf);
+                else wp::resample_env<SENSOR>(p, v, io, nA + hf);   // queue exhausted (e.g. a whole shard timing out at once)
+            }
+        }
+    }
+    int take = -1;
+    if (lane == 0) {
+        const int head = *reinterpret_cast<volatile int*>(s_qhead);
+        int qn = *reinterpret_cast<volatile int*>(s_qn);
+        qn = qn < kQueueCap ? qn : kQueueCap;
+        if (qn - head >= 32 && atomicCAS(s_qhead, head, head + 32) == head) take = head;
+    }
+    take = __shfl_sync(kFull, take, 0);
+    if (take >= 0) {
+        uint32_t ent;
+        do { ent = *reinterpret_cast<volatile uint32_t*>(&s_queue[take + lane]); } while (ent == 0xFFFFFFFFu);
+        __threadfence_block();
+        wp::resample_env<SENSOR>(p, v, io, (int64_t)ent);
+    }
+}
 
 }  // namespace pr
 
@@ -103,12 +202,12 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
     constexpr int kQueueCap = SENSOR ? kQueueCapSensor : kQueueCapPlain;
     constexpr int kThreads = SENSOR ? kThreadsSensor : kThreadsPlain;
     constexpr int kWarps = kThreads / 32;
-    constexpr unsigned kFull = 0xffffffffu;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_queue[kQueueCap];
     __shared__ int s_qn, s_qhead;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
     Row* st = reinterpret_cast<Row*>(smem_raw) + (size_t)w * kRows;
+    Row* srows = st + kRowSensor;                            // SENSOR: the pair's sensor_state rows
     for (int i = tid; i < kQueueCap; i += kThreads) s_queue[i] = 0xFFFFFFFFu;
     if (tid == 0) { s_qn = 0; s_qhead = 0; }
     __syncthreads();
@@ -129,9 +228,14 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
     const int64_t n_chunks = (v.N + 63) >> 6;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
     int64_t c = (int64_t)blockIdx.x * kWarps + w;
-    if (c < n_chunks) prefetch<SENSOR>(v, io.action, x, c << 6, st, lane);
+
+    if (c < n_chunks) {
+        prefetch(v, io.action, x, c << 6, st, lane);
+        if (SENSOR) prefetch_sensor(v, c << 6, srows, lane);
+    }
     for (; c < n_chunks; c += stride) {
-        cp_wait<0>();
+        // cp.async groups complete in order.  SENSOR: pending here = {state(c), sensor(c)}; the state rows are needed now
+        if (SENSOR) cp_wait<1>(); else cp_wait<0>();
         __syncwarp();
         const int64_t n0 = c << 6;
         const int64_t nA = n0 + 2 * lane;                       // env A; env B = nA + 1
@@ -151,13 +255,10 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         float2 a2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a2[k] = lds2(st, kRowAct + k, lane);
-        float2 s2[SENSOR ? kSensorStateDim : 1];
-        if (SENSOR) {
-#pragma unroll
-            for (int k = 0; k < kSensorStateDim; ++k) s2[k] = lds2(st, kRowSensor + k, lane);
-        }
         __syncwarp();                          // every lane has read its pair: the stage is free for the next chunk
-        if (c + stride < n_chunks) prefetch<SENSOR>(v, io.action, x, (c + stride) << 6, st, lane);
+        const bool has_next = c + stride < n_chunks;
+        if (has_next) prefetch(v, io.action, x, (c + stride) << 6, st, lane);
+        else if (SENSOR) cp_commit();           // keep the group count uniform: {sensor(c), state(next) or empty}
 
         Env<float> e[2];
         StepOut<float> o[2];
@@ -262,107 +363,23 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
             }
         }
         if (SENSOR) {
-            // trailing drone_eq call at the new state for both envs at once: acceleration and rotation matrix
-            P2 dy[13], rot[9];
-            drone_rhs2<true>(p, c2, y, dy, rot);
-#if QS_PAIR_SENSOR_ROLLED
-            // The sensor model (~900 instructions, ~60 live values) runs once per half in a ROLLED loop: one copy in the
-            // instruction stream and one env's worth of registers, so that more warps fit; each half writes its own
-            // columns (4-byte stores, the two halves of a 32-byte sector arrive within the same chunk).
-            float* gs = v.sensor_state + nA;
-            float* go = v.sensed_obs + nA;
-#pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const bool hb = h != 0;
-                const bool wm = hb ? warm[1] : warm[0];
-                const uint32_t fl_h = hb ? e[1].flags : e[0].flags, ep_h = hb ? e[1].episode : e[0].episode;
-                const uint32_t i_h = (uint32_t)(hb ? e[1].i : e[0].i);
-                const float fm_h = hb ? ctl[1].f_m : ctl[0].f_m;
-                float z[32], rt[9], yh[13], sn[kSensorStateDim], s_new[kSensorStateDim], so[14], vq[4];
+            P2 sn[kSensorStateDim], so[14], vq[4];
 #pragma unroll
-                for (int k = 0; k < 13; ++k) yh[k] = hb ? y[k].v.y : y[k].v.x;
+            for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
+            PairMeta m;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) vq[k] = hb ? o[1].vq[k] : o[0].vq[k];
-#pragma unroll
-                for (int k = 0; k < kSensorStateDim; ++k) { sn[k] = hb ? s2[k].y : s2[k].x; s_new[k] = sn[k]; }
-#pragma unroll
-                for (int k = 0; k < 9; ++k) rt[k] = hb ? rot[k].v.y : rot[k].v.x;
-                const float g[3] = {hb ? dy[1].v.y : dy[1].v.x, hb ? dy[3].v.y : dy[3].v.x, (hb ? dy[5].v.y : dy[5].v.x) - p.g};
-                const float acc_read[3] = {rt[0] * g[0] + rt[3] * g[1] + rt[6] * g[2], rt[1] * g[0] + rt[4] * g[1] + rt[7] * g[2],
-                                           rt[2] * g[0] + rt[5] * g[1] + rt[8] * g[2]};
-                const uint32_t gid = v.env_id_offset + (uint32_t)(nA + h);
-                sensor_normals(v.seed, gid, ep_h, i_h, z);
-                sensor_step(p, z, yh, acc_read, rt, fm_h, s_new, so);
-#pragma unroll
-                for (int k = 0; k < kSensorStateDim; ++k) sn[k] = wm ? sn[k] : s_new[k];
-                if (wm && (fl_h >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, gid, ep_h, yh, sn);
-#pragma unroll
-                for (int k = 0; k < kSensorStateDim; ++k) gs[(int64_t)k * v.ld + h] = sn[k];
-#pragma unroll
-                for (int k = 0; k < 10; ++k) go[(int64_t)k * v.ld + h] = wm ? yh[k] : so[k];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) go[(int64_t)(10 + k) * v.ld + h] = wm ? vq[k] : so[10 + k];
+            for (int hf = 0; hf < 2; ++hf) {
+                m.episode[hf] = e[hf].episode; m.step_i[hf] = (uint32_t)e[hf].i; m.flags[hf] = e[hf].flags; m.warm[hf] = warm[hf];
             }
-#else
-            float sobs[2][14], sn[2][kSensorStateDim];
-            // The model runs for both envs unconditionally (straight-line code, the two chains interleave); warm-up
-            // steps bypass it afterwards (select) and the last warm-up step re-initialises it (sensor.reset, rare branch).
-#define QS_PAIR_SENSOR(H)                                                                                     \
-            {                                                                                                 \
-                float z[32], rt[9], s_new[kSensorStateDim], so[14];                                           \
-                _Pragma("unroll") for (int k = 0; k < kSensorStateDim; ++k) { sn[H][k] = half_of<H>(s2[k]); s_new[k] = sn[H][k]; } \
-                _Pragma("unroll") for (int k = 0; k < 9; ++k) rt[k] = half_of<H>(rot[k]);                     \
-                const float g[3] = {half_of<H>(dy[1]), half_of<H>(dy[3]), half_of<H>(dy[5]) - p.g};           \
-                const float acc_read[3] = {rt[0] * g[0] + rt[3] * g[1] + rt[6] * g[2],                        \
-                                           rt[1] * g[0] + rt[4] * g[1] + rt[7] * g[2],                        \
-                                           rt[2] * g[0] + rt[5] * g[1] + rt[8] * g[2]};                       \
-                sensor_normals(v.seed, v.env_id_offset + (uint32_t)(nA + H), e[H].episode, (uint32_t)e[H].i, z); \
-                sensor_step(p, z, e[H].y, acc_read, rt, ctl[H].f_m, s_new, so);                               \
-                _Pragma("unroll") for (int k = 0; k < kSensorStateDim; ++k) sn[H][k] = warm[H] ? sn[H][k] : s_new[k]; \
-                _Pragma("unroll") for (int k = 0; k < 10; ++k) sobs[H][k] = warm[H] ? e[H].y[k] : so[k];      \
-                _Pragma("unroll") for (int k = 0; k < 4; ++k) sobs[H][10 + k] = warm[H] ? o[H].vq[k] : so[10 + k]; \
-            }
-            QS_PAIR_SENSOR(0)
-            QS_PAIR_SENSOR(1)
-#undef QS_PAIR_SENSOR
-            if (warm[0] && (e[0].flags >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)nA, e[0].episode, e[0].y, sn[0]);
-            if (warm[1] && (e[1].flags >> EF_WARM_SHIFT) == 0) sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)(nA + 1), e[1].episode, e[1].y, sn[1]);
-            float2* gs2 = reinterpret_cast<float2*>(v.sensor_state + n0) + lane;
-#pragma unroll
-            for (int k = 0; k < kSensorStateDim; ++k) stg2(gs2, ld2, k, sn[0][k], sn[1][k]);
-            float2* go2 = reinterpret_cast<float2*>(v.sensed_obs + n0) + lane;
-#pragma unroll
-            for (int k = 0; k < 14; ++k) stg2(go2, ld2, k, sobs[0][k], sobs[1][k]);
-#endif
+            cp_wait<1>();                      // pending = {sensor(c), state(next) | empty}: the sensor rows have landed
+            __syncwarp();
+            sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
+            __syncwarp();                      // every lane is done with the sensor rows of the stage
+            if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
+            sensor_store(v, n0, lane, sn, so);
         }
-        // ---- resets: push finished envs, claim 32 queued ones if available
-        if (async_reset) {
-            if (__any_sync(kFull, push[0] || push[1])) {
-                __threadfence_block();         // this warp's stores of the finished envs precede the re-sampler's
-#pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
-                    if (push[hf]) {
-                        const int slot = atomicAdd(&s_qn, 1);
-                        if (slot < kQueueCap) *reinterpret_cast<volatile uint32_t*>(&s_queue[slot]) = (uint32_t)(nA + hf);
-                        else wp::resample_env<SENSOR>(p, v, io, nA + hf);   // queue exhausted (e.g. a whole shard timing out at once)
-                    }
-                }
-            }
-            int take = -1;
-            if (lane == 0) {
-                const int head = *reinterpret_cast<volatile int*>(&s_qhead);
-                int qn = *reinterpret_cast<volatile int*>(&s_qn);
-                qn = qn < kQueueCap ? qn : kQueueCap;
-                if (qn - head >= 32 && atomicCAS(&s_qhead, head, head + 32) == head) take = head;
-            }
-            take = __shfl_sync(kFull, take, 0);
-            if (take >= 0) {
-                uint32_t ent;
-                do { ent = *reinterpret_cast<volatile uint32_t*>(&s_queue[take + lane]); } while (ent == 0xFFFFFFFFu);
-                __threadfence_block();
-                wp::resample_env<SENSOR>(p, v, io, (int64_t)ent);
-            }
-        }
+        if (async_reset)
+            reset_queue_step<SENSOR, kQueueCap>(p, v, io, s_queue, &s_qn, &s_qhead, lane, nA, push[0], push[1]);
     }
     __syncthreads();                           // every push of this CTA has been made
     if (async_reset) {

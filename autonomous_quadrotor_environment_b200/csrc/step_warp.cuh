@@ -24,7 +24,16 @@
 // after the CTA's last chunk.  Re-sampling needs nothing of the old episode except its counter.
 #pragma once
 
+#ifndef QS_WARP_STAGES            // shared-memory stages per warp: 2 = prefetch one chunk ahead; 1 = in-place, more resident warps
+#define QS_WARP_STAGES 2
+#endif
+#ifndef QS_WARP_MIN_CTAS
+#define QS_WARP_MIN_CTAS QS_MIN_CTAS
+#endif
+
 namespace wp {
+constexpr int kStagesW = QS_WARP_STAGES;
+constexpr int kMinCtas = QS_WARP_MIN_CTAS;
 
 constexpr int kRowAct = 26;          // stage rows 26..29: the 4 action rows (in)
 constexpr int kRowBytes = 30;        // stage row 30: bytes [0,32) flags (in/out), [32,64) done, [64,96) solved (out)
@@ -153,7 +162,7 @@ __device__ __forceinline__ void wp_store_bytes(const unsigned char* sb, int b, u
 }
 
 template <bool DIRECT, bool SENSOR>
-__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
+__global__ void __launch_bounds__(kBlock, QS_WARP_MIN_CTAS)
 step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                  const __grid_constant__ StepIO<float> io) {
     using namespace wp;
@@ -165,7 +174,7 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
     __shared__ uint32_t s_queue[kQueueCap];
     __shared__ int s_qn, s_qhead;
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    Row* ring = reinterpret_cast<Row*>(smem_raw) + (size_t)w * 2 * kRows;
+    Row* ring = reinterpret_cast<Row*>(smem_raw) + (size_t)w * kStagesW * kRows;
     for (int i = tid; i < kQueueCap; i += kBlock) s_queue[i] = 0xFFFFFFFFu;
     if (tid == 0) { s_qn = 0; s_qhead = 0; }
     __syncthreads();
@@ -188,9 +197,9 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
     int64_t c = (int64_t)blockIdx.x * kWarps + w;
     if (c < n_chunks) prefetch<SENSOR>(v, io.action, x, c << 5, ring, lane);
     for (int j = 0; c < n_chunks; c += stride, ++j) {
-        Row* st = ring + (size_t)(j & 1) * kRows;
+        Row* st = ring + (size_t)(kStagesW == 2 ? (j & 1) : 0) * kRows;
         const int64_t cn = c + stride;
-        if (cn < n_chunks) {                   // the other stage was drained by the previous iteration's store phase
+        if (kStagesW == 2 && cn < n_chunks) {  // the other stage was drained by the previous iteration's store phase
             prefetch<SENSOR>(v, io.action, x, cn << 5, ring + (size_t)((j + 1) & 1) * kRows, lane);
             cp_wait<1>();
         } else {
@@ -252,16 +261,10 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
                 // warm-up steps bypass the sensor; the last one re-initialises it (sensor.reset)
                 const int mode = warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0;
                 if (mode == 0) {
-                    float s[kSensorStateDim], z[32], dy[13], qn[4], rot[9];
+                    float s[kSensorStateDim], z[32], rot[9], acc_read[3];
 #pragma unroll
                     for (int k = 0; k < 17; ++k) s[k] = st[kRowSensor + k][lane];
-                    drone_rhs(p, ctl, e.y, dy);                 // trailing drone_eq call: accel at the new state
-                    quat_normalize(&e.y[6], qn);
-                    quat_rot_mat(qn, rot);
-                    const float g[3] = {dy[1], dy[3], dy[5] - p.g};                 // :371
-                    const float acc_read[3] = {rot[0] * g[0] + rot[3] * g[1] + rot[6] * g[2],
-                                               rot[1] * g[0] + rot[4] * g[1] + rot[7] * g[2],
-                                               rot[2] * g[0] + rot[5] * g[1] + rot[8] * g[2]};
+                    accel_read(p, ctl, e.y, rot, acc_read);     // trailing drone_eq call: rotation matrix, accelerometer reading
                     sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, z);
                     sensor_step(p, z, e.y, acc_read, rot, ctl.f_m, s, sobs);
 #pragma unroll
@@ -326,6 +329,9 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
             store_rows2(st, 12, v.sensed_obs + 12 * ld + n0, ld, lane);
             __syncwarp();
         }
+        // single stage: the stage was drained by the stores above; the next chunk's loads overlap the reset work
+        // of this warp and the arithmetic of the CTA's other warps
+        if (kStagesW == 1 && cn < n_chunks) prefetch<SENSOR>(v, io.action, x, cn << 5, st, lane);
         // ---- resets: push finished envs, claim 32 queued ones if available
         if (async_reset) {
             if (__any_sync(kFull, push)) {

@@ -424,6 +424,34 @@ def test_step_loaders_agree(N, sensor, direct, ext, loader):
     assert sa["n_episodes"] > 0 and int(a.episode.max()) >= 2
 
 
+@pytest.mark.parametrize("gps_blend", [0.0, 30.0])
+def test_packed_sensor_model_equals_scalar_sensor_model(gps_blend):
+    """The sensor model on the packed FP32 pipe (sensor_pair.cuh: loader 3, two envs per lane, Philox blocks drawn on demand,
+    accelerometer reading from the closed form f_b/M - 2G R^T z) against the scalar routine (sensor_device.cuh, loader 1),
+    teacher-forced, with and without the complementary GPS blend: sensed observation and the 20 sensor-state rows agree to
+    FP32 rounding at every step, through warm-up steps and sensor resets."""
+    N, K, seed = 4099, 80, 17
+    mk = lambda ld: BatchedQuad(N, 0.01, 30, T=3, precision="f32", async_reset=True, sensor_noise=True, seed=seed, device=DEV,
+                                params={"gps_blend": gps_blend}).set_step_loader(ld)
+    a, b = mk(3), mk(1)
+    a.reset(); b.reset()
+    g = torch.Generator(device=DEV); g.manual_seed(6)
+    worst = 0.0
+    for t in range(K):
+        b._ws.copy_(a._ws)
+        act = (torch.rand(4, N, device=DEV, generator=g) * 0.6 - 0.3).contiguous()
+        a.step_soa(act); b.step_soa(act)
+        same = (a._field(L.QS_FIELD_DONE) == b._field(L.QS_FIELD_DONE)).all(dim=0) & (a._field(L.QS_FIELD_FLAGS) == b._field(L.QS_FIELD_FLAGS)).all(dim=0)
+        assert int((~same).sum()) <= 1
+        for f in (L.QS_FIELD_SENSED_OBS, L.QS_FIELD_SENSOR_STATE):
+            fa, fb = a._field(f)[:, same], b._field(f)[:, same]
+            assert torch.allclose(fa, fb, rtol=2e-5, atol=2e-5), (t, f, float((fa - fb).abs().max()))
+            worst = max(worst, float((fa - fb).abs().max()))
+    assert int(a.episode.max()) >= 2                      # resets (and therefore sensor resets) happened
+    d = a.sensed_obs[:, 0:6] - a.obs[:, 0:6]
+    assert float(d.abs().max()) > 1e-4                    # the INS estimate really differs from the truth
+
+
 @pytest.mark.parametrize("N,src", [(4096, "philox"), (1002, "buffer"), (4096, "buffer")])
 def test_pair_rollout_equals_scalar_rollout(N, src):
     """rollout_pair_kernel (two envs per thread, RK4 on FFMA2; the default of FP32 handles) vs rollout_kernel (one env per
