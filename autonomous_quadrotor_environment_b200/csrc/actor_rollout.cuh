@@ -102,28 +102,35 @@ struct PolicySmem {
     static constexpr int kW1 = kPG * kXH;
     static constexpr int kW2 = kW1 + kPH * kPKin * 2;
     static constexpr int kW3 = kW2 + kPH * kPH * 2;
-    static constexpr int kB = kW3 + 16 * kPH * 2;
-    static constexpr int kBytes = kB + (kPH + kPH + 16) * 4;
+    static constexpr int kOnes = kW3 + 16 * kPH * 2;                     // A operand of the bias block of layer 2: [128][16], columns 0,1 = 1
+    static constexpr int kW2x = kOnes + kPM * 16 * 2;                    // B operand of that block: [128][16], columns 0,1 = b2 (hi, lo)
+    static constexpr int kB = kW2x + kPH * 16 * 2;
+    static constexpr int kBytes = kB + 16 * 4;                           // b3 (FP32, added in the last epilogue)
 };
+
+// The biases of the two hidden layers ride in the GEMMs: every history entry is 15 floats padded to one K=16 block, the pad
+// column of the A operand holds 1 and the pad columns of W1's first two K blocks hold b1 split in two BF16 pieces
+// (hi = bf16(b), lo = bf16(b - hi): 16 significant bits); layer 2 gets one extra K=16 block [1 1 0 ..] x [b2_hi b2_lo 0 ..].
+// That removes 128 FADD + 32 LDS.128 per thread from each hidden epilogue (the kernel is issue- and MUFU-bound, the tensor
+// pipe is 26 % busy).
+__device__ __forceinline__ float bf16_hi(float x) { return __bfloat162float(__float2bfloat16(x)); }
 
 // barrier among the 128 threads of one group (ids 1..kPG; 0 is __syncthreads)
 __device__ __forceinline__ void group_sync(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kPM) : "memory"); }
 
-// bias + tanh epilogue of one hidden layer: TMEM accumulators (thread = row) -> BF16 A operand of the next layer
-__device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, const float* bias, unsigned char* sH, int row) {
+// tanh epilogue of one hidden layer: TMEM accumulators (thread = row; bias already inside) -> BF16 A operand of the next layer
+__device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, unsigned char* sH, int row) {
 #pragma unroll 1
     for (int c = 0; c < kPH; c += 32) {
         float acc[32];
         tmem_ld_32x32b_x32(lane_addr + (uint32_t)c, acc);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float4 b0 = *reinterpret_cast<const float4*>(bias + c + 8 * j);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 8 * j + 4);
             uint4 o;
-            o.x = pack_bf16x2(tanh_fast(acc[8 * j + 0] + b0.x), tanh_fast(acc[8 * j + 1] + b0.y));
-            o.y = pack_bf16x2(tanh_fast(acc[8 * j + 2] + b0.z), tanh_fast(acc[8 * j + 3] + b0.w));
-            o.z = pack_bf16x2(tanh_fast(acc[8 * j + 4] + b1.x), tanh_fast(acc[8 * j + 5] + b1.y));
-            o.w = pack_bf16x2(tanh_fast(acc[8 * j + 6] + b1.z), tanh_fast(acc[8 * j + 7] + b1.w));
+            o.x = pack_bf16x2(tanh_fast(acc[8 * j + 0]), tanh_fast(acc[8 * j + 1]));
+            o.y = pack_bf16x2(tanh_fast(acc[8 * j + 2]), tanh_fast(acc[8 * j + 3]));
+            o.z = pack_bf16x2(tanh_fast(acc[8 * j + 4]), tanh_fast(acc[8 * j + 5]));
+            o.w = pack_bf16x2(tanh_fast(acc[8 * j + 6]), tanh_fast(acc[8 * j + 7]));
             *reinterpret_cast<uint4*>(sH + umma_canon_offset(row, c + 8 * j, kPH)) = o;
         }
     }
@@ -139,7 +146,9 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
     unsigned char* sW1 = smem + PolicySmem::kW1;
     unsigned char* sW2 = smem + PolicySmem::kW2;
     unsigned char* sW3 = smem + PolicySmem::kW3;
-    float* sB = reinterpret_cast<float*>(smem + PolicySmem::kB);
+    unsigned char* sOnes = smem + PolicySmem::kOnes;
+    unsigned char* sW2x = smem + PolicySmem::kW2x;
+    float* sB3 = reinterpret_cast<float*>(smem + PolicySmem::kB);
     __shared__ uint64_t bars[kPG];
     __shared__ uint32_t tmem_slot;
     uint64_t& bar = bars[grp];
@@ -147,7 +156,10 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
     // ---- one-time: weights fp32 (global) -> bf16 canonical K-major operand tiles (shared, one copy per CTA)
     for (int idx = tid_all; idx < kPH * kPKin; idx += kPM * kPG) {   // W1: input j = 15*slot + e  ->  K index 16*slot + e
         const int n = idx / kPKin, kk = idx % kPKin, a = kk / kPSlotK, e = kk % kPSlotK;
-        const float w = (e < 15) ? act.w1[n * 75 + a * 15 + e] : 0.f;
+        float w = 0.f;
+        if (e < 15) w = act.w1[n * 75 + a * 15 + e];
+        else if (a == 0) w = bf16_hi(act.b1[n]);                     // pad column (A holds 1 there): bias, hi piece
+        else if (a == 1) w = act.b1[n] - bf16_hi(act.b1[n]);         //                                bias, lo piece
         *reinterpret_cast<__nv_bfloat16*>(sW1 + umma_canon_offset(n, kk, kPKin)) = __float2bfloat16(w);
     }
     for (int idx = tid_all; idx < kPH * kPH; idx += kPM * kPG) {
@@ -158,8 +170,13 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
         const int n = idx / kPH, kk = idx % kPH;
         *reinterpret_cast<__nv_bfloat16*>(sW3 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(n < 4 ? act.w3[n * kPH + kk] : 0.f);
     }
-    if (tid_all < kPH) { sB[tid_all] = act.b1[tid_all]; sB[kPH + tid_all] = act.b2[tid_all]; }
-    if (tid_all < 16) sB[2 * kPH + tid_all] = tid_all < 4 ? act.b3[tid_all] : 0.f;
+    for (int idx = tid_all; idx < kPH * 16; idx += kPM * kPG) {
+        const int n = idx / 16, kk = idx % 16;
+        const float b = act.b2[n];
+        *reinterpret_cast<__nv_bfloat16*>(sOnes + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk < 2 ? 1.f : 0.f);
+        *reinterpret_cast<__nv_bfloat16*>(sW2x + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk == 0 ? bf16_hi(b) : (kk == 1 ? b - bf16_hi(b) : 0.f));
+    }
+    if (tid_all < 16) sB3[tid_all] = tid_all < 4 ? act.b3[tid_all] : 0.f;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     constexpr uint32_t kTmemCols = kPG * kPH <= 128 ? 128 : (kPG * kPH <= 256 ? 256 : 512);      // power of two >= 128 accumulator columns per group
     if (tid_all < 32) tmem_alloc(&tmem_slot, kTmemCols);
@@ -197,7 +214,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             float h[16];
 #pragma unroll
             for (int q = 0; q < 15; ++q) h[q] = (active && io.hist) ? io.hist[(int64_t)(s * 15 + q) * v.N + n] : 0.f;
-            h[15] = 0.f;
+            h[15] = 1.f;                                             // pad column = 1: carries b1 through the GEMM
             uint4 lo, hi;
             lo.x = pack_bf16x2(h[0], h[1]); lo.y = pack_bf16x2(h[2], h[3]); lo.z = pack_bf16x2(h[4], h[5]); lo.w = pack_bf16x2(h[6], h[7]);
             hi.x = pack_bf16x2(h[8], h[9]); hi.y = pack_bf16x2(h[10], h[11]); hi.z = pack_bf16x2(h[12], h[13]); hi.w = pack_bf16x2(h[14], h[15]);
@@ -223,7 +240,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             }
             mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            actor_hidden_epilogue(lane_addr, sB, sH, tid);
+            actor_hidden_epilogue(lane_addr, sH, tid);
             tc_fence_before();
             fence_proxy_async_smem();
             group_sync(grp);
@@ -231,11 +248,12 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             if (tid == 0) {
                 tc_fence_after();
                 umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW2), kPH, 0, kPH, kPH, false);
+                umma_gemm_k(tmem_base, smem_u32(sOnes), 16, 0, smem_u32(sW2x), 16, 0, 16, kPH, true);      // + b2
                 umma_commit(&bar);
             }
             mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            actor_hidden_epilogue(lane_addr, sB + kPH, sH, tid);      // MMA 2 has finished reading sH: reuse it
+            actor_hidden_epilogue(lane_addr, sH, tid);                // MMA 2 has finished reading sH: reuse it
             tc_fence_before();
             fence_proxy_async_smem();
             group_sync(grp);
@@ -252,7 +270,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
                 float acc[16];
                 tmem_ld_32x32b_x16(lane_addr, acc);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(acc[k] + sB[2 * kPH + k]);
+                for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(acc[k] + sB3[k]);
             }
             tc_fence_before();
             // ---------------- a ~ Normal(mean, sigma)  (model.py:60-66), per-dimension log-prob
@@ -304,7 +322,7 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
                 lo.x = pack_bf16x2(a[0], a[1]); lo.y = pack_bf16x2(a[2], a[3]);
                 lo.z = pack_bf16x2(e.y[1], e.y[3]); lo.w = pack_bf16x2(e.y[5], e.y[6]);
                 hi.x = pack_bf16x2(e.y[7], e.y[8]); hi.y = pack_bf16x2(e.y[9], o.vq[0]);
-                hi.z = pack_bf16x2(o.vq[1], o.vq[2]); hi.w = pack_bf16x2(o.vq[3], 0.f);
+                hi.z = pack_bf16x2(o.vq[1], o.vq[2]); hi.w = pack_bf16x2(o.vq[3], 1.f);
                 *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK, kPKin)) = lo;
                 *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK + 8, kPKin)) = hi;
                 head = head + 1 == kPSlots ? 0 : head + 1;
