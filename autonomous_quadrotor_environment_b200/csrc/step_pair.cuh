@@ -227,7 +227,10 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
     bool any_end = false;
     const int64_t n_chunks = (v.N + 63) >> 6;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
-    int64_t c = (int64_t)blockIdx.x * kWarps + w;
+    // warp-major chunk order: the LAST, partial round of the grid-stride loop (16,384 chunks over 1,776 warps at 1M envs = 9.2
+    // rounds) is spread over all CTAs as a few warps each instead of keeping the first CTAs full and leaving the others idle
+    // (49.3 -> 47.6 us per step of 1,048,576 envs)
+    int64_t c = (int64_t)w * gridDim.x + blockIdx.x;
 
     if (c < n_chunks) {
         prefetch(v, io.action, x, c << 6, st, lane);

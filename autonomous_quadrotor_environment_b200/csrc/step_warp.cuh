@@ -194,7 +194,7 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
     bool any_end = false;
     const int64_t n_chunks = (v.N + 31) >> 5;
     const int64_t stride = (int64_t)gridDim.x * kWarps;
-    int64_t c = (int64_t)blockIdx.x * kWarps + w;
+    int64_t c = (int64_t)blockIdx.x * kWarps + w;     // CTA-major (warp-major, which helps the pair kernel's tail, costs 2 % here)
     if (c < n_chunks) prefetch<SENSOR>(v, io.action, x, c << 5, ring, lane);
     for (int j = 0; c < n_chunks; c += stride, ++j) {
         Row* st = ring + (size_t)(kStagesW == 2 ? (j & 1) : 0) * kRows;

@@ -403,29 +403,31 @@ def main():
                      "frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (rms * 1e-3) / 1e12 / fp32_peak},
             "note": "K=%d steps per launch, async auto-reset, state in registers, no state/action traffic" % KR}
         del env2
-        # with S >= 3 RK4 sub-intervals per env step the path is compute-bound whatever the launch shape; the
-        # same fused rollout at S = 4 shows how close the integrator itself gets to the FP32 FMA roofline (2,984 FLOPs per env step)
-        S4 = 4
-        env3 = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
-                           substeps=S4, async_reset=True, sensor_noise=False, seed=0, env_id_offset=rank * N, device=dev)
-        env3.reset()
-        for w in range(3):
-            env3.rollout(KR)
-        torch.cuda.synchronize(dev)
-        reps = max(1, args.variant_steps // (KR * 8))
-        v0.record()
-        for k in range(reps):
-            env3.rollout(KR)
-        v1.record()
-        torch.cuda.synchronize(dev)
-        rms4 = v0.elapsed_time(v1) / (reps * KR)
-        variants["rollout_philox_actions_substeps4"] = {
-            "value": N / (rms4 * 1e-3), "unit": UNIT, "steps": reps * KR, "ms_per_env_step_of_all_envs": rms4,
-            "kernel": "rollout_pair_kernel<direct>" if env3.step_loader == 3 else "rollout_kernel<float,RK4,direct>",
-            "fp32": {"achieved_tflops": FLOPS_PER_ENV_STEP(S4) * N / (rms4 * 1e-3) / 1e12, "peak_tflops_probe": fp32_peak,
-                     "frac": FLOPS_PER_ENV_STEP(S4) * N / (rms4 * 1e-3) / 1e12 / fp32_peak, "flops_per_env_step": FLOPS_PER_ENV_STEP(S4)},
-            "note": "as above with 4 RK4 sub-intervals per env step (h = 2.5 ms)"}
-        del env3
+        # with S >= 3 RK4 sub-intervals per env step the path is compute-bound whatever the launch shape (the
+        # north star's "fused multi-substep RK4 kernel"); the same fused rollout at S = 4 and S = 8, without resets, shows how close
+        # the integrator itself gets to the FP32 FMA roofline (701 S + 180 algorithmic FLOPs per env step)
+        for S_ in (4, 8):
+            env3 = BatchedQuad(N, 0.01, 10 ** 9, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
+                               substeps=S_, sensor_noise=False, seed=0, env_id_offset=rank * N, device=dev)
+            env3.reset()
+            for w in range(2):
+                env3.rollout(KR)
+            torch.cuda.synchronize(dev)
+            reps = max(1, args.variant_steps // (KR * 4 * S_))
+            v0.record()
+            for k in range(reps):
+                env3.rollout(KR)
+            v1.record()
+            torch.cuda.synchronize(dev)
+            rms4 = v0.elapsed_time(v1) / (reps * KR)
+            tf = FLOPS_PER_ENV_STEP(S_) * N / (rms4 * 1e-3) / 1e12
+            variants["rollout_philox_actions_substeps%d" % S_] = {
+                "value": N / (rms4 * 1e-3), "unit": UNIT, "steps": reps * KR, "ms_per_env_step_of_all_envs": rms4,
+                "kernel": "rollout_pair_kernel<direct>" if env3.step_loader == 3 else "rollout_kernel<float,RK4,direct>",
+                "fp32": {"achieved_tflops": tf, "peak_tflops_probe": fp32_peak, "frac": tf / fp32_peak,
+                         "flops_per_env_step": FLOPS_PER_ENV_STEP(S_)},
+                "note": "K=%d steps per launch, %d RK4 sub-intervals per env step (h = %.3g ms), no resets" % (KR, S_, 10.0 / S_)}
+            del env3
 
     if rank == 0:
         line = {
