@@ -21,6 +21,7 @@ QS_FLAG_AUTO_RESET = 0x08
 QS_FLAG_SENSOR_NOISE = 0x10
 QS_FLAG_AUX = 0x20
 QS_FLAG_ASYNC_RESET = 0x40
+QS_FLAG_ROBUST = 0x80
 QS_ACT_BUFFER, QS_ACT_PHILOX_UNIFORM = 0, 1
 QS_STATS_DIM = 8
 QS_SENSOR_STATE_DIM = 20
@@ -28,7 +29,7 @@ QS_SENSOR_STATE_DIM = 20
 (QS_FIELD_OBS, QS_FIELD_STATE, QS_FIELD_ANG, QS_FIELD_ANG_VEL, QS_FIELD_STEP_EFFORT, QS_FIELD_W, QS_FIELD_REWARD,
  QS_FIELD_DONE, QS_FIELD_SOLVED, QS_FIELD_I, QS_FIELD_ABS_SUM, QS_FIELD_PREV_SHAPING, QS_FIELD_EP_RETURN,
  QS_FIELD_EPISODE, QS_FIELD_FLAGS, QS_FIELD_ACCEL, QS_FIELD_ACC_READ, QS_FIELD_MAT_ROT, QS_FIELD_SENSED_OBS,
- QS_FIELD_SENSOR_STATE, QS_FIELD_CLIPPED_ACTION, QS_FIELD_FM, QS_FIELD_COUNT) = range(23)
+ QS_FIELD_SENSOR_STATE, QS_FIELD_CLIPPED_ACTION, QS_FIELD_FM, QS_FIELD_GUST_COUNT, QS_FIELD_COUNT) = range(24)
 
 # every symbol include/quadsim.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
@@ -51,6 +52,9 @@ class qs_params(C.Structure):
         ("accel_std", C.c_double), ("accel_bias_drift", C.c_double), ("gyro_std", C.c_double),
         ("gyro_bias_drift", C.c_double), ("magnet_std", C.c_double), ("magnet_bias_drift", C.c_double),
         ("gps_std_p", C.c_double), ("gps_std_v", C.c_double), ("gps_blend", C.c_double),
+        ("robust_d_kf", C.c_double), ("robust_d_km", C.c_double), ("robust_d_m", C.c_double), ("robust_d_ir", C.c_double),
+        ("robust_d_j", C.c_double * 3), ("robust_gust_std", C.c_double * 3),
+        ("robust_gust_period", C.c_int32), ("reserved_", C.c_int32),
     ]
 
 

@@ -27,7 +27,7 @@ class BatchedQuad:
                  direct_control: int = 1, T: int = 1, clipped: bool = True, *, precision: str = "f32",
                  integrator: Optional[str] = None, substeps: int = 1, auto_reset: bool = False,
                  async_reset: bool = False, sensor_noise: bool = False, aux: bool = False, seed: int = 0, device=None,
-                 env_id_offset: int = 0, params: Optional[dict] = None):
+                 env_id_offset: int = 0, params: Optional[dict] = None, robust_control: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedQuad needs a CUDA device: the simulator has no CPU fallback")
         self.lib = L.load_library()
@@ -57,6 +57,7 @@ class BatchedQuad:
         flags |= L.QS_FLAG_ASYNC_RESET if async_reset else 0
         flags |= L.QS_FLAG_SENSOR_NOISE if sensor_noise else 0
         flags |= L.QS_FLAG_AUX if aux else 0
+        flags |= L.QS_FLAG_ROBUST if robust_control else 0     # quad.robust_control = True (quadrotor_env.py:183)
         cfg.flags = flags
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.device = self.device.index
@@ -67,7 +68,7 @@ class BatchedQuad:
                     for i, x in enumerate(v):
                         cur[i] = float(x)
                 else:
-                    setattr(cfg.params, k, float(v))
+                    setattr(cfg.params, k, type(cur)(v))
         nbytes = self.lib.qs_workspace_bytes(C.byref(cfg))
         if nbytes < 0:
             L.check(int(nbytes))
@@ -120,7 +121,7 @@ class BatchedQuad:
             raw = self._ws[d.ws_offset:d.ws_offset + nbytes]
             if d.elem_bytes == 1:
                 t = raw
-            elif f in (L.QS_FIELD_I,):
+            elif f in (L.QS_FIELD_I, L.QS_FIELD_GUST_COUNT):
                 t = raw.view(torch.int32)
             elif f in (L.QS_FIELD_EPISODE,):
                 t = raw.view(torch.int32)          # torch has limited uint32 support; values < 2^31 in practice
@@ -414,6 +415,11 @@ class BatchedQuad:
     @property
     def sensor_state(self):
         return self._field(L.QS_FIELD_SENSOR_STATE).t()
+
+    @property
+    def gust_count(self):
+        """robust_control=True: wind gusts drawn so far by each env (robust_control.wind, quadrotor_env.py:104-109)."""
+        return self._field(L.QS_FIELD_GUST_COUNT)[0]
 
     # ------------------------------------------------------------------ checkpoint / resume (SURVEY §5.4)
     def get_checkpoint(self) -> dict:

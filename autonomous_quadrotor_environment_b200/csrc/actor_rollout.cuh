@@ -367,8 +367,8 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     const uint32_t f = h->cfg.flags;
     if (h->cfg.precision != QS_F32 || h->cfg.integrator != QS_RK4 || !(f & QS_FLAG_DIRECT_CONTROL))
         return fail(QS_ESTATE, "qs_policy_rollout: needs an FP32 / RK4 / direct-control handle");
-    if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET))
-        return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / strict AUTO_RESET (use ASYNC_RESET)");
+    if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET | QS_FLAG_ROBUST))
+        return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / ROBUST / strict AUTO_RESET (use ASYNC_RESET)");
     ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std};
     PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
                 (float*)args->reward_out, args->done_out, (float*)args->hist};

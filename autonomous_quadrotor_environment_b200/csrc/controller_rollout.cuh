@@ -114,7 +114,7 @@ __device__ __forceinline__ void pid_law(const CtrlDev<R>& cd, CtrlMem<R>& m, con
     a[1] = U_2; a[2] = U_3; a[3] = U_4;
 }
 
-template <typename R, int INTEG>
+template <typename R, int INTEG, bool ROBUST = false>
 __global__ void __launch_bounds__(kBlock)
 control_rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                        const __grid_constant__ CtrlDev<R> cd, const __grid_constant__ ControlIO io) {
@@ -148,6 +148,8 @@ control_rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_cons
         StepOut<R> o;
         R reward = R(0);
         bool done = false, solved = false, warm_last = false;
+        int32_t gust_count = ROBUST ? v.gust_count[n] : 0;           // robust_control: kept in a register over the horizon
+        const RobustCtx rc{v.seed, v.env_id_offset + (uint32_t)n, &gust_count};
         for (int t = 0; t < io.horizon; ++t) {
             R a[4];
             if (cd.kind == QS_CTRL_LQR) {
@@ -159,7 +161,7 @@ control_rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_cons
             bool warm = false;
             if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
-            step_core<R, INTEG, false>(p, e, a, o, &c_last);
+            step_core<R, INTEG, false, ROBUST>(p, e, a, o, &c_last, &rc);
             if (warm) o.reward = R(0); else e.ep_return += o.reward;
             reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
 #pragma unroll
@@ -196,6 +198,7 @@ control_rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_cons
             if (io.done_out) io.done_out[(int64_t)t * v.N + n] = (uint8_t)((done ? 1 : 0) | (warm ? 2 : 0));
         }
         store_env(v, n, e, o.vq);
+        if (ROBUST) v.gust_count[n] = gust_count;
         v.reward[n] = reward;
         v.done[n] = (uint8_t)((done ? 1 : 0) | (warm_last ? 2 : 0));
         v.solved[n] = solved;
@@ -231,7 +234,10 @@ template <typename R> static CtrlDev<R> make_ctrl_dev(const qs_sim* s, const qs_
 
 template <typename R, int INTEG, bool DIRECT>
 static void launch_control_rollout(qs_sim* s, const qs_controller* c, const ControlIO& io, cudaStream_t st) {
-    control_rollout_kernel<R, INTEG><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), make_ctrl_dev<R>(s, c), io);
+    if (s->cfg.flags & QS_FLAG_ROBUST)       // robust_control: the same laws against perturbed dynamics and wind gusts
+        control_rollout_kernel<R, INTEG, true><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), make_ctrl_dev<R>(s, c), io);
+    else
+        control_rollout_kernel<R, INTEG><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), make_ctrl_dev<R>(s, c), io);
 }
 
 extern "C" int qs_default_controller(qs_controller* c, int kind, int clipped) {

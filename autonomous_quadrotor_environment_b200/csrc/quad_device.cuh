@@ -145,7 +145,7 @@ template <> struct M_<double> {
 // --------------------------------------------------------------------------------------------
 enum : uint32_t {
     F_DIRECT = 0x01u, F_CLIPPED = 0x02u, F_TRAINING = 0x04u, F_AUTO_RESET = 0x08u,
-    F_SENSOR = 0x10u, F_AUX = 0x20u, F_ASYNC_RESET = 0x40u
+    F_SENSOR = 0x10u, F_AUX = 0x20u, F_ASYNC_RESET = 0x40u, F_ROBUST = 0x80u
 };
 enum : uint32_t { EF_DONE = 1u, EF_HAS_SHAPING = 2u, EF_SOLVED = 4u, EF_WARM_SHIFT = 3u, EF_LOW = 7u };
 
@@ -181,6 +181,9 @@ template <typename R> struct DevParams {
     R s_gps_blend;   // GPS_P in per cent (visual_landing/math_trajectory.py:71-77); 0 = off
     R s_mag[3];      // magnetic field vector, mG (:651)
     R s_ti[9];       // inertial TRIAD basis t1i,t2i,t3i (:682-691), constant
+    // robust_control (:84-109): perturbation scales and wind gusts
+    R rb_kf, rb_m, rb_ir, rb_j[3], rb_gust_std[3];
+    int32_t rb_gust_period;
     int32_t n_limit; // n + T  :157
     int32_t T;
     int32_t substeps;
@@ -192,6 +195,17 @@ template <typename R> struct Ctrl {
     R f_m;           // F / M
     R tau_j[3];      // M_i / J_i
     R gyro_j[2];     // omega_r / Jx, omega_r / Jy
+    // robust_control only (template flag ROBUST; never read otherwise, so they cost nothing in the production kernels)
+    R wind[3];       // wind(i), added to the inertial velocity seen by the drag model  :318-320
+    R sm;            // 1 / (1 + episode_m)                                             :360-361
+    R sj[3];         // 1 / (1 + episode_J_ii)                                          :381-382
+};
+
+// robust_control (:84-109) for one env and one step: the per-episode perturbations and the wind of this step
+template <typename R> struct Robust {
+    R kf[4];         // episode_kf = U(0,1) * D_KF: rotor thrust loss                   :99,:236,:266
+    R ir[4];         // 1 + episode_ir, episode_ir = U(0,1) * D_IR                      :101,:342
+    R sm, sj[3], wind[3];
 };
 
 // --------------------------------------------------------------------------------------------
@@ -257,10 +271,11 @@ __device__ __forceinline__ void euler_quat(const R ang[3], R q[4]) {
 // --------------------------------------------------------------------------------------------
 // f2F :247-272 (direct mode).  a[] already clipped to [-1,1] (:470).
 template <typename R>
-__device__ __forceinline__ void rotor_direct(const DevParams<R>& p, const R a[4], R w[4], R fm[4]) {
+__device__ __forceinline__ void rotor_direct(const DevParams<R>& p, const R a[4], R w[4], R fm[4], const R* kf = nullptr) {
     R f0 = (a[0] + R(1)) * p.c8, f1 = (a[1] + R(1)) * p.c8, f2 = (a[2] + R(1)) * p.c8, f3 = (a[3] + R(1)) * p.c8;
     w[0] = M_<R>::sqrt(f0 * p.inv_kf); w[1] = M_<R>::sqrt(f1 * p.inv_kf);
     w[2] = M_<R>::sqrt(f2 * p.inv_kf); w[3] = M_<R>::sqrt(f3 * p.inv_kf);
+    if (kf) { f0 = f0 - kf[0] * f0; f1 = f1 - kf[1] * f1; f2 = f2 - kf[2] * f2; f3 = f3 - kf[3] * f3; }   // robust :265-266
     fm[0] = f0 + f1 + f2 + f3;
     fm[1] = (f2 - f0) * p.arm;
     fm[2] = (f1 - f3) * p.arm;
@@ -270,7 +285,7 @@ __device__ __forceinline__ void rotor_direct(const DevParams<R>& p, const R a[4]
 // f2w :197-245 (indirect mode): closed-form inverse of the 4x4 mixer the reference solves with LU.
 template <typename R>
 __device__ __forceinline__ void rotor_indirect(const DevParams<R>& p, bool clipped, const R fm_in[4],
-                                               R effort[4], R w[4], R fm[4]) {
+                                               R effort[4], R w[4], R fm[4], const R* kf = nullptr) {
     R uf = fm_in[0] * p.mix_f, ux = fm_in[1] * p.mix_m, uy = fm_in[2] * p.mix_m, uz = fm_in[3] * p.mix_z;
     R u[4] = {uf - ux - uz, uf + uy + uz, uf + ux - uz, uf - uy + uz};
 #pragma unroll
@@ -286,6 +301,7 @@ __device__ __forceinline__ void rotor_indirect(const DevParams<R>& p, bool clipp
             R s = (u[k] < R(0)) ? R(-1) : R(1);
             w[k] = M_<R>::sqrt(M_<R>::abs(u[k])) * s;
         }
+        if (kf) u[k] = u[k] - u[k] * kf[k];                      // robust :235-236 (after w, before FM_new and step_effort)
         effort[k] = u[k] * p.effort_scale - R(1);
     }
     fm[0] = p.k_f * (u[0] + u[1] + u[2] + u[3]);
@@ -295,9 +311,15 @@ __device__ __forceinline__ void rotor_indirect(const DevParams<R>& p, bool clipp
 }
 
 template <typename R>
-__device__ __forceinline__ Ctrl<R> make_ctrl(const DevParams<R>& p, const R fm[4], const R w[4]) {
+__device__ __forceinline__ Ctrl<R> make_ctrl(const DevParams<R>& p, const R fm[4], const R w[4], const Robust<R>* rb = nullptr) {
     Ctrl<R> c;
     R omega_r = (-w[0] + w[1] - w[2] + w[3]) * p.i_r;          // :345
+    if (rb) {                                                    // :341-343  ir_k = I_R (1 + episode_ir_k)
+        omega_r = (-w[0] * rb->ir[0] + w[1] * rb->ir[1] - w[2] * rb->ir[2] + w[3] * rb->ir[3]) * p.i_r;
+        c.sm = rb->sm;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { c.wind[k] = rb->wind[k]; c.sj[k] = rb->sj[k]; }
+    }
     c.f_m = fm[0] * p.inv_m;
     c.tau_j[0] = fm[1] * p.inv_j[0]; c.tau_j[1] = fm[2] * p.inv_j[1]; c.tau_j[2] = fm[3] * p.inv_j[2];
     c.gyro_j[0] = omega_r * p.inv_j[0]; c.gyro_j[1] = omega_r * p.inv_j[1];
@@ -307,19 +329,24 @@ __device__ __forceinline__ Ctrl<R> make_ctrl(const DevParams<R>& p, const R fm[4
 // --------------------------------------------------------------------------------------------
 // drone_eq :274-406 — RHS of the 13-state ODE.  y = [x,vx,y,vy,z,vz,q0..q3,wx,wy,wz]
 // --------------------------------------------------------------------------------------------
-template <typename R>
+// ROBUST (robust_control, :318-320,:360-361,:381-382): wind added to the velocity the drag model sees, body force divided by
+// the perturbed mass, angular acceleration through the perturbed inertia (the w x Jw term keeps the nominal J, :378).
+template <typename R, bool ROBUST = false>
 __device__ __forceinline__ void drone_rhs(const DevParams<R>& p, const Ctrl<R>& c, const R y[13], R dy[13]) {
     R qn[4];
     quat_normalize(&y[6], qn);                                   // :311-312
     R r[9];
     quat_rot_mat(qn, r);                                         // :315
     R vx = y[1], vy = y[3], vz = y[5];
-    R vbx = r[0] * vx + r[3] * vy + r[6] * vz;                   // :322  R^T v
-    R vby = r[1] * vx + r[4] * vy + r[7] * vz;
-    R vbz = r[2] * vx + r[5] * vy + r[8] * vz;
+    R ux = vx, uy = vy, uz = vz;
+    if (ROBUST) { ux += c.wind[0]; uy += c.wind[1]; uz += c.wind[2]; }
+    R vbx = r[0] * ux + r[3] * uy + r[6] * uz;                   // :322  R^T v
+    R vby = r[1] * ux + r[4] * uy + r[7] * uz;
+    R vbz = r[2] * ux + r[5] * uy + r[8] * uz;
     R fx = -p.kd_m[0] * (M_<R>::abs(vbx) * vbx);                 // :323 (already / M)
     R fy = -p.kd_m[1] * (M_<R>::abs(vby) * vby);
     R fz = c.f_m - p.kd_m[2] * (M_<R>::abs(vbz) * vbz);          // :352-353
+    if (ROBUST) { fx *= c.sm; fy *= c.sm; fz *= c.sm; }
     dy[0] = vx; dy[2] = vy; dy[4] = vz;
     dy[1] = r[0] * fx + r[1] * fy + r[2] * fz;                   // :357-367
     dy[3] = r[3] * fx + r[4] * fy + r[5] * fz;
@@ -329,6 +356,7 @@ __device__ __forceinline__ void drone_rhs(const DevParams<R>& p, const Ctrl<R>& 
     dy[10] = c.tau_j[0] - c.gyro_j[0] * wx - p.kdm_j[0] * (M_<R>::abs(wx) * wx) - p.cross_j[0] * (wy * wz);
     dy[11] = c.tau_j[1] + c.gyro_j[1] * wy - p.kdm_j[1] * (M_<R>::abs(wy) * wy) - p.cross_j[1] * (wx * wz);
     dy[12] = c.tau_j[2] - p.kdm_j[2] * (M_<R>::abs(wz) * wz) - p.cross_j[2] * (wx * wy);
+    if (ROBUST) { dy[10] *= c.sj[0]; dy[11] *= c.sj[1]; dy[12] *= c.sj[2]; }
     deriv_quat(&y[10], qn, &dy[6]);                              // :392
 }
 
@@ -338,7 +366,7 @@ __device__ __forceinline__ void drone_rhs(const DevParams<R>& p, const Ctrl<R>& 
 // Fixed-step classical RK4, S sub-intervals of length p.h_sub.  The four stages are a ROLLED loop (one copy of
 // the RHS in the instruction stream instead of four): the kernel is instruction-issue bound and the unrolled
 // form overflowed the instruction cache (ncu: stall_no_instructions) — the cost is 13 dead FMAs per substep.
-template <typename R>
+template <typename R, bool ROBUST = false>
 __device__ __forceinline__ void integrate_rk4(const DevParams<R>& p, const Ctrl<R>& c, R y[13]) {
     const R h = p.h_sub, hh = p.h_sub * R(0.5), h6 = p.h_sub * R(1.0 / 6.0);
     for (int s = 0; s < p.substeps; ++s) {
@@ -347,7 +375,7 @@ __device__ __forceinline__ void integrate_rk4(const DevParams<R>& p, const Ctrl<
         for (int j = 0; j < 13; ++j) { acc[j] = R(0); yt[j] = y[j]; }
 #pragma unroll 1
         for (int st = 0; st < 4; ++st) {
-            drone_rhs(p, c, yt, k);
+            drone_rhs<R, ROBUST>(p, c, yt, k);
             const R wgt = (st == 0 || st == 3) ? R(1) : R(2);
             const R cc = (st < 2) ? hh : h;
 #pragma unroll
@@ -398,13 +426,13 @@ __device__ __forceinline__ R rms13(const R v[13]) {           // scipy/.../commo
 // quadrotor_env.py:483: RungeKutta.__init__ (rk.py:85-105), select_initial_step (common.py:68-134),
 // _step_impl (rk.py:111-183), rk_step (rk.py:14-70), OdeSolver.step (base.py:179-210).
 // Keeps only y(t_bound) like the caller (`self.y[:, -1]`, :485).  Returns the number of RHS calls.
-template <typename R>
+template <typename R, bool ROBUST = false>
 __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>& c, R y[13]) {
     const R rtol = R(1e-3), atol = R(1e-6);
     const R t_bound = p.dt;
     R t = R(0);
     R f[13], tmp[13], scale[13];
-    drone_rhs(p, c, y, f);
+    drone_rhs<R, ROBUST>(p, c, y, f);
     int nfev = 1;
     // ---- select_initial_step
     R h_abs;
@@ -422,7 +450,7 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
         R y1[13], f1[13];
 #pragma unroll
         for (int j = 0; j < 13; ++j) y1[j] = y[j] + h0 * f[j];
-        drone_rhs(p, c, y1, f1);
+        drone_rhs<R, ROBUST>(p, c, y1, f1);
         ++nfev;
 #pragma unroll
         for (int j = 0; j < 13; ++j) tmp[j] = (f1[j] - f[j]) / scale[j];
@@ -447,28 +475,28 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
             // rk_step: K1 = f
 #pragma unroll
             for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A21)) * h;
-            drone_rhs(p, c, tmp, K2);
+            drone_rhs<R, ROBUST>(p, c, tmp, K2);
 #pragma unroll
             for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A31) + K2[j] * R(QS_DP_A32)) * h;
-            drone_rhs(p, c, tmp, K3);
+            drone_rhs<R, ROBUST>(p, c, tmp, K3);
 #pragma unroll
             for (int j = 0; j < 13; ++j)
                 tmp[j] = y[j] + (f[j] * R(QS_DP_A41) + K2[j] * R(QS_DP_A42) + K3[j] * R(QS_DP_A43)) * h;
-            drone_rhs(p, c, tmp, K4);
+            drone_rhs<R, ROBUST>(p, c, tmp, K4);
 #pragma unroll
             for (int j = 0; j < 13; ++j)
                 tmp[j] = y[j] + (f[j] * R(QS_DP_A51) + K2[j] * R(QS_DP_A52) + K3[j] * R(QS_DP_A53) + K4[j] * R(QS_DP_A54)) * h;
-            drone_rhs(p, c, tmp, K5);
+            drone_rhs<R, ROBUST>(p, c, tmp, K5);
 #pragma unroll
             for (int j = 0; j < 13; ++j)
                 tmp[j] = y[j] + (f[j] * R(QS_DP_A61) + K2[j] * R(QS_DP_A62) + K3[j] * R(QS_DP_A63) + K4[j] * R(QS_DP_A64) +
                                  K5[j] * R(QS_DP_A65)) * h;
-            drone_rhs(p, c, tmp, K6);
+            drone_rhs<R, ROBUST>(p, c, tmp, K6);
 #pragma unroll
             for (int j = 0; j < 13; ++j)
                 yn[j] = y[j] + h * (f[j] * R(QS_DP_B1) + K3[j] * R(QS_DP_B3) + K4[j] * R(QS_DP_B4) + K5[j] * R(QS_DP_B5) +
                                     K6[j] * R(QS_DP_B6));
-            drone_rhs(p, c, yn, K7);
+            drone_rhs<R, ROBUST>(p, c, yn, K7);
             nfev += 6;
 #pragma unroll
             for (int j = 0; j < 13; ++j) {
@@ -503,7 +531,7 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
 // --------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al., SC'11) — counter-based RNG for resets / noise / action sampling
 // --------------------------------------------------------------------------------------------
-enum : uint32_t { RNG_RESET = 0, RNG_SENSOR = 1, RNG_ACTION = 2, RNG_POLICY = 3 };
+enum : uint32_t { RNG_RESET = 0, RNG_SENSOR = 1, RNG_ACTION = 2, RNG_POLICY = 3, RNG_ROBUST = 4, RNG_GUST = 5 };
 
 #ifndef QS_PHILOX_UNROLL
 #define QS_PHILOX_UNROLL 10
@@ -578,6 +606,58 @@ __device__ __forceinline__ void sample_reset_state(const DevParams<R>& p, uint64
 }
 
 // --------------------------------------------------------------------------------------------
+// robust_control (:84-109): domain randomisation.  The reference draws from NumPy's global stream; here every draw is a
+// pure function of (seed, global env id, episode / gust counter), so no perturbation has to be stored and any sharding
+// reproduces it.  Per episode (robust_control.reset :98-102, called by quad.reset :426): episode_kf = U(0,1)^4 D_KF,
+// episode_m = N(0, D_M), episode_ir = U(0,1)^4 D_IR, diag(episode_J) = N(0, D_J)^3  [Philox stream RNG_ROBUST of
+// (env, episode): block 0 -> kf, block 1 -> ir, block 2 -> normals m, Jx, Jy, Jz].
+// Wind (:104-109): a new gust N(0, gust_std) whenever i % gust_period == 1 (i = quad.i after the increment of this step, so
+// every episode starts one), the wind ramping linearly from the previous gust to the new one over gust_period steps:
+// np.linspace(last, gust, P)[(i % P) - 1].  The gust sequence of an env continues across episodes (the reference never
+// resets it), numbered by the env's gust counter [stream RNG_GUST of (env, gust counter); gust 0 = 0].
+// Deliberate deviation: the reference re-draws the gust at EVERY drone_eq call of the step in which i % P == 1 (8-14 draws
+// in that step, each evaluation seeing the previous draw) — dead code there, not replicated: one draw per period.
+// --------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ void robust_gust(const DevParams<R>& p, uint64_t seed, uint32_t env_id, int32_t count, R g[3]) {
+    if (count <= 0) { g[0] = g[1] = g[2] = R(0); return; }
+    const uint4 u = philox_block(seed, env_id, (uint32_t)count, 0, RNG_GUST);
+    R n[4];
+    box_muller(u32_to_unit<R>(u.x), u32_to_unit<R>(u.y), &n[0], &n[1]);
+    box_muller(u32_to_unit<R>(u.z), u32_to_unit<R>(u.w), &n[2], &n[3]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) g[k] = n[k] * p.rb_gust_std[k];
+}
+
+// i = quad.i of this step (after the increment); gust_count is the env's persistent gust counter (updated here)
+template <typename R>
+__device__ __forceinline__ void robust_prepare(const DevParams<R>& p, uint64_t seed, uint32_t env_id, uint32_t episode, int32_t i,
+                                               int32_t& gust_count, Robust<R>& rb) {
+    const uint4 a = philox_block(seed, env_id, episode, 0, RNG_ROBUST);
+    const uint4 b = philox_block(seed, env_id, episode, 1, RNG_ROBUST);
+    const uint4 c = philox_block(seed, env_id, episode, 2, RNG_ROBUST);
+    rb.kf[0] = u32_to_unit<R>(a.x) * p.rb_kf; rb.kf[1] = u32_to_unit<R>(a.y) * p.rb_kf;
+    rb.kf[2] = u32_to_unit<R>(a.z) * p.rb_kf; rb.kf[3] = u32_to_unit<R>(a.w) * p.rb_kf;
+    rb.ir[0] = R(1) + u32_to_unit<R>(b.x) * p.rb_ir; rb.ir[1] = R(1) + u32_to_unit<R>(b.y) * p.rb_ir;
+    rb.ir[2] = R(1) + u32_to_unit<R>(b.z) * p.rb_ir; rb.ir[3] = R(1) + u32_to_unit<R>(b.w) * p.rb_ir;
+    R n[4];
+    box_muller(u32_to_unit<R>(c.x), u32_to_unit<R>(c.y), &n[0], &n[1]);
+    box_muller(u32_to_unit<R>(c.z), u32_to_unit<R>(c.w), &n[2], &n[3]);
+    rb.sm = R(1) / (R(1) + n[0] * p.rb_m);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rb.sj[k] = R(1) / (R(1) + n[1 + k] * p.rb_j[k]);
+    const int32_t P = p.rb_gust_period;
+    const int32_t index = (i % P) - 1;                             // :105
+    if (index == 0) gust_count += 1;                               // :106-108
+    R g0[3], g1[3];
+    robust_gust(p, seed, env_id, gust_count - 1, g0);
+    robust_gust(p, seed, env_id, gust_count, g1);
+    const R t = (index < 0) ? R(1) : R(index) / R(P - 1);          // np.linspace(last, gust, P)[index]; index -1 = the last element
+#pragma unroll
+    for (int k = 0; k < 3; ++k) rb.wind[k] = g0[k] + (g1[k] - g0[k]) * t;
+}
+
+// --------------------------------------------------------------------------------------------
 // one environment, in registers
 // --------------------------------------------------------------------------------------------
 __device__ __forceinline__ float div_dt(float x, const DevParams<float>& p) { return x * p.inv_dt; }
@@ -614,7 +694,8 @@ template <typename R> struct StepOut {
 //
 // phase 1 — :467-477: step counter, action clip, rotor map (f2F / f2w) -> rotor command held constant over the RK stages
 template <typename R, bool DIRECT>
-__device__ __forceinline__ Ctrl<R> step_pre(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o, R act[4]) {
+__device__ __forceinline__ Ctrl<R> step_pre(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o, R act[4],
+                                            const Robust<R>* rb = nullptr) {
     e.i += 1;                                                    // :467
     R fm[4];
     if (DIRECT) {
@@ -625,15 +706,15 @@ __device__ __forceinline__ Ctrl<R> step_pre(const DevParams<R>& p, Env<R>& e, co
             v = (v > R(1)) ? R(1) : v;
             act[k] = v; o.effort[k] = v;
         }
-        rotor_direct(p, act, o.w, fm);
+        rotor_direct(p, act, o.w, fm, rb ? rb->kf : nullptr);
     } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k) act[k] = a_in[k];            // reward uses the RAW action :476,:553
-        rotor_indirect(p, (p.flags & F_CLIPPED) != 0, a_in, o.effort, o.w, fm);
+        rotor_indirect(p, (p.flags & F_CLIPPED) != 0, a_in, o.effort, o.w, fm, rb ? rb->kf : nullptr);
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) { o.fm[k] = fm[k]; o.clipped[k] = DIRECT ? act[k] : fm[k]; }
-    return make_ctrl(p, fm, o.w);
+    return make_ctrl(p, fm, o.w, rb);
 }
 
 // phase 3 — :486-498 after the integration: observation tail, Euler angles, done_condition, reward_function, control_effort
@@ -696,14 +777,23 @@ __device__ __forceinline__ void step_post(const DevParams<R>& p, Env<R>& e, cons
     o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
 }
 
-template <typename R, int INTEG, bool DIRECT>
+// robust_control context of an env (ROBUST kernels only): where its Philox streams and its gust counter live
+struct RobustCtx { uint64_t seed; uint32_t env_id; int32_t* gust_count; };
+
+template <typename R, int INTEG, bool DIRECT, bool ROBUST = false>
 __device__ __forceinline__ void step_core(const DevParams<R>& p, Env<R>& e, const R a_in[4], StepOut<R>& o,
-                                          Ctrl<R>* ctrl_out = nullptr) {
+                                          Ctrl<R>* ctrl_out = nullptr, const RobustCtx* rc = nullptr) {
     R act[4];
-    const Ctrl<R> c = step_pre<R, DIRECT>(p, e, a_in, o, act);
+    Robust<R> rb;
+    if (ROBUST) {
+        int32_t gc = *rc->gust_count;
+        robust_prepare(p, rc->seed, rc->env_id, e.episode, e.i + 1, gc, rb);
+        *rc->gust_count = gc;
+    }
+    const Ctrl<R> c = step_pre<R, DIRECT>(p, e, a_in, o, act, ROBUST ? &rb : nullptr);
     if (ctrl_out) *ctrl_out = c;
-    if (INTEG == 1) integrate_rk45(p, c, e.y);                   // :483
-    else integrate_rk4(p, c, e.y);
+    if (INTEG == 1) integrate_rk45<R, ROBUST>(p, c, e.y);        // :483
+    else integrate_rk4<R, ROBUST>(p, c, e.y);
     step_post(p, e, act, o);
 }
 

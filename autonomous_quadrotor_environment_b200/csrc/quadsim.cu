@@ -63,6 +63,7 @@ template <typename R> struct SimView {
     R* fm;
     R* sensed_obs;    // SENSOR (nullable)
     R* sensor_state;
+    int32_t* gust_count;   // ROBUST (nullable): per-env gust counter of robust_control.wind
     double* stats;
     uint64_t seed;
     uint32_t env_id_offset;
@@ -160,6 +161,9 @@ template <typename R> static DevParams<R> make_params(const qs_config& c) {
             p.s_mag[k] = R(mv[k]); p.s_ti[k] = R(gv[k]); p.s_ti[3 + k] = R(t2[k]); p.s_ti[6 + k] = R(t3[k] / n3);
         }
     }
+    p.rb_kf = R(q.robust_d_kf); p.rb_m = R(q.robust_d_m); p.rb_ir = R(q.robust_d_ir);      // robust_control.__init__ :85-93
+    for (int k = 0; k < 3; ++k) { p.rb_j[k] = R(q.robust_d_j[k]); p.rb_gust_std[k] = R(q.robust_gust_std[k]); }
+    p.rb_gust_period = q.robust_gust_period > 1 ? q.robust_gust_period : 500;
     p.n_limit = c.n_max + c.T;                                                             // :157
     p.T = c.T;
     p.substeps = c.substeps;
@@ -191,6 +195,10 @@ extern "C" int qs_default_config(qs_config* cfg) {
     p.tr_p[0] = 3; p.tr_p[1] = 2; p.tr_p[2] = 1;
     p.accel_std = 0.1; p.accel_bias_drift = 0.0005; p.gyro_std = 0.035; p.gyro_bias_drift = 0.00015;
     p.magnet_std = 15; p.magnet_bias_drift = 0.075; p.gps_std_p = 1.71; p.gps_std_v = 0.5; p.gps_blend = 0.0;
+    p.robust_d_kf = 0.1; p.robust_d_km = 0.1; p.robust_d_m = 0.3; p.robust_d_ir = 0.1;      // robust_control.__init__ :85-93
+    p.robust_d_j[0] = p.robust_d_j[1] = p.robust_d_j[2] = 0.1;
+    p.robust_gust_std[0] = 5; p.robust_gust_std[1] = 5; p.robust_gust_std[2] = 2;
+    p.robust_gust_period = 500;
     return QS_OK;
 }
 
@@ -218,6 +226,7 @@ static const RowSpec kRows[] = {
     {QS_FIELD_FM, 4, 0, QS_FLAG_AUX},
     {QS_FIELD_SENSED_OBS, 14, 0, QS_FLAG_SENSOR_NOISE},
     {QS_FIELD_SENSOR_STATE, QS_SENSOR_STATE_DIM, 0, QS_FLAG_SENSOR_NOISE},
+    {QS_FIELD_GUST_COUNT, 1, 4, QS_FLAG_ROBUST},
 };
 static const int kNumRows = sizeof(kRows) / sizeof(kRows[0]);
 
@@ -234,6 +243,8 @@ static int validate(const qs_config* c) {
     if (c->precision != QS_F32 && c->precision != QS_F64) return fail(QS_EINVAL, "bad precision");
     if (c->integrator != QS_RK4 && c->integrator != QS_RK45) return fail(QS_EINVAL, "bad integrator");
     if (c->n_max < 1) return fail(QS_EINVAL, "n_max must be >= 1");
+    if ((c->flags & QS_FLAG_ROBUST) && (c->flags & QS_FLAG_SENSOR_NOISE))
+        return fail(QS_EINVAL, "QS_FLAG_ROBUST cannot be combined with QS_FLAG_SENSOR_NOISE");
     return QS_OK;
 }
 
@@ -285,6 +296,7 @@ template <typename R> static SimView<R> make_view(const qs_sim* s) {
     v.fm = (R*)s->slot[QS_FIELD_FM].ptr;
     v.sensed_obs = (R*)s->slot[QS_FIELD_SENSED_OBS].ptr;
     v.sensor_state = (R*)s->slot[QS_FIELD_SENSOR_STATE].ptr;
+    v.gust_count = (int32_t*)s->slot[QS_FIELD_GUST_COUNT].ptr;
     v.stats = s->stats;
     v.seed = s->seed;
     v.env_id_offset = (uint32_t)s->cfg.env_id_offset;
@@ -294,6 +306,7 @@ template <typename R> static SimView<R> make_view(const qs_sim* s) {
                            &v.w, &v.accel, &v.acc_read, &v.mat_rot, &v.clipped_action, &v.fm, &v.sensed_obs, &v.sensor_state};
         for (R** r : real_rows) if (*r) *r += b;
         v.step_i += b; v.episode += b; v.flags += b; v.done += b; v.solved += b;
+        if (v.gust_count) v.gust_count += b;
         v.N = s->slice_count;
         v.env_id_offset += (uint32_t)b;
     }
@@ -350,7 +363,7 @@ __device__ __forceinline__ void store_env(const SimView<R>& v, int64_t n, const 
 
 // AUX attributes the single-env compatibility class exposes (quad.ang_vel, step_effort, w, accel,
 // accelerometer_read, mat_rot); evaluated at the new state like the reference's trailing drone_eq call.
-template <typename R>
+template <typename R, bool ROBUST = false>
 __device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
                                        const StepOut<R> o, const Ctrl<R> c) {   // by VALUE: callers' structs stay in registers
 #pragma unroll
@@ -361,7 +374,7 @@ __device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& 
         v.clipped_action[k * v.ld + n] = o.clipped[k]; v.fm[k * v.ld + n] = o.fm[k];
     }
     R dy[13], qn[4], r[9];
-    drone_rhs(p, c, e.y, dy);
+    drone_rhs<R, ROBUST>(p, c, e.y, dy);
     quat_normalize(&e.y[6], qn);
     quat_rot_mat(qn, r);
     R a[3] = {dy[1], dy[3], dy[5]};
@@ -419,7 +432,7 @@ __device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<
 
 // quad.reset (:408-454) for one env held in registers: (optionally) sample the initial state with Philox,
 // clear the episode bookkeeping, then take T hover steps.  obs_hist/act_hist: [T][14][N] / [T][4][N] or NULL.
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool ROBUST = false>
 __device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& v, int64_t n, Env<R>& e,
                                        bool sample, StepOut<R>& o, R* obs_hist, R* act_hist) {
     if (sample) {
@@ -429,7 +442,8 @@ __device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& 
     reset_head(e);
     for (int t = 0; t < p.T; ++t) {
         Ctrl<R> c;
-        step_core<R, INTEG, DIRECT>(p, e, p.zero_control, o, &c);
+        const RobustCtx rc{v.seed, v.env_id_offset + (uint32_t)n, ROBUST ? v.gust_count + n : nullptr};
+        step_core<R, INTEG, DIRECT, ROBUST>(p, e, p.zero_control, o, &c, &rc);
         if (obs_hist) {
             R* oh = obs_hist + (int64_t)t * 14 * v.N;
 #pragma unroll
@@ -442,7 +456,7 @@ __device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& 
 #pragma unroll
             for (int k = 0; k < 4; ++k) ah[k * v.N + n] = p.zero_control[k];
         }
-        if ((p.flags & F_AUX) && t == p.T - 1) store_aux(p, v, n, e, o, c);
+        if ((p.flags & F_AUX) && t == p.T - 1) store_aux<R, ROBUST>(p, v, n, e, o, c);
         if ((p.flags & F_SENSOR) && t == p.T - 1) sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], 1);
     }
     e.ep_return = R(0);
@@ -549,7 +563,7 @@ __device__ __forceinline__ void issue_tile(const SimView<R>& v, const R* action,
 }
 
 // quad.step for one env held in registers + all of its stores (shared by both loader variants).
-template <typename R, int INTEG, bool DIRECT, bool SENSOR>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR, bool ROBUST = false>
 __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io, int64_t n,
                                             Env<R>& e, R a[4], LocalStats& ls, bool& any_end, int* s_queue, int* s_qn) {
     bool warm = false;
@@ -557,10 +571,11 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
     const bool was_done = (e.flags & EF_DONE) != 0;
     StepOut<R> o;
     Ctrl<R> c;
-    step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
+    const RobustCtx rc{v.seed, v.env_id_offset + (uint32_t)n, ROBUST ? v.gust_count + n : nullptr};
+    step_core<R, INTEG, DIRECT, ROBUST>(p, e, a, o, &c, &rc);
     if (warm) o.reward = R(0); else e.ep_return += o.reward;
     if (o.done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
-    if (p.flags & F_AUX) store_aux(p, v, n, e, o, c);
+    if (p.flags & F_AUX) store_aux<R, ROBUST>(p, v, n, e, o, c);
     if (SENSOR)                             // warm-up steps bypass the sensor; the last one re-initialises it (sensor.reset)
         sensor_update_inl(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
     if ((p.flags & (F_AUTO_RESET | F_ASYNC_RESET)) && o.done) {
@@ -574,7 +589,7 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
                 async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, te, to.vq);
             } else {
                 te.episode += 1;
-                reset_env<R, INTEG, DIRECT>(p, v, n, te, true, to, nullptr, nullptr);
+                reset_env<R, INTEG, DIRECT, ROBUST>(p, v, n, te, true, to, nullptr, nullptr);
             }
             e = te;
 #pragma unroll
@@ -598,7 +613,7 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
 }
 
 // compacted strict-reset sub-pass + statistics flush (common tail of both step kernels)
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool ROBUST = false>
 __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimView<R>& v, const StepIO<R>& io,
                                               const LocalStats& ls, bool any_end, const int* s_queue, const int* s_qn) {
     __syncthreads();                       // queue complete; the block's global stores are visible to the block
@@ -618,7 +633,7 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
             }
         } else {
             e.episode += 1;
-            reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+            reset_env<R, INTEG, DIRECT, ROBUST>(p, v, n, e, true, o, nullptr, nullptr);
         }
         store_env(v, n, e, o.vq);
         if (io.obs) {
@@ -633,7 +648,7 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
 }
 
 // Loader A — direct: every thread issues its 27 coalesced LDGs up front (one 128-byte line per warp request).
-template <typename R, int INTEG, bool DIRECT, bool SENSOR>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR, bool ROBUST = false>
 __global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                    const __grid_constant__ StepIO<R> io) {
@@ -651,9 +666,9 @@ step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant
         R a[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) a[k] = io.action[k * v.N + n];
-        process_env<R, INTEG, DIRECT, SENSOR>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
+        process_env<R, INTEG, DIRECT, SENSOR, ROBUST>(p, v, io, n, e, a, ls, any_end, s_queue, &s_qn);
     }
-    step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
+    step_epilogue<R, INTEG, DIRECT, ROBUST>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
 
 // Loader B — TMA: 3-stage shared-memory ring filled by cp.async.bulk two tiles ahead of the arithmetic.
@@ -738,7 +753,7 @@ step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ 
 #include "step_pair.cuh"
 
 // quad.reset for the masked envs (det_state given or Philox-sampled).
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool ROBUST = false>
 __global__ void __launch_bounds__(kBlock)
 reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v, const R* det_state,
              const uint8_t* mask, R* obs_hist, R* act_hist) {
@@ -754,7 +769,7 @@ reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ Sim
             e.episode += 1;
         }
         StepOut<R> o;
-        reset_env<R, INTEG, DIRECT>(p, v, n, e, det_state == nullptr, o, obs_hist, act_hist);
+        reset_env<R, INTEG, DIRECT, ROBUST>(p, v, n, e, det_state == nullptr, o, obs_hist, act_hist);
         store_env(v, n, e, o.vq);
         v.reward[n] = R(0);
         v.done[n] = o.done;
@@ -898,6 +913,12 @@ template <> struct WarpKernelOk<float, 0> { static constexpr bool value = true; 
 
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
+    if constexpr (!SENSOR) {
+        if (s->cfg.flags & QS_FLAG_ROBUST) {                   // robust_control: generic kernel with the ROBUST dynamics
+            step_kernel_direct<R, INTEG, DIRECT, false, true><<<grid_step(s), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+            return;
+        }
+    }
     if constexpr (WarpKernelOk<R, INTEG>::value) {
         if (s->step_loader == 3 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
             constexpr int threads = SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain;
@@ -953,8 +974,12 @@ static void launch_step(qs_sim* s, const void* action, void* obs, void* reward, 
 
 template <typename R, int INTEG, bool DIRECT>
 static void launch_reset(qs_sim* s, const void* det, const uint8_t* mask, void* oh, void* ah, cudaStream_t st) {
-    reset_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s),
-                                                                         (const R*)det, mask, (R*)oh, (R*)ah);
+    if (s->cfg.flags & QS_FLAG_ROBUST)
+        reset_kernel<R, INTEG, DIRECT, true><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s),
+                                                                                   (const R*)det, mask, (R*)oh, (R*)ah);
+    else
+        reset_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s),
+                                                                             (const R*)det, mask, (R*)oh, (R*)ah);
 }
 
 template <typename R, int INTEG, bool DIRECT>
@@ -1070,6 +1095,7 @@ extern "C" int qs_get_step_loader(qs_handle h) {
     if (!h) return fail(QS_EINVAL, "qs_get_step_loader: NULL handle");
     const bool warp_ok = h->cfg.precision == QS_F32 && h->cfg.integrator == QS_RK4 &&
                          !(h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET));
+    if (h->cfg.flags & QS_FLAG_ROBUST) return 0;               // robust_control handles always run the generic kernel
     return (h->step_loader >= 2 && !warp_ok) ? 1 : h->step_loader;
 }
 
@@ -1099,8 +1125,8 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
     if (args->action_source == QS_ACT_BUFFER && !args->actions) return fail(QS_EINVAL, "qs_rollout: actions is NULL");
     if (args->action_source != QS_ACT_BUFFER && args->action_source != QS_ACT_PHILOX_UNIFORM)
         return fail(QS_EINVAL, "qs_rollout: bad action_source");
-    if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE))
-        return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_SENSOR_NOISE");
+    if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_ROBUST))
+        return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_SENSOR_NOISE / QS_FLAG_ROBUST");
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_rollout, h, args, st);
     QS_CUDA(cudaGetLastError());
@@ -1116,7 +1142,8 @@ extern "C" int qs_step_host(qs_handle h, const void* action_host, void* obs_host
     const size_t rs = (size_t)h->rs, N = (size_t)h->N, ld = (size_t)h->ld;
     constexpr size_t kSliceMin = 65536;
     size_t n_slices = N / kSliceMin;
-    if (n_slices > 8) n_slices = 8;
+    static const int max_slices = [] { const char* e = getenv("QS_HOST_SLICES"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 8; }();
+    if (n_slices > (size_t)max_slices) n_slices = (size_t)max_slices;
     if (n_slices < 2) {
         QS_CUDA(cudaMemcpyAsync(h->action_stage, action_host, 4 * N * rs, cudaMemcpyHostToDevice, st));
         int rc = qs_step(h, h->action_stage, nullptr, nullptr, nullptr, nullptr, stream);

@@ -64,6 +64,11 @@ extern "C" {
                                      /* (:447-453) run as its next T ordinary lock-step steps (caller's action         */
                                      /* ignored, reward 0, bit1 of the done byte set).  Per-env sequences are exactly  */
                                      /* those of reset()+step(); no lane ever runs T serial steps.                     */
+#define QS_FLAG_ROBUST         0x80u /* quad.robust_control = True (quadrotor_env.py:84-109,:183): per-episode perturbation   */
+                                     /* of rotor thrust (K_F), mass, rotor inertia and J plus linearly ramping wind gusts,    */
+                                     /* every draw a pure function of (seed, global env id, episode / gust counter).  Runs on */
+                                     /* the generic step / reset kernels (any precision / integrator); not available with     */
+                                     /* QS_FLAG_SENSOR_NOISE, qs_rollout, qs_policy_rollout or qs_control_rollout.            */
 
 /* Physical / reward constants.  Defaults (qs_default_config) = environment/quadrotor_env.py:30-80. */
 typedef struct qs_params {
@@ -83,6 +88,10 @@ typedef struct qs_params {
     double magnet_std, magnet_bias_drift, gps_std_p, gps_std_v;
     double gps_blend;                  /* GPS_P of visual_landing/math_trajectory.py:71-77: per cent of the GPS reading blended into the
                                           dead-reckoned position/velocity each step (and written back); 0 = off (the script's GPS = False) */
+    /* robust_control.__init__ :85-93 (QS_FLAG_ROBUST): D_KF, D_KM (unused by the reference too), D_M, D_IR, D_J, gust_std, gust_period */
+    double robust_d_kf, robust_d_km, robust_d_m, robust_d_ir;
+    double robust_d_j[3], robust_gust_std[3];
+    int32_t robust_gust_period, reserved_;
 } qs_params;
 
 /* Mirrors quad.__init__(t_step, n, training, euler, direct_control, T, clipped)  quadrotor_env.py:112 */
@@ -133,6 +142,7 @@ typedef enum qs_field {
     QS_FIELD_SENSOR_STATE = 19,/*[QS_SENSOR_STATE_DIM][N] real (SENSOR_NOISE)                             */
     QS_FIELD_CLIPPED_ACTION = 20,/*[4][N] real quad.clipped_action (AUX)                  :472,:477          */
     QS_FIELD_FM = 21,         /* [4][N]  real  body thrust + moments applied [F,Mx,My,Mz] (AUX) :287-291        */
+    QS_FIELD_GUST_COUNT = 22, /* [N]     i32   gusts drawn so far by robust_control.wind (ROBUST)  :104-109          */
     QS_FIELD_COUNT_
 } qs_field;
 

@@ -308,6 +308,57 @@ def gen_ppo_vectors():
     np.savez_compressed(os.path.join(OUT, "ppo_vectors.npz"), **out)
 
 
+def gen_robust_vectors(ref, rng):
+    """robust_control (quadrotor_env.py:84-109 and the guarded branches :235,:265,:318,:341,:360,:381) is dead code in the
+    reference (quad.robust_control is hard-wired False, :183) and one branch does not run as written on current NumPy
+    (episode_m is a length-1 array -> ragged return value of drone_eq): the perturbations are injected directly, episode_m as
+    the scalar the arithmetic intends, and wind() is replaced by a fixed vector (its ramp is pinned separately below)."""
+    n = 128
+    x = rng.normal(0, 2, (n, 13))
+    x[:, 6:10] = rng.normal(0, 1, (n, 4))
+    x[:, 10:13] = rng.normal(0, 4, (n, 3))
+    a = rng.uniform(-1, 1, (n, 4))
+    kf = rng.random((n, 4)) * 0.1
+    ir = rng.random((n, 4)) * 0.1
+    m = rng.normal(0, 0.3, n)
+    Jp = rng.normal(0, 0.1, (n, 3))
+    wind = rng.normal(0, [5, 5, 2], (n, 3))
+    env = quiet_quad(ref, 0.01, 1000, training=True, direct_control=1, T=1)
+    env.robust_control = True
+    dx_direct = []
+    for k in range(n):
+        rp = env.robust_parameters
+        rp.episode_kf = kf[k].copy(); rp.episode_m = float(m[k]); rp.episode_ir = ir[k].copy(); rp.episode_J = np.eye(3) * Jp[k]
+        rp.wind = lambda i, w=wind[k]: w.reshape(3, 1).copy()
+        dx_direct.append(np.array(env.drone_eq(0, x[k], a[k]), dtype=np.float64))
+    envi = quiet_quad(ref, 0.01, 1000, training=True, direct_control=0, T=1, clipped=True)
+    envi.robust_control = True
+    fm = np.stack([rng.uniform(0, 25, n), rng.normal(0, 0.4, n), rng.normal(0, 0.4, n), rng.normal(0, 0.05, n)], axis=1)
+    eff, wr, fmn, dx_ind = [], [], [], []
+    for k in range(n):
+        rp = envi.robust_parameters
+        rp.episode_kf = kf[k].copy(); rp.episode_m = float(m[k]); rp.episode_ir = ir[k].copy(); rp.episode_J = np.eye(3) * Jp[k]
+        rp.wind = lambda i, w=wind[k]: w.reshape(3, 1).copy()
+        se, w, F_new, M_new = envi.f2w(fm[k, 0], fm[k, 1:4].reshape(3, 1))
+        envi.w = w
+        u = np.append([F_new], M_new)
+        eff.append(np.asarray(se).flatten()); wr.append(w.flatten()); fmn.append(u)
+        dx_ind.append(np.array(envi.drone_eq(0, x[k], u), dtype=np.float64))
+    # wind(): the stateful ramp, called once per step over two "episodes" (i restarts at 1), NumPy's stream seeded
+    rc = ref.robust_control()
+    np.random.seed(11)
+    rc.reset()
+    i_seq = np.concatenate([np.arange(1, 701), np.arange(1, 1201)])
+    winds, gusts = [], []
+    for i in i_seq:
+        winds.append(np.asarray(rc.wind(int(i))).flatten().copy())
+        gusts.append(np.asarray(rc.gust).flatten().copy())
+    np.savez_compressed(os.path.join(OUT, "robust_vectors.npz"), x=x, a=a, kf=kf, ir=ir, m=m, J=Jp, wind=wind,
+                        dx_direct=np.array(dx_direct), fm=fm, effort=np.array(eff), w_rotor=np.array(wr), fm_new=np.array(fmn),
+                        dx_indirect=np.array(dx_ind), wind_i=i_seq, wind_out=np.array(winds), wind_gust=np.array(gusts),
+                        gust_period=rc.gust_period)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load_reference()
@@ -320,6 +371,7 @@ def main():
     gen_actor(ref)
     gen_sensor_stats(ref)
     gen_ppo_vectors()
+    gen_robust_vectors(ref, np.random.default_rng(20261018))
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -129,11 +129,14 @@ def quat_rot_mat(q):
 # --------------------------------------------------------------------------------------
 # rotor / mixer maps
 # --------------------------------------------------------------------------------------
-def f2F(f_action):
-    """Direct mode: normalised rotor commands (N,4) -> w(N,4), F(N), M(N,3). quadrotor_env.py:247-272."""
+def f2F(f_action, kf=None):
+    """Direct mode: normalised rotor commands (N,4) -> w(N,4), F(N), M(N,3). quadrotor_env.py:247-272.
+    kf (N,4): robust_control's episode_kf, applied after w (:265-266)."""
     f = (f_action + 1) * T2WR * M * G / 8
     with np.errstate(invalid="ignore"):
         w = np.sqrt(f / K_F)
+    if kf is not None:
+        f = f - kf * f
     F_new = f[:, 0] + f[:, 1] + f[:, 2] + f[:, 3]
     M_new = np.stack([(f[:, 2] - f[:, 0]) * D,
                       (f[:, 1] - f[:, 3]) * D,
@@ -147,9 +150,10 @@ _MIXER = np.array([[K_F, K_F, K_F, K_F],
                    [-K_M, +K_M, -K_M, +K_M]])
 
 
-def f2w(f, m, clipped=True):
+def f2w(f, m, clipped=True, kf=None):
     """Indirect mode mixer: F(N), M(N,3) -> step_effort(N,4), w(N,4), F_new(N), M_new(N,3).
-    quadrotor_env.py:197-245 (np.linalg.solve of the 4x4 mixer, clip or signed sqrt, FM_new = x.u)."""
+    quadrotor_env.py:197-245 (np.linalg.solve of the 4x4 mixer, clip or signed sqrt, FM_new = x.u).
+    kf (N,4): robust_control's episode_kf, applied to u after w and before FM_new / step_effort (:235-236)."""
     y = np.concatenate([np.asarray(f, dtype=np.float64)[:, None], np.asarray(m, dtype=np.float64)], axis=1)
     u = np.linalg.solve(_MIXER, y.T).T
     if clipped:
@@ -157,6 +161,8 @@ def f2w(f, m, clipped=True):
         w = np.sqrt(u)
     else:
         w = np.sqrt(np.abs(u)) * np.where(u < 0, -1.0, 1.0)
+    if kf is not None:
+        u = u - u * kf
     FM_new = u @ _MIXER.T
     step_effort = (u * K_F / (T2WR * M * G / 4) * 2) - 1
     return step_effort, w, FM_new[:, 0], FM_new[:, 1:4]
@@ -165,8 +171,11 @@ def f2w(f, m, clipped=True):
 # --------------------------------------------------------------------------------------
 # drone_eq — environment/quadrotor_env.py:274-406
 # --------------------------------------------------------------------------------------
-def drone_eq(x, F, Mact, w_rotor, want_aux=False):
+def drone_eq(x, F, Mact, w_rotor, want_aux=False, rb=None):
     """RHS of the 13-state ODE, batched.
+
+    rb (robust_control, :84-109; None = off): dict with wind (N,3) added to the inertial velocity the drag model sees
+    (:318-320), ir (N,4) = episode_ir (:341-343), m (N) = episode_m (:360-361), J (N,3) = diag(episode_J) (:381-382).
 
     x (N,13) = [x,vx,y,vy,z,vz,q0..q3,wx,wy,wz]; F (N) body thrust; Mact (N,3) body moments;
     w_rotor (N,4) rotor speeds (for the gyroscopic term, :345).  Returns dx (N,13) and, if
@@ -179,23 +188,32 @@ def drone_eq(x, F, Mact, w_rotor, want_aux=False):
     with np.errstate(invalid="ignore", divide="ignore"):
         q = q / np.linalg.norm(q, axis=1, keepdims=True)                       # :311-312
     R = quat_rot_mat(q)                                                       # :315
-    v_body = np.einsum("nji,nj->ni", R, vel)                                  # :322  R^T v
+    v_in = vel if rb is None else vel + rb["wind"]                            # :318-320
+    v_body = np.einsum("nji,nj->ni", R, v_in)                                 # :322  R^T v
     f_drag = -0.5 * RHO * C_D * AREA[None, :] * (np.abs(v_body) * v_body)     # :323
     m_drag = np.zeros_like(W)
     for xx in D_XX:                                                           # :328-334
         m_drag[:, 0] += -RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 0]) * (xx * W[:, 0])) * xx
         m_drag[:, 1] += -RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 1]) * (xx * W[:, 1])) * xx
         m_drag[:, 2] += -2 * RHO * C_D * BEAM_THICKNESS * D / 10 * (np.abs(xx * W[:, 2]) * (xx * W[:, 2])) * xx
-    omega_r = (-w_rotor[:, 0] + w_rotor[:, 1] - w_rotor[:, 2] + w_rotor[:, 3]) * I_R   # :345
+    if rb is None:
+        omega_r = (-w_rotor[:, 0] + w_rotor[:, 1] - w_rotor[:, 2] + w_rotor[:, 3]) * I_R   # :345
+    else:
+        ir = I_R * (1.0 + rb["ir"])                                           # :342
+        omega_r = -w_rotor[:, 0] * ir[:, 0] + w_rotor[:, 1] * ir[:, 1] - w_rotor[:, 2] * ir[:, 2] + w_rotor[:, 3] * ir[:, 3]
     m_gyro = np.stack([-W[:, 0] * omega_r, W[:, 1] * omega_r, np.zeros_like(omega_r)], axis=1)  # :347-349
     f_body = f_drag.copy()
     f_body[:, 2] += F                                                         # :352-353
     f_inertial = np.einsum("nij,nj->ni", R, f_body)                           # :357
-    accel = f_inertial / M                                                    # :365-367
+    quad_m = M if rb is None else (M * (1.0 + rb["m"]))[:, None]              # :360-363
+    accel = f_inertial / quad_m                                               # :365-367
     accel[:, 2] -= G
     JW = W * J_DIAG[None, :]
     m_in = Mact + m_gyro + m_drag - np.cross(W, JW)                           # :378
-    accel_ang = m_in * (1.0 / J_DIAG)[None, :]                                # :384-388 (J diagonal)
+    if rb is None:
+        accel_ang = m_in * (1.0 / J_DIAG)[None, :]                            # :384-388 (J diagonal)
+    else:
+        accel_ang = m_in / (J_DIAG[None, :] + J_DIAG[None, :] * rb["J"])      # :382  inv(J + J*episode_J)
     V_q = deriv_quat(W, q)                                                    # :392
     out = np.empty_like(x)
     out[:, 0:6:2] = vel
@@ -370,6 +388,8 @@ STREAM_RESET = 0
 STREAM_SENSOR = 1
 STREAM_ACTION = 2
 STREAM_POLICY = 3
+STREAM_ROBUST = 4
+STREAM_GUST = 5
 
 
 def philox_block(seed, env_id, episode, block, stream):
@@ -411,6 +431,42 @@ def sample_reset_state(seed, env_id, episode):
 
 
 # --------------------------------------------------------------------------------------
+# robust_control — environment/quadrotor_env.py:84-109 with Philox in place of NumPy's global stream
+# (same draw order as csrc/quad_device.cuh: robust_prepare / robust_gust)
+# --------------------------------------------------------------------------------------
+ROBUST_DEFAULTS = dict(d_kf=0.1, d_m=0.3, d_ir=0.1, d_j=(0.1, 0.1, 0.1), gust_std=(5.0, 5.0, 2.0), gust_period=500)   # :85-93
+
+
+def robust_episode(seed, env_id, episode, par=ROBUST_DEFAULTS):
+    """robust_control.reset (:98-102): episode_kf = U(0,1)^4 D_KF; episode_m = N(0, D_M); episode_ir = U(0,1)^4 D_IR;
+    diag(episode_J) = N(0, D_J)^3.  Blocks 0, 1, 2 of stream ROBUST of (env, episode)."""
+    a = u32_to_unit(philox_block(seed, env_id, episode, 0, STREAM_ROBUST))
+    b = u32_to_unit(philox_block(seed, env_id, episode, 1, STREAM_ROBUST))
+    c = u32_to_unit(philox_block(seed, env_id, episode, 2, STREAM_ROBUST))
+    n0, n1 = box_muller(c[:, 0], c[:, 1])
+    n2, n3 = box_muller(c[:, 2], c[:, 3])
+    return dict(kf=a * par["d_kf"], ir=b * par["d_ir"], m=n0 * par["d_m"],
+                J=np.stack([n1, n2, n3], axis=1) * np.asarray(par["d_j"])[None, :])
+
+
+def robust_gust(seed, env_id, count, par=ROBUST_DEFAULTS):
+    """Gust number `count` of each env (count <= 0: no wind yet): N(0, gust_std), block 0 of stream GUST of (env, count)."""
+    count = np.asarray(count, dtype=np.int64)
+    u = u32_to_unit(philox_block(seed, env_id, np.maximum(count, 0), 0, STREAM_GUST))
+    n0, n1 = box_muller(u[:, 0], u[:, 1])
+    n2, _ = box_muller(u[:, 2], u[:, 3])
+    g = np.stack([n0, n1, n2], axis=1) * np.asarray(par["gust_std"])[None, :]
+    return np.where((count > 0)[:, None], g, 0.0)
+
+
+def wind_ramp(last_gust, gust, i, period):
+    """robust_control.wind (:104-109) between two gusts: np.linspace(last, gust, P)[(i % P) - 1]  (index -1 = last element)."""
+    index = (np.asarray(i, dtype=np.int64) % period) - 1
+    t = np.where(index < 0, 1.0, index / (period - 1.0))
+    return last_gust + (gust - last_gust) * t[:, None]
+
+
+# --------------------------------------------------------------------------------------
 # the environment: N independent copies of `quad`, advanced in lock-step
 # --------------------------------------------------------------------------------------
 class BatchQuadOracle:
@@ -420,8 +476,13 @@ class BatchQuadOracle:
     """
 
     def __init__(self, n_envs, t_step, n, training=True, direct_control=1, T=1, clipped=True,
-                 integrator="rk45", substeps=1):
+                 integrator="rk45", substeps=1, robust=None):
+        """robust: None, or dict(seed=..., env_id=(N,) global ids[, par=ROBUST_DEFAULTS-like]) = quad.robust_control True."""
         self.N = n_envs
+        self.robust = robust
+        if robust is not None:
+            self.episode = np.zeros(n_envs, dtype=np.int64)
+            self.gust_count = np.zeros(n_envs, dtype=np.int64)
         self.t_step = t_step
         self.T = T
         self.n = n + T                                                        # :157
@@ -470,21 +531,35 @@ class BatchQuadOracle:
         idx_all = np.nonzero(m)[0]
         action = np.asarray(action, dtype=np.float64)
         self.i[m] += 1
+        rb = None
+        if self.robust is not None:
+            par = self.robust.get("par", ROBUST_DEFAULTS)
+            seed, ids = self.robust["seed"], np.asarray(self.robust["env_id"])
+            rb = robust_episode(seed, ids, self.episode, par)
+            new_gust = m & ((self.i % par["gust_period"]) - 1 == 0)               # :105-108
+            self.gust_count[new_gust] += 1
+            rb["wind"] = wind_ramp(robust_gust(seed, ids, self.gust_count - 1, par), robust_gust(seed, ids, self.gust_count, par),
+                                   self.i, par["gust_period"])
+            self.rb = rb
+        kf = None if rb is None else rb["kf"]
         if self.direct:
             act = np.clip(action, -1, 1)                                      # :470
             self.action = act
             self.clipped_action = act
             step_effort = act
-            w, F, Mact = f2F(act)
+            w, F, Mact = f2F(act, kf)
         else:
             self.action = action
-            step_effort, w, F, Mact = f2w(action[:, 0], action[:, 1:4], self.clipped)   # :476
+            step_effort, w, F, Mact = f2w(action[:, 0], action[:, 1:4], self.clipped, kf)   # :476
             self.clipped_action = np.concatenate([F[:, None], Mact], axis=1)
         self.w = w
 
+        def sub(g):
+            return None if rb is None else {k: v[g] for k, v in rb.items()}
+
         def fun(y, idx):
             g = idx_all[idx]
-            return drone_eq(y, F[g], Mact[g], w[g])
+            return drone_eq(y, F[g], Mact[g], w[g], rb=sub(g))
 
         y0 = self.previous_state[m]
         if self.integrator == "rk45":
@@ -492,7 +567,7 @@ class BatchQuadOracle:
             self.nfev[m] = nfev
         else:
             y = rk4_solve(fun, y0, self.t_step, self.substeps)
-        _, aux = drone_eq(y, F[m], Mact[m], w[m], want_aux=True)             # FSAL stage f(t+h,y_new): last drone_eq call
+        _, aux = drone_eq(y, F[m], Mact[m], w[m], want_aux=True, rb=sub(m))  # FSAL stage f(t+h,y_new): last drone_eq call
         state = self.state.copy()
         state[m] = y
         self.state = state
@@ -568,8 +643,9 @@ class BatchQuadOracle:
     def step_autoreset(self, action, seed, env_id_offset=0):
         """step(); envs that are done are re-sampled with Philox (episode counter + 1) and warmed up for T hover
         steps, exactly like the in-kernel sub-pass.  Returns (obs after reset, terminal reward, terminal done)."""
-        if not hasattr(self, "episode"):
-            self.episode = np.zeros(self.N, dtype=np.int64)
+        if not hasattr(self, "ep_return"):
+            if not hasattr(self, "episode"):
+                self.episode = np.zeros(self.N, dtype=np.int64)
             self.ep_return = np.zeros(self.N)
             self.stats = dict(sum_return=0.0, sum_length=0.0, n_episodes=0, n_solved=0, n_broken=0, n_timeout=0,
                               sum_effort=0.0)
@@ -604,8 +680,9 @@ class BatchQuadOracle:
         returns done begins its next episode at the END of that step: Philox-sampled state (episode counter + 1),
         bookkeeping cleared, T warm-up steps owed; the observation returned with done is the new episode's initial
         observation [s0[0:10], V_q(s0)].  Returns (obs, reward, done, warm)."""
-        if not hasattr(self, "episode"):
-            self.episode = np.zeros(self.N, dtype=np.int64)
+        if not hasattr(self, "ep_return"):
+            if not hasattr(self, "episode"):
+                self.episode = np.zeros(self.N, dtype=np.int64)
             self.ep_return = np.zeros(self.N)
             self.stats = dict(sum_return=0.0, sum_length=0.0, n_episodes=0, n_solved=0, n_broken=0, n_timeout=0,
                               sum_effort=0.0)

@@ -714,6 +714,91 @@ def test_control_rollout_f64_vs_oracle_random_states(kind):
     assert worst < 1e-9, worst
 
 
+# ----------------------------------------------------------------------------------------------------
+# robust_control: per-episode parameter perturbations + wind gusts
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("direct,integ", [(1, "rk45"), (0, "rk45"), (1, "rk4")])
+def test_robust_control_f64_matches_oracle(direct, integ):
+    """quad.robust_control = True on the device (QS_FLAG_ROBUST: Philox-derived episode_kf / episode_m / episode_ir / episode_J,
+    gust counter, linear wind ramp) against the oracle's restatement, which is itself pinned to the reference's guarded
+    branches (tests/golden/robust_vectors.npz): every step within 1e-9, gust counters identical, including a short gust
+    period so that several ramps and the index -1 element are crossed, a second deterministic reset and a Philox reset."""
+    N, steps, seed, off = 192, 70, 13, 5
+    par = dict(qo.ROBUST_DEFAULTS, gust_period=16)
+    env = BatchedQuad(N, 0.01, 10 ** 6, training=False, direct_control=direct, T=2, precision="f64", integrator=integ, aux=True,
+                      robust_control=True, seed=seed, env_id_offset=off, device=DEV, params={"robust_gust_period": 16})
+    ids = np.arange(N) + off
+    ora = qo.BatchQuadOracle(N, 0.01, 10 ** 6, training=False, direct_control=direct, T=2, integrator=integ,
+                             robust=dict(seed=seed, env_id=ids, par=par))
+    rng = np.random.default_rng(4)
+    init = np.zeros((N, 13)); init[:, 6] = 1
+    init[:, 1:6:2] = rng.normal(0, 0.5, (N, 3)); init[:, 10:13] = rng.normal(0, 0.5, (N, 3))
+    worst = 0.0
+    for phase in range(2):
+        oh, _ = env.reset(T64(init)); ro, _ = ora.reset(init)
+        worst = max(worst, float(rel_err(npy(oh), ro)))
+        for t in range(steps):
+            if direct:
+                a = rng.uniform(-0.4, 0.4, (N, 4))
+            else:
+                a = np.stack([rng.uniform(8, 12, N), *(rng.normal(0, 0.02, (3, N)))], axis=1)
+            obs, rew, done = env.step(T64(a))
+            o_ref, r_ref, d_ref = ora.step(a)
+            worst = max(worst, float(rel_err(npy(obs), o_ref)), float(rel_err(npy(rew), r_ref)))
+            worst = max(worst, float(rel_err(npy(env.accel), ora.accel)))
+            assert np.array_equal(npy(done).astype(bool), d_ref)
+        assert np.array_equal(npy(env.gust_count), ora.gust_count)
+    assert worst < 1e-9, worst
+    assert int(ora.gust_count.min()) >= 2 * (1 + steps // 16)
+    # the perturbed plant really differs from the nominal one
+    nom = BatchedQuad(N, 0.01, 10 ** 6, training=False, direct_control=direct, T=2, precision="f64", integrator=integ, device=DEV)
+    nom.reset(T64(init))
+    env.reset(T64(init))
+    a = np.zeros((N, 4)) if direct else np.tile([10.0, 0, 0, 0], (N, 1))
+    for t in range(20):
+        o_n, _, _ = nom.step(T64(a)); o_r, _, _ = env.step(T64(a))
+    assert float((o_n - o_r).abs().max()) > 1e-2
+    # Philox reset: the episode counter advances, so the perturbations are re-drawn
+    env.reset()
+    ora.episode += 1
+    e1 = qo.robust_episode(seed, ids, ora.episode, par)
+    assert not np.allclose(e1["kf"], ora.rb["kf"])
+
+
+def test_robust_control_f32_async_reset_and_controller_rollout():
+    """FP32 production arithmetic with robust_control: (1) lock-step qs_step with asynchronous resets stays finite, counts
+    gusts per env (one at every episode start, one per period) and ends episodes; (2) the batched LQR law against the
+    perturbed plant (qs_control_rollout) still stabilises most envs but is measurably worse than on the nominal plant;
+    (3) the fused rollouts that do not model it refuse the handle."""
+    from autonomous_quadrotor_environment_b200 import controllers as ctl
+    N = 1 << 14
+    env = BatchedQuad(N, 0.01, 300, T=3, precision="f32", async_reset=True, robust_control=True, seed=2, device=DEV)
+    env.reset()
+    assert env.step_loader in (0, 1)
+    g = torch.Generator(device=DEV); g.manual_seed(1)
+    for t in range(150):
+        env.step_soa((torch.rand(4, N, device=DEV, generator=g) * 2 - 1).contiguous())
+    assert torch.isfinite(env.obs).all()
+    s = env.stats()
+    assert s["n_episodes"] > N
+    # T + 150 < gust_period: exactly one gust per episode whose first step has run (an env re-sampled at the end of the last
+    # step has i == 0 and draws its gust on its next step)
+    assert torch.equal(env.gust_count, env.episode - (env.i == 0).int())
+    with pytest.raises(L.QuadSimError):
+        env.rollout(4)
+    res = {}
+    for robust in (False, True):
+        e = BatchedQuad(N, 0.01, 1000, training=False, direct_control=0, T=1, precision="f32", robust_control=robust, seed=6, device=DEV)
+        e.reset()
+        e.control_rollout(ctl.lqr_controller(), 400)
+        v = e.state[:, 1:6:2].norm(dim=1)
+        res[robust] = (float(v.nanmedian()), float(torch.isfinite(v).float().mean()), float((v < 5.0).float().mean()))
+    # N(0, 0.3) mass perturbations leave a handful of envs with a near-zero or negative mass (as in the reference's model)
+    assert res[False][1] == 1.0 and res[True][1] > 0.99, res
+    assert res[False][2] > 0.9 and res[True][2] > 0.5, res
+    assert res[True][0] > 2 * res[False][0], res                  # gusts of N(0, 5) m/s and a wrong mass leave a larger residual speed
+
+
 def test_control_rollout_f32_million_env_comparison():
     """The README's controller comparison at scale: FP32 RK4, 262,144 envs from the reset distribution, 400 fused steps of
     each law.  Property checks (size-independent): both laws stabilise (the median speed at least halves within 4 s),

@@ -188,3 +188,54 @@ def test_lqr_law_equals_script_restatement():
     for n in range(64):
         ref, _ = lqr_action(g["K_t"], g["K_att"], st[n], ang[n], av[n], None)
         assert np.allclose(a[n], ref, rtol=1e-13, atol=1e-13)
+
+
+def test_robust_control_restatement_vs_reference_vectors():
+    """robust_control (quadrotor_env.py:84-109; dead code upstream, quad.robust_control hard-wired False): the oracle's perturbed
+    f2F / f2w / drone_eq against the reference's own guarded branches executed with injected perturbations, and the linear
+    wind ramp against the reference's stateful wind() over two episodes (fixture: oracle/gen_golden.py:gen_robust_vectors)."""
+    g = load_golden("robust_vectors.npz")
+    rb = dict(wind=g["wind"], ir=g["ir"], m=g["m"], J=g["J"])
+    w, F, Ma = qo.f2F(g["a"], g["kf"])
+    assert rel_err(qo.drone_eq(g["x"], F, Ma, w, rb=rb), g["dx_direct"]) < 1e-12
+    se, w, F, Ma = qo.f2w(g["fm"][:, 0], g["fm"][:, 1:4], True, g["kf"])
+    assert rel_err(se, g["effort"]) < 1e-12 and rel_err(w, g["w_rotor"]) < 1e-12
+    assert rel_err(np.c_[F, Ma], g["fm_new"]) < 1e-12
+    assert rel_err(qo.drone_eq(g["x"], F, Ma, w, rb=rb), g["dx_indirect"]) < 1e-12
+    # the perturbations matter: the unperturbed RHS differs
+    w0, F0, Ma0 = qo.f2F(g["a"])
+    assert rel_err(qo.drone_eq(g["x"], F0, Ma0, w0), g["dx_direct"]) > 1e-2
+    # wind(): between two gusts np.linspace(last, gust, P)[(i % P) - 1]; a new gust whenever i % P == 1
+    i, gu, P = g["wind_i"], g["wind_gust"], int(g["gust_period"])
+    cur, prev, lasts, n_new = np.zeros(3), np.zeros(3), [], 0
+    for k in range(len(i)):
+        if not np.array_equal(gu[k], cur):
+            prev, cur = cur, gu[k]
+            n_new += 1
+            assert i[k] % P == 1
+        lasts.append(prev.copy())
+    assert n_new == 5
+    assert np.abs(qo.wind_ramp(np.array(lasts), gu, i, P) - g["wind_out"]).max() < 1e-12
+
+
+def test_robust_oracle_streams_and_gust_counter():
+    """Philox-derived perturbations: ranges / moments of robust_control.reset (:98-102), gust counter advancing once per episode
+    start and once per period, perturbations constant inside an episode."""
+    N = 4096
+    ids = np.arange(N) + 7
+    e = qo.robust_episode(5, ids, np.zeros(N, dtype=np.int64))
+    assert 0 <= e["kf"].min() and e["kf"].max() <= 0.1 and abs(e["kf"].mean() - 0.05) < 2e-3
+    assert 0 <= e["ir"].min() and e["ir"].max() <= 0.1
+    assert abs(e["m"].std() - 0.3) < 0.02 and abs(e["J"].std() - 0.1) < 0.01
+    gst = qo.robust_gust(5, ids, np.full(N, 3))
+    assert np.all(np.abs(gst.std(axis=0) - np.array([5, 5, 2])) < [0.3, 0.3, 0.15])
+    assert np.all(qo.robust_gust(5, ids, np.zeros(N, dtype=np.int64)) == 0)
+    n = 16
+    o = qo.BatchQuadOracle(n, 0.01, 10 ** 6, training=False, T=1, integrator="rk4", robust=dict(seed=5, env_id=np.arange(n)))
+    st = np.zeros((n, 13)); st[:, 6] = 1
+    o.reset(st)
+    assert np.all(o.gust_count == 1)
+    kf0 = o.rb["kf"].copy()
+    for t in range(505):
+        o.step(np.zeros((n, 4)))
+    assert np.all(o.gust_count == 2) and np.array_equal(o.rb["kf"], kf0)
