@@ -113,7 +113,7 @@ def run_reference_arm(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -230,15 +230,40 @@ def run_policy_workload(args):
                              "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel": "policy_rollout_kernel",
                              "note": "the kernel is bound by MUFU (256 tanh per env-step) and its serial MMA->epilogue->dynamics chain, not by the tensor pipe"},
                 "stats": env.stats(all_reduce=False), "mean_reward_last_rollout": mean_r}
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries write there too (NCCL prints its version banner on stdout at
+    NCCL_DEBUG=VERSION and WARN), so file descriptor 1 is pointed at stderr for the duration of the run and the JSON line is
+    written to the saved descriptor."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     args = parse()
-    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":      # NCCL would print its version banner on stdout before the JSON line
+    protect_stdout()
+    # NCCL prints its version banner on STDOUT when its debug level is VERSION (the level may also come from /etc/nccl.conf, which
+    # the environment variable overrides): keep stdout to the one JSON line unless the caller asked for NCCL's own logging
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
         os.environ["NCCL_DEBUG"] = "WARN"
     if args.impl == "reference":
         run_reference_arm(args)
@@ -457,7 +482,7 @@ def main():
             line["variants"] = variants
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.cpu_seconds, args.T)
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
