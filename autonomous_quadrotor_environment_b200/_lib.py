@@ -104,7 +104,8 @@ class qs_controller(C.Structure):
 
 class qs_control_rollout_args(C.Structure):
     _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32), ("ctrl_state", C.c_void_p), ("obs_out", C.c_void_p),
-                ("action_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("aux_out", C.c_void_p)]
+                ("action_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("aux_out", C.c_void_p),
+                ("target_traj", C.c_void_p)]
 
 
 QS_CTRL_LQR, QS_CTRL_PID = 0, 1

@@ -288,13 +288,20 @@ class BatchedQuad:
         return cs
 
     def control_rollout(self, controller, horizon: int, ctrl_state=None, record_obs=False, record_actions=False,
-                        record_reward=False, record_done=False, record_aux=False):
+                        record_reward=False, record_done=False, record_aux=False, target_traj=None):
         """K fused env steps driven by an in-kernel classical control law (controllers.lqr_controller / pid_controller:
         environment/controller/lqr_quad.py:129-157, pid_vel_control.py:29-127) in ONE launch.  Needs direct_control=0.
         record_aux -> (K,10,N): ang(3), ang_vel(3), step_effort(4), i.e. with obs[:, (1,3,5)] the 13 columns of the reference's
-        classical_controller_results logs.  Returns the recorded buffers."""
+        classical_controller_results logs.  target_traj: (K,3) velocity set-points of the PID law, one per step (e.g.
+        mission(...).velocity_setpoints(K): mission_control/mission_control.py); None = controller.target_vel.
+        Returns the recorded buffers."""
         a = L.qs_control_rollout_args()
         a.horizon = int(horizon)
+        if target_traj is not None:
+            target_traj = torch.as_tensor(target_traj, dtype=self.dtype, device=self.device).contiguous()
+            if target_traj.shape != (horizon, 3):
+                raise ValueError("target_traj must have shape (horizon, 3)")
+            a.target_traj = target_traj.data_ptr()
         if ctrl_state is not None:
             if ctrl_state.shape != (L.QS_CTRL_STATE_DIM, self.N) or ctrl_state.dtype != self.dtype or not ctrl_state.is_contiguous():
                 raise ValueError("ctrl_state must be a contiguous (%d,N) %s tensor" % (L.QS_CTRL_STATE_DIM, self.dtype))

@@ -24,6 +24,7 @@ struct ControlIO {
     void* reward_out;             // [K][N]
     uint8_t* done_out;            // [K][N]
     void* aux_out;                // [K][10][N]  ang(3), ang_vel(3), step_effort(4) — the columns of the reference's logs after vel
+    const void* target_traj;      // [K][3] or NULL: velocity set-point in force at step t (mission.velocity), PID law only
 };
 
 template <typename R> struct CtrlMem {
@@ -83,10 +84,11 @@ __device__ __forceinline__ R pid_scalar(const CtrlDev<R>& cd, CtrlMem<R>& m, int
 
 // pid_control.control :97-110 = lower_control :48-63 + upper_control :66-95 (3x3 inverse in closed form)
 template <typename R>
-__device__ __forceinline__ void pid_law(const CtrlDev<R>& cd, CtrlMem<R>& m, const R y[13], const R ang[3], R a[4]) {
-    const R u_1 = pid_scalar(cd, m, 0, y[1], cd.xd[0], R(0));
-    const R u_2 = pid_scalar(cd, m, 1, y[3], cd.xd[1], R(0));
-    const R u_3 = pid_scalar(cd, m, 2, y[5], cd.xd[2], R(0));
+__device__ __forceinline__ void pid_law(const CtrlDev<R>& cd, CtrlMem<R>& m, const R y[13], const R ang[3], R a[4],
+                                        const R xd[3]) {              // xd: the script's constant set-point (:150) or the mission's
+    const R u_1 = pid_scalar(cd, m, 0, y[1], xd[0], R(0));
+    const R u_2 = pid_scalar(cd, m, 1, y[3], xd[1], R(0));
+    const R u_3 = pid_scalar(cd, m, 2, y[5], xd[2], R(0));
     const R theta_d = M_<R>::atan2(u_1, u_3 + cd.g);
     R std_, ctd_, spd_, cpd_;
     M_<R>::sincos(theta_d, &std_, &ctd_);
@@ -187,7 +189,13 @@ control_rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_cons
             } else if (warm) {
                 ctrl_fresh(cd, m);                                   // ... i.e. after reset's T hover steps: nothing is remembered across them
             } else if (cd.kind == QS_CTRL_PID) {
-                pid_law(cd, m, e.y, e.prev_ang, m.pending);          // controller.control(...) after the step (:153)
+                // controller.control(...) after the step (:153); with a mission the set-point is the one in force at this step
+                R xd[3] = {cd.xd[0], cd.xd[1], cd.xd[2]};
+                if (io.target_traj) {
+                    const R* tp = (const R*)io.target_traj + 3 * t;
+                    xd[0] = tp[0]; xd[1] = tp[1]; xd[2] = tp[2];
+                }
+                pid_law(cd, m, e.y, e.prev_ang, m.pending, xd);
             }
             if (io.action_out) {
                 R* at = (R*)io.action_out + (int64_t)t * 4 * v.N;
@@ -265,7 +273,9 @@ extern "C" int qs_control_rollout(qs_handle h, const qs_controller* c, const qs_
         return fail(QS_ESTATE, "qs_control_rollout: not available with SENSOR_NOISE / strict AUTO_RESET (use ASYNC_RESET)");
     if ((f & QS_FLAG_AUX) && (f & QS_FLAG_ASYNC_RESET))
         return fail(QS_ESTATE, "qs_control_rollout: AUX rows are not maintained across asynchronous resets");
-    ControlIO io{a->horizon, a->ctrl_state, a->obs_out, a->action_out, a->reward_out, a->done_out, a->aux_out};
+    if (a->target_traj && c->kind != QS_CTRL_PID)
+        return fail(QS_EINVAL, "qs_control_rollout: target_traj (velocity set-points) applies to the PID law only");
+    ControlIO io{a->horizon, a->ctrl_state, a->obs_out, a->action_out, a->reward_out, a->done_out, a->aux_out, a->target_traj};
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_control_rollout, h, c, io, st);
     QS_CUDA(cudaGetLastError());

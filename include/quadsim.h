@@ -240,6 +240,8 @@ typedef struct qs_control_rollout_args {
     uint8_t* done_out;         /* [K][N]     or NULL */
     void* aux_out;             /* [K][10][N] or NULL : ang(3), ang_vel(3), step_effort(4) — with the velocities of obs_out the */
                                /*                      13 columns of the reference's classical_controller_results logs         */
+    const void* target_traj;   /* [K][3] or NULL (PID only): velocity set-point in force at step t, e.g. the `velocity` array of */
+                               /* a mission (mission_control/mission_control.py); NULL = the constant qs_controller.target_vel  */
 } qs_control_rollout_args;
 
 /* ---- lifecycle ----------------------------------------------------------------------------- */

@@ -359,6 +359,27 @@ def gen_robust_vectors(ref, rng):
                         gust_period=rc.gust_period)
 
 
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from conftest import MISSION_CASES  # noqa: E402  (the same argument sets the test replays)
+
+
+def gen_mission_vectors():
+    """mission_control/mission_control.py executed as it is: trajectories, velocities and the get_error stream (three calls
+    past the end, so the extrapolation branch :69-70 is recorded) of the cases in MISSION_CASES."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_mission", os.path.join(REF, "mission_control", "mission_control.py"))
+    rm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rm)
+    out = {}
+    for name, f in MISSION_CASES.items():
+        m = rm.mission(0.01)
+        f(m)
+        out[name + "_trajectory"] = m.trajectory.copy()
+        out[name + "_velocity"] = m.velocity.copy()
+        out[name + "_errors"] = np.array([m.get_error(0) for _ in range(m.trajectory_total_steps + 3)])
+    np.savez_compressed(os.path.join(OUT, "mission_vectors.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = ref_import.load_reference()
@@ -372,6 +393,7 @@ def main():
     gen_sensor_stats(ref)
     gen_ppo_vectors()
     gen_robust_vectors(ref, np.random.default_rng(20261018))
+    gen_mission_vectors()
     for f in sorted(os.listdir(OUT)):
         print("%-28s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))
 

@@ -50,3 +50,14 @@ def lqr_action(K_t, K_att, env_state, env_ang, env_ang_vel, euler_t_ant, dt=0.01
     action = np.dot(K_att, state_att)
     action[0] = U_1
     return action, euler_t
+
+
+# argument sets of the mission-generator fixture (oracle/gen_golden.py:gen_mission_vectors) and of the test that replays them
+MISSION_CASES = {
+    "gen": lambda m: m.gen_trajectory(500, 200, np.array([1., -2., 3.])),
+    "gen_add": lambda m: m.gen_trajectory(300, 100, np.array([1., -2., 3.]), additive=np.arange(14) * 0.1),
+    "gen_vel": lambda m: m.gen_trajectory(250, 250, np.zeros(3), velocity=np.array([1., .5, -.2])),
+    "sin": lambda m: m.sin_trajectory(400, 2.0, 0.3, np.array([1., 2., 0.]), np.array([1., 0.5, 0.])),
+    "spiral": lambda m: m.spiral_trajectory(150, 400, 0.5, 1.5, 2.0, np.array([0., 1., 2.])),
+}
+

@@ -714,6 +714,50 @@ def test_control_rollout_f64_vs_oracle_random_states(kind):
     assert worst < 1e-9, worst
 
 
+def test_pid_tracks_a_mission_velocity_profile_f64_vs_oracle():
+    """SURVEY 8(f)3, set-point generation: the velocity profile of a `mission` (mission_control/mission_control.py; mission.py
+    is bit-identical to it) drives the in-kernel velocity PID through target_traj, one set-point per step, in two launches;
+    the oracle's PID restatement fed the same rows step by step agrees within 1e-9 (spiral mission), and with a straight-line
+    mission the quads end up flying at the commanded velocity."""
+    from autonomous_quadrotor_environment_b200 import controllers as ctl
+    from autonomous_quadrotor_environment_b200.mission import mission
+    N, K = 128, 240
+    init, _ = qo.sample_reset_state(33, np.arange(N), 0)
+    init[:, 10:13] *= 0.2
+    init[:, 1:6:2] *= 0.1
+    env = BatchedQuad(N, 0.01, 10 ** 5, training=False, direct_control=0, T=1, clipped=True, precision="f64", aux=True, device=DEV)
+    ora = qo.BatchQuadOracle(N, 0.01, 10 ** 5, training=False, direct_control=0, T=1, clipped=True, integrator="rk45")
+    env.reset(T64(init)); ora.reset(init)
+    ms = mission(0.01)
+    ms.spiral_trajectory(150, K, 0.5, 1.5, 1.0, np.zeros(3))
+    vel = ms.velocity.copy()
+    c = ctl.pid_controller(target_psi=0.0)
+    cs = env.controller_state()
+    recs = [env.control_rollout(c, K // 2, ctrl_state=cs, record_obs=True, record_aux=True, record_actions=True,
+                                target_traj=ms.velocity_setpoints(K // 2, device=DEV, dtype=torch.float64)) for _ in range(2)]
+    assert ms.trajectory_step == K
+    rows = np.concatenate([_log_rows(r) for r in recs])
+    acts = np.concatenate([r["actions"].cpu().numpy() for r in recs]).transpose(0, 2, 1)
+    pid = qo.PidControllerOracle(N)
+    action = np.tile(np.array([9.82 * 1.03, 0, 0, 0]), (N, 1))
+    worst = 0.0
+    for t in range(K):
+        worst = max(worst, float(rel_err(acts[t], action)))
+        ora.step(action)
+        action = pid.control(ora.state, ora.ang, vel[t], 0.0)
+        ref = np.concatenate([ora.state[:, 1:6:2], ora.ang, ora.ang_vel, ora.step_effort], axis=1)
+        worst = max(worst, float(rel_err(rows[t], ref)))
+    assert worst < 1e-9, worst
+    line = mission(0.01)
+    line.gen_trajectory(600, 600, np.array([6.0, -3.0, 1.5]))          # constant velocity (1, -0.5, 0.25) m/s from step 1 on
+    rec = env.control_rollout(c, 600, record_obs=True, target_traj=line.velocity_setpoints(600, device=DEV, dtype=torch.float64))
+    v_end = rec["obs"][-1][(1, 3, 5), :].t().cpu().numpy()
+    v_sp = line.velocity[-1]
+    assert np.median(np.linalg.norm(v_end - v_sp[None, :], axis=1)) < 0.25 * np.linalg.norm(v_sp)
+    with pytest.raises(L.QuadSimError):
+        env.control_rollout(ctl.lqr_controller(), 4, target_traj=np.zeros((4, 3)))
+
+
 # ----------------------------------------------------------------------------------------------------
 # robust_control (SURVEY 8(f)4): per-episode parameter perturbations + wind gusts
 # ----------------------------------------------------------------------------------------------------

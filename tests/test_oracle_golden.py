@@ -239,3 +239,21 @@ def test_robust_oracle_streams_and_gust_counter():
     for t in range(505):
         o.step(np.zeros((n, 4)))
     assert np.all(o.gust_count == 2) and np.array_equal(o.rb["kf"], kf0)
+
+
+def test_mission_generator_is_bit_identical_to_the_reference():
+    """mission.py (whole-array NumPy) against mission_control/mission_control.py (Python loops) run as it is
+    (oracle/gen_golden.py:gen_mission_vectors): trajectories, velocities and the get_error stream incl. the extrapolation past
+    the end, identical to the last bit."""
+    from conftest import MISSION_CASES
+    from autonomous_quadrotor_environment_b200.mission import mission
+    g = load_golden("mission_vectors.npz")
+    for name, f in MISSION_CASES.items():
+        m = mission(0.01)
+        f(m)
+        assert np.array_equal(m.trajectory, g[name + "_trajectory"]), name
+        assert np.array_equal(m.velocity, g[name + "_velocity"]), name
+        err = np.array([m.get_error(0) for _ in range(m.trajectory_total_steps + 3)])
+        assert np.array_equal(err, g[name + "_errors"]), name
+    with pytest.raises(ValueError):
+        mission(0.01).gen_trajectory(300, 100, np.zeros(3), velocity=np.ones(3))
