@@ -1,9 +1,10 @@
 // actor_rollout.cuh — the reference's actor MLP (environment/controller/model.py:27-34: Linear(75,H)-Tanh-Linear(H,H)-
 // Tanh-Linear(H,4)-Tanh) and its observation-history input (environment/controller/dl_auxiliary.py:15-32) fused into
-// the K-step rollout: per CTA 128 envs = one UMMA M=128 tile; the three layers are tcgen05.mma (BF16 operands staged
-// in shared memory in the canonical K-major layout, FP32 accumulators in TMEM), the epilogues read TMEM with
-// tcgen05.ld, apply bias + tanh and write the next layer's A operand back to shared memory; the dynamics run on the
-// same 128 threads (thread = env = TMEM lane) with the env state in registers.
+// the K-step rollout: per group of 128 threads 128 envs = one UMMA M=128 tile; the two hidden layers are tcgen05.mma (BF16
+// operands staged in shared memory in the canonical K-major layout, FP32 accumulators in TMEM, biases folded into the
+// GEMMs), the first epilogue reads TMEM with tcgen05.ld, applies tanh and writes the next layer's A operand back to shared
+// memory, the second one applies tanh and the 128 -> 4 output layer on the FP32 pipe (weights in constant memory); the
+// dynamics run on the same 128 threads (thread = env = TMEM lane) with the env state in registers.
 // Included at the end of quadsim.cu (single translation unit).
 #pragma once
 #include "umma.cuh"
@@ -101,12 +102,26 @@ struct PolicySmem {
     static constexpr int kHd = kPM * kPKin * 2;
     static constexpr int kW1 = kPG * kXH;
     static constexpr int kW2 = kW1 + kPH * kPKin * 2;
-    static constexpr int kW3 = kW2 + kPH * kPH * 2;
-    static constexpr int kOnes = kW3 + 16 * kPH * 2;                     // A operand of the bias block of layer 2: [128][16], columns 0,1 = 1
+    static constexpr int kOnes = kW2 + kPH * kPH * 2;                    // A operand of the bias block of layer 2: [128][16], columns 0,1 = 1
     static constexpr int kW2x = kOnes + kPM * 16 * 2;                    // B operand of that block: [128][16], columns 0,1 = b2 (hi, lo)
-    static constexpr int kB = kW2x + kPH * 16 * 2;
-    static constexpr int kBytes = kB + 16 * 4;                           // b3 (FP32, added in the last epilogue)
+    static constexpr int kBytes = kW2x + kPH * 16 * 2;
 };
+
+// Output layer (Linear(128,4) + Tanh, model.py:33-34) on the FP32 pipe: 128 -> 4 is 512 FMAs per env, and as a third UMMA it
+// cost a full issue -> commit -> mbarrier round trip (~700 cycles, 5 % of the step: ncu long_scoreboard on the wait) plus a
+// BF16 pack + 16 STS.128 per thread to stage its A operand.  The weights sit in constant memory (FFMA takes them as
+// c[bank][imm] operands, no load instruction) and the FMAs issue in the shadow of the MUFU-bound tanh sequence of the second
+// hidden epilogue; the hidden activations enter in FP32, not rounded to BF16.
+// The symbol is written by a stream-ordered device-to-device copy in qs_policy_rollout: rollouts with DIFFERENT actors must
+// not run concurrently on different streams of one device.
+__constant__ float c_actor_w3[kPH * 4];      // [j][k] = w3[k][j]
+__constant__ float c_actor_b3[4];
+
+__global__ void k_pack_w3(const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ out) {
+    const int j = threadIdx.x;               // out: [128][4] then b3[4]
+    if (j < kPH) { for (int k = 0; k < 4; ++k) out[j * 4 + k] = w3[k * kPH + j]; }
+    if (j < 4) out[kPH * 4 + j] = b3[j];
+}
 
 // The biases of the two hidden layers ride in the GEMMs: every history entry is 15 floats padded to one K=16 block, the pad
 // column of the A operand holds 1 and the pad columns of W1's first two K blocks hold b1 split in two BF16 pieces
@@ -136,6 +151,25 @@ __device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, unsign
     }
 }
 
+// tanh epilogue of the second hidden layer fused with the output layer: mean[k] = tanh(b3[k] + sum_j tanh(acc_j) w3[k][j])
+__device__ __forceinline__ void actor_output_epilogue(uint32_t lane_addr, float mean[4]) {
+    float m0 = c_actor_b3[0], m1 = c_actor_b3[1], m2 = c_actor_b3[2], m3 = c_actor_b3[3];
+#pragma unroll
+    for (int c = 0; c < kPH; c += 32) {
+        float acc[32];
+        tmem_ld_32x32b_x32(lane_addr + (uint32_t)c, acc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            const float h = tanh_fast(acc[i]);
+            m0 = fmaf(h, c_actor_w3[(c + i) * 4 + 0], m0);
+            m1 = fmaf(h, c_actor_w3[(c + i) * 4 + 1], m1);
+            m2 = fmaf(h, c_actor_w3[(c + i) * 4 + 2], m2);
+            m3 = fmaf(h, c_actor_w3[(c + i) * 4 + 3], m3);
+        }
+    }
+    mean[0] = tanh_fast(m0); mean[1] = tanh_fast(m1); mean[2] = tanh_fast(m2); mean[3] = tanh_fast(m3);
+}
+
 __global__ void __launch_bounds__(kPM * kPG, 1)
 policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                       const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
@@ -145,10 +179,8 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
     unsigned char* sH = smem + grp * PolicySmem::kXH + PolicySmem::kHd;
     unsigned char* sW1 = smem + PolicySmem::kW1;
     unsigned char* sW2 = smem + PolicySmem::kW2;
-    unsigned char* sW3 = smem + PolicySmem::kW3;
     unsigned char* sOnes = smem + PolicySmem::kOnes;
     unsigned char* sW2x = smem + PolicySmem::kW2x;
-    float* sB3 = reinterpret_cast<float*>(smem + PolicySmem::kB);
     __shared__ uint64_t bars[kPG];
     __shared__ uint32_t tmem_slot;
     uint64_t& bar = bars[grp];
@@ -166,17 +198,12 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
         const int n = idx / kPH, kk = idx % kPH;
         *reinterpret_cast<__nv_bfloat16*>(sW2 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(act.w2[n * kPH + kk]);
     }
-    for (int idx = tid_all; idx < 16 * kPH; idx += kPM * kPG) {
-        const int n = idx / kPH, kk = idx % kPH;
-        *reinterpret_cast<__nv_bfloat16*>(sW3 + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(n < 4 ? act.w3[n * kPH + kk] : 0.f);
-    }
     for (int idx = tid_all; idx < kPH * 16; idx += kPM * kPG) {
         const int n = idx / 16, kk = idx % 16;
         const float b = act.b2[n];
         *reinterpret_cast<__nv_bfloat16*>(sOnes + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk < 2 ? 1.f : 0.f);
         *reinterpret_cast<__nv_bfloat16*>(sW2x + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk == 0 ? bf16_hi(b) : (kk == 1 ? b - bf16_hi(b) : 0.f));
     }
-    if (tid_all < 16) sB3[tid_all] = tid_all < 4 ? act.b3[tid_all] : 0.f;
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     constexpr uint32_t kTmemCols = kPG * kPH <= 128 ? 128 : (kPG * kPH <= 256 ? 256 : 512);      // power of two >= 128 accumulator columns per group
     if (tid_all < 32) tmem_alloc(&tmem_slot, kTmemCols);
@@ -253,25 +280,9 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             }
             mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            actor_hidden_epilogue(lane_addr, sH, tid);                // MMA 2 has finished reading sH: reuse it
-            tc_fence_before();
-            fence_proxy_async_smem();
-            group_sync(grp);
-            // ---------------- layer 3: [128 x 128] x W3^T (N padded 4 -> 16)
-            if (tid == 0) {
-                tc_fence_after();
-                umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW3), kPH, 0, kPH, 16, false);
-                umma_commit(&bar);
-            }
-            mbar_wait(&bar, phase); phase ^= 1;
-            tc_fence_after();
+            // ---------------- second tanh + layer 3 (128 -> 4) + tanh on the FP32 pipe, straight from the accumulators
             float mean[4];
-            {
-                float acc[16];
-                tmem_ld_32x32b_x16(lane_addr, acc);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(acc[k] + sB3[k]);
-            }
+            actor_output_epilogue(lane_addr, mean);
             tc_fence_before();
             // ---------------- a ~ Normal(mean, sigma)  (model.py:60-66), per-dimension log-prob
             float a[4], logp[4];
@@ -376,6 +387,12 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     if (!attr_set) {
         QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PolicySmem::kBytes));
         attr_set = true;
+    }
+    {   // output layer -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
+        float* tmp = (float*)h->action_stage;
+        k_pack_w3<<<1, kPH, 0, (cudaStream_t)stream>>>(actor->w3, actor->b3, tmp);
+        QS_CUDA(cudaMemcpyToSymbolAsync(c_actor_w3, tmp, sizeof(float) * kPH * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        QS_CUDA(cudaMemcpyToSymbolAsync(c_actor_b3, tmp + kPH * 4, sizeof(float) * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
     const int64_t tiles = (h->N + kPM - 1) / kPM;
     int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, kPG tiles in flight each
