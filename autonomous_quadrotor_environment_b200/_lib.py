@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
     "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_gae", "qs_adv_normalize", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
-    "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest",
+    "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest", "qs_umma_selftest_ts",
 ]
 
 
@@ -166,6 +166,7 @@ def load_library():
         "qs_version": (C.c_int, []),
         "qs_fp32_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_float), vp]),
         "qs_umma_selftest": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp]),
+        "qs_umma_selftest_ts": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

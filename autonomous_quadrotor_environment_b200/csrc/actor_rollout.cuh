@@ -58,6 +58,74 @@ __global__ void __launch_bounds__(128) k_umma_selftest(int N, int K, const float
     if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
+// the same product with the A operand staged in TENSOR memory (thread = row writes its packed BF16 row with tcgen05.st)
+__global__ void __launch_bounds__(128) k_umma_selftest_ts(int N, int K, const float* A, const float* B, float* D) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sB = smem;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int k = 0; k < K; k += 8) {
+        if (tid < N) {
+            uint4 v;
+            v.x = pack_bf16x2(B[tid * K + k + 0], B[tid * K + k + 1]);
+            v.y = pack_bf16x2(B[tid * K + k + 2], B[tid * K + k + 3]);
+            v.z = pack_bf16x2(B[tid * K + k + 4], B[tid * K + k + 5]);
+            v.w = pack_bf16x2(B[tid * K + k + 6], B[tid * K + k + 7]);
+            *reinterpret_cast<uint4*>(sB + umma_canon_offset(tid, k, K)) = v;
+        }
+    }
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const uint32_t a_col = 128;                                      // A operand: columns [128, 128 + K/2)
+    for (int k = 0; k < K; k += 32) {
+        uint32_t r[16];
+        for (int i = 0; i < 16; ++i) {
+            const int kk = k + 2 * i;
+            r[i] = kk < K ? pack_bf16x2(A[tid * K + kk], A[tid * K + kk + 1]) : 0u;
+        }
+        tmem_st_32x32b_x16(lane_addr + a_col + (uint32_t)(k >> 1), r);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16_f32(128, N);
+        for (int k = 0; k < K; k += 16) {
+            const uint64_t db = umma_smem_desc(smem_u32(sB) + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(K >> 3) * 128u);
+            umma_bf16_ts(tmem_base, tmem_base + a_col + (uint32_t)(k >> 1), db, idesc, k > 0);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        for (int i = 0; i < 16; ++i) D[tid * N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 256);
+}
+
+extern "C" int qs_umma_selftest_ts(int N, int K, const float* A, const float* B, float* D, void* stream) {
+    if (N < 16 || N > 128 || (N % 16) || K < 32 || K > 128 || (K % 32) || !A || !B || !D)
+        return fail(QS_EINVAL, "qs_umma_selftest_ts: need 16 <= N <= 128 (multiple of 16), 32 <= K <= 128 (multiple of 32)");
+    const size_t smem = (size_t)N * K * 2;
+    QS_CUDA(cudaFuncSetAttribute(k_umma_selftest_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_umma_selftest_ts<<<1, 128, smem, (cudaStream_t)stream>>>(N, K, A, B, D);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
 extern "C" int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, void* stream) {
     if (N < 16 || N > 128 || (N % 16) || K < 16 || K > 128 || (K % 16) || !A || !B || !D)
         return fail(QS_EINVAL, "qs_umma_selftest: need 16 <= N,K <= 128, multiples of 16");
@@ -94,13 +162,25 @@ struct PolicyIO {
 #ifndef QS_POLICY_GROUPS
 #define QS_POLICY_GROUPS 3      // 128-env tiles in flight per CTA (one per group of 4 warps), sharing one copy of the weights
 #endif
-constexpr int kPG = QS_POLICY_GROUPS;
+#ifndef QS_POLICY_TS            // 1 (default): hidden activations stay in TENSOR memory (TS form of tcgen05.mma), 4 tiles in flight
+#define QS_POLICY_TS 1
+#endif
 
-struct PolicySmem {
-    static constexpr int kXH = kPM * kPKin * 2 + kPM * kPH * 2;          // per group: history/A tile + hidden tile
+// Two data paths for the hidden activations H1 = tanh(X W1^T + b1), selected at compile time:
+//   TS = false  H1 is packed to BF16 into a 32 KB shared-memory tile per group (A operand of layer 2 from shared memory);
+//               with the 20 KB history tile that is 52 KB per group: THREE tiles in flight per SM next to the weights.
+//   TS = true   H1 never leaves tensor memory: the epilogue writes the packed BF16 row back with tcgen05.st IN PLACE over the
+//               first 64 of the 128 accumulator columns it has just read, and layer 2 takes its A operand from there.  Layer 2
+//               runs as two N = 64 halves into the other 64 columns (the output layer is fused into its epilogue, so nothing
+//               of H2 is stored): 128 TMEM columns and 20 KB of shared memory per group -> FOUR tiles in flight per SM
+//               (512 TMEM columns, 140 KB), which is what the kernel needs: every tile is a serial chain MMA -> tanh -> MMA ->
+//               tanh -> dynamics and the SM is only busy while other tiles fill its gaps.
+template <bool TS> struct PolicyCfg {
+    static constexpr int kG = TS ? 4 : QS_POLICY_GROUPS;                 // tiles (groups of 128 threads) per CTA
+    static constexpr int kXH = kPM * kPKin * 2 + (TS ? 0 : kPM * kPH * 2);   // per group: history/A tile (+ hidden tile)
     static constexpr int kX = 0;
     static constexpr int kHd = kPM * kPKin * 2;
-    static constexpr int kW1 = kPG * kXH;
+    static constexpr int kW1 = kG * kXH;
     static constexpr int kW2 = kW1 + kPH * kPKin * 2;
     static constexpr int kOnes = kW2 + kPH * kPH * 2;                    // A operand of the bias block of layer 2: [128][16], columns 0,1 = 1
     static constexpr int kW2x = kOnes + kPM * 16 * 2;                    // B operand of that block: [128][16], columns 0,1 = b2 (hi, lo)
@@ -151,28 +231,48 @@ __device__ __forceinline__ void actor_hidden_epilogue(uint32_t lane_addr, unsign
     }
 }
 
-// tanh epilogue of the second hidden layer fused with the output layer: mean[k] = tanh(b3[k] + sum_j tanh(acc_j) w3[k][j])
-__device__ __forceinline__ void actor_output_epilogue(uint32_t lane_addr, float mean[4]) {
-    float m0 = c_actor_b3[0], m1 = c_actor_b3[1], m2 = c_actor_b3[2], m3 = c_actor_b3[3];
+// tanh epilogue of the second hidden layer fused with the output layer: m[k] += sum_j tanh(acc_j) w3[k][j] over the hidden
+// units [J0, J0 + NJ) whose accumulators sit in the NJ columns starting at taddr; the caller starts from b3 and applies tanh
+template <int J0, int NJ>
+__device__ __forceinline__ void actor_output_accumulate(uint32_t taddr, float m[4]) {
+    float2 m01 = make_float2(m[0], m[1]), m23 = make_float2(m[2], m[3]);
 #pragma unroll
+    for (int c = 0; c < NJ; c += 32) {
+        float acc[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c, acc);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {                                // two packed FMAs per hidden unit: h x (w0,w1), h x (w2,w3);
+            const float h = tanh_fast(acc[i]);                       // the weight pairs arrive in uniform registers (LDCU.128)
+            const float2 hh = make_float2(h, h);
+            const float* w = &c_actor_w3[(J0 + c + i) * 4];
+            m01 = __ffma2_rn(hh, make_float2(w[0], w[1]), m01);
+            m23 = __ffma2_rn(hh, make_float2(w[2], w[3]), m23);
+        }
+    }
+    m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
+}
+
+// tanh epilogue of the first hidden layer, TS path: accumulator columns [0,128) -> packed BF16 row in columns [0,64), in place
+// (chunk c reads columns [32c, 32c+32) and writes [16c, 16c+16): always columns this thread has already consumed)
+__device__ __forceinline__ void actor_hidden_epilogue_tmem(uint32_t lane_addr) {
+#pragma unroll 1
     for (int c = 0; c < kPH; c += 32) {
         float acc[32];
         tmem_ld_32x32b_x32(lane_addr + (uint32_t)c, acc);
+        uint32_t o[16];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            const float h = tanh_fast(acc[i]);
-            m0 = fmaf(h, c_actor_w3[(c + i) * 4 + 0], m0);
-            m1 = fmaf(h, c_actor_w3[(c + i) * 4 + 1], m1);
-            m2 = fmaf(h, c_actor_w3[(c + i) * 4 + 2], m2);
-            m3 = fmaf(h, c_actor_w3[(c + i) * 4 + 3], m3);
-        }
+        for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(tanh_fast(acc[2 * i]), tanh_fast(acc[2 * i + 1]));
+        tmem_st_32x32b_x16(lane_addr + (uint32_t)(c >> 1), o);
     }
-    mean[0] = tanh_fast(m0); mean[1] = tanh_fast(m1); mean[2] = tanh_fast(m2); mean[3] = tanh_fast(m3);
+    tmem_st_wait();
 }
 
-__global__ void __launch_bounds__(kPM * kPG, 1)
+template <bool TS>
+__global__ void __launch_bounds__(kPM * PolicyCfg<TS>::kG, 1)
 policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                       const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
+    using PolicySmem = PolicyCfg<TS>;
+    constexpr int kPG = PolicySmem::kG;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid_all = threadIdx.x, grp = tid_all / kPM, tid = tid_all % kPM, warp = tid >> 5;   // group-local thread / warp
     unsigned char* sX = smem + grp * PolicySmem::kXH + PolicySmem::kX;
@@ -267,23 +367,53 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             }
             mbar_wait(&bar, phase); phase ^= 1;
             tc_fence_after();
-            actor_hidden_epilogue(lane_addr, sH, tid);
-            tc_fence_before();
-            fence_proxy_async_smem();
-            group_sync(grp);
-            // ---------------- layer 2: [128 x 128] x W2^T
-            if (tid == 0) {
+            float mean[4] = {c_actor_b3[0], c_actor_b3[1], c_actor_b3[2], c_actor_b3[3]};
+            if constexpr (!TS) {
+                actor_hidden_epilogue(lane_addr, sH, tid);
+                tc_fence_before();
+                fence_proxy_async_smem();
+                group_sync(grp);
+                // ---------------- layer 2: [128 x 128] x W2^T
+                if (tid == 0) {
+                    tc_fence_after();
+                    umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW2), kPH, 0, kPH, kPH, false);
+                    umma_gemm_k(tmem_base, smem_u32(sOnes), 16, 0, smem_u32(sW2x), 16, 0, 16, kPH, true);      // + b2
+                    umma_commit(&bar);
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
                 tc_fence_after();
-                umma_gemm_k(tmem_base, smem_u32(sH), kPH, 0, smem_u32(sW2), kPH, 0, kPH, kPH, false);
-                umma_gemm_k(tmem_base, smem_u32(sOnes), 16, 0, smem_u32(sW2x), 16, 0, 16, kPH, true);      // + b2
-                umma_commit(&bar);
+                // ---------------- second tanh + layer 3 (128 -> 4) on the FP32 pipe, straight from the accumulators
+                actor_output_accumulate<0, kPH>(lane_addr, mean);
+                tc_fence_before();
+            } else {
+                actor_hidden_epilogue_tmem(lane_addr);                   // H1 -> TMEM columns [0,64) of the group
+                tc_fence_before();
+                group_sync(grp);
+                // ---------------- layer 2 in two N = 64 halves: D[64,128) = H1 (TMEM) x W2[64 half ..][:]^T + b2
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    if (tid == 0) {
+                        tc_fence_after();
+                        constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
+                        const uint32_t b_rows = smem_u32(sW2) + (uint32_t)half * umma_canon_offset(64, 0, kPH);
+#pragma unroll
+                        for (int k = 0; k < kPH; k += 16)
+                            umma_bf16_ts(tmem_base + 64u, tmem_base + (uint32_t)(k >> 1),
+                                         umma_smem_desc(b_rows + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(kPH >> 3) * 128u), idesc, k > 0);
+                        umma_bf16(tmem_base + 64u, umma_smem_desc(smem_u32(sOnes), 128u, 256u),
+                                  umma_smem_desc(smem_u32(sW2x) + (uint32_t)half * umma_canon_offset(64, 0, 16), 128u, 256u), idesc, true);   // + b2
+                        umma_commit(&bar);
+                    }
+                    mbar_wait(&bar, phase); phase ^= 1;
+                    tc_fence_after();
+                    if (half == 0) actor_output_accumulate<0, 64>(lane_addr + 64u, mean);
+                    else actor_output_accumulate<64, 64>(lane_addr + 64u, mean);
+                    tc_fence_before();
+                    if (half == 0) group_sync(grp);                      // every thread has read the half before it is overwritten
+                }
             }
-            mbar_wait(&bar, phase); phase ^= 1;
-            tc_fence_after();
-            // ---------------- second tanh + layer 3 (128 -> 4) + tanh on the FP32 pipe, straight from the accumulators
-            float mean[4];
-            actor_output_epilogue(lane_addr, mean);
-            tc_fence_before();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(mean[k]);
             // ---------------- a ~ Normal(mean, sigma)  (model.py:60-66), per-dimension log-prob
             float a[4], logp[4];
             if (sigma > 0.f) {
@@ -383,9 +513,11 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std};
     PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
                 (float*)args->reward_out, args->done_out, (float*)args->hist};
+    constexpr bool kTS = QS_POLICY_TS != 0;
+    using Cfg = PolicyCfg<kTS>;
     static bool attr_set = false;
     if (!attr_set) {
-        QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PolicySmem::kBytes));
+        QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kBytes));
         attr_set = true;
     }
     {   // output layer -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
@@ -395,10 +527,10 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
         QS_CUDA(cudaMemcpyToSymbolAsync(c_actor_b3, tmp + kPH * 4, sizeof(float) * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     }
     const int64_t tiles = (h->N + kPM - 1) / kPM;
-    int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, kPG tiles in flight each
-    const int64_t need = (tiles + kPG - 1) / kPG;
+    int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, Cfg::kG tiles in flight each
+    const int64_t need = (tiles + Cfg::kG - 1) / Cfg::kG;
     if (grid > need) grid = need;
-    policy_rollout_kernel<<<(int)grid, kPM * kPG, PolicySmem::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+    policy_rollout_kernel<kTS><<<(int)grid, kPM * Cfg::kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }

@@ -327,6 +327,9 @@ int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, u
 /* tcgen05 self-test: D[128][N] = A[128][K] * B[N][K]^T with BF16 operands / FP32 accumulation through the same
  * shared-memory operand layout, descriptors and TMEM read-back the fused actor rollout uses (row-major fp32 in/out). */
 int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, void* stream);
+/* The same product with the A operand staged in TENSOR memory (tcgen05.st by the thread that owns the row, TS form of
+ * tcgen05.mma): 16 <= N <= 128 (multiple of 16), 32 <= K <= 128 (multiple of 32). */
+int qs_umma_selftest_ts(int N, int K, const float* A, const float* B, float* D, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* qs_last_error(void);

@@ -562,6 +562,18 @@ def test_umma_selftest_gemm():
         assert (D - ref).abs().max().item() < 1e-3
 
 
+def test_umma_selftest_gemm_a_operand_in_tensor_memory():
+    """TS form of tcgen05.mma: the thread that owns row r writes its packed BF16 row into TMEM with tcgen05.st and the MMA reads
+    the A operand from there (the data path of hidden activations that never touch shared memory)."""
+    lib = L.load_library()
+    torch.manual_seed(1)
+    for N, K in [(16, 32), (64, 128), (128, 128), (128, 64)]:
+        A = torch.randn(128, K, device=DEV); B = torch.randn(N, K, device=DEV); D = torch.zeros(128, N, device=DEV)
+        L.check(lib.qs_umma_selftest_ts(N, K, A.data_ptr(), B.data_ptr(), D.data_ptr(), None))
+        ref = A.bfloat16().float() @ B.bfloat16().float().t()
+        assert (D - ref).abs().max().item() < 1e-3, (N, K, (D - ref).abs().max().item())
+
+
 def _torch_actor(W, x):
     h = torch.tanh(x @ W["actor_0_weight"].t() + W["actor_0_bias"])
     h = torch.tanh(h @ W["actor_2_weight"].t() + W["actor_2_bias"])
