@@ -404,7 +404,7 @@ __device__ __forceinline__ void sensor_update_inl(const DevParams<R>& p, const S
         const R g[3] = {dy[1], dy[3], dy[5] - p.g};               // :371
         const R acc_read[3] = {rot[0] * g[0] + rot[3] * g[1] + rot[6] * g[2], rot[1] * g[0] + rot[4] * g[1] + rot[7] * g[2],
                                rot[2] * g[0] + rot[5] * g[1] + rot[8] * g[2]};
-        sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, z);
+        sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, p.s_gps_blend > R(0), z);
         sensor_step(p, z, e.y, acc_read, rot, c.f_m, s, obs);
 #pragma unroll
         for (int k = 0; k < kSensorStateDim; ++k) v.sensor_state[k * v.ld + n] = s[k];
@@ -865,14 +865,14 @@ static int grid_for(const qs_sim* s, int64_t n) {
 }
 
 // QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 per-warp cp.async pipeline (one env per lane),
-// 3 per-warp pipeline with two envs per lane on the packed FP32 pipe.  Unset = per handle: 3 without the sensor model
-// (49 vs 57 us per step of 1,048,576 envs), 2 with it (the sensor phase needs ~250 registers for an env pair, which
-// halves the resident warps and cancels the gain: 110 us either way).
+// 3 per-warp pipeline with two envs per lane on the packed FP32 pipe.  Unset = 3 for every FP32 / RK4 handle: 47.6 vs 57 us
+// per step of 1,048,576 envs without the sensor model, 102 vs 108 us with it (packed sensor model, sensor_pair.cuh).
 static int default_step_loader(uint32_t flags) {
     static int v = -2;
     if (v == -2) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : -1; }
     if (v >= 0) return v;
-    return (flags & QS_FLAG_SENSOR_NOISE) ? 2 : 3;
+    (void)flags;
+    return 3;
 }
 
 // persistent grid of the staged step kernel: a few CTAs per SM, each looping over 256-env tiles

@@ -25,21 +25,38 @@ namespace qs {
 
 constexpr int kSensorStateDim = 20;
 
-// 27 normals from 4 Philox blocks: every 32-bit word yields two 16-bit uniforms (u = (h + 0.5) / 65536), i.e. one
-// Box-Muller pair.  16-bit resolution truncates the noise at 4.8 sigma with 1.5e-5 granularity — irrelevant for a
-// sensor-noise model and it halves the integer work of the generator, the dominant cost of this sub-pass.
+// 27 normals per env step; every 32-bit Philox word yields two 16-bit uniforms (u = (h + 0.5) / 65536), i.e. one Box-Muller
+// pair.  16-bit resolution truncates the noise at 4.8 sigma with 1.5e-5 granularity — irrelevant for a sensor-noise model
+// and it halves the integer work of the generator, the dominant cost of this sub-pass.
+// Mapping (the test-side checker restates it): blocks 0..2 of the step give the physical normals P[0..23];
+// z[0..14] = P[0..14] (accel_int, first triad, gyro_int, gyro), z[21..26] = P[15..20] (second triad); the six GPS normals
+// z[15..20] come from block 3 and are drawn only when the GPS blend consumes them (gps = p.s_gps_blend > 0; the reference's
+// gps() draws them on every step and throws them away, :642-647) — with a counter-based generator unused draws cost nothing.
 template <typename R>
-__device__ __forceinline__ void sensor_normals(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t step, R z[32]) {
+__device__ __forceinline__ void sensor_block_normals(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t step, int b, R out[8]) {
+    const uint4 u = philox_block(seed, env_id, episode, step * 4u + (uint32_t)b, RNG_SENSOR);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        const uint4 u = philox_block(seed, env_id, episode, step * 4u + (uint32_t)b, RNG_SENSOR);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int k = 0; k < 4; ++k) {
+        const R u1 = (R(w[k] & 0xFFFFu) + R(0.5)) * R(1.0 / 65536.0);
+        const R u2 = (R(w[k] >> 16) + R(0.5)) * R(1.0 / 65536.0);
+        box_muller(u1, u2, &out[2 * k], &out[2 * k + 1]);
+    }
+}
+template <typename R>
+__device__ __forceinline__ void sensor_normals(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t step, bool gps, R z[32]) {
+    R P[24];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const R u1 = (R(w[k] & 0xFFFFu) + R(0.5)) * R(1.0 / 65536.0);
-            const R u2 = (R(w[k] >> 16) + R(0.5)) * R(1.0 / 65536.0);
-            box_muller(u1, u2, &z[8 * b + 2 * k], &z[8 * b + 2 * k + 1]);
-        }
+    for (int b = 0; b < 3; ++b) sensor_block_normals(seed, env_id, episode, step, b, &P[8 * b]);
+#pragma unroll
+    for (int k = 0; k < 15; ++k) z[k] = P[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { z[21 + k] = P[15 + k]; z[15 + k] = R(0); }
+    if (gps) {
+        R g[8];
+        sensor_block_normals(seed, env_id, episode, step, 3, g);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) z[15 + k] = g[k];
     }
 }
 

@@ -4,8 +4,8 @@
 // with every FP32 operation on the packed pipe (FFMA2 / FMUL2 / FADD2: one issue slot for both envs).  Only the Philox
 // rounds, the int->float conversions and the MUFU calls (log2, sqrt, rsqrt, sin, cos) remain per env.
 //
-// Normals are produced one Philox block (8 normals per env) at a time, right before their first use, so that at most two
-// blocks are live: the sensor phase then fits the register budget of the two-envs-per-lane step kernel (step_pair.cuh).
+// Normals are produced one Philox block (8 normals per env) at a time, right before their first use (mapping: sensor_normals,
+// sensor_device.cuh — blocks 0..2 for the model, block 3 only when the GPS blend reads it), so that at most two blocks are live: the sensor phase then fits the register budget of the two-envs-per-lane step kernel (step_pair.cuh).
 // The mapping counter -> normal is the one of sensor_normals (16-bit uniforms, Box-Muller at 2*pi*(u2-1/2)); results agree
 // with the scalar routine to FP32 rounding (the test compares the two kernels field by field).
 #pragma once
@@ -154,11 +154,12 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
 #pragma unroll
     for (int k = 0; k < 3; ++k) w2[k] = pfma(sg, z1[4 + k], padd(y[10 + k], s[1]));        // z[12..14]
     deriv_quat2(w2, qg, qv);                                                               // rl_worker.py:168
-    // ---- gps :642-647 consumes z[15..20]; read only by the optional complementary blend (math_trajectory.py:71-77)
-    sensor_normals_block2(rng, 2, z0);                                                     // z[16..23]
+    // ---- gps :642-647: z[15..20] = block 3, drawn only when the optional complementary blend reads them (math_trajectory.py:71-77)
+    const P2 z21 = z1[7];                                                                  // P[15] = z[21]
     if (p.s_gps_blend > 0.f) {
         const P2 wg = bc(p.s_gps_blend * 0.01f), wa = bc((100.f - p.s_gps_blend) * 0.01f);
-        const P2 zp[3] = {z1[7], z0[0], z0[1]}, zv[3] = {z0[2], z0[3], z0[4]};
+        sensor_normals_block2(rng, 3, z1);
+        const P2 zp[3] = {z1[0], z1[1], z1[2]}, zv[3] = {z1[3], z1[4], z1[5]};
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const P2 pos_gps = pfma(bc(p.s_gps_p), zp[k], y[2 * k]);
@@ -168,15 +169,15 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
         }
     }
     // ---- triad :649-697 (updates self.R for the next step)
-    sensor_normals_block2(rng, 3, z1);                                                     // z[24..31]
+    sensor_normals_block2(rng, 2, z0);                                                     // P[16..23]: z[22..26] = P[16..20]
     {
         s[0] = pfma(s[2], dt, s[0]);
         P2 gb[3], mi[3], mb[3], R2[9];
-        gb[0] = pfma(ng, Rm[2], pfma(sa, z0[5], padd(acc_read[0], s[0])));                 // z[21..23]
-        gb[1] = pfma(ng, Rm[5], pfma(sa, z0[6], padd(acc_read[1], s[0])));
-        gb[2] = psub(pfma(ng, Rm[8], pfma(sa, z0[7], padd(acc_read[2], s[0]))), f_m);
+        gb[0] = pfma(ng, Rm[2], pfma(sa, z21, padd(acc_read[0], s[0])));                   // z[21..23]
+        gb[1] = pfma(ng, Rm[5], pfma(sa, z0[0], padd(acc_read[1], s[0])));
+        gb[2] = psub(pfma(ng, Rm[8], pfma(sa, z0[1], padd(acc_read[2], s[0]))), f_m);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) mi[k] = pfma(sm, z1[k], bc(p.s_mag[k]));               // z[24..26]
+        for (int k = 0; k < 3; ++k) mi[k] = pfma(sm, z0[2 + k], bc(p.s_mag[k]));           // z[24..26]
 #pragma unroll
         for (int c = 0; c < 3; ++c) mb[c] = pfma(rot[c], mi[0], pfma(rot[3 + c], mi[1], pmul(rot[6 + c], mi[2])));
         triad2<false>(p, gb, mb, R2);

@@ -265,7 +265,7 @@ step_kernel_warp(const __grid_constant__ DevParams<float> p, const __grid_consta
 #pragma unroll
                     for (int k = 0; k < 17; ++k) s[k] = st[kRowSensor + k][lane];
                     accel_read(p, ctl, e.y, rot, acc_read);     // trailing drone_eq call: rotation matrix, accelerometer reading
-                    sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, z);
+                    sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, p.s_gps_blend > 0.f, z);
                     sensor_step(p, z, e.y, acc_read, rot, ctl.f_m, s, sobs);
 #pragma unroll
                     for (int k = 0; k < kSensorStateDim; ++k) st[kRowSensor + k][lane] = s[k];

@@ -473,9 +473,10 @@ def main():
                          "frac": achieved_gbs / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "kernel": kernel_name, "algorithmic_bytes_per_env_step": algo_bytes,
                          "kernel_ms": kernel_ms,
-                         "note": "HBM is the roof of a one-step launch (SURVEY 8(d)); the kernel itself is instruction-issue bound: "
-                                 "2,180 warp-instructions per 32 env-steps with the sensor model, issue-active 65 % "
-                                 "(profiles/r01_prof_step_warp_sensor_v2.txt; DESIGN.md lists the variants measured against it)"},
+                         "note": "HBM is the roof of a one-step launch (SURVEY 8(d)); the kernel itself is bound by instruction issue and "
+                                 "the latency of its dependency chains: 2,866 warp-instructions per 64 env-steps with the sensor model "
+                                 "(two envs per lane on FFMA2/FMUL2), 8 warps per SM at 236 registers "
+                                 "(profiles/r01_prof_step_pair_sensor.txt; DESIGN.md lists the variants measured against it)"},
             "fp32": {"achieved_tflops": flops, "peak_tflops_probe": fp32_peak, "frac": flops / fp32_peak,
                      "flops_per_env_step": FLOPS_PER_ENV_STEP(args.substeps),
                      "note": "algorithmic FLOPs (SURVEY.md 8(d)) vs an in-run dependent-FFMA probe"},

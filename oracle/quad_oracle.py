@@ -732,17 +732,22 @@ MAGNET_VEC = np.array([-4047, 12911, -9899]) * 0.01          # :651
 
 
 def sensor_normals(seed, env_id, episode, step):
-    """27(+5 spare) normals per env step from 4 Philox blocks; every 32-bit word gives two 16-bit uniforms
-    (one Box-Muller pair) — the same mapping as csrc/sensor_device.cuh."""
+    """27 normals per env step; every 32-bit Philox word gives two 16-bit uniforms (one Box-Muller pair).  Mapping shared with
+    csrc/sensor_device.cuh: blocks 0..2 of the step give the physical normals P[0..23]; z[0..14] = P[0..14], z[21..26] =
+    P[15..20]; the six GPS normals z[15..20] come from block 3 (the device draws them only when the GPS blend reads them)."""
     env_id = np.asarray(env_id)
-    z = np.zeros((env_id.shape[0], 32))
+    P = np.zeros((env_id.shape[0], 32))
     step = np.asarray(step, dtype=np.uint32)
     for b in range(4):
         w = philox_block(seed, env_id, episode, step * np.uint32(4) + np.uint32(b), STREAM_SENSOR)
         for k in range(4):
             u1 = ((w[:, k] & np.uint32(0xFFFF)).astype(np.float64) + 0.5) / 65536.0
             u2 = ((w[:, k] >> np.uint32(16)).astype(np.float64) + 0.5) / 65536.0
-            z[:, 8 * b + 2 * k], z[:, 8 * b + 2 * k + 1] = box_muller(u1, u2)
+            P[:, 8 * b + 2 * k], P[:, 8 * b + 2 * k + 1] = box_muller(u1, u2)
+    z = np.zeros_like(P)
+    z[:, 0:15] = P[:, 0:15]
+    z[:, 21:27] = P[:, 15:21]
+    z[:, 15:21] = P[:, 24:30]
     return z
 
 
