@@ -291,7 +291,7 @@ int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* rew
 /* Select the implementation of qs_step for this handle (all produce the same results to FP32 rounding): 0 = plain coalesced
  * loads, 1 = CTA-wide TMA-staged ring, 2 = per-warp cp.async pipeline with 16-byte vector loads/stores (one env per lane),
  * 3 = per-warp pipeline with two envs per lane, the RK4 stages on the packed FP32 instructions (FFMA2).  Default for
- * FP32/RK4 handles: 3 without QS_FLAG_SENSOR_NOISE, 2 with it; other configurations fall back to 1.  Tuning / A-B testing
+ * FP32/RK4 handles: 3 (with or without QS_FLAG_SENSOR_NOISE); other configurations fall back to 1.  Tuning / A-B testing
  * only.  qs_get_step_loader returns the loader a handle will use. */
 int qs_get_step_loader(qs_handle h);
 int qs_set_step_loader(qs_handle h, int loader);
