@@ -510,15 +510,17 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
         return fail(QS_ESTATE, "qs_policy_rollout: needs an FP32 / RK4 / direct-control handle");
     if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET | QS_FLAG_ROBUST))
         return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / ROBUST / strict AUTO_RESET (use ASYNC_RESET)");
+    QS_USE_DEVICE(h);
     ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std};
     PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
                 (float*)args->reward_out, args->done_out, (float*)args->hist};
     constexpr bool kTS = QS_POLICY_TS != 0;
     using Cfg = PolicyCfg<kTS>;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
+    const uint64_t attr_bit = 1ull << (h->cfg.device & 63);
+    if (!(attr_set & attr_bit)) {
         QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kBytes));
-        attr_set = true;
+        attr_set |= attr_bit;
     }
     {   // output layer -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
         float* tmp = (float*)h->action_stage;

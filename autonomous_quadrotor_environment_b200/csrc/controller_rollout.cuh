@@ -275,6 +275,7 @@ extern "C" int qs_control_rollout(qs_handle h, const qs_controller* c, const qs_
         return fail(QS_ESTATE, "qs_control_rollout: AUX rows are not maintained across asynchronous resets");
     if (a->target_traj && c->kind != QS_CTRL_PID)
         return fail(QS_EINVAL, "qs_control_rollout: target_traj (velocity set-points) applies to the PID law only");
+    QS_USE_DEVICE(h);
     ControlIO io{a->horizon, a->ctrl_state, a->obs_out, a->action_out, a->reward_out, a->done_out, a->aux_out, a->target_traj};
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_control_rollout, h, c, io, st);

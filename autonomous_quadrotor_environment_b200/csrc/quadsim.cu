@@ -924,10 +924,11 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
             constexpr int threads = SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain;
             constexpr int warps = threads / 32;
             constexpr size_t smem = (size_t)(SENSOR ? pr::kRowsSensor : pr::kRowsPlain) * 256 * warps;
-            static bool attr_set = false;
-            if (!attr_set) {
+            static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
+            const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
+            if (!(attr_set & attr_bit)) {
                 cudaFuncSetAttribute(step_kernel_pair<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = true;
+                attr_set |= attr_bit;
             }
             const int64_t chunks = (s->slice_count + 63) / 64;
             int64_t g = (int64_t)s->sm_count;
@@ -938,10 +939,11 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
         }
         if (s->step_loader >= 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
             constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * wp::kStagesW * (kBlock / 32);
-            static bool attr_set = false;
-            if (!attr_set) {
+            static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
+            const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
+            if (!(attr_set & attr_bit)) {
                 cudaFuncSetAttribute(step_kernel_warp<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set = true;
+                attr_set |= attr_bit;
             }
             const int64_t chunks = (s->slice_count + 31) / 32;
             int64_t g = (int64_t)s->sm_count * wp::kMinCtas;
@@ -953,10 +955,11 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
     }
     if (s->step_loader >= 1) {
         constexpr size_t smem = kStages * sizeof(Stage<R>);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
+        const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
+        if (!(attr_set & attr_bit)) {
             cudaFuncSetAttribute(step_kernel_tma<R, INTEG, DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set = true;
+            attr_set |= attr_bit;
         }
         step_kernel_tma<R, INTEG, DIRECT, SENSOR><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
     } else {
@@ -1099,10 +1102,19 @@ extern "C" int qs_get_step_loader(qs_handle h) {
     return (h->step_loader >= 2 && !warp_ok) ? 1 : h->step_loader;
 }
 
+// Launches go to the handle's device even when the calling thread's current device is another one (one process driving
+// several GPUs); like every CUDA library entry point that does this, the current device is left on the handle's.
+#define QS_USE_DEVICE(h)                                                               \
+    do {                                                                               \
+        int cur_ = -1;                                                                 \
+        QS_CUDA(cudaGetDevice(&cur_));                                                 \
+        if (cur_ != (h)->cfg.device) QS_CUDA(cudaSetDevice((h)->cfg.device));          \
+    } while (0)
+
 extern "C" int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_hist, void* act_hist,
                         void* stream) {
     if (!h) return fail(QS_EINVAL, "qs_reset: NULL handle");
-    QS_CUDA(cudaSetDevice(h->cfg.device));
+    QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_reset, h, det_state, mask, obs_hist, act_hist, st);
     QS_CUDA(cudaGetLastError());
@@ -1113,6 +1125,7 @@ extern "C" int qs_step(qs_handle h, const void* action, void* obs, void* reward,
                        void* stream) {
     if (!h) return fail(QS_EINVAL, "qs_step: NULL handle");
     if (!action) return fail(QS_EINVAL, "qs_step: action is NULL");
+    QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_step, h, action, obs, reward, done, solved, st);
     QS_CUDA(cudaGetLastError());
@@ -1127,6 +1140,7 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
         return fail(QS_EINVAL, "qs_rollout: bad action_source");
     if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_ROBUST))
         return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_SENSOR_NOISE / QS_FLAG_ROBUST");
+    QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_rollout, h, args, st);
     QS_CUDA(cudaGetLastError());
@@ -1138,6 +1152,7 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
 extern "C" int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host,
                             uint8_t* done_host, void* stream) {
     if (!h || !action_host) return fail(QS_EINVAL, "qs_step_host: NULL argument");
+    QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t rs = (size_t)h->rs, N = (size_t)h->N, ld = (size_t)h->ld;
     constexpr size_t kSliceMin = 65536;

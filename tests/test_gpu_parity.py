@@ -906,3 +906,27 @@ def test_full_size_properties_1M_envs():
     assert s["n_solved"] + s["n_broken"] + s["n_timeout"] == s["n_episodes"]
     # episode counters: every finished episode bumped exactly one counter (plus the initial reset)
     assert int(a.episode.sum().item()) == N + int(s["n_episodes"])
+
+
+@pytest.mark.gpu
+def test_handle_on_second_device_while_first_is_current():
+    """One process driving two GPUs: a handle created on cuda:1 keeps launching there (kernels, shared-memory attributes,
+    host-buffer pipeline) while the thread's current device is cuda:0, and produces the same trajectory as on cuda:0."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    N, seed = 4096, 4
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.cuda.set_device(0)
+        env = BatchedQuad(N, 0.01, 50, T=3, precision="f32", async_reset=True, sensor_noise=True, seed=seed, device=dev)
+        env.reset()
+        g = torch.Generator(device="cpu"); g.manual_seed(2)
+        for t in range(40):
+            torch.cuda.set_device(0)
+            a = (torch.rand(4, N, generator=g) * 2 - 1).to(dev).contiguous()
+            torch.cuda.synchronize(dev)
+            env.step_soa(a)
+        torch.cuda.synchronize(dev)
+        outs.append((env.obs.cpu(), env.sensed_obs.cpu(), env.episode.cpu()))
+    assert torch.equal(outs[0][2], outs[1][2])
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
