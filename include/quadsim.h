@@ -68,7 +68,7 @@ extern "C" {
                                      /* of rotor thrust (K_F), mass, rotor inertia and J plus linearly ramping wind gusts,    */
                                      /* every draw a pure function of (seed, global env id, episode / gust counter).  Runs on */
                                      /* the generic step / reset kernels (any precision / integrator); not available with     */
-                                     /* QS_FLAG_SENSOR_NOISE, qs_rollout, qs_policy_rollout or qs_control_rollout.            */
+                                     /* QS_FLAG_SENSOR_NOISE, qs_rollout or qs_policy_rollout (qs_control_rollout supports it). */
 
 /* Physical / reward constants.  Defaults (qs_default_config) = environment/quadrotor_env.py:30-80. */
 typedef struct qs_params {
@@ -198,7 +198,9 @@ typedef struct qs_actor {
 
 /* Fused PPO rollout (BASELINE.json configs[4]): per step  history -> actor MLP (tcgen05 tensor cores, BF16 operands,
  * FP32 accumulate) -> a ~ N(mean, sigma) (Philox) -> quad.step -> history push, K steps per launch with the env state in
- * registers.  Replaces the per-step loop of environment/controller/ppo.py:238-257.  Output buffers are [K][C][N]. */
+ * registers.  Replaces the per-step loop of environment/controller/ppo.py:238-257.  Output buffers are [K][C][N].
+ * The output layer's weights are staged in constant memory by a stream-ordered copy at every call: rollouts with DIFFERENT
+ * actors must not run concurrently on different streams of one device. */
 typedef struct qs_policy_rollout_args {
     int32_t horizon;
     int32_t reserved;
