@@ -66,6 +66,11 @@ __device__ __forceinline__ float fast_rsqrtf(float x) {           // MUFU.RSQ wi
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
 }
+__device__ __forceinline__ float fast_log2f(float x) {            // MUFU.LG2 without the denormal pre-scaling of __log2f()
+    float r;                                                      // (FSETP + FMUL 2^24 + FADD -24 around every call)
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
 __device__ __forceinline__ float fast_rcpf(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -549,6 +554,23 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
     return c;
 }
 
+// Same function with the ten round keys (k + r * (0x9E3779B9, 0xBB67AE85)) precomputed on the host (SimView::rk): the key is
+// the handle's seed, i.e. uniform over the launch, so the round keys can be constant-bank operands of the XORs instead of
+// twenty live registers.
+__device__ __forceinline__ uint4 philox4x32_10_rk(uint4 c, const uint32_t* __restrict__ rk) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ rk[2 * r], lo1, hi0 ^ c.w ^ rk[2 * r + 1], lo0);
+    }
+    return c;
+}
+__host__ __device__ inline void philox_round_keys(uint64_t seed, uint32_t rk[20]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { rk[2 * r] = k0; rk[2 * r + 1] = k1; k0 += 0x9E3779B9u; k1 += 0xBB67AE85u; }
+}
+
 __device__ __forceinline__ uint4 philox_block(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t block,
                                               uint32_t stream) {
     return philox4x32_10(make_uint4(env_id, episode, block, stream),
@@ -567,7 +589,7 @@ template <typename R> __device__ __forceinline__ void box_muller(R u1, R u2, R* 
 }
 // FP32: MUFU sin/cos are most accurate on [-pi,pi] -> evaluate at 2*pi*(u2-1/2) and flip both signs.
 template <> __device__ __forceinline__ void box_muller<float>(float u1, float u2, float* n0, float* n1) {
-    float r = fast_sqrtf(-2.f * __logf(u1));
+    float r = fast_sqrtf((-2.f * 0.693147182f) * fast_log2f(u1));     // u1 >= 2^-17: never denormal
     float s, c;
     __sincosf(6.28318548f * (u2 - 0.5f), &s, &c);
     *n0 = -r * c; *n1 = -r * s;

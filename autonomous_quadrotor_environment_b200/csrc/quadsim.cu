@@ -67,6 +67,7 @@ template <typename R> struct SimView {
     double* stats;
     uint64_t seed;
     uint32_t env_id_offset;
+    uint32_t rk[20];       // Philox round keys of seed (philox_round_keys)
 };
 
 struct Slot { void* ptr; int32_t channels; int32_t elem; };
@@ -300,6 +301,7 @@ template <typename R> static SimView<R> make_view(const qs_sim* s) {
     v.stats = s->stats;
     v.seed = s->seed;
     v.env_id_offset = (uint32_t)s->cfg.env_id_offset;
+    qs::philox_round_keys(s->seed, v.rk);
     if (s->slice_begin != 0 || s->slice_count != s->N) {       // a 256-aligned sub-range of the shard: same rows, shifted columns
         const int64_t b = s->slice_begin;
         R** real_rows[] = {&v.obs17, &v.prev_ang, &v.prev_shaping, &v.abs_sum, &v.ep_return, &v.reward, &v.ang_vel, &v.step_effort,

@@ -18,12 +18,17 @@ __device__ __forceinline__ P2 psub(P2 a, P2 b) { return pfma(b, bc(-1.f), a); }
 __device__ __forceinline__ P2 pneg(P2 a) { return pmul(a, bc(-1.f)); }
 __device__ __forceinline__ P2 psel(bool ca, bool cb, P2 t, P2 f) { return pk(ca ? t.v.x : f.v.x, cb ? t.v.y : f.v.y); }
 
-struct SensorRng2 { uint64_t seed; uint32_t id[2], ep[2], step[2]; };
+struct SensorRng2 { uint64_t seed; const uint32_t* rk; uint32_t id[2], ep[2], step[2]; };   // rk = SimView::rk (round keys of seed)
 
 // 8 normals per env from Philox block b of the env's sensor stream (sensor_normals, sensor_device.cuh)
 __device__ __forceinline__ void sensor_normals_block2(const SensorRng2& r, int b, P2 z[8]) {
+#ifdef QS_PHILOX_KEYS_IN_REGS
     const uint4 ua = philox_block(r.seed, r.id[0], r.ep[0], r.step[0] * 4u + (uint32_t)b, RNG_SENSOR);
     const uint4 ub = philox_block(r.seed, r.id[1], r.ep[1], r.step[1] * 4u + (uint32_t)b, RNG_SENSOR);
+#else
+    const uint4 ua = philox4x32_10_rk(make_uint4(r.id[0], r.ep[0], r.step[0] * 4u + (uint32_t)b, RNG_SENSOR), r.rk);
+    const uint4 ub = philox4x32_10_rk(make_uint4(r.id[1], r.ep[1], r.step[1] * 4u + (uint32_t)b, RNG_SENSOR), r.rk);
+#endif
     const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -31,7 +36,7 @@ __device__ __forceinline__ void sensor_normals_block2(const SensorRng2& r, int b
         const P2 h2 = pk((float)(wa[k] >> 16), (float)(wb[k] >> 16));
         const P2 u1 = pfma(h1, bc(1.0f / 65536.0f), bc(0.5f / 65536.0f));                  // (h + 1/2) / 65536, exact
         const P2 ang = pfma(h2, bc(6.28318548f / 65536.0f), bc(6.28318548f * (0.5f / 65536.0f - 0.5f)));   // 2 pi (u2 - 1/2)
-        const P2 l = pmul(pk(__log2f(u1.v.x), __log2f(u1.v.y)), bc(-2.0f * 0.693147182f));  // -2 ln u1
+        const P2 l = pmul(pk(fast_log2f(u1.v.x), fast_log2f(u1.v.y)), bc(-2.0f * 0.693147182f));  // -2 ln u1
         const P2 nr = pk(-fast_sqrtf(l.v.x), -fast_sqrtf(l.v.y));
         const P2 cs = pk(__cosf(ang.v.x), __cosf(ang.v.y)), sn = pk(__sinf(ang.v.x), __sinf(ang.v.y));
         z[2 * k] = pmul(nr, cs);

@@ -120,7 +120,7 @@ __device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const Si
 #pragma unroll
     for (int k = 0; k < kSensorStateDim; ++k) sn[k].v = lds2(srows, k, lane);
     SensorRng2 rng;
-    rng.seed = v.seed;
+    rng.seed = v.seed; rng.rk = v.rk;
     rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
     rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
     rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
