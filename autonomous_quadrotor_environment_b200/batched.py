@@ -161,6 +161,7 @@ class BatchedQuad:
     def seed(self, seed: int):
         """quad.seed (quadrotor_env.py:189-193): re-keys the Philox streams."""
         L.check(self.lib.qs_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
+        self._cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF       # get_checkpoint() saves the key in force
 
     def reset(self, det_state=None, mask=None):
         """quad.reset (quadrotor_env.py:408-454) for the masked envs (all if mask is None).

@@ -429,7 +429,9 @@ def test_packed_sensor_model_equals_scalar_sensor_model(gps_blend):
     """The sensor model on the packed FP32 pipe (sensor_pair.cuh: loader 3, two envs per lane, Philox blocks drawn on demand,
     accelerometer reading from the closed form f_b/M - 2G R^T z) against the scalar routine (sensor_device.cuh, loader 1),
     teacher-forced, with and without the complementary GPS blend: sensed observation and the 20 sensor-state rows agree to
-    FP32 rounding at every step, through warm-up steps and sensor resets."""
+    FP32 rounding at every step, through warm-up steps and sensor resets.  Half way both handles are re-seeded with a seed whose
+    high word is set: the packed kernel takes its Philox round keys from the view (SimView::rk, precomputed on the host per
+    launch), the scalar one derives them from the seed in the kernel — the streams must stay identical, and must change."""
     N, K, seed = 4099, 80, 17
     mk = lambda ld: BatchedQuad(N, 0.01, 30, T=3, precision="f32", async_reset=True, sensor_noise=True, seed=seed, device=DEV,
                                 params={"gps_blend": gps_blend}).set_step_loader(ld)
@@ -440,7 +442,16 @@ def test_packed_sensor_model_equals_scalar_sensor_model(gps_blend):
     for t in range(K):
         b._ws.copy_(a._ws)
         act = (torch.rand(4, N, device=DEV, generator=g) * 0.6 - 0.3).contiguous()
+        if t == K // 2:                                       # same state and action under the old and the new seed
+            ck = a.get_checkpoint()
+            a.step_soa(act)
+            old_noise = a.sensed_obs.clone()
+            a.set_checkpoint(ck)
+            for env in (a, b):
+                env.seed(0x9E3779B97F4A7C15)
         a.step_soa(act); b.step_soa(act)
+        if t == K // 2:
+            assert float((a.sensed_obs - old_noise).abs().max()) > 1e-4     # the new seed drew different noise
         same = (a._field(L.QS_FIELD_DONE) == b._field(L.QS_FIELD_DONE)).all(dim=0) & (a._field(L.QS_FIELD_FLAGS) == b._field(L.QS_FIELD_FLAGS)).all(dim=0)
         assert int((~same).sum()) <= 1
         for f in (L.QS_FIELD_SENSED_OBS, L.QS_FIELD_SENSOR_STATE):
@@ -522,6 +533,13 @@ def test_checkpoint_resume():
     a.rollout(15)
     b = BatchedQuad(N, 0.01, 50, T=1, precision="f32", auto_reset=True, seed=999, device=DEV)
     b.set_checkpoint(ck); b.rollout(15)
+    assert torch.equal(a.state, b.state) and torch.equal(a.episode, b.episode)
+    a.seed(12345)                                         # a checkpoint taken after quad.seed carries the key in force
+    ck = a.get_checkpoint()
+    assert ck["seed"] == 12345
+    a.rollout(40)
+    b.set_checkpoint(ck); b.rollout(40)
+    assert int(a.episode.max()) >= 1                      # resets drew from the re-keyed streams
     assert torch.equal(a.state, b.state) and torch.equal(a.episode, b.episode)
 
 
