@@ -158,6 +158,130 @@ __device__ __forceinline__ void sensor_store(const SimView<float>& v, int64_t n0
     for (int k = 0; k < 14; ++k) go2[(int64_t)k * ld2] = so[k].v;
 }
 
+// fast_atan2f / fast_asinf (quad_device.cuh) for an env pair: the same operation sequence, the polynomial parts on the packed
+// pipe, min / max / compare / select / MUFU per env (no packed form in the ISA).  Bit-identical to the scalar routines.
+__device__ __forceinline__ qs::P2 patan2(qs::P2 y, qs::P2 x) {
+    using namespace qs;
+    const float ax0 = fabsf(x.v.x), ay0 = fabsf(y.v.x), ax1 = fabsf(x.v.y), ay1 = fabsf(y.v.y);
+    const float mx0 = fmaxf(ax0, ay0), mn0 = fminf(ax0, ay0), mx1 = fmaxf(ax1, ay1), mn1 = fminf(ax1, ay1);
+    P2 a = pmul(pk(mn0, mn1), pk(fast_rcpf(mx0), fast_rcpf(mx1)));
+    a = pk(mx0 == 0.f ? 0.f : a.v.x, mx1 == 0.f ? 0.f : a.v.y);
+    const P2 s2 = pmul(a, a);
+    P2 r = bc(0.0027856871f);
+    r = pfma(r, s2, bc(-0.0158660002f));
+    r = pfma(r, s2, bc(0.042472221f));
+    r = pfma(r, s2, bc(-0.0749753043f));
+    r = pfma(r, s2, bc(0.106448799f));
+    r = pfma(r, s2, bc(-0.142070308f));
+    r = pfma(r, s2, bc(0.199934542f));
+    r = pfma(r, s2, bc(-0.333331466f));
+    r = pmul(r, s2);
+    r = pfma(r, a, a);
+    float r0 = r.v.x, r1 = r.v.y;
+    r0 = (ay0 > ax0) ? (1.57079637f - r0) : r0;  r1 = (ay1 > ax1) ? (1.57079637f - r1) : r1;
+    r0 = (x.v.x < 0.f) ? (3.14159274f - r0) : r0;  r1 = (x.v.y < 0.f) ? (3.14159274f - r1) : r1;
+    return pk(copysignf(r0, y.v.x), copysignf(r1, y.v.y));
+}
+__device__ __forceinline__ qs::P2 pasin(qs::P2 x) {
+    using namespace qs;
+    const float ax0 = fabsf(x.v.x), ax1 = fabsf(x.v.y);
+    const bool big0 = ax0 > 0.5f, big1 = ax1 > 0.5f;
+    const P2 z = pk(big0 ? fmaf(-0.5f, ax0, 0.5f) : ax0 * ax0, big1 ? fmaf(-0.5f, ax1, 0.5f) : ax1 * ax1);
+    const P2 sq = pk(big0 ? fast_sqrtf(z.v.x) : ax0, big1 ? fast_sqrtf(z.v.y) : ax1);
+    P2 pz = bc(4.2163199048e-2f);
+    pz = pfma(pz, z, bc(2.4181311049e-2f));
+    pz = pfma(pz, z, bc(4.5470025998e-2f));
+    pz = pfma(pz, z, bc(7.4953002686e-2f));
+    pz = pfma(pz, z, bc(1.6666752422e-1f));
+    const P2 r = pfma(pmul(sq, z), pz, sq);
+    float r0 = r.v.x, r1 = r.v.y;
+    r0 = big0 ? fmaf(-2.f, r0, 1.57079637f) : r0;  r1 = big1 ? fmaf(-2.f, r1, 1.57079637f) : r1;
+    r0 = (ax0 > 1.f) ? __int_as_float(0x7fc00000) : r0;  r1 = (ax1 > 1.f) ? __int_as_float(0x7fc00000) : r1;
+    return pk(copysignf(r0, x.v.x), copysignf(r1, x.v.y));
+}
+
+// Phase 3 of quad.step (step_post, quad_device.cuh: :486-498 observation tail, Euler angles, done_condition, reward_function,
+// control_effort) for an env pair.  Everything both envs compute alike — quaternion normalisation, V_q, the Euler-angle
+// arguments and polynomials, the sums of squares of the reward, the action penalty, the effort norm — runs on the packed
+// pipe; thresholds, the reward cascade and the flag logic stay per env (branch-free, the two chains interleave).
+__device__ __forceinline__ void step_post2(const DevParams<float>& p, const qs::P2 y[13], Env<float> e[2], const float act[2][4],
+                                           StepOut<float> o[2]) {
+    using namespace qs;
+    const P2 inv = prsqrt(pfma(y[6], y[6], pfma(y[7], y[7], pfma(y[8], y[8], pmul(y[9], y[9])))));        // :488-489
+    const P2 q[4] = {pmul(y[6], inv), pmul(y[7], inv), pmul(y[8], inv), pmul(y[9], inv)};
+    P2 vq[4];
+    deriv_quat2(&y[10], q, vq);                                                                         // :392
+    // quat_euler utility:39-48
+    const P2 two = bc(2.f), m2 = bc(-2.f), one = bc(1.f);
+    const P2 sx = pmul(two, pfma(q[0], q[1], pmul(q[2], q[3])));
+    const P2 cx = pfma(m2, pfma(q[1], q[1], pmul(q[2], q[2])), one);
+    const P2 sy = pmul(two, pfma(q[0], q[2], pmul(pmul(q[3], bc(-1.f)), q[1])));
+    const P2 sz = pmul(two, pfma(q[0], q[3], pmul(q[1], q[2])));
+    const P2 cz = pfma(m2, pfma(q[2], q[2], pmul(q[3], q[3])), one);
+    const P2 phi = patan2(sx, cx);
+    const P2 theta = pasin(pk(asin_arg<float>(sy.v.x), asin_arg<float>(sy.v.y)));
+    const P2 psi = patan2(sz, cz);
+    // reward_function :511-573, the sums
+    const P2 v2 = pfma(y[1], y[1], pfma(y[3], y[3], pmul(y[5], y[5])));
+    const P2 e2 = pfma(phi, phi, pmul(theta, theta));
+    const P2 psi2 = pmul(psi, psi);
+    const P2 w2 = pfma(y[10], y[10], pfma(y[11], y[11], pmul(y[12], y[12])));
+    const P2 cur = padd(v2, padd(padd(e2, psi2), w2));                                                   // :558
+    const P2 nr2 = padd(v2, psi2);
+    P2 pen = bc(0.f);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const P2 d = padd(pk(act[0][k], act[1][k]), bc(-p.zero_control[k]));
+        pen = pfma(d, d, pen);
+    }
+    const P2 ef2 = pfma(pk(o[0].effort[0], o[1].effort[0]), pk(o[0].effort[0], o[1].effort[0]),
+                   pfma(pk(o[0].effort[1], o[1].effort[1]), pk(o[0].effort[1], o[1].effort[1]),
+                   pfma(pk(o[0].effort[2], o[1].effort[2]), pk(o[0].effort[2], o[1].effort[2]),
+                   pmul(pk(o[0].effort[3], o[1].effort[3]), pk(o[0].effort[3], o[1].effort[3])))));
+    const P2 nv = pk(fast_sqrtf(v2.v.x), fast_sqrtf(v2.v.y)), ne = pk(fast_sqrtf(e2.v.x), fast_sqrtf(e2.v.y));
+    const P2 shaping0 = pmul(bc(-1.f), pfma(bc(p.sh_v), nv, pfma(bc(p.sh_psi), pk(fabsf(psi.v.x), fabsf(psi.v.y)), pmul(bc(p.sh_ang), ne))));   // :529-531
+    const P2 pen_c = pmul(pen, bc(-p.p_c));
+#define QS_POST2_HALF(H)                                                                                      \
+    {                                                                                                         \
+        const float ang[3] = {half_of<H>(phi), half_of<H>(theta), half_of<H>(psi)};                           \
+        _Pragma("unroll") for (int k = 0; k < 4; ++k) o[H].vq[k] = half_of<H>(vq[k]);                         \
+        _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                                       \
+            o[H].ang[k] = ang[k];                                                                             \
+            o[H].ang_vel[k] = div_dt(ang[k] - e[H].prev_ang[k], p);                                           \
+            e[H].prev_ang[k] = ang[k];                                                                        \
+        }                                                                                                     \
+        bool done = (e[H].flags & EF_DONE) != 0;                                                              \
+        const float cx9[9] = {half_of<H>(y[1]), half_of<H>(y[3]), half_of<H>(y[5]), ang[0], ang[1], ang[2],   \
+                              half_of<H>(y[10]), half_of<H>(y[11]), half_of<H>(y[12])};                       \
+        _Pragma("unroll") for (int k = 0; k < 9; ++k) done = done | (fabsf(cx9[k]) >= p.bb[k]);               \
+        const float nrh = fast_sqrtf(half_of<H>(nr2)), neh = half_of<H>(ne);                                  \
+        float shaping = half_of<H>(shaping0);                                                                 \
+        bool taken = false;                                                                                   \
+        _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                                       \
+            const bool c1 = (!taken) & (nrh < p.tr_r[k]);                                                     \
+            const bool c2 = c1 & (neh < p.tr_e[k]);                                                           \
+            shaping += c1 ? p.tr_p[k] : 0.f;                                                                  \
+            shaping += c2 ? p.tr_p[k] : 0.f;                                                                  \
+            taken = taken | c1;                                                                               \
+        }                                                                                                     \
+        float reward = (e[H].flags & EF_HAS_SHAPING) ? (shaping - e[H].prev_shaping) : 0.f;                   \
+        e[H].prev_shaping = shaping;                                                                          \
+        reward += half_of<H>(pen_c);                                                                          \
+        const bool is_solved = half_of<H>(cur) < p.target_state;                                              \
+        const bool timeout = (!is_solved) & (e[H].i >= p.n_limit);                                            \
+        const bool broken = (!is_solved) & (!timeout) & done;                                                 \
+        reward = is_solved ? reward + p.solved_reward : (broken ? reward + p.broken_reward : reward);         \
+        const bool solved = is_solved | (((e[H].flags & EF_SOLVED) != 0) & (!timeout) & (!broken));           \
+        done = done | (is_solved & ((p.flags & F_TRAINING) != 0)) | timeout;                                  \
+        e[H].flags = (e[H].flags & ~EF_LOW) | (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u); \
+        e[H].abs_sum += fast_sqrtf(half_of<H>(ef2));                                                          \
+        o[H].reward = reward; o[H].done = done; o[H].solved = solved; o[H].broken = broken; o[H].timeout = timeout; \
+    }
+    QS_POST2_HALF(0)
+    QS_POST2_HALF(1)
+#undef QS_POST2_HALF
+}
+
 // QS_FLAG_ASYNC_RESET, once per chunk: push the finished envs of this lane's pair on the CTA's queue (AFTER all of their
 // rows have been stored), then claim 32 queued envs if available and re-sample them with all lanes busy
 template <bool SENSOR, int kQueueCap>
@@ -288,10 +412,21 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         const Ctrl2 c2 = pack_ctrl(ctl[0], ctl[1]);
         integrate_rk4_2(p, c2, y);
         // ---- phase 3 per env: observation tail, Euler angles, done, reward
+        // -DQS_PAIR_PACKED_POST: phase 3 on the packed pipe (step_post2).  Measured 100.6 vs 102.0 us with the sensor model and
+        // 46.9 vs 47.05 us without (1,048,576 envs); NOT the default yet: test_step_loaders_agree[65536-True-1-False-3] fails
+        // against the scalar phase of loader 1 with it — the pitch angle of one env next to gimbal lock differs by 1.5e-4
+        // (asin amplifies the one-ulp difference of its argument 2(q0 q2 - q3 q1), which the packed form rounds in another
+        // order); the comparison needs a bound that follows the conditioning of asin before the switch.
+#ifdef QS_PAIR_PACKED_POST
+#define QS_PAIR_POST_CALL(H)
+        step_post2(p, y, e, act, o);
+#else
+#define QS_PAIR_POST_CALL(H) step_post(p, e[H], act[H], o[H]);
+#endif
 #define QS_PAIR_POST(H)                                                                                       \
         {                                                                                                     \
             _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);                      \
-            step_post(p, e[H], act[H], o[H]);                                                                 \
+            QS_PAIR_POST_CALL(H)                                                                              \
             o[H].reward = warm[H] ? 0.f : o[H].reward;                                                        \
             e[H].ep_return += o[H].reward;                                                                    \
             push[H] = async_reset & act_[H] & o[H].done;                                                      \
@@ -301,6 +436,7 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         if (act_[0] && o[0].done && !was_done[0]) { count_episode(ls, p, e[0], o[0]); any_end = true; }
         if (act_[1] && o[1].done && !was_done[1]) { count_episode(ls, p, e[1], o[1]); any_end = true; }
 #undef QS_PAIR_POST
+#undef QS_PAIR_POST_CALL
         // ---- results -> HBM straight from the register pairs (rows of the handle are padded to whole chunks)
         {
             float2* g2 = reinterpret_cast<float2*>(v.obs17 + n0) + lane;
