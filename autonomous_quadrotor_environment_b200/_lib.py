@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
     "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_gae", "qs_adv_normalize", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
-    "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest", "qs_umma_selftest_ts",
+    "qs_sensor_call", "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest", "qs_umma_selftest_ts",
 ]
 
 
@@ -109,6 +109,10 @@ class qs_control_rollout_args(C.Structure):
 
 
 QS_CTRL_LQR, QS_CTRL_PID = 0, 1
+(QS_SENSOR_RESET, QS_SENSOR_ACCEL, QS_SENSOR_GYRO, QS_SENSOR_GPS, QS_SENSOR_TRIAD, QS_SENSOR_ACCEL_INT, QS_SENSOR_GYRO_INT,
+ QS_SENSOR_STEP) = range(8)
+SENSOR_Z_ROWS = (3, 3, 3, 6, 6, 9, 3, 27)        # rows of z / out per method (include/quadsim.h, qs_sensor_call)
+SENSOR_OUT_ROWS = (0, 3, 3, 6, 13, 9, 4, 14)
 QS_CTRL_STATE_DIM = 22
 
 
@@ -162,6 +166,7 @@ def load_library():
         "qs_drone_eq": (C.c_int, [C.c_int, P(qs_params), i64, C.c_int, vp, vp, vp, vp, vp]),
         "qs_f2w": (C.c_int, [C.c_int, P(qs_params), i64, C.c_int, vp, vp, vp, vp, vp]),
         "qs_philox_raw": (C.c_int, [u64, i64, i64, u32, u32, u32, vp, vp]),
+        "qs_sensor_call": (C.c_int, [C.c_int, P(qs_params), C.c_double, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
         "qs_last_error": (C.c_char_p, []),
         "qs_version": (C.c_int, []),
         "qs_fp32_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_float), vp]),

@@ -5,7 +5,7 @@
 // GEMMs), the first epilogue reads TMEM with tcgen05.ld, applies tanh and writes the next layer's A operand back to shared
 // memory, the second one applies tanh and the 128 -> 4 output layer on the FP32 pipe (weights in constant memory); the
 // dynamics run on the same 128 threads (thread = env = TMEM lane) with the env state in registers.
-// Included at the end of quadsim.cu (single translation unit).
+// Own translation unit (actor_rollout.cu).
 #pragma once
 #include "umma.cuh"
 
@@ -516,12 +516,7 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
                 (float*)args->reward_out, args->done_out, (float*)args->hist};
     constexpr bool kTS = QS_POLICY_TS != 0;
     using Cfg = PolicyCfg<kTS>;
-    static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
-    const uint64_t attr_bit = 1ull << (h->cfg.device & 63);
-    if (!(attr_set & attr_bit)) {
-        QS_CUDA(cudaFuncSetAttribute(policy_rollout_kernel<kTS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kBytes));
-        attr_set |= attr_bit;
-    }
+    QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS>), Cfg::kBytes);
     {   // output layer -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
         float* tmp = (float*)h->action_stage;
         k_pack_w3<<<1, kPH, 0, (cudaStream_t)stream>>>(actor->w3, actor->b3, tmp);

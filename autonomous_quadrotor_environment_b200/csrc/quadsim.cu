@@ -8,93 +8,19 @@
 //   prev_shaping, abs_sum, ep_return, reward [ld];  step_i i32[ld]; episode u32[ld]; flags/done/solved u8[ld]
 //   (+ AUX rows and sensor rows when enabled)
 // A warp reads/writes 32 consecutive envs of one row = one 128-byte line per request (FP32).
-#include "../../include/quadsim.h"
-#include "quad_device.cuh"
-#include "sensor_device.cuh"
-
-#include <cmath>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <new>
-
-using namespace qs;
+#include "quadsim_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+int qs_fail_(int code, const char* fmt, const char* a, const char* b) {
     snprintf(g_err, sizeof(g_err), fmt, a, b);
     return code;
 }
-#define QS_CUDA(call)                                                                   \
-    do {                                                                                \
-        cudaError_t e_ = (call);                                                        \
-        if (e_ != cudaSuccess) return fail(QS_ECUDA, "%s: %s", #call, cudaGetErrorString(e_)); \
-    } while (0)
 
 extern "C" const char* qs_last_error(void) { return g_err; }
 extern "C" int qs_version(void) { return QS_VERSION; }
-
-// ------------------------------------------------------------------------------------------------
-// handle
-// ------------------------------------------------------------------------------------------------
-template <typename R> struct SimView {
-    int64_t N, ld;
-    R* obs17;
-    R* prev_ang;
-    R* prev_shaping;
-    R* abs_sum;
-    R* ep_return;
-    R* reward;
-    int32_t* step_i;
-    uint32_t* episode;
-    uint8_t* flags;
-    uint8_t* done;
-    uint8_t* solved;
-    R* ang_vel;       // AUX (nullable)
-    R* step_effort;
-    R* w;
-    R* accel;
-    R* acc_read;
-    R* mat_rot;
-    R* clipped_action;
-    R* fm;
-    R* sensed_obs;    // SENSOR (nullable)
-    R* sensor_state;
-    int32_t* gust_count;   // ROBUST (nullable): per-env gust counter of robust_control.wind
-    double* stats;
-    uint64_t seed;
-    uint32_t env_id_offset;
-    uint32_t rk[20];       // Philox round keys of seed (philox_round_keys)
-};
-
-struct Slot { void* ptr; int32_t channels; int32_t elem; };
-
-struct qs_sim {
-    qs_config cfg;
-    int64_t N, ld;
-    int rs;                 // sizeof(real)
-    char* ws;
-    size_t ws_bytes;
-    bool owns_ws;
-    Slot slot[QS_FIELD_COUNT_];
-    void* obs17;
-    void* action_stage;     // [4][ld] staging for qs_step_host
-    double* stats;
-    DevParams<float> pf;
-    DevParams<double> pd;
-    int sm_count;
-    uint64_t seed;
-    int64_t slice_begin, slice_count;   // env range the step launchers address (whole shard except inside qs_step_host's pipeline)
-    cudaStream_t host_streams[4];       // qs_step_host: slices of the shard flow H2D -> step -> D2H on these, overlapping both PCIe directions
-    cudaEvent_t host_ev[5];
-    bool host_pipe_ready;
-    int step_loader;        // 0 direct LDG, 1 CTA-wide TMA ring, 2 per-warp cp.async pipeline, 3 per-warp pipeline with env pairs (packed FP32)
-};
-
-static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 template <typename R> static DevParams<R> make_params(const qs_config& c) {
     const qs_params& q = c.params;
@@ -272,124 +198,6 @@ extern "C" int64_t qs_workspace_bytes(const qs_config* cfg) {
     return (int64_t)layout(cfg, nullptr);
 }
 
-template <typename R> static SimView<R> make_view(const qs_sim* s) {
-    SimView<R> v;
-    memset(&v, 0, sizeof(v));
-    v.N = s->N; v.ld = s->ld;
-    v.obs17 = (R*)s->obs17;
-    v.prev_ang = (R*)s->slot[QS_FIELD_ANG].ptr;
-    v.prev_shaping = (R*)s->slot[QS_FIELD_PREV_SHAPING].ptr;
-    v.abs_sum = (R*)s->slot[QS_FIELD_ABS_SUM].ptr;
-    v.ep_return = (R*)s->slot[QS_FIELD_EP_RETURN].ptr;
-    v.reward = (R*)s->slot[QS_FIELD_REWARD].ptr;
-    v.step_i = (int32_t*)s->slot[QS_FIELD_I].ptr;
-    v.episode = (uint32_t*)s->slot[QS_FIELD_EPISODE].ptr;
-    v.flags = (uint8_t*)s->slot[QS_FIELD_FLAGS].ptr;
-    v.done = (uint8_t*)s->slot[QS_FIELD_DONE].ptr;
-    v.solved = (uint8_t*)s->slot[QS_FIELD_SOLVED].ptr;
-    v.ang_vel = (R*)s->slot[QS_FIELD_ANG_VEL].ptr;
-    v.step_effort = (R*)s->slot[QS_FIELD_STEP_EFFORT].ptr;
-    v.w = (R*)s->slot[QS_FIELD_W].ptr;
-    v.accel = (R*)s->slot[QS_FIELD_ACCEL].ptr;
-    v.acc_read = (R*)s->slot[QS_FIELD_ACC_READ].ptr;
-    v.mat_rot = (R*)s->slot[QS_FIELD_MAT_ROT].ptr;
-    v.clipped_action = (R*)s->slot[QS_FIELD_CLIPPED_ACTION].ptr;
-    v.fm = (R*)s->slot[QS_FIELD_FM].ptr;
-    v.sensed_obs = (R*)s->slot[QS_FIELD_SENSED_OBS].ptr;
-    v.sensor_state = (R*)s->slot[QS_FIELD_SENSOR_STATE].ptr;
-    v.gust_count = (int32_t*)s->slot[QS_FIELD_GUST_COUNT].ptr;
-    v.stats = s->stats;
-    v.seed = s->seed;
-    v.env_id_offset = (uint32_t)s->cfg.env_id_offset;
-    qs::philox_round_keys(s->seed, v.rk);
-    if (s->slice_begin != 0 || s->slice_count != s->N) {       // a 256-aligned sub-range of the shard: same rows, shifted columns
-        const int64_t b = s->slice_begin;
-        R** real_rows[] = {&v.obs17, &v.prev_ang, &v.prev_shaping, &v.abs_sum, &v.ep_return, &v.reward, &v.ang_vel, &v.step_effort,
-                           &v.w, &v.accel, &v.acc_read, &v.mat_rot, &v.clipped_action, &v.fm, &v.sensed_obs, &v.sensor_state};
-        for (R** r : real_rows) if (*r) *r += b;
-        v.step_i += b; v.episode += b; v.flags += b; v.done += b; v.solved += b;
-        if (v.gust_count) v.gust_count += b;
-        v.N = s->slice_count;
-        v.env_id_offset += (uint32_t)b;
-    }
-    return v;
-}
-
-// ------------------------------------------------------------------------------------------------
-// kernels
-// ------------------------------------------------------------------------------------------------
-#ifndef QS_BLOCK
-#define QS_BLOCK 256          // threads (= envs) per CTA tile
-#endif
-#ifndef QS_MIN_CTAS
-#define QS_MIN_CTAS 2         // resident CTAs per SM the step / rollout kernels are compiled for
-#endif
-#ifndef QS_STAGES
-#define QS_STAGES 3           // depth of the TMA staging ring
-#endif
-constexpr int kBlock = QS_BLOCK;
-
-template <typename R>
-__device__ __forceinline__ void load_env(const SimView<R>& v, int64_t n, Env<R>& e) {
-#pragma unroll
-    for (int k = 0; k < 10; ++k) e.y[k] = v.obs17[k * v.ld + n];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) e.y[10 + k] = v.obs17[(14 + k) * v.ld + n];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) e.prev_ang[k] = v.prev_ang[k * v.ld + n];
-    e.prev_shaping = v.prev_shaping[n];
-    e.abs_sum = v.abs_sum[n];
-    e.ep_return = v.ep_return[n];
-    e.i = v.step_i[n];
-    e.flags = v.flags[n];
-    e.episode = v.episode[n];
-}
-
-template <typename R>
-__device__ __forceinline__ void store_env(const SimView<R>& v, int64_t n, const Env<R>& e, const R vq[4]) {
-#pragma unroll
-    for (int k = 0; k < 10; ++k) v.obs17[k * v.ld + n] = e.y[k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) v.obs17[(10 + k) * v.ld + n] = vq[k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v.obs17[(14 + k) * v.ld + n] = e.y[10 + k];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v.prev_ang[k * v.ld + n] = e.prev_ang[k];
-    v.prev_shaping[n] = e.prev_shaping;
-    v.abs_sum[n] = e.abs_sum;
-    v.ep_return[n] = e.ep_return;
-    v.step_i[n] = e.i;
-    v.flags[n] = (uint8_t)e.flags;
-    v.episode[n] = e.episode;
-}
-
-// AUX attributes the single-env compatibility class exposes (quad.ang_vel, step_effort, w, accel,
-// accelerometer_read, mat_rot); evaluated at the new state like the reference's trailing drone_eq call.
-template <typename R, bool ROBUST = false>
-__device__ __noinline__ void store_aux(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
-                                       const StepOut<R> o, const Ctrl<R> c) {   // by VALUE: callers' structs stay in registers
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v.ang_vel[k * v.ld + n] = o.ang_vel[k];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        v.step_effort[k * v.ld + n] = o.effort[k]; v.w[k * v.ld + n] = o.w[k];
-        v.clipped_action[k * v.ld + n] = o.clipped[k]; v.fm[k * v.ld + n] = o.fm[k];
-    }
-    R dy[13], qn[4], r[9];
-    drone_rhs<R, ROBUST>(p, c, e.y, dy);
-    quat_normalize(&e.y[6], qn);
-    quat_rot_mat(qn, r);
-    R a[3] = {dy[1], dy[3], dy[5]};
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v.accel[k * v.ld + n] = a[k];
-    R g[3] = {a[0], a[1], a[2] - p.g};                                   // :371  R^T (accel + [0,0,-G])
-    v.acc_read[0 * v.ld + n] = r[0] * g[0] + r[3] * g[1] + r[6] * g[2];
-    v.acc_read[1 * v.ld + n] = r[1] * g[0] + r[4] * g[1] + r[7] * g[2];
-    v.acc_read[2 * v.ld + n] = r[2] * g[0] + r[5] * g[1] + r[8] * g[2];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) v.mat_rot[k * v.ld + n] = r[k];
-}
-
 // Sensor sub-pass for one env (QS_FLAG_SENSOR_NOISE).  mode 0: one step of the sensor model; mode 1: sensor.reset
 // from the true state (end of an episode's warm-up) and pass the true observation through; mode 2: pass-through only.
 template <typename R>
@@ -464,55 +272,6 @@ __device__ __noinline__ void reset_env(const DevParams<R>& p, const SimView<R>& 
     e.ep_return = R(0);
 }
 
-// thread-local episode statistics, reduced warp -> block -> device accumulators
-struct LocalStats {
-    float v[7];
-    __device__ __forceinline__ void clear() {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) v[k] = 0.f;
-    }
-};
-
-__device__ __forceinline__ void flush_stats(const LocalStats& ls, bool any_local, double* stats) {
-    __shared__ float s_acc[7];
-    __shared__ int s_any;
-    if (threadIdx.x == 0) s_any = 0;
-    if (threadIdx.x < 7) s_acc[threadIdx.x] = 0.f;
-    __syncthreads();
-    const unsigned full = 0xffffffffu;
-    if (__any_sync(full, any_local)) {
-#pragma unroll
-        for (int k = 0; k < 7; ++k) {
-            float x = ls.v[k];
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(full, x, d);
-            if ((threadIdx.x & 31) == 0 && x != 0.f) atomicAdd(&s_acc[k], x);
-        }
-        if ((threadIdx.x & 31) == 0) s_any = 1;
-    }
-    __syncthreads();
-    if (s_any && threadIdx.x < 7 && s_acc[threadIdx.x] != 0.f) atomicAdd(&stats[threadIdx.x], (double)s_acc[threadIdx.x]);
-}
-
-template <typename R>
-__device__ __forceinline__ void count_episode(LocalStats& ls, const DevParams<R>& p, const Env<R>& e, const StepOut<R>& o) {
-    ls.v[0] += (float)e.ep_return;
-    ls.v[1] += (float)(e.i - p.T);
-    ls.v[2] += 1.f;
-    ls.v[3] += o.solved ? 1.f : 0.f;
-    ls.v[4] += o.broken ? 1.f : 0.f;
-    ls.v[5] += o.timeout ? 1.f : 0.f;
-    ls.v[6] += (float)e.abs_sum;
-}
-
-template <typename R> struct StepIO {
-    const R* action;     // [4][N]
-    R* obs;              // [14][N] or NULL
-    R* reward;           // [N] or NULL
-    uint8_t* done;       // [N] or NULL
-    uint8_t* solved;     // [N] or NULL
-};
-
 // quad.step for every env of the shard: persistent CTAs, one thread per env, 256-env tiles.
 //
 // Staging.  Each tile's 22 SoA row segments (13 state + 3 prev_ang + prev_shaping + abs_sum + ep_return reals,
@@ -527,7 +286,6 @@ template <typename R> struct StepIO {
 // shared-memory queue which is drained after the block's main pass with one env per thread, i.e. full warps.
 // If more than kResetQueueCap envs of one block finish in the same step the surplus is reset in-lane.
 // QS_FLAG_ASYNC_RESET needs no sub-pass at all (see async_reset_prologue).
-constexpr int kResetQueueCap = 4096;
 constexpr int kTile = kBlock;
 constexpr int kStageRealRows = 19 + 4;      // 13 state, 3 prev_ang, prev_shaping, abs_sum, ep_return, 4 action
 
@@ -751,8 +509,6 @@ step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ 
     step_epilogue<R, INTEG, DIRECT>(p, v, io, ls, any_end, s_queue, &s_qn);
 }
 
-#include "step_warp.cuh"
-#include "step_pair.cuh"
 
 // quad.reset for the masked envs (det_state given or Philox-sampled).
 template <typename R, int INTEG, bool DIRECT, bool ROBUST = false>
@@ -778,17 +534,6 @@ reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ Sim
         v.solved[n] = o.solved;
     }
 }
-
-// K fused env steps per launch: state stays in registers, only actions/outputs stream through HBM.
-template <typename R> struct RolloutIO {
-    int32_t horizon;
-    int32_t action_source;
-    const R* actions;
-    R* obs_out;
-    R* action_out;
-    R* reward_out;
-    uint8_t* done_out;
-};
 
 template <typename R, int INTEG, bool DIRECT>
 __global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
@@ -851,27 +596,14 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);
 }
 
-#include "rollout_pair.cuh"
-
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-static int grid_for(const qs_sim* s, int64_t n) {
-    int64_t blocks = (n + kBlock - 1) / kBlock;
-    int64_t cap = (int64_t)s->sm_count * 8;           // grid-stride beyond 8 CTAs per SM ...
-    int64_t need = (n + kResetQueueCap - 1) / kResetQueueCap;   // ... but a block never owns more envs than its reset queue holds
-    if (cap < need) cap = need;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
-
 // QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 per-warp cp.async pipeline (one env per lane),
 // 3 per-warp pipeline with two envs per lane on the packed FP32 pipe.  Unset = 3 for every FP32 / RK4 handle: 47.6 vs 57 us
 // per step of 1,048,576 envs without the sensor model, 102 vs 108 us with it (packed sensor model, sensor_pair.cuh).
 static int default_step_loader(uint32_t flags) {
-    static int v = -2;
-    if (v == -2) { const char* e = getenv("QS_STEP_LOADER"); v = e ? atoi(e) : -1; }
+    static const int v = [] { const char* e = getenv("QS_STEP_LOADER"); return e ? atoi(e) : -1; }();   // thread-safe (C++11)
     if (v >= 0) return v;
     (void)flags;
     return 3;
@@ -879,39 +611,16 @@ static int default_step_loader(uint32_t flags) {
 
 // persistent grid of the staged step kernel: a few CTAs per SM, each looping over 256-env tiles
 static int grid_step(const qs_sim* s) {
-    static int ctas_per_sm = 0;
-    if (ctas_per_sm == 0) {
+    static const int ctas_per_sm = [] {
         const char* e = getenv("QS_STEP_CTAS_PER_SM");
-        ctas_per_sm = e ? atoi(e) : QS_MIN_CTAS;
-        if (ctas_per_sm < 1) ctas_per_sm = QS_MIN_CTAS;
-    }
+        const int v = e ? atoi(e) : QS_MIN_CTAS;
+        return v < 1 ? QS_MIN_CTAS : v;
+    }();
     const int64_t tiles = (s->slice_count + kTile - 1) / kTile;
     int64_t g = (int64_t)s->sm_count * ctas_per_sm;
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
 }
-
-#define QS_DISPATCH(s, FN, ...)                                                                          \
-    do {                                                                                                 \
-        const bool direct_ = ((s)->cfg.flags & QS_FLAG_DIRECT_CONTROL) != 0;                             \
-        const bool rk45_ = (s)->cfg.integrator == QS_RK45;                                               \
-        if ((s)->cfg.precision == QS_F32) {                                                              \
-            if (rk45_) { if (direct_) FN<float, 1, true>(__VA_ARGS__); else FN<float, 1, false>(__VA_ARGS__); } \
-            else       { if (direct_) FN<float, 0, true>(__VA_ARGS__); else FN<float, 0, false>(__VA_ARGS__); } \
-        } else {                                                                                         \
-            if (rk45_) { if (direct_) FN<double, 1, true>(__VA_ARGS__); else FN<double, 1, false>(__VA_ARGS__); } \
-            else       { if (direct_) FN<double, 0, true>(__VA_ARGS__); else FN<double, 0, false>(__VA_ARGS__); } \
-        }                                                                                                \
-    } while (0)
-
-template <typename R> static const DevParams<R>& params_of(const qs_sim* s);
-template <> const DevParams<float>& params_of<float>(const qs_sim* s) { return s->pf; }
-template <> const DevParams<double>& params_of<double>(const qs_sim* s) { return s->pd; }
-
-// the per-warp pipeline exists for the production configuration only: FP32, fixed-step RK4, no AUX rows, resets
-// either asynchronous or none (strict lock-step resets run T serial hover steps per env and keep the CTA-wide kernel)
-template <typename R, int INTEG> struct WarpKernelOk { static constexpr bool value = false; };
-template <> struct WarpKernelOk<float, 0> { static constexpr bool value = true; };
 
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
@@ -921,48 +630,12 @@ static void launch_step_v(qs_sim* s, const StepIO<R>& io, cudaStream_t st) {
             return;
         }
     }
-    if constexpr (WarpKernelOk<R, INTEG>::value) {
-        if (s->step_loader == 3 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
-            constexpr int threads = SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain;
-            constexpr int warps = threads / 32;
-            constexpr size_t smem = (size_t)(SENSOR ? pr::kRowsSensor : pr::kRowsPlain) * 256 * warps;
-            static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
-            const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
-            if (!(attr_set & attr_bit)) {
-                cudaFuncSetAttribute(step_kernel_pair<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set |= attr_bit;
-            }
-            const int64_t chunks = (s->slice_count + 63) / 64;
-            int64_t g = (int64_t)s->sm_count;
-            const int64_t need = (chunks + warps - 1) / warps;
-            if (g > need) g = need;
-            step_kernel_pair<DIRECT, SENSOR><<<(int)(g < 1 ? 1 : g), threads, smem, st>>>(s->pf, make_view<float>(s), io);
-            return;
-        }
-        if (s->step_loader >= 2 && !(s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET))) {
-            constexpr size_t smem = (size_t)(SENSOR ? wp::kRowsSensor : wp::kRowsPlain) * 128 * wp::kStagesW * (kBlock / 32);
-            static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
-            const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
-            if (!(attr_set & attr_bit)) {
-                cudaFuncSetAttribute(step_kernel_warp<DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                attr_set |= attr_bit;
-            }
-            const int64_t chunks = (s->slice_count + 31) / 32;
-            int64_t g = (int64_t)s->sm_count * wp::kMinCtas;
-            const int64_t need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
-            if (g > need) g = need;
-            step_kernel_warp<DIRECT, SENSOR><<<(int)(g < 1 ? 1 : g), kBlock, smem, st>>>(s->pf, make_view<float>(s), io);
-            return;
-        }
+    if constexpr (WarpKernelOk<R, INTEG>::value) {             // FP32 / RK4: the per-warp pipelines of step_fast.cu
+        if (launch_step_fast(s, io, DIRECT, SENSOR, st)) return;
     }
     if (s->step_loader >= 1) {
         constexpr size_t smem = kStages * sizeof(Stage<R>);
-        static uint64_t attr_set = 0;                   // one bit per device: function attributes are per context
-        const uint64_t attr_bit = 1ull << (s->cfg.device & 63);
-        if (!(attr_set & attr_bit)) {
-            cudaFuncSetAttribute(step_kernel_tma<R, INTEG, DIRECT, SENSOR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            attr_set |= attr_bit;
-        }
+        QS_SET_SMEM_ONCE(s, (step_kernel_tma<R, INTEG, DIRECT, SENSOR>), smem);
         step_kernel_tma<R, INTEG, DIRECT, SENSOR><<<grid_step(s), kBlock, smem, st>>>(params_of<R>(s), make_view<R>(s), io);
     } else {
         step_kernel_direct<R, INTEG, DIRECT, SENSOR><<<grid_step(s), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
@@ -989,21 +662,14 @@ static void launch_reset(qs_sim* s, const void* det, const uint8_t* mask, void* 
 
 template <typename R, int INTEG, bool DIRECT>
 static void launch_rollout(qs_sim* s, const qs_rollout_args* a, cudaStream_t st) {
+    if constexpr (WarpKernelOk<R, INTEG>::value) {             // FP32 / RK4: two envs per thread (rollout_fast.cu)
+        if (launch_rollout_fast(s, a, DIRECT, st)) return;
+    }
     RolloutIO<R> io{a->horizon, a->action_source, (const R*)a->actions, (R*)a->obs_out, (R*)a->action_out,
                     (R*)a->reward_out, a->done_out};
-    if constexpr (WarpKernelOk<R, INTEG>::value) {
-        // production mode (FP32, RK4; no strict in-lane resets; even shard; 8-byte aligned caller buffers): two envs per thread
-        const bool use_pair = s->step_loader == 3;     // qs_set_step_loader(h, 0..2) selects the one-env-per-thread kernel
-        const uintptr_t al = (uintptr_t)a->actions | (uintptr_t)a->obs_out | (uintptr_t)a->action_out | (uintptr_t)a->reward_out;
-        if (use_pair && !(s->cfg.flags & QS_FLAG_AUTO_RESET) && (s->N & 1) == 0 && (al & 7) == 0 && ((uintptr_t)a->done_out & 1) == 0) {
-            int64_t g = (s->N / 2 + QS_ROLLOUT_PAIR_THREADS - 1) / QS_ROLLOUT_PAIR_THREADS;
-            if (g > (int64_t)s->sm_count * 8) g = (int64_t)s->sm_count * 8;
-            rollout_pair_kernel<DIRECT><<<(int)g, QS_ROLLOUT_PAIR_THREADS, 0, st>>>(s->pf, make_view<float>(s), io);
-            return;
-        }
-    }
     rollout_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
+
 
 // ------------------------------------------------------------------------------------------------
 // C ABI
@@ -1103,15 +769,6 @@ extern "C" int qs_get_step_loader(qs_handle h) {
     if (h->cfg.flags & QS_FLAG_ROBUST) return 0;               // robust_control handles always run the generic kernel
     return (h->step_loader >= 2 && !warp_ok) ? 1 : h->step_loader;
 }
-
-// Launches go to the handle's device even when the calling thread's current device is another one (one process driving
-// several GPUs); like every CUDA library entry point that does this, the current device is left on the handle's.
-#define QS_USE_DEVICE(h)                                                               \
-    do {                                                                               \
-        int cur_ = -1;                                                                 \
-        QS_CUDA(cudaGetDevice(&cur_));                                                 \
-        if (cur_ != (h)->cfg.device) QS_CUDA(cudaSetDevice((h)->cfg.device));          \
-    } while (0)
 
 extern "C" int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_hist, void* act_hist,
                         void* stream) {
@@ -1227,6 +884,7 @@ extern "C" int qs_field_info(qs_handle h, qs_field f, qs_field_desc* out) {
 static int copy_field(qs_handle h, qs_field f, void* ext, bool to_ext, cudaStream_t st) {
     if (!h || !ext) return fail(QS_EINVAL, "qs_get/qs_set: NULL argument");
     if ((int)f < 0 || f >= QS_FIELD_COUNT_) return fail(QS_EINVAL, "qs_get/qs_set: bad field");
+    QS_USE_DEVICE(h);
     const size_t N = (size_t)h->N, ld = (size_t)h->ld;
     if (f == QS_FIELD_STATE) {
         const size_t rs = (size_t)h->rs;
@@ -1268,6 +926,7 @@ extern "C" int qs_stats_device(qs_handle h, double** dptr) {
 
 extern "C" int qs_stats_read(qs_handle h, qs_stats* out_host, int reset_after, void* stream) {
     if (!h || !out_host) return fail(QS_EINVAL, "qs_stats_read: NULL argument");
+    QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     QS_CUDA(cudaMemcpyAsync(out_host, h->stats, sizeof(qs_stats), cudaMemcpyDeviceToHost, st));
     if (reset_after) QS_CUDA(cudaMemsetAsync(h->stats, 0, sizeof(qs_stats), st));
@@ -1417,6 +1076,64 @@ extern "C" int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t
     return QS_OK;
 }
 
+// The reference's `sensor` class (environment/quadrotor_env.py:579-724), ONE METHOD per launch, for n independent sensors with
+// caller-provided draws (see qs_sensor_call in include/quadsim.h).
+template <typename R>
+__global__ void k_sensor_call(const __grid_constant__ DevParams<R> p, int64_t n, int method, R* st, const R* qstate, const R* acc_read,
+                              const R* mat_rot, const R* f_m, const R* z, R* out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    R s[kSensorStateDim], y[13], ar[3], rot[9], zz[32], o[16];
+    for (int k = 0; k < kSensorStateDim; ++k) s[k] = st[k * n + i];
+    for (int k = 0; k < 13; ++k) y[k] = qstate ? qstate[k * n + i] : R(0);
+    for (int k = 0; k < 3; ++k) ar[k] = acc_read ? acc_read[k * n + i] : R(0);
+    for (int k = 0; k < 9; ++k) rot[k] = mat_rot ? mat_rot[k * n + i] : R(0);
+    const R fm = f_m ? f_m[i] : R(0);
+    static const int kZ[8] = {3, 3, 3, 6, 6, 9, 3, 27}, kO[8] = {0, 3, 3, 6, 13, 9, 4, 14};
+    for (int k = 0; k < kZ[method]; ++k) zz[k] = z[k * n + i];
+    switch (method) {
+    case QS_SENSOR_RESET:                                             // sensor.reset :630-640 + bias_reset :600-608; z = U(0,1) draws
+        s[0] = R(0); s[1] = R(0);
+        s[2] = (zz[0] - R(0.5)) * R(2) * p.s_accel_drift;             // :602
+        s[3] = (zz[1] - R(0.5)) * R(2) * p.s_gyro_drift;              // :604   (zz[2]: m_b_d :606, never read by the class)
+        s[4] = y[1]; s[5] = y[3]; s[6] = y[5]; s[7] = y[0]; s[8] = y[2]; s[9] = y[4];
+        s[10] = y[6]; s[11] = y[7]; s[12] = y[8]; s[13] = y[9];
+        s[17] = R(0); s[18] = R(0); s[19] = R(0);                     // self.R is NOT touched by sensor.reset (only __init__ sets it)
+        break;
+    case QS_SENSOR_ACCEL: sensor_accel(p, s, ar, zz, o); break;
+    case QS_SENSOR_GYRO: sensor_gyro(p, s, y, zz, o); break;
+    case QS_SENSOR_GPS: sensor_gps(p, y, zz, o, o + 3); break;
+    case QS_SENSOR_TRIAD: sensor_triad(p, s, ar, rot, fm, zz, o + 4); rot_to_quat_scipy(o + 4, o); break;
+    case QS_SENSOR_ACCEL_INT:
+        sensor_accel_int(p, s, ar, rot, fm, zz, o);
+        for (int k = 0; k < 3; ++k) { o[3 + k] = s[4 + k]; o[6 + k] = s[7 + k]; }
+        break;
+    case QS_SENSOR_GYRO_INT: sensor_gyro_int(p, s, y, zz, o); break;
+    default: sensor_step(p, zz, y, ar, rot, fm, s, o); break;        // QS_SENSOR_STEP
+    }
+    for (int k = 0; k < kSensorStateDim; ++k) st[k * n + i] = s[k];
+    for (int k = 0; k < kO[method]; ++k) out[k * n + i] = o[k];
+}
+
+extern "C" int qs_sensor_call(int precision, const qs_params* p, double t_step, int64_t n, int method, void* sensor_state,
+                              const void* quad_state, const void* acc_read, const void* mat_rot, const void* f_m, const void* z,
+                              void* out, void* stream) {
+    int rc = check_util(precision, n); if (rc) return rc;
+    if (method < QS_SENSOR_RESET || method > QS_SENSOR_STEP) return fail(QS_EINVAL, "qs_sensor_call: bad method");
+    if (!sensor_state || !z || (method != QS_SENSOR_RESET && !out)) return fail(QS_EINVAL, "qs_sensor_call: NULL argument");
+    if (!(t_step > 0)) return fail(QS_EINVAL, "qs_sensor_call: t_step must be > 0");
+    qs_config c = cfg_from_params(p, 1);
+    c.t_step = t_step;
+    if (precision == QS_F32)
+        k_sensor_call<float><<<QS_UTIL_GRID(n)>>>(make_params<float>(c), n, method, (float*)sensor_state, (const float*)quad_state,
+                                                  (const float*)acc_read, (const float*)mat_rot, (const float*)f_m, (const float*)z, (float*)out);
+    else
+        k_sensor_call<double><<<QS_UTIL_GRID(n)>>>(make_params<double>(c), n, method, (double*)sensor_state, (const double*)quad_state,
+                                                   (const double*)acc_read, (const double*)mat_rot, (const double*)f_m, (const double*)z, (double*)out);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
 // FP32 FFMA peak probe: 8 independent dependent-chains per thread.
 __global__ void k_fp32_peak(int iters, float* sink) {
     float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f,
@@ -1451,6 +1168,3 @@ extern "C" int qs_fp32_peak_probe(int blocks, int threads, int iters, float* ms_
     return QS_OK;
 }
 
-#include "controller_rollout.cuh"
-#include "ppo_kernels.cuh"
-#include "actor_rollout.cuh"

@@ -120,74 +120,129 @@ __device__ __forceinline__ void sensor_reset(const DevParams<R>& p, uint64_t see
     s[17] = R(0); s[18] = R(0); s[19] = R(0);                             // acceleration_t0 :633
 }
 
-// One env step of the sensor model.  y = TRUE state after the step, acc_read = quad.accelerometer_read (:371),
-// rot = quad.mat_rot (:315), f_m = F/M (induced acceleration of the rotors, :658).  Updates s, writes obs14.
+// ---- the methods of the class, one device function each.  s = the 20-row sensor state; z = the standard normals the
+// reference's np.random.normal calls of that method consume, in call order.  The same functions serve the fused per-step
+// model (sensor_step, Philox normals) and the per-method entry point qs_sensor_call (caller-provided normals), which is what
+// pins the arithmetic to the reference class itself (tests/golden/sensor_vectors.npz).
+
+// sensor.accel :611-620 — read_accel_body + N(a_b_accel, a_std)
+template <typename R>
+__device__ __forceinline__ void sensor_accel(const DevParams<R>& p, R s[kSensorStateDim], const R acc_read[3], const R z[3], R out[3]) {
+    s[0] += s[2] * p.dt;                                                                   // :613
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = acc_read[k] + (s[0] + p.s_accel_std * z[k]);      // :615-619
+}
+
+// sensor.gyro :622-628 — read_gyro + N(g_b, g_std)
+template <typename R>
+__device__ __forceinline__ void sensor_gyro(const DevParams<R>& p, R s[kSensorStateDim], const R y[13], const R z[3], R out[3]) {
+    s[1] += s[3] * p.dt;                                                                   // :624
+#pragma unroll
+    for (int k = 0; k < 3; ++k) out[k] = (s[1] + p.s_gyro_std * z[k]) + y[10 + k];         // :626-628
+}
+
+// sensor.gps :642-647 — z[0..2] position errors, z[3..5] velocity errors
+template <typename R>
+__device__ __forceinline__ void sensor_gps(const DevParams<R>& p, const R y[13], const R z[6], R pos[3], R vel[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pos[k] = p.s_gps_p * z[k] + y[2 * k];
+        vel[k] = p.s_gps_v * z[3 + k] + y[2 * k + 1];
+    }
+}
+
+// sensor.triad :649-697 — z[0..2] feed its accel() call, z[3..5] the magnetometer noise.  Reads the third column of the
+// previous self.R (s[14..16], :658), writes the new one, returns R = tb @ ti^T (row-major).
+template <typename R>
+__device__ __forceinline__ void sensor_triad(const DevParams<R>& p, R s[kSensorStateDim], const R acc_read[3], const R rot[9], R f_m,
+                                             const R z[6], R Rm[9]) {
+    const R ind[3] = {p.g * s[14], p.g * s[15], f_m + p.g * s[16]};                        // :658  f_in/M - R@[0,0,-G]
+    R gb[3];
+    sensor_accel(p, s, acc_read, z, gb);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) gb[k] -= ind[k];                                           // :659
+    const R mi[3] = {p.s_mag[0] + p.s_mag_std * z[3], p.s_mag[1] + p.s_mag_std * z[4], p.s_mag[2] + p.s_mag_std * z[5]};
+    const R mb[3] = {rot[0] * mi[0] + rot[3] * mi[1] + rot[6] * mi[2], rot[1] * mi[0] + rot[4] * mi[1] + rot[7] * mi[2],
+                     rot[2] * mi[0] + rot[5] * mi[1] + rot[8] * mi[2]};                   // :662  mat_rot.T @ ...
+    triad(p, gb, mb, Rm);
+    s[14] = Rm[2]; s[15] = Rm[5]; s[16] = Rm[8];                                           // self.R = tb @ ti.T  :693
+}
+
+// q of sensor.triad's return value (:695-696): Rotation.from_matrix(R.T).as_quat() re-ordered scalar-first.  SciPy's
+// conversion of an orthogonal matrix (spatial/transform/_rotation: Markley's method — pick the largest of the diagonal
+// entries and the trace, build the quaternion from that row, normalise); m = R^T row-major.
+template <typename R>
+__device__ __forceinline__ void rot_to_quat_scipy(const R Rm[9], R q[4]) {
+    const R m00 = Rm[0], m01 = Rm[3], m02 = Rm[6], m10 = Rm[1], m11 = Rm[4], m12 = Rm[7], m20 = Rm[2], m21 = Rm[5], m22 = Rm[8];
+    const R tr = m00 + m11 + m22;
+    const R dec[4] = {m00, m11, m22, tr};
+    int choice = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) choice = (dec[k] > dec[choice]) ? k : choice;              // argmax: first maximum
+    R x, y, zq, w;
+    if (choice == 0)      { x = R(1) - tr + R(2) * m00; y = m10 + m01; zq = m20 + m02; w = m21 - m12; }
+    else if (choice == 1) { x = m10 + m01; y = R(1) - tr + R(2) * m11; zq = m21 + m12; w = m02 - m20; }
+    else if (choice == 2) { x = m20 + m02; y = m21 + m12; zq = R(1) - tr + R(2) * m22; w = m10 - m01; }
+    else                  { x = m21 - m12; y = m02 - m20; zq = m10 - m01; w = R(1) + tr; }
+    const R inv = R(1) / M_<R>::sqrt(x * x + y * y + zq * zq + w * w);
+    q[0] = w * inv; q[1] = x * inv; q[2] = y * inv; q[3] = zq * inv;
+}
+
+// sensor.accel_int :700-715 — z[0..2] its own accel() call, z[3..8] the triad() call.  out: acceleration, velocity, position
+template <typename R>
+__device__ __forceinline__ void sensor_accel_int(const DevParams<R>& p, R s[kSensorStateDim], const R acc_read[3], const R rot[9],
+                                                 R f_m, const R z[9], R a_in[3]) {
+    R acc1[3], Rm[9];
+    sensor_accel(p, s, acc_read, z, acc1);                                                 // :702
+    sensor_triad(p, s, acc_read, rot, f_m, z + 3, Rm);                                     // :703
+    a_in[0] = Rm[0] * acc1[0] + Rm[3] * acc1[1] + Rm[6] * acc1[2];                         // :705  R.T @ accel_body + [0,0,G]
+    a_in[1] = Rm[1] * acc1[0] + Rm[4] * acc1[1] + Rm[7] * acc1[2];
+    a_in[2] = Rm[2] * acc1[0] + Rm[5] * acc1[1] + Rm[8] * acc1[2] + p.g;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        s[4 + k] += a_in[k] * p.dt;                                                        // velocity :707
+        s[7 + k] += s[4 + k] * p.dt;                                                       // position :708
+        s[17 + k] = a_in[k];                                                               // :710
+    }
+}
+
+// sensor.gyro_int :717-724 — returns q BEFORE normalisation (the reference returns the array it updated in place)
+template <typename R>
+__device__ __forceinline__ void sensor_gyro_int(const DevParams<R>& p, R s[kSensorStateDim], const R y[13], const R z[3], R qg[4]) {
+    R w1[3], dq[4];
+    sensor_gyro(p, s, y, z, w1);                                                           // :718
+    deriv_quat(w1, &s[10], dq);                                                            // :720
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qg[k] = s[10 + k] + dq[k] * p.dt;                          // :721-722
+    quat_normalize(qg, &s[10]);                                                            // :723
+}
+
+// One env step of the sensor model in the canonical call order.  y = TRUE state after the step, acc_read =
+// quad.accelerometer_read (:371), rot = quad.mat_rot (:315), f_m = F/M (induced acceleration of the rotors, :658).
+// Updates s, writes obs14 (rl_worker.py:171-173 / math_trajectory.py:61-83).
 template <typename R>
 __device__ __forceinline__ void sensor_step(const DevParams<R>& p, const R z[32], const R y[13], const R acc_read[3],
                                             const R rot[9], R f_m, R s[kSensorStateDim], R obs[14]) {
-    const R dt = p.dt;
-    // ---- accel_int :700-715
-    s[0] += s[2] * dt;                                                                     // accel() :613
-    const R acc1[3] = {acc_read[0] + s[0] + p.s_accel_std * z[0], acc_read[1] + s[0] + p.s_accel_std * z[1],
-                       acc_read[2] + s[0] + p.s_accel_std * z[2]};
-    R Rm[9];
-    {   // triad()
-        s[0] += s[2] * dt;
-        const R ind[3] = {p.g * s[14], p.g * s[15], f_m + p.g * s[16]};                    // :658  f_in/M - R@[0,0,-G]
-        const R gb[3] = {acc_read[0] + s[0] + p.s_accel_std * z[3] - ind[0], acc_read[1] + s[0] + p.s_accel_std * z[4] - ind[1],
-                         acc_read[2] + s[0] + p.s_accel_std * z[5] - ind[2]};
-        const R mi[3] = {p.s_mag[0] + p.s_mag_std * z[6], p.s_mag[1] + p.s_mag_std * z[7], p.s_mag[2] + p.s_mag_std * z[8]};
-        const R mb[3] = {rot[0] * mi[0] + rot[3] * mi[1] + rot[6] * mi[2], rot[1] * mi[0] + rot[4] * mi[1] + rot[7] * mi[2],
-                         rot[2] * mi[0] + rot[5] * mi[1] + rot[8] * mi[2]};               // :662  mat_rot.T @ ...
-        triad(p, gb, mb, Rm);
-    }
-    const R a_in[3] = {Rm[0] * acc1[0] + Rm[3] * acc1[1] + Rm[6] * acc1[2], Rm[1] * acc1[0] + Rm[4] * acc1[1] + Rm[7] * acc1[2],
-                       Rm[2] * acc1[0] + Rm[5] * acc1[1] + Rm[8] * acc1[2] + p.g};        // :705  R.T @ accel_body + [0,0,G]
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        s[4 + k] += a_in[k] * dt;                                                          // velocity :707
-        s[7 + k] += s[4 + k] * dt;                                                         // position :708
-        s[17 + k] = a_in[k];
-    }
-    // ---- gyro_int :717-724
-    s[1] += s[3] * dt;                                                                     // gyro() :624
-    const R w1[3] = {y[10] + s[1] + p.s_gyro_std * z[9], y[11] + s[1] + p.s_gyro_std * z[10], y[12] + s[1] + p.s_gyro_std * z[11]};
-    R dq[4], qg[4];
-    deriv_quat(w1, &s[10], dq);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) qg[k] = s[10 + k] + dq[k] * dt;                            // :721-722 (returned un-normalised)
-    quat_normalize(qg, &s[10]);                                                            // :723
-    // ---- gyro :622-628
-    s[1] += s[3] * dt;
-    const R w2[3] = {y[10] + s[1] + p.s_gyro_std * z[12], y[11] + s[1] + p.s_gyro_std * z[13], y[12] + s[1] + p.s_gyro_std * z[14]};
-    R qv[4];
+    R a_in[3], qg[4], w2[3], qv[4];
+    sensor_accel_int(p, s, acc_read, rot, f_m, z, a_in);                                   // z[0..8]
+    sensor_gyro_int(p, s, y, z + 9, qg);                                                   // z[9..11]
+    sensor_gyro(p, s, y, z + 12, w2);                                                      // z[12..14]
     deriv_quat(w2, qg, qv);                                                                // rl_worker.py:168
-    // ---- gps :642-647 consumes z[15..20].  Its readings enter only through the optional complementary blend of the landing
-    //      stack (visual_landing/math_trajectory.py:71-77, GPS_P per cent; off by default like the script's GPS = False),
-    //      which also writes the blended estimate back into the dead-reckoning integrators.
+    // gps :642-647 consumes z[15..20].  Its readings enter only through the optional complementary blend of the landing
+    // stack (visual_landing/math_trajectory.py:71-77, GPS_P per cent; off by default like the script's GPS = False),
+    // which also writes the blended estimate back into the dead-reckoning integrators.
     if (p.s_gps_blend > R(0)) {
+        R pos_gps[3], vel_gps[3];
+        sensor_gps(p, y, z + 15, pos_gps, vel_gps);
         const R wg = p.s_gps_blend, wa = R(100) - p.s_gps_blend;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-            const R pos_gps = y[2 * k] + p.s_gps_p * z[15 + k];
-            const R vel_gps = y[2 * k + 1] + p.s_gps_v * z[18 + k];
-            s[7 + k] = (wa * s[7 + k] + wg * pos_gps) / R(100);
-            s[4 + k] = (wa * s[4 + k] + wg * vel_gps) / R(100);
+            s[7 + k] = (wa * s[7 + k] + wg * pos_gps[k]) / R(100);
+            s[4 + k] = (wa * s[4 + k] + wg * vel_gps[k]) / R(100);
         }
     }
-    // ---- triad :649-697 (updates self.R for the next step)
-    {
-        s[0] += s[2] * dt;
-        const R ind[3] = {p.g * Rm[2], p.g * Rm[5], f_m + p.g * Rm[8]};
-        const R gb[3] = {acc_read[0] + s[0] + p.s_accel_std * z[21] - ind[0], acc_read[1] + s[0] + p.s_accel_std * z[22] - ind[1],
-                         acc_read[2] + s[0] + p.s_accel_std * z[23] - ind[2]};
-        const R mi[3] = {p.s_mag[0] + p.s_mag_std * z[24], p.s_mag[1] + p.s_mag_std * z[25], p.s_mag[2] + p.s_mag_std * z[26]};
-        const R mb[3] = {rot[0] * mi[0] + rot[3] * mi[1] + rot[6] * mi[2], rot[1] * mi[0] + rot[4] * mi[1] + rot[7] * mi[2],
-                         rot[2] * mi[0] + rot[5] * mi[1] + rot[8] * mi[2]};
-        R R2[9];
-        triad(p, gb, mb, R2);
-        s[14] = R2[2]; s[15] = R2[5]; s[16] = R2[8];
-    }
+    R R2[9];
+    sensor_triad(p, s, acc_read, rot, f_m, z + 21, R2);                                    // z[21..26]; updates self.R for the next step
     obs[0] = s[7]; obs[1] = s[4]; obs[2] = s[8]; obs[3] = s[5]; obs[4] = s[9]; obs[5] = s[6];   // rl_worker.py:171-173
 #pragma unroll
     for (int k = 0; k < 4; ++k) { obs[6 + k] = qg[k]; obs[10 + k] = qv[k]; }

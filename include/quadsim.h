@@ -326,6 +326,37 @@ int qs_f2w(int precision, const qs_params* p, int64_t n, int clipped, const void
 int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, uint32_t block, uint32_t stream_id,
                   uint32_t* out /*[4][n]*/, void* stream);
 
+/* The reference's `sensor` class (environment/quadrotor_env.py:579-724), one METHOD per call, for n independent sensors whose random
+ * draws are supplied by the caller: z [k][n] holds the STANDARD-normal draws the method's np.random.normal calls consume, in call
+ * order (QS_SENSOR_RESET: the three U(0,1) draws of bias_reset :600-608).  This is the entry point behind the single-env drop-in
+ * `sensor` (which draws from the global NumPy stream in the reference's order, so a seeded script sees the reference's readings) and
+ * what pins the in-kernel sensor model (QS_FLAG_SENSOR_NOISE: same device functions, Philox draws) to the reference class.
+ *   sensor_state [QS_SENSOR_STATE_DIM][n] in/out: 0 a_b_accel, 1 g_b, 2 a_b_d, 3 g_b_d, 4..6 velocity_t0, 7..9 position_t0,
+ *                10..13 quaternion_t0, 14..16 third column of self.R (the part :658 reads), 17..19 acceleration_t0
+ *   quad_state [13][n] = quad.state, acc_read [3][n] = quad.accelerometer_read (:371), mat_rot [9][n] = quad.mat_rot row-major (:315),
+ *   f_m [n] = quad.f_in[2] / M (:658); each may be NULL when the method does not read it.
+ *   method            z rows  out rows
+ *   QS_SENSOR_RESET     3       0    sensor.reset :630-640 (+ bias_reset); reads quad_state
+ *   QS_SENSOR_ACCEL     3       3    sensor.accel :611-620 -> accelerometer reading
+ *   QS_SENSOR_GYRO      3       3    sensor.gyro :622-628 -> gyro reading
+ *   QS_SENSOR_GPS       6       6    sensor.gps :642-647 -> position(3), velocity(3)
+ *   QS_SENSOR_TRIAD     6      13    sensor.triad :649-697 -> q scalar-first (4), R row-major (9); z = accel(3), magnetometer(3)
+ *   QS_SENSOR_ACCEL_INT 9       9    sensor.accel_int :700-715 -> acceleration(3), velocity(3), position(3); z = accel(3), triad(6)
+ *   QS_SENSOR_GYRO_INT  3       4    sensor.gyro_int :717-724 -> q before normalisation
+ *   QS_SENSOR_STEP     27      14    accel_int, gyro_int, gyro, gps, triad in the order of every caller (visual_landing/rl_worker.py:
+ *                                    164-175, math_trajectory.py:61-83 incl. the GPS blend p->gps_blend) -> sensed observation */
+#define QS_SENSOR_RESET 0
+#define QS_SENSOR_ACCEL 1
+#define QS_SENSOR_GYRO 2
+#define QS_SENSOR_GPS 3
+#define QS_SENSOR_TRIAD 4
+#define QS_SENSOR_ACCEL_INT 5
+#define QS_SENSOR_GYRO_INT 6
+#define QS_SENSOR_STEP 7
+int qs_sensor_call(int precision, const qs_params* p, double t_step, int64_t n, int method, void* sensor_state,
+                   const void* quad_state, const void* acc_read, const void* mat_rot, const void* f_m, const void* z, void* out,
+                   void* stream);
+
 /* tcgen05 self-test: D[128][N] = A[128][K] * B[N][K]^T with BF16 operands / FP32 accumulation through the same
  * shared-memory operand layout, descriptors and TMEM read-back the fused actor rollout uses (row-major fp32 in/out). */
 int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, void* stream);
