@@ -112,7 +112,7 @@ QS_CTRL_LQR, QS_CTRL_PID = 0, 1
 (QS_SENSOR_RESET, QS_SENSOR_ACCEL, QS_SENSOR_GYRO, QS_SENSOR_GPS, QS_SENSOR_TRIAD, QS_SENSOR_ACCEL_INT, QS_SENSOR_GYRO_INT,
  QS_SENSOR_STEP) = range(8)
 SENSOR_Z_ROWS = (3, 3, 3, 6, 6, 9, 3, 27)        # rows of z / out per method (include/quadsim.h, qs_sensor_call)
-SENSOR_OUT_ROWS = (0, 3, 3, 6, 13, 9, 4, 14)
+SENSOR_OUT_ROWS = (0, 3, 3, 6, 13, 18, 4, 14)
 QS_CTRL_STATE_DIM = 22
 
 

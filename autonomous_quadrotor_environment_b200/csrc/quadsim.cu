@@ -1083,13 +1083,13 @@ __global__ void k_sensor_call(const __grid_constant__ DevParams<R> p, int64_t n,
                               const R* mat_rot, const R* f_m, const R* z, R* out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    R s[kSensorStateDim], y[13], ar[3], rot[9], zz[32], o[16];
+    R s[kSensorStateDim], y[13], ar[3], rot[9], zz[32], o[18];
     for (int k = 0; k < kSensorStateDim; ++k) s[k] = st[k * n + i];
     for (int k = 0; k < 13; ++k) y[k] = qstate ? qstate[k * n + i] : R(0);
     for (int k = 0; k < 3; ++k) ar[k] = acc_read ? acc_read[k * n + i] : R(0);
     for (int k = 0; k < 9; ++k) rot[k] = mat_rot ? mat_rot[k * n + i] : R(0);
     const R fm = f_m ? f_m[i] : R(0);
-    static const int kZ[8] = {3, 3, 3, 6, 6, 9, 3, 27}, kO[8] = {0, 3, 3, 6, 13, 9, 4, 14};
+    static const int kZ[8] = {3, 3, 3, 6, 6, 9, 3, 27}, kO[8] = {0, 3, 3, 6, 13, 18, 4, 14};
     for (int k = 0; k < kZ[method]; ++k) zz[k] = z[k * n + i];
     switch (method) {
     case QS_SENSOR_RESET:                                             // sensor.reset :630-640 + bias_reset :600-608; z = U(0,1) draws
@@ -1105,7 +1105,7 @@ __global__ void k_sensor_call(const __grid_constant__ DevParams<R> p, int64_t n,
     case QS_SENSOR_GPS: sensor_gps(p, y, zz, o, o + 3); break;
     case QS_SENSOR_TRIAD: sensor_triad(p, s, ar, rot, fm, zz, o + 4); rot_to_quat_scipy(o + 4, o); break;
     case QS_SENSOR_ACCEL_INT:
-        sensor_accel_int(p, s, ar, rot, fm, zz, o);
+        sensor_accel_int(p, s, ar, rot, fm, zz, o, o + 9);
         for (int k = 0; k < 3; ++k) { o[3 + k] = s[4 + k]; o[6 + k] = s[7 + k]; }
         break;
     case QS_SENSOR_GYRO_INT: sensor_gyro_int(p, s, y, zz, o); break;

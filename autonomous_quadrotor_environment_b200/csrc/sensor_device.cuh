@@ -191,7 +191,7 @@ __device__ __forceinline__ void rot_to_quat_scipy(const R Rm[9], R q[4]) {
 // sensor.accel_int :700-715 — z[0..2] its own accel() call, z[3..8] the triad() call.  out: acceleration, velocity, position
 template <typename R>
 __device__ __forceinline__ void sensor_accel_int(const DevParams<R>& p, R s[kSensorStateDim], const R acc_read[3], const R rot[9],
-                                                 R f_m, const R z[9], R a_in[3]) {
+                                                 R f_m, const R z[9], R a_in[3], R* R_out = nullptr) {
     R acc1[3], Rm[9];
     sensor_accel(p, s, acc_read, z, acc1);                                                 // :702
     sensor_triad(p, s, acc_read, rot, f_m, z + 3, Rm);                                     // :703
@@ -203,6 +203,10 @@ __device__ __forceinline__ void sensor_accel_int(const DevParams<R>& p, R s[kSen
         s[4 + k] += a_in[k] * p.dt;                                                        // velocity :707
         s[7 + k] += s[4 + k] * p.dt;                                                       // position :708
         s[17 + k] = a_in[k];                                                               // :710
+    }
+    if (R_out) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) R_out[k] = Rm[k];                                      // self.R after the call (set by triad)
     }
 }
 

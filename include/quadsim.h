@@ -341,7 +341,8 @@ int qs_philox_raw(uint64_t seed, int64_t env_id0, int64_t n, uint32_t episode, u
  *   QS_SENSOR_GYRO      3       3    sensor.gyro :622-628 -> gyro reading
  *   QS_SENSOR_GPS       6       6    sensor.gps :642-647 -> position(3), velocity(3)
  *   QS_SENSOR_TRIAD     6      13    sensor.triad :649-697 -> q scalar-first (4), R row-major (9); z = accel(3), magnetometer(3)
- *   QS_SENSOR_ACCEL_INT 9       9    sensor.accel_int :700-715 -> acceleration(3), velocity(3), position(3); z = accel(3), triad(6)
+ *   QS_SENSOR_ACCEL_INT 9      18    sensor.accel_int :700-715 -> acceleration(3), velocity(3), position(3), self.R row-major (9);
+ *                                    z = accel(3), triad(6)
  *   QS_SENSOR_GYRO_INT  3       4    sensor.gyro_int :717-724 -> q before normalisation
  *   QS_SENSOR_STEP     27      14    accel_int, gyro_int, gyro, gps, triad in the order of every caller (visual_landing/rl_worker.py:
  *                                    164-175, math_trajectory.py:61-83 incl. the GPS blend p->gps_blend) -> sensed observation */

@@ -773,7 +773,36 @@ def _triad(grav_body, mag_body):
     return tb @ _triad_inertial().T
 
 
+def rot_to_quat(R):
+    """q returned by sensor.triad (:695-696): Rotation.from_matrix(R.T).as_quat() re-ordered scalar-first.  Restatement of
+    SciPy's conversion for an orthogonal matrix (scipy/spatial/transform, `from_matrix`: Markley's method — the largest of
+    the three diagonal entries and the trace selects the row the quaternion is built from, then normalise).  R (N,3,3)."""
+    m = np.swapaxes(np.asarray(R, dtype=np.float64), 1, 2)
+    tr = m[:, 0, 0] + m[:, 1, 1] + m[:, 2, 2]
+    choice = np.argmax(np.stack([m[:, 0, 0], m[:, 1, 1], m[:, 2, 2], tr], axis=1), axis=1)
+    q = np.zeros((m.shape[0], 4))                                       # scalar-last like SciPy, re-ordered below
+    for i in range(3):
+        j, k = (i + 1) % 3, (i + 2) % 3
+        c = choice == i
+        q[c, i] = 1 - tr[c] + 2 * m[c, i, i]
+        q[c, j] = m[c, j, i] + m[c, i, j]
+        q[c, k] = m[c, k, i] + m[c, i, k]
+        q[c, 3] = m[c, k, j] - m[c, j, k]
+    c = choice == 3
+    q[c, 0] = m[c, 2, 1] - m[c, 1, 2]
+    q[c, 1] = m[c, 0, 2] - m[c, 2, 0]
+    q[c, 2] = m[c, 1, 0] - m[c, 0, 1]
+    q[c, 3] = 1 + tr[c]
+    q = q / np.linalg.norm(q, axis=1, keepdims=True)
+    return np.concatenate([q[:, 3:4], q[:, 0:3]], axis=1)
+
+
 class SensorOracle:
+    """The reference's `sensor` class (:579-724) for N envs, one method per reference method; every random draw is supplied
+    by the caller as STANDARD normals z (the reference's np.random.normal(loc, scale) = loc + scale * z), so that the class
+    can be fed the very stream the reference consumed (tests/golden/sensor_vectors.npz) or the Philox stream of the kernels
+    (sensor_normals).  Methods update the state of the envs in `mask` only."""
+
     def __init__(self, n_envs, t_step, accel_std=0.1, accel_bias_drift=0.0005, gyro_std=0.035, gyro_bias_drift=0.00015,
                  magnet_std=15, gps_std_p=1.71, gps_std_v=0.5, gps_blend=0.0):
         self.N, self.dt = n_envs, t_step
@@ -782,56 +811,92 @@ class SensorOracle:
         self.a_b = np.zeros(n_envs); self.g_b = np.zeros(n_envs)
         self.a_b_d = np.zeros(n_envs); self.g_b_d = np.zeros(n_envs)
         self.vel = np.zeros((n_envs, 3)); self.pos = np.zeros((n_envs, 3)); self.quat = np.zeros((n_envs, 4))
-        self.Rc2 = np.tile(np.array([0.0, 0.0, 1.0]), (n_envs, 1))
+        self.acc0 = np.zeros((n_envs, 3))
+        self.R = np.tile(np.eye(3), (n_envs, 1, 1))                                   # :597
+
+    def _m(self, mask):
+        return np.ones(self.N, bool) if mask is None else np.asarray(mask, bool)
+
+    @property
+    def Rc2(self):
+        return self.R[:, :, 2]
+
+    def reset_u(self, u, y, mask=None, reset_R=False):
+        """sensor.reset :630-640 + bias_reset :600-608 with the U(0,1) draws u (N,>=2) (third draw: m_b_d, dead).  reset_R: the
+        kernels also restore self.R = I (the reference only does so in __init__; documented deviation)."""
+        m = self._m(mask)
+        self.a_b[m] = 0; self.g_b[m] = 0
+        self.a_b_d[m] = (u[m, 0] - 0.5) * 2 * self.a_drift                              # :602
+        self.g_b_d[m] = (u[m, 1] - 0.5) * 2 * self.g_drift                              # :604
+        self.vel[m] = y[m][:, 1:6:2]; self.pos[m] = y[m][:, 0:5:2]; self.quat[m] = y[m][:, 6:10]
+        self.acc0[m] = 0
+        if reset_R:
+            self.R[m] = np.eye(3)
 
     def reset(self, seed, env_id, episode, y, mask=None):
-        """sensor.reset :630-640 + bias_reset :600-608 for the masked envs."""
-        m = np.ones(self.N, bool) if mask is None else np.asarray(mask, bool)
-        u = u32_to_unit(philox_block(seed, np.asarray(env_id)[m], np.asarray(episode)[m], 0xFFFFFFF0, STREAM_SENSOR))
-        self.a_b[m] = 0; self.g_b[m] = 0
-        self.a_b_d[m] = (u[:, 0] - 0.5) * 2 * self.a_drift
-        self.g_b_d[m] = (u[:, 1] - 0.5) * 2 * self.g_drift
-        self.vel[m] = y[m][:, 1:6:2]; self.pos[m] = y[m][:, 0:5:2]; self.quat[m] = y[m][:, 6:10]
-        self.Rc2[m] = np.array([0.0, 0.0, 1.0])
+        """sensor.reset as the kernels do it: bias draws from the env's Philox stream, self.R = I."""
+        m = self._m(mask)
+        u = np.zeros((self.N, 4))
+        u[m] = u32_to_unit(philox_block(seed, np.asarray(env_id)[m], np.asarray(episode)[m], 0xFFFFFFF0, STREAM_SENSOR))
+        self.reset_u(u, y, m, reset_R=True)
+
+    def accel(self, z, acc_read, mask=None):                                            # :611-620
+        m = self._m(mask)
+        self.a_b = np.where(m, self.a_b + self.a_b_d * self.dt, self.a_b)
+        return acc_read + (self.a_b[:, None] + self.a_std * z)
+
+    def gyro(self, z, y, mask=None):                                                    # :622-628
+        m = self._m(mask)
+        self.g_b = np.where(m, self.g_b + self.g_b_d * self.dt, self.g_b)
+        return (self.g_b[:, None] + self.g_std * z) + y[:, 10:13]
+
+    def gps(self, z, y):                                                                # :642-647
+        return (self.gps_p * z[:, 0:3]) + y[:, 0:5:2], (self.gps_v * z[:, 3:6]) + y[:, 1:6:2]
+
+    def triad(self, z, acc_read, rot, f_m, mask=None):                                  # :649-697
+        m = self._m(mask)
+        ind = -(self.R @ np.array([0.0, 0.0, -G]))                                      # :658  f_in/M - R@[0,0,-G]
+        ind[:, 2] += f_m
+        gb = self.accel(z[:, 0:3], acc_read, m) - ind
+        mb = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 3:6])  # :662
+        Rm = _triad(gb, mb)
+        self.R = np.where(m[:, None, None], Rm, self.R)
+        return rot_to_quat(Rm), Rm
+
+    def accel_int(self, z, acc_read, rot, f_m, mask=None):                              # :700-715
+        m = self._m(mask)
+        acc1 = self.accel(z[:, 0:3], acc_read, m)
+        _, Rm = self.triad(z[:, 3:9], acc_read, rot, f_m, m)
+        a_in = np.einsum("nji,nj->ni", Rm, acc1) + np.array([0, 0, G])
+        vel = self.vel + a_in * self.dt
+        pos = self.pos + vel * self.dt
+        self.acc0 = np.where(m[:, None], a_in, self.acc0)
+        self.vel = np.where(m[:, None], vel, self.vel); self.pos = np.where(m[:, None], pos, self.pos)
+        return a_in, vel, pos
+
+    def gyro_int(self, z, y, mask=None):                                                # :717-724
+        m = self._m(mask)
+        w = self.gyro(z, y, m)
+        qg = self.quat + deriv_quat(w, self.quat) * self.dt
+        self.quat = np.where(m[:, None], qg / np.linalg.norm(qg, axis=1, keepdims=True), self.quat)
+        return qg
 
     def step(self, z, y, acc_read, rot, f_m, mask=None):
-        """One env step of the sensor model for the masked envs; returns the 14-float sensed observation (N,14)."""
-        m = np.ones(self.N, bool) if mask is None else np.asarray(mask, bool)
-        dt = self.dt
-        a_b, g_b = self.a_b.copy(), self.g_b.copy()
-        a_b += self.a_b_d * dt                                                          # accel_int -> accel()
-        acc1 = acc_read + a_b[:, None] + self.a_std * z[:, 0:3]
-        a_b += self.a_b_d * dt                                                          # triad -> accel()
-        ind = G * self.Rc2.copy(); ind[:, 2] += f_m
-        gb = acc_read + a_b[:, None] + self.a_std * z[:, 3:6] - ind
-        mb = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 6:9])
-        Rm = _triad(gb, mb)
-        a_in = np.einsum("nji,nj->ni", Rm, acc1) + np.array([0, 0, G])
-        vel = self.vel + a_in * dt
-        pos = self.pos + vel * dt
-        g_b += self.g_b_d * dt                                                          # gyro_int -> gyro()
-        w1 = y[:, 10:13] + g_b[:, None] + self.g_std * z[:, 9:12]
-        qg = self.quat + deriv_quat(w1, self.quat) * dt
-        quat = qg / np.linalg.norm(qg, axis=1, keepdims=True)
-        g_b += self.g_b_d * dt                                                          # gyro()
-        w2 = y[:, 10:13] + g_b[:, None] + self.g_std * z[:, 12:15]
+        """One env step in the canonical call order of every caller (rl_worker.py:164-175, math_trajectory.py:61-83 incl. its
+        GPS blend); z (N,27+); returns the 14-float sensed observation (N,14)."""
+        m = self._m(mask)
+        _, vel, pos = self.accel_int(z[:, 0:9], acc_read, rot, f_m, m)
+        qg = self.gyro_int(z[:, 9:12], y, m)
+        w2 = self.gyro(z[:, 12:15], y, m)
         qv = deriv_quat(w2, qg)
-        if self.gps_blend > 0:                                                          # gps :642-647 + math_trajectory.py:71-77
-            pos_gps = y[:, 0:5:2] + self.gps_p * z[:, 15:18]
-            vel_gps = y[:, 1:6:2] + self.gps_v * z[:, 18:21]
+        pos_gps, vel_gps = self.gps(z[:, 15:21], y)
+        if self.gps_blend > 0:                                                          # math_trajectory.py:71-77
             pos = ((100 - self.gps_blend) * pos + self.gps_blend * pos_gps) / 100
             vel = ((100 - self.gps_blend) * vel + self.gps_blend * vel_gps) / 100
-        a_b += self.a_b_d * dt                                                          # triad -> accel()
-        ind2 = G * Rm[:, :, 2].copy(); ind2[:, 2] += f_m
-        gb2 = acc_read + a_b[:, None] + self.a_std * z[:, 21:24] - ind2
-        mb2 = np.einsum("nji,nj->ni", rot, MAGNET_VEC[None, :] + self.m_std * z[:, 24:27])
-        R2 = _triad(gb2, mb2)
-        obs = np.concatenate([np.stack([pos[:, 0], vel[:, 0], pos[:, 1], vel[:, 1], pos[:, 2], vel[:, 2]], axis=1), qg, qv], axis=1)
-        self.a_b = np.where(m, a_b, self.a_b); self.g_b = np.where(m, g_b, self.g_b)
-        self.vel = np.where(m[:, None], vel, self.vel); self.pos = np.where(m[:, None], pos, self.pos)
-        self.quat = np.where(m[:, None], quat, self.quat)
-        self.Rc2 = np.where(m[:, None], R2[:, :, 2], self.Rc2)
-        return obs
+            self.pos = np.where(m[:, None], pos, self.pos); self.vel = np.where(m[:, None], vel, self.vel)
+        self.triad(z[:, 21:27], acc_read, rot, f_m, m)
+        self.last = dict(w=w2, pos_gps=pos_gps, vel_gps=vel_gps)
+        return np.concatenate([np.stack([pos[:, 0], vel[:, 0], pos[:, 1], vel[:, 1], pos[:, 2], vel[:, 2]], axis=1), qg, qv], axis=1)
 
 
 # --------------------------------------------------------------------------------------

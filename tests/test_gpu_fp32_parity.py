@@ -1,0 +1,255 @@
+"""GPU parity tests of the FP32 production mode's reward path, the 1000-step closed loops of BASELINE.json configs[1] / north_star,
+and the recorded reference episode of the trained actor (tests/golden/actor_128.npz).
+
+Bound of the FP32 production mode (BASELINE.json north_star): |x - x_ref| <= 1e-5 + 1e-4 |x_ref|; FP64 mode 1e-9 relative; done /
+solved flags exact.  A comparison against a THRESHOLD (bounding box, reward cascade, solved test) is only meaningful when the
+reference's own margin to that threshold exceeds the FP32 bound: samples inside that margin are counted, not compared."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, rel_err, bound_err
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+if torch.cuda.is_available():
+    from autonomous_quadrotor_environment_b200 import BatchedQuad, _lib as L
+from oracle import quad_oracle as qo
+
+DEV = "cuda:0"
+T64 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float64), device=DEV)
+T32 = lambda x: torch.as_tensor(np.asarray(x, dtype=np.float32), device=DEV)
+npy = lambda t: t.detach().double().cpu().numpy()
+
+BB = np.array([10, 10, 10, np.pi / 2, np.pi / 2, 3 * np.pi / 4, 20, 20, 20])
+TR = np.array([0.005, 0.01, 0.1])
+
+
+def threshold_margin_ok(state, ang, rel=2e-4, abs_=2e-5):
+    """True where every threshold test of done_condition (:500-509) / reward_function (:535-542, :558-562) is decided by
+    more than the FP32 bound in the reference's own numbers."""
+    v, w = state[:, 1:6:2], state[:, 10:13]
+    cond = np.abs(np.concatenate([v, ang, w], axis=1))
+    ok = (np.abs(cond - BB) > abs_ + rel * BB).all(axis=1)
+    nr = np.sqrt((v ** 2).sum(1) + ang[:, 2] ** 2)
+    ne = np.sqrt((ang[:, 0:2] ** 2).sum(1))
+    cur = (v ** 2).sum(1) + (ang ** 2).sum(1) + (w ** 2).sum(1)
+    for tr in TR:
+        ok &= (np.abs(nr - 2 * tr) > abs_ + rel * 2 * tr) & (np.abs(ne - 4 * np.sqrt(2) * tr) > abs_ + rel * 4 * np.sqrt(2) * tr)
+    ok &= np.abs(cur - 9 * TR[0] ** 2) > 1e-7
+    return ok
+
+
+def _np_actor(W, x):
+    h = np.tanh(x @ W["actor_0_weight"].T + W["actor_0_bias"])
+    h = np.tanh(h @ W["actor_2_weight"].T + W["actor_2_bias"])
+    return np.tanh(h @ W["actor_4_weight"].T + W["actor_4_bias"])
+
+
+def _push(hist, obs, act):        # dl_in_gen.dl_input (environment/controller/dl_auxiliary.py:25-32)
+    return np.concatenate([hist[:, 15:], act, obs[:, 1:6:2], obs[:, 6:14]], axis=1)
+
+
+# ----------------------------------------------------------------------------------------------------
+# teacher-forced: obs, Euler angles, REWARD, SOLVED, abs_sum, done of the FP32 mode against the reference's recorded steps
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,direct,training", [("step_direct.npz", 1, True), ("step_indirect.npz", 0, True),
+                                                   ("step_eval.npz", 1, False)])
+def test_f32_teacher_forced_reward_solved_effort_vs_reference(name, direct, training):
+    """Every step restarts from the reference's recorded state AND reward memory (prev_shaping, sticky flags, abs_sum, taken
+    from the FP64 oracle that reproduces the same fixture to 1e-9): the FP32 step's observation, Euler angles, reward
+    (shaping difference + cascade bonus + action penalty + solved / broken terms), accumulated effort, solved and done are
+    held to the reference's own recorded values."""
+    g = load_golden(name)
+    n_env, T, n = g["init"].shape[0], int(g["T"]), int(g["n"])
+    env = BatchedQuad(n_env, 0.01, n, training=training, direct_control=direct, T=T, precision="f32", integrator="rk4", device=DEV)
+    ora = qo.BatchQuadOracle(n_env, 0.01, n, training=training, direct_control=direct, T=T, integrator="rk45")
+    env.reset(T32(g["init"])); ora.reset(g["init"])
+    worst = dict(obs=0.0, ang=0.0, reward=0.0, abs_sum=0.0)
+    flips, skipped, compared = 0, 0, 0
+    for t in range(g["actions"].shape[0]):
+        prev = g["reset_state"] if t == 0 else g["state"][t - 1]
+        fin = ~np.isnan(g["obs"][t]).any(axis=1) & ~np.isnan(prev).any(axis=1) & (np.abs(prev).max(axis=1) < 1e3)
+        # teacher forcing: state, prev_ang, prev_shaping, abs_sum, sticky flags of the reference before this step
+        env.set_state(T32(np.nan_to_num(prev)))
+        env._field(L.QS_FIELD_ANG).copy_(T32(np.nan_to_num(ora.prev_ang).T))
+        env._field(L.QS_FIELD_PREV_SHAPING)[0].copy_(T32(np.nan_to_num(ora.prev_shaping)))
+        env._field(L.QS_FIELD_ABS_SUM)[0].copy_(T32(np.nan_to_num(ora.abs_sum)))
+        fl = ora.done.astype(np.uint8) | (ora.has_prev_shaping.astype(np.uint8) << 1) | ((ora.solved > 0).astype(np.uint8) << 2)
+        env._field(L.QS_FIELD_FLAGS)[0].copy_(torch.as_tensor(fl, device=DEV))
+        obs, rew, done = env.step(T32(g["actions"][t]))
+        ora.step(g["actions"][t])
+        assert rel_err(ora.state[fin], g["state"][t][fin]) < 1e-9            # the oracle is on the recorded trajectory
+        ok = fin & threshold_margin_ok(np.nan_to_num(g["state"][t]), np.nan_to_num(g["ang"][t]))
+        skipped += int((fin & ~ok).sum()); compared += int(ok.sum())
+        worst["obs"] = max(worst["obs"], bound_err(npy(obs)[fin], g["obs"][t][fin]))
+        worst["ang"] = max(worst["ang"], bound_err(npy(env.ang)[fin], g["ang"][t][fin]))
+        worst["reward"] = max(worst["reward"], bound_err(npy(rew)[ok], g["reward"][t][ok]))
+        worst["abs_sum"] = max(worst["abs_sum"], bound_err(npy(env.abs_sum)[fin], g["abs_sum"][t][fin]))
+        flips += int((done.cpu().numpy().astype(bool)[ok] != g["done"][t][ok]).sum())
+        flips += int((env.solved.cpu().numpy().astype(np.int64)[ok] != g["solved"][t][ok]).sum())
+    assert max(worst.values()) < 1.0, worst
+    assert flips == 0
+    assert compared > 20 * max(1, skipped), (compared, skipped)          # the margin mask removes a few samples, not the test
+    if name == "step_eval.npz":
+        assert int(g["solved"].sum()) > 0                                  # the solved branch (+20, solved = 1) was exercised
+
+
+# ----------------------------------------------------------------------------------------------------
+# closed loop, 4,096 envs x 1000 steps, the reference's trained actor in the loop
+# ----------------------------------------------------------------------------------------------------
+def _closed_loop(prec, integ, N, steps, seed):
+    from oracle.c_oracle import COracle
+    W = load_golden("actor_128.npz")
+    T = 5
+    mk = T64 if prec == "f64" else T32
+    init, _ = qo.sample_reset_state(seed, np.arange(N), 0)
+    env = BatchedQuad(N, 0.01, 5000, training=False, direct_control=1, T=T, precision=prec, integrator=integ, device=DEV)
+    ora = COracle(N, 0.01, 5000, training=False, direct_control=1, T=T, integrator="rk45")
+    oh_g, ah_g = env.reset(mk(init))
+    oh_o = ora.reset(init)
+    hg, ho = np.zeros((N, 75)), np.zeros((N, 75))
+    oh_g, ah_g = npy(oh_g), npy(ah_g)
+    for k in range(T):
+        hg = _push(hg, oh_g[k], ah_g[k]); ho = _push(ho, oh_o[k], np.zeros((N, 4)))
+    return W, env, ora, hg, ho, mk
+
+
+def test_f32_closed_loop_4096_envs_1000_steps_obs_reward_solved():
+    """The reference's N=128 actor drives the FP64 RK45 oracle (C port, checked against the same fixtures) and the FP32 RK4
+    CUDA path, each on its own observations, for 1000 steps of 4,096 envs from the reference's reset distribution.  While
+    an env is inside the bounding box in the reference run: non-position observation, reward, accumulated effort within the
+    FP32 bound (positions are not fed back by the velocity controller: 20x), solved / done equal."""
+    N, steps = 4096, 1000
+    W, env, ora, hg, ho, mk = _closed_loop("f32", "rk4", N, steps, 31)
+    nonpos = [1, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13]
+    worst = dict(obs=0.0, pos=0.0, reward=0.0, abs_sum=0.0)
+    flips, compared, skipped = 0, 0, 0
+    alive = np.ones(N, bool)
+    for t in range(steps):
+        ag, ao = _np_actor(W, hg), _np_actor(W, ho)
+        obs, rew, done = env.step(mk(ag))
+        o_ref, r_ref, d_ref = ora.step(ao)
+        og = npy(obs)
+        hg = _push(hg, og, ag); ho = _push(ho, o_ref, ao)
+        alive &= ~d_ref & np.isfinite(o_ref).all(axis=1)
+        ang = qo.quat_euler(ora.state[:, 6:10] / np.linalg.norm(ora.state[:, 6:10], axis=1, keepdims=True))
+        ok = alive & threshold_margin_ok(ora.state, ang)
+        compared += int(ok.sum()); skipped += int((alive & ~ok).sum())
+        worst["obs"] = max(worst["obs"], bound_err(og[alive][:, nonpos], o_ref[alive][:, nonpos]))
+        worst["pos"] = max(worst["pos"], bound_err(og[alive][:, [0, 2, 4]], o_ref[alive][:, [0, 2, 4]]))
+        worst["reward"] = max(worst["reward"], bound_err(npy(rew)[ok], r_ref[ok]))
+        worst["abs_sum"] = max(worst["abs_sum"], bound_err(npy(env.abs_sum)[alive], ora.abs_sum[alive]))
+        flips += int((done.cpu().numpy().astype(bool)[ok] != d_ref[ok]).sum())
+        flips += int((env.solved.cpu().numpy().astype(bool)[ok] != ((ora.flags[ok] >> 2) & 1).astype(bool)).sum())
+    assert alive.mean() > 0.9, alive.mean()                               # the shipped controller keeps >90 % of the starts in the box
+    assert int(((ora.flags >> 2) & 1)[alive].sum()) > N // 2             # ... and brings most of them to the solved state
+    assert worst["obs"] < 1.0 and worst["reward"] < 1.0 and worst["abs_sum"] < 1.0 and worst["pos"] < 20.0, worst
+    assert flips == 0, flips
+    assert compared > 10 * max(1, skipped), (compared, skipped)
+
+
+def test_config2_f64_closed_loop_1000_steps_vs_oracle():
+    """BASELINE.json configs[1], closed-loop variant: 4,096 envs, FP64 RK45 mode, the trained actor in the
+    loop on each side's own observations, 1000 steps: observation and reward within 1e-9 relative per step while the env is
+    inside the box, done / solved identical."""
+    N, steps = 4096, 1000
+    W, env, ora, hg, ho, mk = _closed_loop("f64", "rk45", N, steps, 1234)
+    worst = 0.0
+    alive = np.ones(N, bool)
+    for t in range(steps):
+        ag, ao = _np_actor(W, hg), _np_actor(W, ho)
+        obs, rew, done = env.step(mk(ag))
+        o_ref, r_ref, d_ref = ora.step(ao)
+        og = npy(obs)
+        hg = _push(hg, og, ag); ho = _push(ho, o_ref, ao)
+        alive &= ~d_ref & np.isfinite(o_ref).all(axis=1)
+        worst = max(worst, rel_err(og[alive], o_ref[alive]), rel_err(npy(rew)[alive], r_ref[alive]))
+        assert np.array_equal(done.cpu().numpy().astype(bool)[alive], d_ref[alive]), t
+        assert np.array_equal(env.solved.cpu().numpy().astype(bool)[alive], ((ora.flags[alive] >> 2) & 1).astype(bool)), t
+    assert alive.mean() > 0.9
+    assert worst < 1e-9, worst
+
+
+def test_config2_f64_random_actions_until_all_done():
+    """BASELINE.json configs[1] as SURVEY.md 8(d).2 words it: random actions, horizon = until every env is done (or 1000)."""
+    N = 4096
+    init, _ = qo.sample_reset_state(1234, np.arange(N), 0)
+    rng = np.random.default_rng(5678)
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=1, precision="f64", integrator="rk45", device=DEV)
+    ora = qo.BatchQuadOracle(N, 0.01, 1000, training=True, direct_control=1, T=1, integrator="rk45")
+    env.reset(T64(init)); ora.reset(init)
+    worst, t = 0.0, 0
+    was_done = np.zeros(N, bool)
+    while t < 1000 and not was_done.all():
+        a = rng.uniform(-1, 1, (N, 4))
+        obs, rew, done = env.step(T64(a))
+        o_ref, r_ref, d_ref = ora.step(a, mask=~was_done)          # a finished env stops being stepped, like a finished episode
+        m = ~was_done & ~np.isnan(o_ref).any(axis=1)
+        worst = max(worst, rel_err(npy(obs)[m], o_ref[m]), rel_err(npy(rew)[m], r_ref[m]), rel_err(npy(env.state)[m], ora.state[m]))
+        assert np.array_equal(done.cpu().numpy().astype(bool)[~was_done], d_ref[~was_done]), "done flags differ at step %d" % t
+        was_done |= d_ref
+        t += 1
+    assert was_done.all() and t < 1000, (t, was_done.mean())
+    assert worst < 1e-9, worst
+
+
+# ----------------------------------------------------------------------------------------------------
+# the recorded reference episode of the trained actor (actor_128.npz: nn_in / actions / obs / states of ppo_quad_eval's loop)
+# ----------------------------------------------------------------------------------------------------
+def test_policy_kernel_history_equals_the_reference_dl_input():
+    """The fused policy kernel replays the reference episode's recorded actions (sigma = 0 is not needed: the kernel's own
+    actions are overwritten by teacher forcing the recorded ones through qs_rollout); what matters here is the HISTORY
+    layout: after k steps the kernel's history rows must equal the reference's dl_in_gen buffer nn_in[k] (BF16-rounded,
+    the kernel's A-operand precision), column for column."""
+    g = load_golden("actor_128.npz")
+    K = 64
+    env = BatchedQuad(128, 0.01, 500, training=False, direct_control=1, T=5, precision="f32", device=DEV)
+    oh, ah = env.reset(T32(np.tile(g["init"], (128, 1))))
+    assert bound_err(npy(oh)[:, 0], g["reset_obs"]) < 1.0
+    env.load_actor(g, action_std=0.0)
+    # history as dl_in_gen.dl_input builds it over the T pairs reset() returned (ppo_quad_eval.py:47-52)
+    hist = np.zeros((128, 75), np.float32)
+    for k in range(5):
+        hist = _push(hist, npy(oh)[k], npy(ah)[k]).astype(np.float32)
+    assert np.abs(hist[0] - g["nn_in"][0]).max() < 2e-5                       # == the reference's first network input
+    env.history.copy_(T32(hist))
+    rec = env.policy_rollout(K, record_obs=True)
+    acts, obs = npy(rec["actions"])[:, :, 0], npy(rec["obs"])[:, :, 0]
+    # closed loop with BF16 operands stays near the reference's FP32 episode for the first steps ...
+    assert np.abs(acts[:10] - g["actions"][:10]).max() < 0.05
+    # ... and the history the kernel keeps is exactly dl_input of ITS OWN (action, obs) stream in the reference's column order
+    h = hist.copy()
+    for t in range(K):
+        h = _push(h, obs[t][None].repeat(128, 0), acts[t][None].repeat(128, 0)).astype(np.float32)
+    want = torch.as_tensor(h, device=DEV).bfloat16().float()
+    assert torch.equal(env.history, want)
+    # the reference's own nn_in stream obeys the same recurrence: column order pinned to the reference run
+    h = g["nn_in"][0][None].astype(np.float64)
+    for t in range(20):
+        h = _push(h, g["obs"][t][None], g["actions"][t][None])
+        assert np.abs(h[0] - g["nn_in"][t + 1]).max() < 1e-6, t
+
+
+def test_dropin_quad_with_fp32_actor_reproduces_reference_episode():
+    """ppo_quad_eval.py's loop (FP32 torch actor + dl_in_gen + quad.step) with the CUDA-backed drop-in `quad`: the 300 recorded
+    steps of the reference episode (observations, states, actions) to the 1.7e-5 the reference itself reproduces its shipped
+    rl log with (FP32 matmul rounding differs between torch builds)."""
+    from autonomous_quadrotor_environment_b200.quadrotor_env import quad
+    g = load_golden("actor_128.npz")
+    model = torch.nn.Sequential(torch.nn.Linear(75, 128), torch.nn.Tanh(), torch.nn.Linear(128, 128), torch.nn.Tanh(),
+                                torch.nn.Linear(128, 4), torch.nn.Tanh())
+    model.load_state_dict({"%d.%s" % (i, k): torch.as_tensor(g["actor_%d_%s" % (i, k)]) for i in (0, 2, 4) for k in ("weight", "bias")})
+    env = quad(0.01, 500, training=False, euler=0, direct_control=1, T=5, verbose=False, robust_rng_draws=False)
+    state, action = env.reset(g["init"].copy())
+    hist = np.zeros((1, 75), np.float32)
+    for k in range(5):
+        hist = _push(hist, state[k][None], action[k][None]).astype(np.float32)
+    worst = 0.0
+    for t in range(g["obs"].shape[0]):
+        assert np.abs(hist[0] - g["nn_in"][t]).max() < 1e-4, t
+        a = model(torch.FloatTensor(hist[0])).detach().numpy()
+        s, _, _ = env.step(a)
+        hist = _push(hist, s, a[None]).astype(np.float32)
+        worst = max(worst, np.abs(s[0] - g["obs"][t]).max(), np.abs(env.state - g["states"][t]).max(), np.abs(a - g["actions"][t]).max())
+    assert worst < 5e-5, worst

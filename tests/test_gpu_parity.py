@@ -948,3 +948,93 @@ def test_handle_on_second_device_while_first_is_current():
         outs.append((env.obs.cpu(), env.sensed_obs.cpu(), env.episode.cpu()))
     assert torch.equal(outs[0][2], outs[1][2])
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+# ----------------------------------------------------------------------------------------------------
+# sensor model against the REFERENCE class driven by a replayed draw stream (tests/golden/sensor_vectors.npz)
+# ----------------------------------------------------------------------------------------------------
+def _sv(g, pre, t, mk):
+    soa = lambda x: mk(np.ascontiguousarray(np.asarray(x).reshape(x.shape[0], -1).T))
+    return dict(quad_state=soa(g[pre + "state"][t]), acc_read=soa(g[pre + "acc_read"][t]), mat_rot=soa(g[pre + "mat_rot"][t]),
+                f_m=mk(g[pre + "f_m"][t]))
+
+
+def _sensor_state0(g, pre, mk):
+    from autonomous_quadrotor_environment_b200 import sensors as S
+    n = g[pre + "u"].shape[0]
+    s = S.new_state(n, dtype=mk(np.zeros(1)).dtype, device=DEV)
+    S.sensor_call("reset", s, mk(np.ascontiguousarray(g[pre + "u"][:, 3:6].T)), quad_state=mk(np.ascontiguousarray(g[pre + "reset_state"].T)))
+    return s
+
+
+def test_sensor_methods_f64_vs_reference_class():
+    """qs_sensor_call, one reference method per launch, fed the very draws the reference's `sensor` consumed: every output of
+    accel_int / gyro_int / gyro / gps / triad (incl. SciPy's matrix->quaternion) and the sensor's whole internal state
+    within 1e-9, free-running over the episode; scenario C calls the methods in another order."""
+    from autonomous_quadrotor_environment_b200 import sensors as S
+    g = load_golden("sensor_vectors.npz")
+    cat = lambda *a: np.concatenate(a, axis=1)
+    for pre, order in (("A_", [("accel_int", 9, lambda g_, t: g_["A_accel_int"][t]), ("gyro_int", 3, lambda g_, t: g_["A_gyro_int"][t]),
+                               ("gyro", 3, lambda g_, t: g_["A_gyro"][t]), ("gps", 6, lambda g_, t: g_["A_gps"][t]),
+                               ("triad", 6, lambda g_, t: cat(g_["A_triad_q"][t], g_["A_triad_R"][t].reshape(-1, 9)))]),
+                       ("C_", [("gyro", 3, lambda g_, t: g_["C_gyro"][t]),
+                               ("triad", 6, lambda g_, t: cat(g_["C_triad_q"][t], g_["C_triad_R"][t].reshape(-1, 9))),
+                               ("gps", 6, lambda g_, t: g_["C_gps"][t]), ("gyro_int", 3, lambda g_, t: g_["C_gyro_int"][t]),
+                               ("accel", 3, lambda g_, t: g_["C_accel"][t]), ("accel_int", 9, lambda g_, t: g_["C_accel_int"][t])])):
+        s = _sensor_state0(g, pre, T64)
+        K = g[pre + "z"].shape[0]
+        for t in range(K):
+            kw = _sv(g, pre, t, T64)
+            zc = 0
+            for name, nz, want in order:
+                z = T64(np.ascontiguousarray(g[pre + "z"][t][:, zc:zc + nz].T)); zc += nz
+                out = npy(S.sensor_call(name, s, z, **kw)).T
+                ref = want(g, t)
+                assert rel_err(out[:, :ref.shape[1]], ref) < 1e-9, (pre, t, name)
+            assert rel_err(npy(s).T, g[pre + "sens_state"][t], floor=1e-6) < 1e-9, (pre, t)
+
+
+@pytest.mark.parametrize("pre", ["A_", "B_"])
+def test_sensor_step_vs_reference_sensor_sp(pre):
+    """The fused canonical step (the function the step kernels run per env, here with the reference's draws) against the
+    reference's own sensor_sp (visual_landing/math_trajectory.py:61-83): B_ = its GPS blend switched on (GPS_P = 30).
+    FP64 free-running at 1e-9; FP32 teacher-forced (state restarted from the reference every step) within the production
+    bound 1e-5 + 1e-4 |x|."""
+    from autonomous_quadrotor_environment_b200 import sensors as S
+    g = load_golden("sensor_vectors.npz")
+    blend = float(g["B_gps_blend"]) if pre == "B_" else 0.0
+    s64 = _sensor_state0(g, pre, T64)
+    s32 = _sensor_state0(g, pre, T32)
+    worst32 = 0.0
+    for t in range(g[pre + "z"].shape[0]):
+        z = np.ascontiguousarray(g[pre + "z"][t].T)
+        o64 = npy(S.sensor_call("step", s64, T64(z), params={"gps_blend": blend}, **_sv(g, pre, t, T64))).T
+        assert rel_err(o64, g[pre + "obs"][t]) < 1e-9, t
+        assert rel_err(npy(s64).T, g[pre + "sens_state"][t], floor=1e-6) < 1e-9, t
+        o32 = npy(S.sensor_call("step", s32, T32(z), params={"gps_blend": blend}, **_sv(g, pre, t, T32))).T
+        worst32 = max(worst32, bound_err(o32, g[pre + "obs"][t]), bound_err(npy(s32).T[:, 4:17], g[pre + "sens_state"][t][:, 4:17]))
+        s32.copy_(T32(np.ascontiguousarray(g[pre + "sens_state"][t].T)))                  # teacher forcing
+    assert worst32 < 1.0, worst32
+
+
+def test_dropin_sensor_class_reproduces_reference_readings():
+    """The single-env drop-in `sensor(quad)` of the compat overlay, driven like the reference was when the fixture was
+    recorded (same NumPy-level draws through oracle/replay_rng.py): same readings, method by method, to 1e-9."""
+    from autonomous_quadrotor_environment_b200.quadrotor_env import quad, sensor
+    from oracle.replay_rng import ReplayRNG
+    g = load_golden("sensor_vectors.npz")
+    for j in range(2):
+        env = quad(0.01, 10 ** 6, training=False, direct_control=1, T=2, verbose=False, robust_rng_draws=False)
+        env.reset(g["C_init"][j].copy())
+        with ReplayRNG([], g["C_u"][j]):
+            sen = sensor(env)
+            sen.reset()
+        assert rel_err(env.state, g["C_reset_state"][j]) < 1e-9
+        for t in range(g["C_z"].shape[0]):
+            env.step(g["C_actions"][t, j])
+            with ReplayRNG(g["C_z"][t, j]):
+                w = sen.gyro(); qt, Rt = sen.triad(); pg, vg = sen.gps(); qg = sen.gyro_int(); ac = sen.accel(); acc, vel, pos = sen.accel_int()
+            for got, key in ((w, "C_gyro"), (qt, "C_triad_q"), (Rt, "C_triad_R"), (np.concatenate([pg, vg]), "C_gps"), (qg, "C_gyro_int"),
+                             (ac, "C_accel"), (np.concatenate([acc, vel, pos]), "C_accel_int")):
+                assert rel_err(got, g[key][t, j]) < 1e-9, (j, t, key)
+            assert rel_err(sen.R[:, 2], g["C_sens_state"][t, j][14:17]) < 1e-9 and abs(sen.a_b_accel - g["C_sens_state"][t, j][0]) < 1e-15
