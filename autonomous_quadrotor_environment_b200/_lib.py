@@ -82,7 +82,7 @@ class qs_stats(C.Structure):
 class qs_rollout_args(C.Structure):
     _fields_ = [("horizon", C.c_int32), ("action_source", C.c_int32), ("actions", C.c_void_p),
                 ("obs_out", C.c_void_p), ("action_out", C.c_void_p), ("reward_out", C.c_void_p),
-                ("done_out", C.c_void_p)]
+                ("done_out", C.c_void_p), ("sensed_obs_out", C.c_void_p)]
 
 
 class qs_actor(C.Structure):

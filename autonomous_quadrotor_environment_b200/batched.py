@@ -197,7 +197,7 @@ class BatchedQuad:
         return self.step_soa(self._as_soa(action, 4))
 
     def rollout(self, horizon: int, actions=None, record_obs=False, record_actions=False, record_reward=False,
-                record_done=False):
+                record_done=False, record_sensed=False):
         """K fused env steps in ONE launch (state stays in registers).  actions: (K,4,N) tensor, or None to draw
         a ~ U(-1,1)^4 in-kernel with Philox.  Returns a dict of the recorded (K,C,N) buffers."""
         a = L.qs_rollout_args()
@@ -222,6 +222,9 @@ class BatchedQuad:
         if record_done:
             out["done"] = torch.empty(horizon, self.N, dtype=torch.uint8, device=self.device)
             a.done_out = out["done"].data_ptr()
+        if record_sensed:                      # sensor_noise=True handles: the sensor-based observation of every step
+            out["sensed_obs"] = torch.empty(horizon, 14, self.N, dtype=self.dtype, device=self.device)
+            a.sensed_obs_out = out["sensed_obs"].data_ptr()
         L.check(self.lib.qs_rollout(self._h, C.byref(a), self._stream()))
         return out
 

@@ -347,6 +347,12 @@ __device__ __forceinline__ void process_env(const DevParams<R>& p, const SimView
             StepOut<R> to;
             if (p.flags & F_ASYNC_RESET) {
                 async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, te, to.vq);
+                if (SENSOR) {               // like the queued path (step_epilogue): the sensed observation returned with done is
+#pragma unroll                              // the new episode's initial observation
+                    for (int k = 0; k < 10; ++k) v.sensed_obs[k * v.ld + n] = te.y[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v.sensed_obs[(10 + k) * v.ld + n] = to.vq[k];
+                }
             } else {
                 te.episode += 1;
                 reset_env<R, INTEG, DIRECT, ROBUST>(p, v, n, te, true, to, nullptr, nullptr);
@@ -563,14 +569,30 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
             bool warm = false;
             if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
-            step_core<R, INTEG, DIRECT>(p, e, a, o, nullptr);
+            Ctrl<R> c;
+            step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
             if (warm) o.reward = R(0); else e.ep_return += o.reward;
             reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
             if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
-            if ((p.flags & F_ASYNC_RESET) && done) async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+            if (p.flags & F_SENSOR)                 // generic path: the sensor rows stay in HBM (the FP32 pair kernel keeps them on chip)
+                sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
+            if ((p.flags & F_ASYNC_RESET) && done) {
+                async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+                if (p.flags & F_SENSOR) {
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) v.sensed_obs[k * v.ld + n] = e.y[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v.sensed_obs[(10 + k) * v.ld + n] = o.vq[k];
+                }
+            }
             if ((p.flags & F_AUTO_RESET) && done) {
                 e.episode += 1;
                 reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
+            }
+            if ((p.flags & F_SENSOR) && io.sensed_out) {
+                R* so = io.sensed_out + (int64_t)t * 14 * v.N;
+#pragma unroll
+                for (int k = 0; k < 14; ++k) so[k * v.N + n] = v.sensed_obs[k * v.ld + n];
             }
             if (io.obs_out) {
                 R* ot = io.obs_out + (int64_t)t * 14 * v.N;
@@ -666,7 +688,7 @@ static void launch_rollout(qs_sim* s, const qs_rollout_args* a, cudaStream_t st)
         if (launch_rollout_fast(s, a, DIRECT, st)) return;
     }
     RolloutIO<R> io{a->horizon, a->action_source, (const R*)a->actions, (R*)a->obs_out, (R*)a->action_out,
-                    (R*)a->reward_out, a->done_out};
+                    (R*)a->reward_out, a->done_out, (R*)a->sensed_obs_out};
     rollout_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
 
@@ -797,8 +819,10 @@ extern "C" int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream
     if (args->action_source == QS_ACT_BUFFER && !args->actions) return fail(QS_EINVAL, "qs_rollout: actions is NULL");
     if (args->action_source != QS_ACT_BUFFER && args->action_source != QS_ACT_PHILOX_UNIFORM)
         return fail(QS_EINVAL, "qs_rollout: bad action_source");
-    if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_ROBUST))
-        return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_SENSOR_NOISE / QS_FLAG_ROBUST");
+    if (h->cfg.flags & (QS_FLAG_AUX | QS_FLAG_ROBUST))
+        return fail(QS_ESTATE, "qs_rollout: not available with QS_FLAG_AUX / QS_FLAG_ROBUST");
+    if (args->sensed_obs_out && !(h->cfg.flags & QS_FLAG_SENSOR_NOISE))
+        return fail(QS_ESTATE, "qs_rollout: sensed_obs_out needs a QS_FLAG_SENSOR_NOISE handle");
     QS_USE_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     QS_DISPATCH(h, launch_rollout, h, args, st);

@@ -264,6 +264,7 @@ template <typename R> struct RolloutIO {
     R* action_out;
     R* reward_out;
     uint8_t* done_out;
+    R* sensed_out;       // [K][14][N] or NULL (QS_FLAG_SENSOR_NOISE handles)
 };
 
 

@@ -12,19 +12,38 @@
 #ifndef QS_ROLLOUT_PAIR_THREADS
 #define QS_ROLLOUT_PAIR_THREADS 256
 #endif
+#ifndef QS_ROLLOUT_SENSOR_STREAM
+#define QS_ROLLOUT_SENSOR_STREAM 1              // sensor phase of the rollout kernel: 1 = streaming (state rows read / written in place in
+#endif                                          // shared memory), 0 = whole state and sensed observation in registers (252 registers)
+#ifndef QS_ROLLOUT_PAIR_THREADS_SENSOR
+#define QS_ROLLOUT_PAIR_THREADS_SENSOR 256      // 384 (168 registers, 12 warps per SM) measured slower with recording: 96.5 vs 87.8 us
+#endif
+template <bool SENSOR> struct RolloutPairCfg { static constexpr int kThreads = SENSOR ? QS_ROLLOUT_PAIR_THREADS_SENSOR : QS_ROLLOUT_PAIR_THREADS; };
 
-template <bool DIRECT>
-__global__ void __launch_bounds__(QS_ROLLOUT_PAIR_THREADS, 1)
+// SENSOR (QS_FLAG_SENSOR_NOISE): the packed sensor model of the step kernel (sensor_pair.cuh via pr::sensor_phase) runs after
+// every step; the pair's 20 sensor-state rows live in shared memory for the whole horizon (one 256-byte row segment per warp
+// and row: lane l holds its pair as one float2, conflict-free LDS.64 / STS.64), so a K-step launch moves the sensor state
+// through HBM once instead of K times and the per-step traffic is the recorded stream only (sensed observation, reward, done).
+template <bool DIRECT, bool SENSOR>
+__global__ void __launch_bounds__(RolloutPairCfg<SENSOR>::kThreads, 1)
 rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                     const __grid_constant__ RolloutIO<float> io) {
     using pr::half_of;
+    extern __shared__ __align__(16) float s_sensor[];           // SENSOR: [warps][20] rows of 64 floats (dynamic shared memory)
+    pr::Row* srows = reinterpret_cast<pr::Row*>(s_sensor) + (threadIdx.x >> 5) * qs::kSensorStateDim;
+    const int lane = threadIdx.x & 31;
     LocalStats ls;
     ls.clear();
     bool any_end = false;
     const bool async_reset = (p.flags & F_ASYNC_RESET) != 0;
     const int64_t N2 = v.N >> 1, ld2 = v.ld >> 1;                   // v.N is even (checked by the launcher)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N2; m += stride) {
+    // Whole warps only: the sensor phase uses warp-wide votes, so every lane of a warp that has work runs the iteration.  Lanes past
+    // the last pair (m >= N2) compute on the padding columns of the handle's rows (ld is a multiple of 256 envs) and never touch the
+    // caller's unpadded [K][C][N] buffers or the statistics.
+    const int64_t N2r = (N2 + 31) & ~(int64_t)31;
+    for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N2r; m += stride) {
+        const bool live = m < N2;          // (`act` is the clipped-action array below)
         const int64_t nA = 2 * m;
         const float2* g2 = reinterpret_cast<const float2*>(v.obs17) + m;
         P2 y[13];
@@ -45,6 +64,11 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
             const uint32_t fl = reinterpret_cast<const uint16_t*>(v.flags)[m];
             e[0].flags = fl & 0xffu; e[1].flags = fl >> 8;
         }
+        if (SENSOR) {
+            const float2* gs2 = reinterpret_cast<const float2*>(v.sensor_state) + m;
+#pragma unroll
+            for (int k = 0; k < qs::kSensorStateDim; ++k) { const float2 t = gs2[(int64_t)k * ld2]; pr::sts2(srows, k, lane, t.x, t.y); }
+        }
         StepOut<float> o[2];
         bool warm[2] = {false, false};
         for (int t = 0; t < io.horizon; ++t) {
@@ -61,7 +85,7 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
             } else {
                 const float2* at = reinterpret_cast<const float2*>(io.actions + (int64_t)t * 4 * v.N) + m;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { const float2 q = at[(int64_t)k * N2]; a[0][k] = q.x; a[1][k] = q.y; }
+                for (int k = 0; k < 4; ++k) { const float2 q = live ? at[(int64_t)k * N2] : make_float2(0.f, 0.f); a[0][k] = q.x; a[1][k] = q.y; }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -81,29 +105,73 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
             QS_RP_POST(0)
             QS_RP_POST(1)
 #undef QS_RP_POST
+            if (SENSOR) {                // the sensor model sees the state the step left (before a finished env is re-sampled)
+                pr::PairMeta pm;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    pm.episode[h] = e[h].episode; pm.step_i[h] = (uint32_t)e[h].i; pm.flags[h] = e[h].flags; pm.warm[h] = warm[h];
+                }
+                const bool last = (t == io.horizon - 1);
+                float2* rec2 = (io.sensed_out && live) ? reinterpret_cast<float2*>(io.sensed_out + (int64_t)t * 14 * v.N) + m : nullptr;
+                float2* go2 = reinterpret_cast<float2*>(v.sensed_obs) + m;
+#if QS_ROLLOUT_SENSOR_STREAM
+                const bool any_warm = __any_sync(0xffffffffu, warm[0] | warm[1]);
+                const bool w0 = warm[0], w1 = warm[1];
+                pr::sensor_phase_stream(p, v, srows, lane, nA, y, c2.f_m, pm, any_warm, [&](int k, P2 val) {
+                    if (any_warm) {          // warm-up steps pass the true observation through
+                        const P2 tr = k < 10 ? y[k] : pk(o[0].vq[k - 10], o[1].vq[k - 10]);
+                        val = psel(w0, w1, tr, val);
+                    }
+                    if (rec2) rec2[(int64_t)k * N2] = val.v;
+                    if (last) go2[(int64_t)k * ld2] = val.v;
+                });
+#else
+                P2 sn[qs::kSensorStateDim], so[14], vq[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
+                pr::sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, pm, sn, so);
+#pragma unroll
+                for (int k = 0; k < qs::kSensorStateDim; ++k) pr::sts2(srows, k, lane, sn[k].v.x, sn[k].v.y);
+#pragma unroll
+                for (int k = 0; k < 14; ++k) {
+                    if (rec2) rec2[(int64_t)k * N2] = so[k].v;
+                    if (last) go2[(int64_t)k * ld2] = so[k].v;
+                }
+#endif
+            }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-                if (o[h].done && !was_done[h]) { count_episode(ls, p, e[h], o[h]); any_end = true; }
+                if (live && o[h].done && !was_done[h]) { count_episode(ls, p, e[h], o[h]); any_end = true; }
                 if (async_reset && o[h].done) {
                     async_resample(p, v.seed, v.env_id_offset + (uint32_t)(nA + h), e[h], o[h].vq);
 #pragma unroll
                     for (int k = 0; k < 13; ++k) { if (h == 0) y[k].v.x = e[0].y[k]; else y[k].v.y = e[1].y[k]; }
+                    if (SENSOR) {        // the sensed observation returned with done is the new episode's initial observation
+                        float* rec = (io.sensed_out && live) ? io.sensed_out + (int64_t)t * 14 * v.N + nA + h : nullptr;
+                        float* go = v.sensed_obs + nA + h;
+#pragma unroll
+                        for (int k = 0; k < 14; ++k) {
+                            const float x = k < 10 ? e[h].y[k] : o[h].vq[k - 10];
+                            if (rec) rec[(int64_t)k * v.N] = x;
+                            if (t == io.horizon - 1) go[(int64_t)k * v.ld] = x;
+                        }
+                    }
                 }
             }
-            if (io.obs_out) {
+            if (io.obs_out && live) {
                 float2* ot = reinterpret_cast<float2*>(io.obs_out + (int64_t)t * 14 * v.N) + m;
 #pragma unroll
                 for (int k = 0; k < 10; ++k) ot[(int64_t)k * N2] = y[k].v;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) ot[(int64_t)(10 + k) * N2] = make_float2(o[0].vq[k], o[1].vq[k]);
             }
-            if (io.action_out) {
+            if (io.action_out && live) {
                 float2* at = reinterpret_cast<float2*>(io.action_out + (int64_t)t * 4 * v.N) + m;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) at[(int64_t)k * N2] = make_float2(a[0][k], a[1][k]);
             }
-            if (io.reward_out) reinterpret_cast<float2*>(io.reward_out + (int64_t)t * v.N)[m] = make_float2(o[0].reward, o[1].reward);
-            if (io.done_out)
+            if (io.reward_out && live) reinterpret_cast<float2*>(io.reward_out + (int64_t)t * v.N)[m] = make_float2(o[0].reward, o[1].reward);
+            if (io.done_out && live)
                 reinterpret_cast<uint16_t*>(io.done_out + (int64_t)t * v.N)[m] =
                     (uint16_t)(((o[0].done ? 1u : 0u) | (warm[0] ? 2u : 0u)) | (((o[1].done ? 1u : 0u) | (warm[1] ? 2u : 0u)) << 8));
         }
@@ -127,6 +195,11 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
         reinterpret_cast<uint16_t*>(v.done)[m] =
             (uint16_t)(((o[0].done ? 1u : 0u) | (warm[0] ? 2u : 0u)) | (((o[1].done ? 1u : 0u) | (warm[1] ? 2u : 0u)) << 8));
         reinterpret_cast<uint16_t*>(v.solved)[m] = (uint16_t)((o[0].solved ? 1u : 0u) | ((o[1].solved ? 1u : 0u) << 8));
+        if (SENSOR) {
+            float2* gs2 = reinterpret_cast<float2*>(v.sensor_state) + m;
+#pragma unroll
+            for (int k = 0; k < qs::kSensorStateDim; ++k) gs2[(int64_t)k * ld2] = pr::lds2(srows, k, lane);
+        }
     }
     flush_stats(ls, any_end, v.stats);
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&v.stats[7], (double)v.N * io.horizon);

@@ -193,4 +193,126 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
     for (int k = 0; k < 4; ++k) { obs[6 + k] = qg[k]; obs[10 + k] = qv[k]; }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// STREAMING form of sensor_step2: the pair's 20 state rows stay in shared memory and are read right before / written right
+// after each use, and every output is handed to `out` the moment it exists, so that neither the state (40 registers) nor the
+// sensed observation (28) is ever held in registers as a whole: the sensor phase then fits the register budget of 12 warps
+// per SM (168) next to the dynamics.  Same operations in the same order per quantity as sensor_step2 (the GPS blend reloads the
+// integrators it has just stored), hence the same results.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SensorMem {
+    float2* st;              // shared memory; row k of this lane's pair = st[k * 32]
+    bool any_warm;           // warp-uniform: some env of the warp is in a warm-up step of quad.reset (state kept, sensor bypassed)
+    bool w0, w1;             // ... this pair's halves
+    __device__ __forceinline__ P2 ld(int k) const { P2 r; r.v = st[k * 32]; return r; }
+    __device__ __forceinline__ void stv(int k, P2 x) const {
+        if (any_warm) x = psel(w0, w1, ld(k), x);
+        st[k * 32] = x.v;
+    }
+};
+
+// out(k, value): row k of the 14-float sensed observation of the pair (computed value; the caller substitutes the true
+// observation for envs in a warm-up step)
+template <typename Out>
+__device__ __forceinline__ void sensor_step2_stream(const DevParams<float>& p, const SensorRng2& rng, const P2 y[13], P2 f_m,
+                                                    const SensorMem& sm, Out&& out) {
+    const P2 dt = bc(p.dt), sa = bc(p.s_accel_std), sg = bc(p.s_gyro_std), smg = bc(p.s_mag_std), ng = bc(-p.g);
+    P2 rot[9], acc_read[3];
+    accel_read2(p, f_m, y, rot, acc_read);
+    P2 z0[8], z1[8];
+    sensor_normals_block2(rng, 0, z0);                                                     // z[0..7]
+    // ---- accel_int :700-715
+    const P2 drift_a = sm.ld(2);
+    P2 ab = pfma(drift_a, dt, sm.ld(0));                                                   // accel() :613
+    P2 acc1[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) acc1[k] = pfma(sa, z0[k], padd(acc_read[k], ab));
+    sensor_normals_block2(rng, 1, z1);                                                     // z[8..15]
+    P2 rc[3];                                                                              // third column of the first TRIAD rotation
+    {
+        P2 Rm[9];
+        {   // triad()
+            ab = pfma(drift_a, dt, ab);
+            P2 gb[3], mi[3], mb[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gb[k] = pfma(ng, sm.ld(14 + k), pfma(sa, z0[3 + k], padd(acc_read[k], ab)));   // :658
+            gb[2] = psub(gb[2], f_m);
+            mi[0] = pfma(smg, z0[6], bc(p.s_mag[0])); mi[1] = pfma(smg, z0[7], bc(p.s_mag[1])); mi[2] = pfma(smg, z1[0], bc(p.s_mag[2]));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) mb[c] = pfma(rot[c], mi[0], pfma(rot[3 + c], mi[1], pmul(rot[6 + c], mi[2])));   // :662
+            triad2<true>(p, gb, mb, Rm);
+        }
+        P2 a_in[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) a_in[c] = pfma(Rm[c], acc1[0], pfma(Rm[3 + c], acc1[1], pmul(Rm[6 + c], acc1[2])));   // :705
+        a_in[2] = padd(a_in[2], bc(p.g));
+        rc[0] = Rm[2]; rc[1] = Rm[5]; rc[2] = Rm[8];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const P2 vel = pfma(a_in[k], dt, sm.ld(4 + k));                                // velocity :707
+            const P2 pos = pfma(vel, dt, sm.ld(7 + k));                                    // position :708
+            sm.stv(4 + k, vel); sm.stv(7 + k, pos); sm.stv(17 + k, a_in[k]);
+        }
+    }
+    // ---- gyro_int :717-724
+    const P2 drift_g = sm.ld(3);
+    P2 gbias = pfma(drift_g, dt, sm.ld(1));                                                // gyro() :624
+    P2 qg[4];
+    {
+        P2 w1[3], dq[4], q0[4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w1[k] = pfma(sg, z1[1 + k], padd(y[10 + k], gbias));   // z[9..11]
+#pragma unroll
+        for (int k = 0; k < 4; ++k) q0[k] = sm.ld(10 + k);
+        deriv_quat2(w1, q0, dq);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qg[k] = pfma(dq[k], dt, q0[k]);                        // :721-722 (returned un-normalised)
+        const P2 inv = prsqrt(pfma(qg[0], qg[0], pfma(qg[1], qg[1], pfma(qg[2], qg[2], pmul(qg[3], qg[3])))));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { sm.stv(10 + k, pmul(qg[k], inv)); out(6 + k, qg[k]); }   // :723
+    }
+    // ---- gyro :622-628
+    gbias = pfma(drift_g, dt, gbias);
+    sm.stv(1, gbias);
+    {
+        P2 w2[3], qv[4];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) w2[k] = pfma(sg, z1[4 + k], padd(y[10 + k], gbias));   // z[12..14]
+        deriv_quat2(w2, qg, qv);                                                           // rl_worker.py:168
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out(10 + k, qv[k]);
+    }
+    // ---- gps :642-647: z[15..20] = block 3, drawn only when the optional complementary blend reads them (math_trajectory.py:71-77)
+    const P2 z21 = z1[7];                                                                  // P[15] = z[21]
+    if (p.s_gps_blend > 0.f) {
+        const P2 wg = bc(p.s_gps_blend * 0.01f), wa = bc((100.f - p.s_gps_blend) * 0.01f);
+        sensor_normals_block2(rng, 3, z1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const P2 pos_gps = pfma(bc(p.s_gps_p), z1[k], y[2 * k]);
+            const P2 vel_gps = pfma(bc(p.s_gps_v), z1[3 + k], y[2 * k + 1]);
+            sm.stv(7 + k, pfma(wa, sm.ld(7 + k), pmul(wg, pos_gps)));
+            sm.stv(4 + k, pfma(wa, sm.ld(4 + k), pmul(wg, vel_gps)));
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { out(2 * k, sm.ld(7 + k)); out(2 * k + 1, sm.ld(4 + k)); }
+    // ---- triad :649-697 (updates self.R for the next step)
+    sensor_normals_block2(rng, 2, z0);                                                     // P[16..23]: z[22..26] = P[16..20]
+    {
+        ab = pfma(drift_a, dt, ab);
+        sm.stv(0, ab);
+        P2 gb[3], mi[3], mb[3], R2[9];
+        gb[0] = pfma(ng, rc[0], pfma(sa, z21, padd(acc_read[0], ab)));                     // z[21..23]
+        gb[1] = pfma(ng, rc[1], pfma(sa, z0[0], padd(acc_read[1], ab)));
+        gb[2] = psub(pfma(ng, rc[2], pfma(sa, z0[1], padd(acc_read[2], ab))), f_m);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) mi[k] = pfma(smg, z0[2 + k], bc(p.s_mag[k]));          // z[24..26]
+#pragma unroll
+        for (int c = 0; c < 3; ++c) mb[c] = pfma(rot[c], mi[0], pfma(rot[3 + c], mi[1], pmul(rot[6 + c], mi[2])));
+        triad2<false>(p, gb, mb, R2);
+        sm.stv(14, R2[2]); sm.stv(15, R2[5]); sm.stv(16, R2[8]);
+    }
+}
+
 }  // namespace qs

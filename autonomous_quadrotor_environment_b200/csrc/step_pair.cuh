@@ -41,8 +41,11 @@ constexpr int kRowsSensor = 46;
 #ifndef QS_PAIR_THREADS
 #define QS_PAIR_THREADS 384
 #endif
+#ifndef QS_SENSOR_STREAM
+#define QS_SENSOR_STREAM 0          // 1 = streaming sensor phase in the STEP kernel (state rows stay in shared memory, 168 registers,
+#endif                              // 12 warps per SM): measured slower, 127.9 vs 101.8 us per step of 1M envs; tuning builds only
 #ifndef QS_PAIR_THREADS_SENSOR
-#define QS_PAIR_THREADS_SENSOR 256
+#define QS_PAIR_THREADS_SENSOR (QS_SENSOR_STREAM ? 384 : 256)
 #endif
 constexpr int kThreadsPlain = QS_PAIR_THREADS;
 constexpr int kThreadsSensor = QS_PAIR_THREADS_SENSOR;
@@ -156,6 +159,45 @@ __device__ __forceinline__ void sensor_store(const SimView<float>& v, int64_t n0
     float2* go2 = reinterpret_cast<float2*>(v.sensed_obs + n0) + lane;
 #pragma unroll
     for (int k = 0; k < 14; ++k) go2[(int64_t)k * ld2] = so[k].v;
+}
+
+// Streaming sensor phase (sensor_step2_stream): state rows read / written in place in the warp's shared-memory stage, outputs
+// handed to `out(k, value)` as they are produced (value = what the sensor model computed: the caller substitutes the true
+// observation for envs in a warm-up step).  The last warm-up step of an episode re-initialises the sensor (sensor.reset).
+template <typename Out>
+__device__ __forceinline__ void sensor_phase_stream(const DevParams<float>& p, const SimView<float>& v, Row* srows, int lane, int64_t nA,
+                                                    const qs::P2 y[13], qs::P2 f_m, const PairMeta& m, bool any_warm, Out&& out) {
+    using namespace qs;
+    SensorMem sm;
+    sm.st = reinterpret_cast<float2*>(srows[0]) + lane;
+    sm.any_warm = any_warm; sm.w0 = m.warm[0]; sm.w1 = m.warm[1];
+    SensorRng2 rng;
+    rng.seed = v.seed; rng.rk = v.rk;
+    rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
+    rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
+    rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
+    sensor_step2_stream(p, rng, y, f_m, sm, out);
+    if (any_warm) {
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            if (m.warm[hf] && (m.flags[hf] >> EF_WARM_SHIFT) == 0) {
+                float yh[13], sh_[kSensorStateDim];
+#pragma unroll
+                for (int k = 0; k < 13; ++k) yh[k] = hf ? y[k].v.y : y[k].v.x;
+                sensor_reset(p, v.seed, rng.id[hf], rng.ep[hf], yh, sh_);
+#pragma unroll
+                for (int k = 0; k < kSensorStateDim; ++k) srows[k][2 * lane + hf] = sh_[k];
+            }
+        }
+    }
+}
+
+// the pair's sensor-state rows: shared memory -> HBM
+__device__ __forceinline__ void sensor_rows_store(const SimView<float>& v, int64_t n0, int lane, const Row* srows) {
+    const int64_t ld2 = v.ld >> 1;
+    float2* gs2 = reinterpret_cast<float2*>(v.sensor_state + n0) + lane;
+#pragma unroll
+    for (int k = 0; k < qs::kSensorStateDim; ++k) gs2[(int64_t)k * ld2] = lds2(srows, k, lane);
 }
 
 // fast_atan2f / fast_asinf (quad_device.cuh) for an env pair: the same operation sequence, the polynomial parts on the packed
@@ -502,9 +544,6 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
             }
         }
         if (SENSOR) {
-            P2 sn[kSensorStateDim], so[14], vq[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
             PairMeta m;
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
@@ -512,10 +551,31 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
             }
             cp_wait<1>();                      // pending = {sensor(c), state(next) | empty}: the sensor rows have landed
             __syncwarp();
-            sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
-            __syncwarp();                      // every lane is done with the sensor rows of the stage
-            if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
-            sensor_store(v, n0, lane, sn, so);
+#if QS_SENSOR_STREAM
+            {
+                const bool any_warm = __any_sync(0xffffffffu, warm[0] | warm[1]);
+                float2* go2 = reinterpret_cast<float2*>(v.sensed_obs + n0) + lane;
+                const float2* gt2 = reinterpret_cast<const float2*>(v.obs17 + n0) + lane;     // rows 0..13 = the true observation, stored above
+                const bool w0 = warm[0], w1 = warm[1];
+                sensor_phase_stream(p, v, srows, lane, nA, y, c2.f_m, m, any_warm, [&](int k, P2 val) {
+                    if (any_warm) { P2 t; t.v = gt2[(int64_t)k * ld2]; val = psel(w0, w1, t, val); }   // warm-up steps pass the true observation through
+                    go2[(int64_t)k * ld2] = val.v;
+                });
+                sensor_rows_store(v, n0, lane, srows);
+                __syncwarp();                  // every lane is done with the sensor rows of the stage
+                if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
+            }
+#else
+            {
+                P2 sn[kSensorStateDim], so[14], vq[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
+                sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
+                __syncwarp();                  // every lane is done with the sensor rows of the stage
+                if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
+                sensor_store(v, n0, lane, sn, so);
+            }
+#endif
         }
         if (async_reset)
             reset_queue_step<SENSOR, kQueueCap>(p, v, io, s_queue, &s_qn, &s_qhead, lane, nA, push[0], push[1]);

@@ -112,10 +112,21 @@ class BatchedPPO:
         entries = self.history_entries(rec)
         K, N = horizon, env.N
         value = torch.empty(K + 1, N, dtype=torch.float32, device=self.dev)
+        # old_logprobs of the update's ratio (ppo.py:187) must come from the SAME evaluation path as the new ones: the reference's
+        # policy_old is an exact copy of policy, so the ratio is exactly 1 at the first epoch.  The fused kernel's own log-probs
+        # (BF16 operands, tanh.approx) differ from the update's FP32/TF32 re-evaluation by O(0.1-1) in the tails, which would
+        # clip or over-weight those samples: they are kept as a diagnostic (batch["logprob_kernel"]) and the ratio's
+        # denominator is re-evaluated here, on the recorded actions, by the network the update differentiates.
+        logprob = torch.empty(K, 4, N, dtype=torch.float32, device=self.dev)
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.tf32
         for n0 in range(0, N, self.chunk):
             n1 = min(N, n0 + self.chunk)
             x = self.network_inputs(hist0, entries, n0, n1)
             value[:, n0:n1] = self.policy.critic(x).squeeze(-1)
+            lp, _, _ = self.policy.evaluate(x[:K], rec["actions"][:, :, n0:n1].permute(0, 2, 1))
+            logprob[:, :, n0:n1] = lp.permute(0, 2, 1)
+        torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         ret = torch.empty(K, N, dtype=torch.float32, device=self.dev)
         adv = torch.empty(K, N, dtype=torch.float32, device=self.dev)
         weight = torch.empty(K, N, dtype=torch.float32, device=self.dev)
@@ -126,7 +137,7 @@ class BatchedPPO:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.moments)                                 # normalise over the GLOBAL batch
         L.check(env.lib.qs_adv_normalize(K * N, rec["done"].data_ptr(), self.moments.data_ptr(), adv.data_ptr(), weight.data_ptr(), st))
-        return dict(hist0=hist0, entries=entries, actions=rec["actions"], logprob=rec["logprob"], reward=rec["reward"],
+        return dict(hist0=hist0, entries=entries, actions=rec["actions"], logprob=logprob, logprob_kernel=rec["logprob"], reward=rec["reward"],
                     done=rec["done"], value=value, returns=ret, adv=adv, weight=weight, count=float(self.moments[0].item()))
 
     def update(self, batch):
@@ -165,6 +176,7 @@ class BatchedPPO:
     def iterate(self, horizon: int = 128):
         batch = self.collect(horizon)
         losses = self.update(batch)
-        r = batch["reward"]
-        return dict(mean_reward=float((r * batch["weight"]).sum().item() / max(1.0, batch["count"])), losses=losses,
-                    stats=self.env.stats(reset=True))
+        rsum = (batch["reward"] * batch["weight"]).sum().double()
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(rsum)                                         # batch["count"] is the GLOBAL number of valid transitions
+        return dict(mean_reward=float(rsum.item()) / max(1.0, batch["count"]), losses=losses, stats=self.env.stats(reset=True))

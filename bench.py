@@ -80,36 +80,85 @@ def cpu_reference_run(n_envs, steps, warmup, T, threads=0):
     return n_envs * steps / dt, dt, cores
 
 
+def python_reference_run(seconds, T, steps=None, warmup=None):
+    """The reference's OWN quad.step (unmodified; bytecode build oracle/_ref) on all host cores: P worker processes x m envs each,
+    U(-1,1) actions, reset() on done.  Either a time budget (seconds) or an explicit (steps, warmup) sweep count."""
+    from oracle import cpu_reference as cr
+    probe = cr.run_isolated(2, 20, 2, T)                         # ~ 0.1 s per worker: per-core rate incl. resets
+    per_core = probe["rate"] / probe["cores"]
+    if steps is None:
+        m, warmup = 4, 2
+        steps = max(10, int(per_core * seconds / m))
+    else:
+        m = int(max(1, min(4096, per_core * seconds / max(1, steps + warmup))))
+    r = cr.run_isolated(m, steps, warmup, T)
+    r["m"], r["steps"] = m, steps
+    return r
+
+
 def cpu_baseline(seconds, T):
+    """cpu_baseline of the default line: the reference itself when its bytecode build travelled with the tree (kind "reference"),
+    else the C port; the C port and the vectorised NumPy oracle are always reported as labelled extras."""
+    import numpy as np
+    from oracle import cpu_reference as cr
+    from oracle import quad_oracle as qo
     n = 8192
     rate, _, cores = cpu_reference_run(n, 4, 1, T)
-    steps = max(4, int(rate * seconds / n))
+    steps = max(4, int(rate * min(seconds, 5.0) / n))
     rate, dt, cores = cpu_reference_run(n, steps, 2, T)
-    return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d envs x %d steps (%.1f s) of the FP64 SciPy-RK45-replica step the reference runs "
-                      "(oracle/quad_oracle.c, OpenMP); the Python reference itself measured 678 env-steps/s/core "
-                      "(BASELINE.md)" % (n, steps, dt)}
+    port = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d envs x %d steps (%.1f s) of the FP64 SciPy-RK45-replica step (oracle/quad_oracle.c, OpenMP)" % (n, steps, dt)}
+    nv = 4096                                                    # "best NumPy": the vectorised FP64 oracle, one process
+    ora = qo.BatchQuadOracle(nv, 0.01, 10 ** 9, training=False, direct_control=1, T=T, integrator="rk45")
+    init, _ = qo.sample_reset_state(0, np.arange(nv), 0)
+    ora.reset(init)
+    rng = np.random.default_rng(0)
+    t0 = time.perf_counter()
+    k = 0
+    while time.perf_counter() - t0 < 3.0:
+        ora.step(rng.uniform(-0.05, 0.05, (nv, 4)))
+        k += 1
+    numpy_vec = {"value": nv * k / (time.perf_counter() - t0), "unit": UNIT, "cores": 1, "kind": "port",
+                 "sample": "%d envs x %d steps of oracle/quad_oracle.py (vectorised NumPy FP64 RK45 replica), one process" % (nv, k)}
+    if cr.available():
+        r = python_reference_run(seconds, T)
+        return {"value": r["rate"], "unit": UNIT, "cores": r["cores"], "kind": "reference",
+                "sample": "the reference's own quad.step (unmodified, bytecode build oracle/_ref): %d worker processes x %d envs x %d "
+                          "steps (%.1f s), direct control, T=%d, U(-1,1) actions, reset() on done (%d resets)"
+                          % (r["cores"], r["m"], r["steps"], r["seconds"], T, r["resets"]),
+                "extra": {"c_port_all_cores": port, "numpy_vectorised_one_process": numpy_vec}}
+    port["extra"] = {"numpy_vectorised_one_process": numpy_vec}
+    port["sample"] += "; oracle/_ref (the Python reference itself) was not shipped with this tree"
+    return port
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import cpu_reference as cr
     n_gpu_envs = args.envs_per_gpu or (1 << 20 if args.gpus == 1 else 1 << 21)
-    probe_n = 4096
-    rate, _, cores = cpu_reference_run(probe_n, 4, 1, args.T)
-    budget_s = 90.0
-    n = int(max(256, min(65536, rate * budget_s / max(1, args.steps + args.warmup))))
-    t0 = time.perf_counter()
-    rate, dt, cores = cpu_reference_run(n, args.steps, args.warmup, args.T)
+    if cr.available():
+        r = python_reference_run(90.0, args.T, steps=args.steps, warmup=args.warmup)
+        rate, dt, cores, n = r["rate"], r["seconds"], r["cores"], r["n_envs"]
+        kind, dtype = "reference", "f64"
+        how = ("the reference's own quad.step (unmodified Python/NumPy/SciPy, bytecode build oracle/_ref), %d worker processes x %d "
+               "envs, U(-1,1) actions, reset() on done" % (cores, r["m"]))
+    else:
+        probe_n = 4096
+        rate, _, cores = cpu_reference_run(probe_n, 4, 1, args.T)
+        n = int(max(256, min(65536, rate * 90.0 / max(1, args.steps + args.warmup))))
+        rate, dt, cores = cpu_reference_run(n, args.steps, args.warmup, args.T)
+        kind, dtype = "port", "f64"
+        how = "reference algorithm (FP64 RK45 rtol 1e-3), C port oracle/quad_oracle.c with OpenMP (oracle/_ref not shipped with this tree)"
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "bounded sample (%d envs per step) of the %d-env lock-step workload, reference algorithm "
-                               "(FP64 RK45 rtol 1e-3) on host cores" % (n, n_gpu_envs * args.gpus), "T": args.T},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d envs x %d steps, oracle/quad_oracle.c with OpenMP" % (n, args.steps)},
+        "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+        "config": {"workload": "bounded sample (%d envs per step) of the %d-env lock-step workload on the host cores: %s"
+                               % (n, n_gpu_envs * args.gpus, how), "T": args.T},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": "%d envs x %d steps (%.1f s)" % (n, args.steps, dt)},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -165,37 +214,30 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-def run_policy_workload(args):
-    """BASELINE.json configs[4]: fused actor-MLP rollout.  Same metric (env-steps/s); a bench 'step' is one K-step launch."""
+def policy_measure(args, dev, rank, world, steps, warm):
+    """BASELINE.json configs[4]: fused actor-MLP rollout; one bench 'step' is one K-step launch.  Returns the measurement dict
+    (value = env-steps/s of this rank's shard x world when the caller all-reduces the time)."""
     import numpy as np
     import torch
-    from autonomous_quadrotor_environment_b200 import BatchedQuad
-    from autonomous_quadrotor_environment_b200.sharding import init_distributed
     import torch.distributed as dist
-    rank, world, local = init_distributed()
-    dev = torch.device("cuda", local)
-    torch.cuda.set_device(dev)
+    from autonomous_quadrotor_environment_b200 import BatchedQuad
     N = args.envs_per_gpu or (1 << 20)
     K = args.horizon
     env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", async_reset=True, seed=0,
                       env_id_offset=rank * N, device=dev)
     env.reset()
     env.load_actor(dict(np.load(os.path.join(ROOT, "tests", "golden", "actor_128.npz"))), action_std=0.1)
-    steps, warm = min(args.steps, 20), max(3, min(args.warmup, 3))
     for _ in range(warm):
         rec = env.policy_rollout(K)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(local) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
     e0.record()
     for _ in range(steps):
         rec = env.policy_rollout(K)                        # records actions, log-probs, rewards, dones: (K,*,N) buffers in HBM
     e1.record()
     torch.cuda.synchronize(dev)
-    t1 = time.perf_counter()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -204,32 +246,50 @@ def run_policy_workload(args):
     # e2e: the per-iteration statistic a PPO driver reads back (mean reward of the rollout) is reduced on the device and read
     mean_r = float(rec["reward"].mean().item())            # untimed: loads torch's reduction kernel (lazy module loading)
     torch.cuda.synchronize(dev)
-    e2e_iters = 5
+    e2e_iters = 3
     te0 = time.perf_counter()
     for _ in range(e2e_iters):
         rec = env.policy_rollout(K)
         mean_r = float(rec["reward"].mean().item())
     torch.cuda.synchronize(dev)
     e2e = N * world * K * e2e_iters / (time.perf_counter() - te0)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1367.3))
+    mlp_flops = 2 * (80 * 128 + 128 * 128 + 128 * 16)          # per env-step as issued (K padded 75->80, N 4->16)
+    ach = mlp_flops * N * K * steps / (ms * 1e-3) / 1e12
+    return {"value": value, "unit": UNIT, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "envs_per_gpu": N, "horizon": K,
+            "workload": "PPO rollout: %d envs/GPU x %d-step horizon per launch, actor MLP 75-128-128-4 (BF16 tcgen05, FP32 accumulate) + "
+                        "Normal(sigma=0.1) sampling + FP32 RK4 quad.step fused, async auto-reset, T=%d; records actions/log-probs/"
+                        "rewards/dones" % (N, K, args.T),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
+                    "api": "BatchedQuad.policy_rollout + mean reward read back (actions are produced on the device by the fused actor: no per-step host input exists)"},
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                         "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel": "policy_rollout_kernel",
+                         "note": "the kernel is bound by MUFU (256 tanh per env-step) and its serial MMA->epilogue->dynamics chain, not by the tensor pipe"},
+            "stats": env.stats(all_reduce=False), "mean_reward_last_rollout": mean_r}
+
+
+def run_policy_workload(args):
+    """--workload policy: configs[4] as the headline line.  Same metric (env-steps/s)."""
+    import torch
+    from autonomous_quadrotor_environment_b200.sharding import init_distributed
+    import torch.distributed as dist
+    rank, world, local = init_distributed()
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    steps, warm = min(args.steps, 20), max(3, min(args.warmup, 3))
+    sampler = ClockSampler(local) if rank == 0 else None
+    t0 = time.perf_counter()
+    m = policy_measure(args, dev, rank, world, steps, warm)
+    t1 = time.perf_counter()
     if rank == 0:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
-        tf_peak = float(peaks.get("bf16_tflops_sustained", 1367.3))
-        mlp_flops = 2 * (80 * 128 + 128 * 128 + 128 * 16)          # per env-step as issued (K padded 75->80, N 4->16)
-        ach = mlp_flops * N * K * steps / (ms * 1e-3) / 1e12 / world
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
-                "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic",
-                "config": {"workload": "PPO rollout: %d envs/GPU x %d-step horizon per launch, actor MLP 75-128-128-4 (BF16 tcgen05, "
-                                       "FP32 accumulate) + Normal(sigma=0.1) sampling + FP32 RK4 quad.step fused, async auto-reset, T=%d; "
-                                       "records actions/log-probs/rewards/dones" % (N, K, args.T),
-                           "envs_per_gpu": N, "horizon": K, "l2": "rollout buffers %.1f GB/launch >> 126 MB L2" % (N * K * 37 / 1e9)},
-                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 4,
-                        "api": "BatchedQuad.policy_rollout + mean reward read back (actions are produced on the device by the fused actor: no per-step host input exists)"},
-                "gpu_launches": steps, "clocks": sampler.stop(t0, t1) if sampler else None,
-                "roofline": {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
-                             "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel": "policy_rollout_kernel",
-                             "note": "the kernel is bound by MUFU (256 tanh per env-step) and its serial MMA->epilogue->dynamics chain, not by the tensor pipe"},
-                "stats": env.stats(all_reduce=False), "mean_reward_last_rollout": mean_r}
+                "config": {"workload": m["workload"], "envs_per_gpu": m["envs_per_gpu"], "horizon": m["horizon"],
+                           "l2": "rollout buffers %.1f GB/launch >> 126 MB L2" % (m["envs_per_gpu"] * m["horizon"] * 37 / 1e9)},
+                "e2e": m["e2e"], "gpu_launches": steps, "clocks": sampler.stop(t0, t1) if sampler else None,
+                "roofline": m["roofline"], "stats": m["stats"], "mean_reward_last_rollout": m["mean_reward_last_rollout"]}
         emit_line(line)
     if world > 1:
         dist.barrier()
@@ -295,17 +355,44 @@ def main():
     lib, h = env.lib, env._h
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     stats_buf = torch.zeros(8, dtype=torch.float64, device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    side = torch.cuda.Stream(dev)                        # the statistics exchange never sits between two step kernels
+    period = max(1, min(128, args.steps))                # BASELINE.json configs[3]: one all-reduce of the episode statistics per 128 steps
+    n_exchanges = [0]
 
-    def step(k):
+    def exchange_stats():
+        """The path's only collective: snapshot the 8 accumulators and sum them over the ranks (NCCL), on the side stream."""
+        ev = torch.cuda.Event()
+        ev.record(main_stream)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            stats_buf.copy_(env.stats_tensor())
+            allreduce_stats(stats_buf)
+        n_exchanges[0] += 1
+
+    def step(k, exchange=True):
         rc = lib.qs_step(h, ptrs[k % P], None, None, None, None, stream)
         if rc != 0:
             L.check(rc)
-        if world > 1 and k % 128 == 127:                 # the path's only collective: episode statistics
-            stats_buf.copy_(env.stats_tensor())
-            allreduce_stats(stats_buf)
+        if exchange and (k + 1) % period == 0:
+            exchange_stats()
 
+    # untimed pre-roll: right after reset() every env is at step 0 of its first episode; the reset rate (and with it the
+    # kernel's re-sampling work) only becomes stationary once the first episodes have turned over (~50-step episodes under
+    # random actions): roll until the episode count of a 32-step window stops changing by more than 2 %
+    preroll, last = 0, None
+    while preroll < 2000:
+        before = float(env.stats_tensor()[2].item())
+        for k in range(32):
+            step(preroll + k, exchange=False)
+        preroll += 32
+        rate = float(env.stats_tensor()[2].item()) - before
+        if last is not None and last > 0 and abs(rate - last) <= 0.02 * last and preroll >= 256:
+            break
+        last = rate
     for w in range(args.warmup):
-        step(w)
+        step(w, exchange=False)
+    env.stats_tensor().zero_()                           # the statistics reported below are those of the timed region
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -316,6 +403,9 @@ def main():
     ev0.record()
     for k in range(args.steps):
         step(k)
+    if args.steps % period != 0:
+        exchange_stats()                                 # the last iteration's exchange
+    main_stream.wait_stream(side)                        # the timed region ends when the last collective has
     ev1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
@@ -329,6 +419,12 @@ def main():
     ms_max = float(tmax.item())
     total_envs = N * world
     value = total_envs * args.steps / (ms_max * 1e-3)
+    from autonomous_quadrotor_environment_b200.sharding import stats_dict
+    stats_all = stats_dict(stats_buf)                    # ALL-REDUCED statistics of the timed region (last exchange)
+    stats_all["exchanges_in_timed_region"] = n_exchanges[0]
+    stats_all["preroll_steps"] = preroll
+    if stats_all["n_steps"] != float(total_envs) * args.steps:
+        raise SystemExit("all-reduced n_steps %r != envs x ranks x steps %r" % (stats_all["n_steps"], float(total_envs) * args.steps))
 
     # ---- e2e: qs_step_host with pinned host buffers (H2D actions, D2H obs/reward/done inside the timed region)
     e2e_steps = max(1, args.e2e_steps)
@@ -361,8 +457,11 @@ def main():
     sensor = int(bool(args.sensor_noise))
     kernel_name = {0: "step_kernel_direct<float,RK4,direct,sensor=%d>", 1: "step_kernel_tma<float,RK4,direct,sensor=%d>",
                    2: "step_kernel_warp<direct,sensor=%d>", 3: "step_kernel_pair<direct,sensor=%d>"}[env.step_loader] % sensor
-    # algorithmic bytes per env-step: 181 B; the sensor model adds its 17-float state in + out and the
-    # 14-float sensed observation out
+    # algorithmic bytes per env-step: 181 B; the sensor model adds the 17 rows of its state that it reads AND
+    # writes back (biases, drift rates, velocity_t0, position_t0, quaternion_t0, third column of R: 2 x 68 B) and the 14-float
+    # sensed observation it writes (56 B) = 192 B.  The three acceleration_t0 rows of the 20-row QS_FIELD_SENSOR_STATE are a
+    # write-only diagnostic (sensor.acceleration_t0, never read back) and are NOT counted, although the kernel moves them:
+    # the DRAM traffic (`traffic`, 402 MB per launch) therefore sits above the 391 MB counted here
     algo_bytes = ALGO_BYTES_PER_ENV_STEP + (192 if sensor else 0)
     achieved_gbs = algo_bytes * N / (kernel_ms * 1e-3) / 1e9
     traffic = None
@@ -454,6 +553,36 @@ def main():
                 "note": "K=%d steps per launch, %d RK4 sub-intervals per env step (h = %.3g ms), no resets" % (KR, S_, 10.0 / S_)}
             del env3
 
+    if world == 1 and args.variant_steps > 0:
+        # (a) the per-GPU shard of BASELINE.json configs[3] (2,097,152 envs) on ONE GPU: the like-for-like base point of the
+        #     weak-scaling series the N > 1 runs of this script produce
+        N2 = 1 << 21
+        envb = BatchedQuad(N2, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
+                           substeps=args.substeps, async_reset=True, sensor_noise=bool(args.sensor_noise), seed=0, device=dev)
+        envb.reset()
+        actsb = [(torch.rand(4, N2, device=dev, generator=g) * 2 - 1).contiguous() for _ in range(8)]
+        for w in range(400):
+            L.check(lib.qs_step(envb._h, C.c_void_p(actsb[w % 8].data_ptr()), None, None, None, None, stream))
+        torch.cuda.synchronize(dev)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nb = max(100, args.variant_steps // 4)
+        b0.record()
+        for k in range(nb):
+            L.check(lib.qs_step(envb._h, C.c_void_p(actsb[k % 8].data_ptr()), None, None, None, None, stream))
+        b1.record()
+        torch.cuda.synchronize(dev)
+        bms = b0.elapsed_time(b1) / nb
+        variants["envs_per_gpu=2097152"] = {
+            "value": N2 / (bms * 1e-3), "unit": UNIT, "steps": nb, "kernel_ms": bms,
+            "note": "same workload as the headline at the per-GPU shard size of the N > 1 runs (400 untimed pre-roll steps)",
+            "roofline_frac": algo_bytes * N2 / (bms * 1e-3) / 1e9 / hbm_peak}
+        del envb, actsb
+        # (b) BASELINE.json configs[4]: PPO rollout, 1M envs x 128-step horizon per launch, actor MLP fused in on tcgen05
+        try:
+            variants["policy_rollout_1Mx128"] = policy_measure(args, dev, 0, 1, steps=4, warm=2)
+        except Exception as ex:                                  # a variant must not take the headline line down with it
+            variants["policy_rollout_1Mx128"] = {"error": repr(ex)}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -480,7 +609,7 @@ def main():
             "fp32": {"achieved_tflops": flops, "peak_tflops_probe": fp32_peak, "frac": flops / fp32_peak,
                      "flops_per_env_step": FLOPS_PER_ENV_STEP(args.substeps),
                      "note": "algorithmic FLOPs (SURVEY.md 8(d)) vs an in-run dependent-FFMA probe"},
-            "stats": env.stats(all_reduce=False),
+            "stats": stats_all,
         }
         if variants:
             line["variants"] = variants

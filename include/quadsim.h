@@ -181,6 +181,8 @@ typedef struct qs_rollout_args {
     void* action_out;            /* [K][4][N] or NULL                                              */
     void* reward_out;            /* [K][N] or NULL                                                 */
     uint8_t* done_out;           /* [K][N] or NULL                                                 */
+    void* sensed_obs_out;        /* [K][14][N] or NULL: the sensor-based observation of every step  */
+                                 /* (QS_FLAG_SENSOR_NOISE handles; visual_landing/rl_worker.py:171) */
 } qs_rollout_args;
 
 /* Actor of the reference's PPO controller (environment/controller/model.py:27-34): Linear(in_dim,H)-Tanh-Linear(H,H)-

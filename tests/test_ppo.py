@@ -143,13 +143,20 @@ def test_ppo_iteration_on_device():
     x = ppo.network_inputs(b["hist0"], b["entries"], 0, 512)[:K]
     with torch.no_grad():
         mean = ppo.policy.actor(x)                                         # (K, 512, 4)
-    a = b["actions"][:, :, :512].permute(0, 2, 1); lp = b["logprob"][:, :, :512].permute(0, 2, 1)
+    a = b["actions"][:, :, :512].permute(0, 2, 1); lp = b["logprob_kernel"][:, :, :512].permute(0, 2, 1)
     sigma = ppo.policy.std
     lp_torch = -((a - mean) ** 2) / (2 * sigma * sigma) - np.log(sigma) - 0.9189385
     ok = (b["weight"][:, :512] > 0).unsqueeze(-1).expand_as(lp)
     # BF16 operands in the kernel vs FP32 here: |mean error| ~ 1e-2 -> log-prob error ~ |z| * 0.1 + small
     err = (lp_torch - lp)[ok].abs()
     assert float(err.median()) < 0.05 and float(err.quantile(0.99)) < 1.0, (float(err.median()), float(err.quantile(0.99)))
+    # the ratio's denominator is the update network's OWN evaluation of the recorded actions (policy_old == policy at epoch 0,
+    # ppo.py:187,:206): the first epoch's ratio is exactly 1 for every valid sample
+    with torch.no_grad():
+        lp_new, _, _ = ppo.policy.evaluate(x, a)
+    assert torch.allclose(lp_new, b["logprob"][:, :, :512].permute(0, 2, 1), rtol=0, atol=1e-4)
+    ratio = torch.exp(lp_new.sum(-1) - b["logprob"][:, :, :512].permute(0, 2, 1).sum(-1))
+    assert float((ratio - 1).abs().max()) < 1e-3
     before = torch.cat([p.detach().reshape(-1) for p in ppo.policy.parameters()]).clone()
     out = ppo.iterate(K)
     after = torch.cat([p.detach().reshape(-1) for p in ppo.policy.parameters()])

@@ -63,10 +63,13 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
     cfg.update(kw)
     env = BatchedQuad(N, 0.01, cfg["n"], training=True, direct_control=1, T=cfg["T"], precision=cfg["precision"],
                       integrator=cfg["integrator"], substeps=cfg["substeps"], auto_reset=cfg["auto_reset"],
-                      async_reset=cfg["async_reset"], seed=0, device=DEV)
+                      async_reset=cfg["async_reset"], sensor_noise=cfg.get("sensor_noise", False), seed=0, device=DEV)
     env.reset()
-    ms = time_ms(lambda: env.rollout(K), iters, warm=3)
-    emit({"case": "rollout", "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
+    rec = cfg.get("record", False)                 # record = the stream a trainer reads: sensed (or true) observation, reward, done
+    sens = bool(cfg.get("sensor_noise", False))
+    fn = (lambda: env.rollout(K, record_sensed=sens, record_obs=not sens, record_reward=True, record_done=True)) if rec else (lambda: env.rollout(K))
+    ms = time_ms(fn, iters, warm=3)
+    emit({"case": "rollout" + ("+rec" if rec else ""), "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
 
 
 def case_policy(N=1 << 20, K=128, iters=3, sigma=0.1, record=True):
@@ -111,6 +114,14 @@ if __name__ == "__main__":
         case_step(N=1 << 21, async_reset=True, T=5)
         case_step(N=1 << 18, async_reset=True, T=5)
         case_step(N=1 << 16, iters=100, precision="f64", integrator="rk45", async_reset=True, T=5)
+    if "sensorrollout" in which:
+        case_rollout(async_reset=True, T=5, sensor_noise=True)
+        case_rollout(async_reset=True, T=5, sensor_noise=True, record=True)
+        case_rollout(async_reset=True, T=5, sensor_noise=True, K=128, iters=4)
+        case_rollout(async_reset=True, T=5)
+        case_rollout(async_reset=True, T=5, record=True)
+    if "profsensorrollout" in which:
+        case_rollout(async_reset=True, T=5, sensor_noise=True, K=32, iters=2)
     if "rollout" in which or "all" in which:
         case_rollout(n=10 ** 9)
         case_rollout(async_reset=True, T=5)
