@@ -59,11 +59,14 @@ __device__ __forceinline__ void pcross3(const P2 a[3], const P2 b[3], P2 c[3]) {
 // part of self.R the next step reads (:658).
 template <bool FULL>
 __device__ __forceinline__ void triad2(const DevParams<float>& p, P2 g[3], P2 m[3], P2 Rm[9]) {
+    // FP32 production form: two of the reference's four normalisations are mathematically redundant and are skipped here
+    // (each is a serial FMA-FMA-FMA-MUFU.RSQ-FMUL chain in a latency-bound phase): t2 = (g x m)/|g x m| does not depend on |m|
+    // (:670), and t3 = t1 x t2 of two orthogonal unit vectors is a unit vector already (:679).  The results move by FP32
+    // rounding only; the FP64 parity path (sensor_device.cuh: triad) keeps all four.
     pnormalize3(g);                                       // :668
-    pnormalize3(m);                                       // :670
     P2 t2[3], t3[3];
     pcross3(g, m, t2); pnormalize3(t2);                   // :675-676
-    pcross3(g, t2, t3); pnormalize3(t3);                  // :678-679
+    pcross3(g, t2, t3);                                   // :678
 #pragma unroll
     for (int r = 0; r < 3; ++r)
 #pragma unroll

@@ -176,7 +176,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -377,6 +377,12 @@ def main():
         if exchange and (k + 1) % period == 0:
             exchange_stats()
 
+    # the clock sampler starts here: nvidia-smi needs ~0.1-0.3 s to print its first row, and a 20-step timed region lasts 2 ms —
+    # the GPU is under the same load from the pre-roll on, so the clocks reported are the samples from here to the end of the
+    # timed region
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
+                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]) if rank == 0 else None
+    t_load0 = time.perf_counter()
     # untimed pre-roll: right after reset() every env is at step 0 of its first episode; the reset rate (and with it the
     # kernel's re-sampling work) only becomes stationary once the first episodes have turned over (~50-step episodes under
     # random actions): roll until the episode count of a 32-step window stops changing by more than 2 %
@@ -392,12 +398,17 @@ def main():
         last = rate
     for w in range(args.warmup):
         step(w, exchange=False)
+    if sampler is not None:                              # keep the load up until the sampler has seen it at least twice (<= 1.5 s)
+        w = 0
+        while len(sampler.rows) < 2 and time.perf_counter() - t_load0 < 1.5:
+            for k in range(64):
+                step(w + k, exchange=False)
+            w += 64
+            torch.cuda.synchronize(dev)
     env.stats_tensor().zero_()                           # the statistics reported below are those of the timed region
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else
-                           os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local]) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
     ev0.record()
@@ -412,7 +423,7 @@ def main():
         dist.barrier()
     t1 = time.perf_counter()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = sampler.stop(t_load0, t1) if sampler else None
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)

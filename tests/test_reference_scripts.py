@@ -49,9 +49,11 @@ def test_unmodified_reference_script_drives_the_dropin(key, script, switches, lo
         elif sc[key + "_self_err"][ep] < 1e-9:
             assert np.abs(got[ep] - log[ep]).max() < 1e-8, (ep, np.abs(got[ep] - log[ep]).max())
             pinned += 1
-        else:
+        elif ep == 0 or sc[key + "_self_err"][ep - 1] < 1e-9:
             # a diverging (unstable closed loop) episode doubles a 1e-16 difference every few steps: only its first steps say anything
             here = sc["%s_here_ep%d" % (key, ep)]
             k = 8
             assert np.max(np.abs(got[ep, :k] - here[:k]) / np.maximum(np.abs(here[:k]), 1.0)) < 1e-6, ep
+        # else: the episode FOLLOWS a diverged one and inherits its final Euler angles (quad.prev_ang survives reset, a reference
+        # quirk that is reproduced): its very first ang_vel already differs between any two runs — nothing to compare
     assert pinned >= 15
