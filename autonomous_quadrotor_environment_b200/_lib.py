@@ -88,12 +88,14 @@ class qs_rollout_args(C.Structure):
 class qs_actor(C.Structure):
     _fields_ = [("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p),
                 ("b3", C.c_void_p), ("hidden", C.c_int32), ("in_dim", C.c_int32), ("action_std", C.c_float),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("cw1", C.c_void_p), ("cb1", C.c_void_p), ("cw2", C.c_void_p), ("cb2", C.c_void_p),
+                ("cw3", C.c_void_p), ("cb3", C.c_void_p)]
 
 
 class qs_policy_rollout_args(C.Structure):
     _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32), ("obs_out", C.c_void_p), ("action_out", C.c_void_p),
-                ("logprob_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("hist", C.c_void_p)]
+                ("logprob_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("hist", C.c_void_p),
+                ("value_out", C.c_void_p)]
 
 
 class qs_controller(C.Structure):

@@ -229,11 +229,15 @@ class BatchedQuad:
         return out
 
     # ------------------------------------------------------------------ fused actor rollout (config 5)
-    def load_actor(self, source, action_std: float = 0.1):
+    def load_actor(self, source, action_std: float = 0.1, critic=None):
         """Prepare the reference's actor (environment/controller/model.py:27-34) for policy_rollout.
-        source: path to a solved/*.pth state dict, a state dict, or a dict/npz with keys actor_{0,2,4}_{weight,bias}."""
+        source: path to a solved/*.pth state dict, a state dict, or a dict/npz with keys actor_{0,2,4}_{weight,bias}.
+        critic: None, True (take critic.{0,2,4}.* from `source`) or a dict with those keys: the critic head (model.py:36-43) is then
+        evaluated by the same kernel on every network input and policy_rollout(record_values=True) returns the state values."""
         if isinstance(source, (str, bytes)):
             source = torch.load(source, map_location="cpu")
+        if critic is True:
+            critic = source
 
         def get(i, kind):
             for key in ("actor.%d.%s" % (i, kind), "actor_%d_%s" % (i, kind), "%d.%s" % (i, kind)):
@@ -245,6 +249,16 @@ class BatchedQuad:
              "w3": get(4, "weight"), "b3": get(4, "bias")}
         if w["w1"].shape != (128, 75) or w["w2"].shape != (128, 128) or w["w3"].shape != (4, 128):
             raise ValueError("only the 75-128-128-4 actor is supported by the fused kernel")
+        if critic is not None:                                  # model.py:36-43: Linear(75,128)-Tanh-Linear(128,128)-Tanh-Linear(128,1)
+            def getc(i, kind):
+                for key in ("critic.%d.%s" % (i, kind), "critic_%d_%s" % (i, kind), "%d.%s" % (i, kind)):
+                    if key in critic:
+                        return torch.as_tensor(critic[key]).to(device=self.device, dtype=torch.float32).contiguous()
+                raise KeyError("critic layer %d %s not found" % (i, kind))
+            w.update({"cw1": getc(0, "weight"), "cb1": getc(0, "bias"), "cw2": getc(2, "weight"), "cb2": getc(2, "bias"),
+                      "cw3": getc(4, "weight"), "cb3": getc(4, "bias")})
+            if w["cw1"].shape != (128, 75) or w["cw2"].shape != (128, 128) or w["cw3"].numel() != 128:
+                raise ValueError("only the 75-128-128-1 critic is supported by the fused kernel")
         a = L.qs_actor()
         for k, t in w.items():
             setattr(a, k, t.data_ptr())
@@ -260,7 +274,7 @@ class BatchedQuad:
         return self._hist.t()
 
     def policy_rollout(self, horizon: int, record_obs=False, record_actions=True, record_logprob=True,
-                       record_reward=True, record_done=True):
+                       record_reward=True, record_done=True, record_values=False):
         """K fused steps of  history -> actor MLP (tcgen05) -> Normal sample -> quad.step -> history push  in ONE launch
         (the loop of environment/controller/ppo.py:238-257).  Returns the recorded (K,C,N) buffers."""
         if getattr(self, "_actor", None) is None:
@@ -281,6 +295,8 @@ class BatchedQuad:
             out["reward"] = torch.empty(horizon, self.N, dtype=f32, device=self.device); a.reward_out = out["reward"].data_ptr()
         if record_done:
             out["done"] = torch.empty(horizon, self.N, dtype=torch.uint8, device=self.device); a.done_out = out["done"].data_ptr()
+        if record_values:                      # (K+1,N): V of the network input of every step + the bootstrap row (load_actor(critic=...))
+            out["value"] = torch.empty(horizon + 1, self.N, dtype=f32, device=self.device); a.value_out = out["value"].data_ptr()
         L.check(self.lib.qs_policy_rollout(self._h, C.byref(self._actor[0]), C.byref(a), self._stream()))
         return out
 

@@ -148,6 +148,7 @@ constexpr int kPKin = kPSlots * kPSlotK;   // 80
 struct ActorView {
     const float *w1, *b1, *w2, *b2, *w3, *b3;   // PyTorch Linear layout [out][in]: (128,75) (128,128) (4,128)
     float action_std;                            // sigma of the fixed-std Normal policy (model.py:62); <= 0: deterministic
+    const float *cw1, *cb1, *cw2, *cb2;          // critic (model.py:36-43) hidden layers, same shapes; NULL = no critic
 };
 struct PolicyIO {
     int32_t horizon;
@@ -157,6 +158,7 @@ struct PolicyIO {
     float* reward_out;    // [K][N]     or NULL
     uint8_t* done_out;    // [K][N]     or NULL  (bit0 done, bit1 warm-up step)
     float* hist;          // [75][N] in/out: dl_in_gen.deep_learning_input per env (oldest entry first), or NULL
+    float* value_out;     // [K+1][N] or NULL (critic handles): V of the network input of step t; row K = V of the input after the last step
 };
 
 #ifndef QS_POLICY_GROUPS
@@ -175,7 +177,7 @@ struct PolicyIO {
 //               of H2 is stored): 128 TMEM columns and 20 KB of shared memory per group -> FOUR tiles in flight per SM
 //               (512 TMEM columns, 140 KB), which is what the kernel needs: every tile is a serial chain MMA -> tanh -> MMA ->
 //               tanh -> dynamics and the SM is only busy while other tiles fill its gaps.
-template <bool TS> struct PolicyCfg {
+template <bool TS, bool CRITIC = false> struct PolicyCfg {
     static constexpr int kG = TS ? 4 : QS_POLICY_GROUPS;                 // tiles (groups of 128 threads) per CTA
     static constexpr int kXH = kPM * kPKin * 2 + (TS ? 0 : kPM * kPH * 2);   // per group: history/A tile (+ hidden tile)
     static constexpr int kX = 0;
@@ -184,7 +186,10 @@ template <bool TS> struct PolicyCfg {
     static constexpr int kW2 = kW1 + kPH * kPKin * 2;
     static constexpr int kOnes = kW2 + kPH * kPH * 2;                    // A operand of the bias block of layer 2: [128][16], columns 0,1 = 1
     static constexpr int kW2x = kOnes + kPM * 16 * 2;                    // B operand of that block: [128][16], columns 0,1 = b2 (hi, lo)
-    static constexpr int kBytes = kW2x + kPH * 16 * 2;
+    static constexpr int kW1c = kW2x + kPH * 16 * 2;                     // CRITIC: the critic's W1 / W2 / b2 operand tiles (one copy per CTA)
+    static constexpr int kW2c = kW1c + kPH * kPKin * 2;
+    static constexpr int kW2xc = kW2c + kPH * kPH * 2;
+    static constexpr int kBytes = CRITIC ? kW2xc + kPH * 16 * 2 : kW1c;
 };
 
 // Output layer (Linear(128,4) + Tanh, model.py:33-34) on the FP32 pipe: 128 -> 4 is 512 FMAs per env, and as a third UMMA it
@@ -196,6 +201,8 @@ template <bool TS> struct PolicyCfg {
 // not run concurrently on different streams of one device.
 __constant__ float c_actor_w3[kPH * 4];      // [j][k] = w3[k][j]
 __constant__ float c_actor_b3[4];
+__constant__ float c_critic_w3[kPH];         // critic output layer Linear(128,1) (model.py:42)
+__constant__ float c_critic_b3[1];
 
 __global__ void k_pack_w3(const float* __restrict__ w3, const float* __restrict__ b3, float* __restrict__ out) {
     const int j = threadIdx.x;               // out: [128][4] then b3[4]
@@ -252,6 +259,23 @@ __device__ __forceinline__ void actor_output_accumulate(uint32_t taddr, float m[
     m[0] = m01.x; m[1] = m01.y; m[2] = m23.x; m[3] = m23.y;
 }
 
+// critic: tanh epilogue of the second hidden layer fused with Linear(128,1): v += sum_j tanh(acc_j) w3c[j]
+template <int J0, int NJ>
+__device__ __forceinline__ float critic_output_accumulate(uint32_t taddr, float vacc) {
+    float v0 = vacc, v1 = 0.f;
+#pragma unroll
+    for (int c = 0; c < NJ; c += 32) {
+        float acc[32];
+        tmem_ld_32x32b_x32(taddr + (uint32_t)c, acc);
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+            v0 = fmaf(tanh_fast(acc[i]), c_critic_w3[J0 + c + i], v0);
+            v1 = fmaf(tanh_fast(acc[i + 1]), c_critic_w3[J0 + c + i + 1], v1);
+        }
+    }
+    return v0 + v1;
+}
+
 // tanh epilogue of the first hidden layer, TS path: accumulator columns [0,128) -> packed BF16 row in columns [0,64), in place
 // (chunk c reads columns [32c, 32c+32) and writes [16c, 16c+16): always columns this thread has already consumed)
 __device__ __forceinline__ void actor_hidden_epilogue_tmem(uint32_t lane_addr) {
@@ -267,11 +291,12 @@ __device__ __forceinline__ void actor_hidden_epilogue_tmem(uint32_t lane_addr) {
     tmem_st_wait();
 }
 
-template <bool TS>
-__global__ void __launch_bounds__(kPM * PolicyCfg<TS>::kG, 1)
+template <bool TS, bool CRITIC>
+__global__ void __launch_bounds__(kPM * PolicyCfg<TS, CRITIC>::kG, 1)
 policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                       const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
-    using PolicySmem = PolicyCfg<TS>;
+    static_assert(TS || !CRITIC, "the critic head exists on the TS path only");
+    using PolicySmem = PolicyCfg<TS, CRITIC>;
     constexpr int kPG = PolicySmem::kG;
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid_all = threadIdx.x, grp = tid_all / kPM, tid = tid_all % kPM, warp = tid >> 5;   // group-local thread / warp
@@ -281,6 +306,9 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
     unsigned char* sW2 = smem + PolicySmem::kW2;
     unsigned char* sOnes = smem + PolicySmem::kOnes;
     unsigned char* sW2x = smem + PolicySmem::kW2x;
+    unsigned char* sW1c = smem + PolicySmem::kW1c;
+    unsigned char* sW2c = smem + PolicySmem::kW2c;
+    unsigned char* sW2xc = smem + PolicySmem::kW2xc;
     __shared__ uint64_t bars[kPG];
     __shared__ uint32_t tmem_slot;
     uint64_t& bar = bars[grp];
@@ -303,6 +331,25 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
         const float b = act.b2[n];
         *reinterpret_cast<__nv_bfloat16*>(sOnes + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk < 2 ? 1.f : 0.f);
         *reinterpret_cast<__nv_bfloat16*>(sW2x + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk == 0 ? bf16_hi(b) : (kk == 1 ? b - bf16_hi(b) : 0.f));
+    }
+    if constexpr (CRITIC) {
+        for (int idx = tid_all; idx < kPH * kPKin; idx += kPM * kPG) {
+            const int n = idx / kPKin, kk = idx % kPKin, a = kk / kPSlotK, e = kk % kPSlotK;
+            float w = 0.f;
+            if (e < 15) w = act.cw1[n * 75 + a * 15 + e];
+            else if (a == 0) w = bf16_hi(act.cb1[n]);
+            else if (a == 1) w = act.cb1[n] - bf16_hi(act.cb1[n]);
+            *reinterpret_cast<__nv_bfloat16*>(sW1c + umma_canon_offset(n, kk, kPKin)) = __float2bfloat16(w);
+        }
+        for (int idx = tid_all; idx < kPH * kPH; idx += kPM * kPG) {
+            const int n = idx / kPH, kk = idx % kPH;
+            *reinterpret_cast<__nv_bfloat16*>(sW2c + umma_canon_offset(n, kk, kPH)) = __float2bfloat16(act.cw2[n * kPH + kk]);
+        }
+        for (int idx = tid_all; idx < kPH * 16; idx += kPM * kPG) {
+            const int n = idx / 16, kk = idx % 16;
+            const float b = act.cb2[n];
+            *reinterpret_cast<__nv_bfloat16*>(sW2xc + umma_canon_offset(n, kk, 16)) = __float2bfloat16(kk == 0 ? bf16_hi(b) : (kk == 1 ? b - bf16_hi(b) : 0.f));
+        }
     }
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
     constexpr uint32_t kTmemCols = kPG * kPH <= 128 ? 128 : (kPG * kPH <= 256 ? 256 : 512);      // power of two >= 128 accumulator columns per group
@@ -352,6 +399,51 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
         StepOut<float> o;
         float reward = 0.f;
         bool done = false, solved = false, warm_last = false;
+        // Critic head (model.py:36-43, Linear-Tanh-Linear-Tanh-Linear(128,1)) on the SAME history tile as the actor: the group's
+        // 128 TMEM columns are re-used once the actor's output is out (the two networks of a step form one serial chain per tile;
+        // the other tiles of the CTA fill its gaps), the hidden layers are the same two UMMA rounds with the critic's operand
+        // tiles, the 128 -> 1 output layer rides in the second tanh epilogue.  Called by every thread of the group.
+        auto critic_value = [&]() -> float {
+            tc_fence_before();
+            fence_proxy_async_smem();
+            group_sync(grp);                                             // the actor's accumulators are consumed; sX is visible
+            if (tid == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int a = 0; a < kPSlots; ++a) {
+                    int s_ = head + a; s_ = s_ >= kPSlots ? s_ - kPSlots : s_;
+                    umma_gemm_k(tmem_base, smem_u32(sX), kPKin, s_ * kPSlotK, smem_u32(sW1c), kPKin, a * kPSlotK, kPSlotK, kPH, a > 0);
+                }
+                umma_commit(&bar);
+            }
+            mbar_wait(&bar, phase); phase ^= 1;
+            tc_fence_after();
+            actor_hidden_epilogue_tmem(lane_addr);
+            tc_fence_before();
+            group_sync(grp);
+            float val = c_critic_b3[0];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                if (tid == 0) {
+                    tc_fence_after();
+                    constexpr uint32_t idesc = umma_idesc_bf16_f32(128, 64);
+                    const uint32_t b_rows = smem_u32(sW2c) + (uint32_t)half * umma_canon_offset(64, 0, kPH);
+#pragma unroll
+                    for (int k = 0; k < kPH; k += 16)
+                        umma_bf16_ts(tmem_base + 64u, tmem_base + (uint32_t)(k >> 1),
+                                     umma_smem_desc(b_rows + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(kPH >> 3) * 128u), idesc, k > 0);
+                    umma_bf16(tmem_base + 64u, umma_smem_desc(smem_u32(sOnes), 128u, 256u),
+                              umma_smem_desc(smem_u32(sW2xc) + (uint32_t)half * umma_canon_offset(64, 0, 16), 128u, 256u), idesc, true);
+                    umma_commit(&bar);
+                }
+                mbar_wait(&bar, phase); phase ^= 1;
+                tc_fence_after();
+                val = half == 0 ? critic_output_accumulate<0, 64>(lane_addr + 64u, val) : critic_output_accumulate<64, 64>(lane_addr + 64u, val);
+                tc_fence_before();
+                if (half == 0) group_sync(grp);
+            }
+            return val;
+        };
         for (int t = 0; t < io.horizon; ++t) {
             // ---------------- layer 1: [128 x 80] x W1^T, one K=16 MMA per history slot, oldest first
             fence_proxy_async_smem();
@@ -414,6 +506,10 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             }
 #pragma unroll
             for (int k = 0; k < 4; ++k) mean[k] = tanh_fast(mean[k]);
+            if constexpr (CRITIC) {                                      // V of the input the actor has just seen (memory.values, model.py:68)
+                const float val = critic_value();
+                if (active && io.value_out) io.value_out[(int64_t)t * v.N + n] = val;
+            }
             // ---------------- a ~ Normal(mean, sigma)  (model.py:60-66), per-dimension log-prob
             float a[4], logp[4];
             if (sigma > 0.f) {
@@ -469,6 +565,10 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
                 head = head + 1 == kPSlots ? 0 : head + 1;
             }
         }
+        if constexpr (CRITIC) {                                          // bootstrap value of the input after the last step (GAE, ppo.py:384)
+            const float val = critic_value();
+            if (active && io.value_out) io.value_out[(int64_t)io.horizon * v.N + n] = val;
+        }
         if (active) {
             store_env(v, n, e, o.vq);
             v.reward[n] = reward;
@@ -511,23 +611,43 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET | QS_FLAG_ROBUST))
         return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / ROBUST / strict AUTO_RESET (use ASYNC_RESET)");
     QS_USE_DEVICE(h);
-    ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std};
+    const bool critic = actor->cw1 != nullptr;
+    if (critic && (!actor->cb1 || !actor->cw2 || !actor->cb2 || !actor->cw3 || !actor->cb3))
+        return fail(QS_EINVAL, "qs_policy_rollout: the critic needs all six of cw1, cb1, cw2, cb2, cw3, cb3");
+    if (args->value_out && !critic) return fail(QS_EINVAL, "qs_policy_rollout: value_out needs the critic weights (qs_actor.cw1 ...)");
+    ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std,
+                 actor->cw1, actor->cb1, actor->cw2, actor->cb2};
     PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
-                (float*)args->reward_out, args->done_out, (float*)args->hist};
+                (float*)args->reward_out, args->done_out, (float*)args->hist, (float*)args->value_out};
     constexpr bool kTS = QS_POLICY_TS != 0;
-    using Cfg = PolicyCfg<kTS>;
-    QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS>), Cfg::kBytes);
-    {   // output layer -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
+    if (critic && !kTS) return fail(QS_ESTATE, "qs_policy_rollout: the critic head needs the TS build (QS_POLICY_TS=1)");
+    {   // output layers -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
         float* tmp = (float*)h->action_stage;
         k_pack_w3<<<1, kPH, 0, (cudaStream_t)stream>>>(actor->w3, actor->b3, tmp);
         QS_CUDA(cudaMemcpyToSymbolAsync(c_actor_w3, tmp, sizeof(float) * kPH * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
         QS_CUDA(cudaMemcpyToSymbolAsync(c_actor_b3, tmp + kPH * 4, sizeof(float) * 4, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        if (critic) {
+            QS_CUDA(cudaMemcpyToSymbolAsync(c_critic_w3, actor->cw3, sizeof(float) * kPH, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+            QS_CUDA(cudaMemcpyToSymbolAsync(c_critic_b3, actor->cb3, sizeof(float), 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+        }
     }
     const int64_t tiles = (h->N + kPM - 1) / kPM;
-    int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, Cfg::kG tiles in flight each
-    const int64_t need = (tiles + Cfg::kG - 1) / Cfg::kG;
+    int64_t grid = (int64_t)h->sm_count;                             // one CTA per SM, kG tiles in flight each
+    constexpr int kG = PolicyCfg<kTS>::kG;
+    const int64_t need = (tiles + kG - 1) / kG;
     if (grid > need) grid = need;
-    policy_rollout_kernel<kTS><<<(int)grid, kPM * Cfg::kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+    if constexpr (kTS) {
+        if (critic) {
+            using Cfg = PolicyCfg<kTS, true>;
+            QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS, true>), Cfg::kBytes);
+            policy_rollout_kernel<kTS, true><<<(int)grid, kPM * kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+            QS_CUDA(cudaGetLastError());
+            return QS_OK;
+        }
+    }
+    using Cfg = PolicyCfg<kTS, false>;
+    QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS, false>), Cfg::kBytes);
+    policy_rollout_kernel<kTS, false><<<(int)grid, kPM * kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }

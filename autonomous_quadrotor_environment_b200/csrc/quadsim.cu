@@ -541,7 +541,7 @@ reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ Sim
     }
 }
 
-template <typename R, int INTEG, bool DIRECT>
+template <typename R, int INTEG, bool DIRECT, bool SENSOR>
 __global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
 rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                const __grid_constant__ RolloutIO<R> io) {
@@ -570,15 +570,15 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
             if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
             Ctrl<R> c;
-            step_core<R, INTEG, DIRECT>(p, e, a, o, &c);
+            step_core<R, INTEG, DIRECT>(p, e, a, o, SENSOR ? &c : nullptr);
             if (warm) o.reward = R(0); else e.ep_return += o.reward;
             reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
             if (done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
-            if (p.flags & F_SENSOR)                 // generic path: the sensor rows stay in HBM (the FP32 pair kernel keeps them on chip)
+            if (SENSOR)                             // generic path: the sensor rows stay in HBM (the FP32 pair kernel keeps them on chip)
                 sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
             if ((p.flags & F_ASYNC_RESET) && done) {
                 async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
-                if (p.flags & F_SENSOR) {
+                if (SENSOR) {
 #pragma unroll
                     for (int k = 0; k < 10; ++k) v.sensed_obs[k * v.ld + n] = e.y[k];
 #pragma unroll
@@ -589,7 +589,7 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
                 e.episode += 1;
                 reset_env<R, INTEG, DIRECT>(p, v, n, e, true, o, nullptr, nullptr);
             }
-            if ((p.flags & F_SENSOR) && io.sensed_out) {
+            if (SENSOR && io.sensed_out) {
                 R* so = io.sensed_out + (int64_t)t * 14 * v.N;
 #pragma unroll
                 for (int k = 0; k < 14; ++k) so[k * v.N + n] = v.sensed_obs[k * v.ld + n];
@@ -689,7 +689,10 @@ static void launch_rollout(qs_sim* s, const qs_rollout_args* a, cudaStream_t st)
     }
     RolloutIO<R> io{a->horizon, a->action_source, (const R*)a->actions, (R*)a->obs_out, (R*)a->action_out,
                     (R*)a->reward_out, a->done_out, (R*)a->sensed_obs_out};
-    rollout_kernel<R, INTEG, DIRECT><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+    if (s->cfg.flags & QS_FLAG_SENSOR_NOISE)
+        rollout_kernel<R, INTEG, DIRECT, true><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
+    else
+        rollout_kernel<R, INTEG, DIRECT, false><<<grid_for(s, s->N), kBlock, 0, st>>>(params_of<R>(s), make_view<R>(s), io);
 }
 
 

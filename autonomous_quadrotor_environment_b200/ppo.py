@@ -2,7 +2,7 @@
 `environment/controller/ppo.py` (class PPO :80-209, model.py ActorCritic) for the batched simulator:
 
     rollout   BatchedQuad.policy_rollout   history -> actor (tcgen05) -> Normal sample -> quad.step, K steps per launch
-    values    critic over the recorded network inputs (torch / cuBLAS GEMMs, chunked over envs)
+    values    critic head of the same kernel (second pair of tcgen05 GEMMs on the same history tile; fused_critic=False: torch GEMMs)
     GAE       qs_gae / qs_adv_normalize    hand-written backward scan + masked normalisation on the [K][N] buffers
     update    K_epochs full-batch clipped-surrogate steps (ppo.py:164-206), gradients accumulated over env chunks and
               all-reduced across ranks (the path's second collective: ~0.2 MB per step), Adam
@@ -37,6 +37,11 @@ class ActorCritic(nn.Module):
         self.std, self._var, self._log_std = float(s32), float(s32 * s32), float(torch.log(s32))
         self._entropy = float(0.5 + 0.5 * math.log(2 * math.pi) + torch.log(s32))     # Normal.entropy() stays float32
 
+    def logprob(self, state, action):
+        """Per-dimension log-prob of `action` under Normal(actor(state), std) (the actor half of evaluate)."""
+        mean = self.actor(state)
+        return -((action - mean) ** 2) / (2 * self._var) - self._log_std - math.log(math.sqrt(2 * math.pi))
+
     def evaluate(self, state, action):
         """model.py:74-88: per-dimension log-prob of `action` under Normal(actor(state), std), state value, entropy."""
         mean = self.actor(state)
@@ -65,8 +70,9 @@ class BatchedPPO:
 
     def __init__(self, env, hidden: int = 128, action_std: float = 0.1, lr: float = 5e-4, betas=(0.9, 0.999), gamma: float = 0.99,
                  lmbda: float = 0.99, K_epochs: int = 10, eps_clip: float = 0.2, chunk_envs: int = 16384, seed: int = 0,
-                 tf32: bool = True):
+                 tf32: bool = True, fused_critic: bool = True):
         self.env = env
+        self.fused_critic = bool(fused_critic)   # state values from the critic head of the fused rollout kernel (BF16 tensor cores)
         self.dev = env.device if env is not None else torch.device("cpu")     # env=None: update()-only use (tests on CPU / gloo)
         torch.manual_seed(seed)
         self.policy = ActorCritic(hidden, 75, 4, action_std).to(self.dev)
@@ -82,7 +88,9 @@ class BatchedPPO:
         if self.env is None:
             return
         self.env.load_actor({"actor_%d_%s" % (i, k): getattr(self.policy.actor[i], k).detach() for i in (0, 2, 4) for k in ("weight", "bias")},
-                            action_std=self.policy.std)
+                            action_std=self.policy.std,
+                            critic={"critic_%d_%s" % (i, k): getattr(self.policy.critic[i], k).detach() for i in (0, 2, 4) for k in ("weight", "bias")}
+                            if self.fused_critic else None)
 
     # ---------------------------------------------------------------------------------------------------------
     @staticmethod
@@ -108,10 +116,10 @@ class BatchedPPO:
         env = self.env
         hist0 = env.history.t().contiguous().clone()                      # (75, N)
         rec = env.policy_rollout(horizon, record_obs=True, record_actions=True, record_logprob=True, record_reward=True,
-                                 record_done=True)
+                                 record_done=True, record_values=self.fused_critic)
         entries = self.history_entries(rec)
         K, N = horizon, env.N
-        value = torch.empty(K + 1, N, dtype=torch.float32, device=self.dev)
+        value = rec["value"] if self.fused_critic else torch.empty(K + 1, N, dtype=torch.float32, device=self.dev)
         # old_logprobs of the update's ratio (ppo.py:187) must come from the SAME evaluation path as the new ones: the reference's
         # policy_old is an exact copy of policy, so the ratio is exactly 1 at the first epoch.  The fused kernel's own log-probs
         # (BF16 operands, tanh.approx) differ from the update's FP32/TF32 re-evaluation by O(0.1-1) in the tails, which would
@@ -123,8 +131,9 @@ class BatchedPPO:
         for n0 in range(0, N, self.chunk):
             n1 = min(N, n0 + self.chunk)
             x = self.network_inputs(hist0, entries, n0, n1)
-            value[:, n0:n1] = self.policy.critic(x).squeeze(-1)
-            lp, _, _ = self.policy.evaluate(x[:K], rec["actions"][:, :, n0:n1].permute(0, 2, 1))
+            if not self.fused_critic:
+                value[:, n0:n1] = self.policy.critic(x).squeeze(-1)
+            lp = self.policy.logprob(x[:K], rec["actions"][:, :, n0:n1].permute(0, 2, 1))
             logprob[:, :, n0:n1] = lp.permute(0, 2, 1)
         torch.backends.cuda.matmul.allow_tf32 = prev_tf32
         ret = torch.empty(K, N, dtype=torch.float32, device=self.dev)

@@ -196,6 +196,12 @@ typedef struct qs_actor {
     int32_t in_dim;                     /* 75 = 15 floats x history T=5 (environment/controller/dl_auxiliary.py:15-23) */
     float   action_std;                 /* sigma; <= 0 -> deterministic (evaluation, ppo_quad_eval.py:53) */
     int32_t reserved;
+    /* optional critic (model.py:36-43: Linear(in_dim,H)-Tanh-Linear(H,H)-Tanh-Linear(H,1); keys critic.{0,2,4}.{weight,bias}): when
+     * cw1 is not NULL qs_policy_rollout also evaluates it on every network input (same history tile, same tensor-core path) and
+     * can record the state values PPO's memory.values holds (model.py:68). */
+    const float* cw1; const float* cb1; /* [hidden][in_dim], [hidden] */
+    const float* cw2; const float* cb2; /* [hidden][hidden], [hidden] */
+    const float* cw3; const float* cb3; /* [1][hidden], [1]           */
 } qs_actor;
 
 /* Fused PPO rollout (BASELINE.json configs[4]): per step  history -> actor MLP (tcgen05 tensor cores, BF16 operands,
@@ -212,6 +218,8 @@ typedef struct qs_policy_rollout_args {
     void* reward_out;     /* [K][N]     float or NULL */
     uint8_t* done_out;    /* [K][N]     or NULL : bit0 done, bit1 warm-up step                          */
     void* hist;           /* [75][N] float in/out: dl_in_gen.deep_learning_input per env, oldest first; NULL = zeros */
+    void* value_out;      /* [K+1][N]   float or NULL : critic value of the network input of step t (needs qs_actor.cw1..cb3); row K = */
+                          /*                            value of the input after the last step (the GAE bootstrap, ppo.py:125-141)      */
 } qs_policy_rollout_args;
 
 /* Classical comparison controllers of the reference as in-kernel control laws: LQR

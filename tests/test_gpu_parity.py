@@ -1084,3 +1084,39 @@ def test_sensor_rollout_equals_repeated_steps(prec, integ, N, src):
     assert int(a.episode.max()) >= 2                                   # resets, warm-up steps and sensor resets happened
     d = a.sensed_obs[:, 10:14] - a.obs[:, 10:14]
     assert 0.003 < float(d.std()) < 0.06                               # the noise is there (gyro sigma 0.035 rad/s)
+
+
+def test_fused_critic_head_values_match_torch_critic():
+    """Critic head of the fused policy kernel (model.py:36-43 on the same history tile as the actor): (1) the rollout itself is
+    untouched — actions, observations, dones bit-identical to the kernel without the critic; (2) the recorded state values,
+    rows 0..K-1 = V(input of step t) and row K = V(input after the last step), equal the FP32 torch critic evaluated on the
+    reconstructed (BF16-rounded) network inputs up to BF16-operand error."""
+    from autonomous_quadrotor_environment_b200 import ppo as P
+    g = load_golden("actor_128.npz")
+    N, K, seed = 1000, 24, 4
+    torch.manual_seed(3)
+    ac = P.ActorCritic(128, 75, 4, 0.1).to(DEV)
+    with torch.no_grad():                                            # a critic with O(1) outputs and both signs in every layer
+        for m in ac.critic:
+            if hasattr(m, "weight"):
+                m.weight.mul_(2.0); m.bias.normal_(0, 0.3)
+    crit = {"critic_%d_%s" % (i, k): getattr(ac.critic[i], k).detach() for i in (0, 2, 4) for k in ("weight", "bias")}
+    mk = lambda: BatchedQuad(N, 0.01, 300, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=seed, device=DEV)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    a.load_actor(g, action_std=0.1, critic=crit)
+    b.load_actor(g, action_std=0.1)
+    hist0 = a.history.t().contiguous().clone()
+    ra = a.policy_rollout(K, record_obs=True, record_values=True)
+    rb = b.policy_rollout(K, record_obs=True)
+    for k in ("actions", "obs", "done", "reward", "logprob"):
+        assert torch.equal(ra[k], rb[k]), k
+    entries = P.BatchedPPO.history_entries(ra)
+    x = P.BatchedPPO.network_inputs(None, hist0, entries, 0, N)      # (K+1, N, 75)
+    with torch.no_grad():
+        v_ref = ac.critic(x).squeeze(-1)
+    err = (ra["value"] - v_ref).abs()
+    assert float(v_ref.abs().mean()) > 0.2                           # the comparison is not about zeros
+    assert float(err.max()) < 0.06 and float(err.mean()) < 0.01, (float(err.max()), float(err.mean()))
+    with pytest.raises(L.QuadSimError):
+        b.policy_rollout(4, record_values=True)                      # no critic loaded
