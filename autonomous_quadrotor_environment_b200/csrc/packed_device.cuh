@@ -103,4 +103,47 @@ __device__ __forceinline__ void integrate_rk4_2(const DevParams<float>& p, const
     }
 }
 
+// The same integration with the four stages UNROLLED and a caller-provided piece of independent work placed after each stage
+// (`between(st)`, st a compile-time constant after unrolling): everything lands in one basic block, so that the instruction
+// scheduler can interleave that work — the integer Philox rounds and the MUFU chains of the sensor model's normal draws — with
+// the FP32 stage arithmetic inside ONE warp (the kernels run 8 warps per SM: too few to hide those latencies across warps).
+// First sub-interval only; further sub-intervals (S > 1) use the rolled loop.
+template <typename F>
+__device__ __forceinline__ void integrate_rk4_2_fused(const DevParams<float>& p, const Ctrl2& c, P2 y[13], F&& between) {
+    const float h = p.h_sub, hh = p.h_sub * 0.5f, h6 = p.h_sub * (1.0f / 6.0f);
+    {
+        P2 k[13], acc[13], yt[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { acc[j] = bc(0.f); yt[j] = y[j]; }
+#pragma unroll
+        for (int st = 0; st < 4; ++st) {
+            drone_rhs2<false>(p, c, yt, k, nullptr);
+            k[0] = yt[1]; k[2] = yt[3]; k[4] = yt[5];
+            const P2 wgt = bc((st == 0 || st == 3) ? 1.f : 2.f);
+            const P2 cc = bc((st < 2) ? hh : h);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) { acc[j] = pfma(wgt, k[j], acc[j]); yt[j] = pfma(cc, k[j], y[j]); }
+            between(st);
+        }
+#pragma unroll
+        for (int j = 0; j < 13; ++j) y[j] = pfma(bc(h6), acc[j], y[j]);
+    }
+    for (int s = 1; s < p.substeps; ++s) {
+        P2 k[13], acc[13], yt[13];
+#pragma unroll
+        for (int j = 0; j < 13; ++j) { acc[j] = bc(0.f); yt[j] = y[j]; }
+#pragma unroll 1
+        for (int st = 0; st < 4; ++st) {
+            drone_rhs2<false>(p, c, yt, k, nullptr);
+            k[0] = yt[1]; k[2] = yt[3]; k[4] = yt[5];
+            const P2 wgt = bc((st == 0 || st == 3) ? 1.f : 2.f);
+            const P2 cc = bc((st < 2) ? hh : h);
+#pragma unroll
+            for (int j = 0; j < 13; ++j) { acc[j] = pfma(wgt, k[j], acc[j]); yt[j] = pfma(cc, k[j], y[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 13; ++j) y[j] = pfma(bc(h6), acc[j], y[j]);
+    }
+}
+
 }  // namespace qs

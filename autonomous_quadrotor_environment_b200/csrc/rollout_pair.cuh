@@ -94,7 +94,23 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                 ctl[h] = step_pre<float, DIRECT>(p, e[h], a[h], o[h], act[h]);
             }
             const Ctrl2 c2 = pack_ctrl(ctl[0], ctl[1]);
+#if QS_SENSOR_FUSED_NORMALS
+            P2 zpre[SENSOR ? 24 : 1];
+            if constexpr (SENSOR) {                 // the sensor model's normals are drawn inside the unrolled RK4 stages (packed_device.cuh)
+                SensorRng2 rng;
+                rng.seed = v.seed; rng.rk = v.rk;
+                rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
+                rng.ep[0] = e[0].episode; rng.ep[1] = e[1].episode;
+                rng.step[0] = (uint32_t)e[0].i; rng.step[1] = (uint32_t)e[1].i;
+                integrate_rk4_2_fused(p, c2, y, [&](int st) {
+                    if (st < 3) sensor_normals_block2(rng, st, &zpre[8 * st]);
+                });
+            } else {
+                integrate_rk4_2(p, c2, y);
+            }
+#else
             integrate_rk4_2(p, c2, y);
+#endif
 #define QS_RP_POST(H)                                                                                         \
             {                                                                                                 \
                 _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);                  \
@@ -124,12 +140,20 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                     }
                     if (rec2) rec2[(int64_t)k * N2] = val.v;
                     if (last) go2[(int64_t)k * ld2] = val.v;
-                });
+                }
+#if QS_SENSOR_FUSED_NORMALS
+                , zpre
+#endif
+                );
 #else
                 P2 sn[qs::kSensorStateDim], so[14], vq[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
+#if QS_SENSOR_FUSED_NORMALS
+                pr::sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, pm, sn, so, zpre);
+#else
                 pr::sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, pm, sn, so);
+#endif
 #pragma unroll
                 for (int k = 0; k < qs::kSensorStateDim; ++k) pr::sts2(srows, k, lane, sn[k].v.x, sn[k].v.y);
 #pragma unroll

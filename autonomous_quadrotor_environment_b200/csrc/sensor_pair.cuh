@@ -110,17 +110,22 @@ __device__ __forceinline__ void accel_read2(const DevParams<float>& p, P2 f_m, c
 
 // One env step of the sensor model for a pair.  y = TRUE state after the step, acc_read / rot from accel_read2, f_m = F/M.
 // Updates s, writes obs14 (rl_worker.py:171-173).
+// zpre: NULL, or the 24 normals of blocks 0..2 drawn ahead of time (integrate_rk4_2_fused: zpre[8 b + k] = normal k of block b)
 __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const SensorRng2& rng, const P2 y[13], const P2 acc_read[3],
-                                             const P2 rot[9], P2 f_m, P2 s[kSensorStateDim], P2 obs[14]) {
+                                             const P2 rot[9], P2 f_m, P2 s[kSensorStateDim], P2 obs[14], const P2* zpre = nullptr) {
     const P2 dt = bc(p.dt), sa = bc(p.s_accel_std), sg = bc(p.s_gyro_std), sm = bc(p.s_mag_std), ng = bc(-p.g);
     P2 z0[8], z1[8];
+    if (zpre) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { z0[k] = zpre[k]; z1[k] = zpre[8 + k]; }
+    } else
     sensor_normals_block2(rng, 0, z0);                                                     // z[0..7]
     // ---- accel_int :700-715
     s[0] = pfma(s[2], dt, s[0]);                                                           // accel() :613
     P2 acc1[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc1[k] = pfma(sa, z0[k], padd(acc_read[k], s[0]));
-    sensor_normals_block2(rng, 1, z1);                                                     // z[8..15]
+    if (!zpre) sensor_normals_block2(rng, 1, z1);                                          // z[8..15]
     P2 Rm[9];
     {   // triad()
         s[0] = pfma(s[2], dt, s[0]);
@@ -177,6 +182,10 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
         }
     }
     // ---- triad :649-697 (updates self.R for the next step)
+    if (zpre) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z0[k] = zpre[16 + k];
+    } else
     sensor_normals_block2(rng, 2, z0);                                                     // P[16..23]: z[22..26] = P[16..20]
     {
         s[0] = pfma(s[2], dt, s[0]);
@@ -218,11 +227,15 @@ struct SensorMem {
 // observation for envs in a warm-up step)
 template <typename Out>
 __device__ __forceinline__ void sensor_step2_stream(const DevParams<float>& p, const SensorRng2& rng, const P2 y[13], P2 f_m,
-                                                    const SensorMem& sm, Out&& out) {
+                                                    const SensorMem& sm, Out&& out, const P2* zpre = nullptr) {
     const P2 dt = bc(p.dt), sa = bc(p.s_accel_std), sg = bc(p.s_gyro_std), smg = bc(p.s_mag_std), ng = bc(-p.g);
     P2 rot[9], acc_read[3];
     accel_read2(p, f_m, y, rot, acc_read);
     P2 z0[8], z1[8];
+    if (zpre) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { z0[k] = zpre[k]; z1[k] = zpre[8 + k]; }
+    } else
     sensor_normals_block2(rng, 0, z0);                                                     // z[0..7]
     // ---- accel_int :700-715
     const P2 drift_a = sm.ld(2);
@@ -230,7 +243,7 @@ __device__ __forceinline__ void sensor_step2_stream(const DevParams<float>& p, c
     P2 acc1[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc1[k] = pfma(sa, z0[k], padd(acc_read[k], ab));
-    sensor_normals_block2(rng, 1, z1);                                                     // z[8..15]
+    if (!zpre) sensor_normals_block2(rng, 1, z1);                                          // z[8..15]
     P2 rc[3];                                                                              // third column of the first TRIAD rotation
     {
         P2 Rm[9];
@@ -301,6 +314,10 @@ __device__ __forceinline__ void sensor_step2_stream(const DevParams<float>& p, c
 #pragma unroll
     for (int k = 0; k < 3; ++k) { out(2 * k, sm.ld(7 + k)); out(2 * k + 1, sm.ld(4 + k)); }
     // ---- triad :649-697 (updates self.R for the next step)
+    if (zpre) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) z0[k] = zpre[16 + k];
+    } else
     sensor_normals_block2(rng, 2, z0);                                                     // P[16..23]: z[22..26] = P[16..20]
     {
         ab = pfma(drift_a, dt, ab);

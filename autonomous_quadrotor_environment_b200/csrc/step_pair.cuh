@@ -44,6 +44,11 @@ constexpr int kRowsSensor = 46;
 #ifndef QS_SENSOR_STREAM
 #define QS_SENSOR_STREAM 0          // 1 = streaming sensor phase in the STEP kernel (state rows stay in shared memory, 168 registers,
 #endif                              // 12 warps per SM): measured slower, 127.9 vs 101.8 us per step of 1M envs; tuning builds only
+#ifndef QS_SENSOR_FUSED_NORMALS
+#define QS_SENSOR_FUSED_NORMALS 0   // 1 = draw the sensor model's normals (Philox + Box-Muller) inside the UNROLLED RK4 stages of the same env
+#endif                              // pair (one basic block: six Philox chains + MUFU chains next to the FP32 stage arithmetic).  Measured:
+                                    // step kernel 106.1 vs 101.6 us (228 registers, 3 more copies of the RHS in the instruction stream),
+                                    // rollout kernel 82.6 vs 82.8 us — tuning builds only
 #ifndef QS_PAIR_THREADS_SENSOR
 #define QS_PAIR_THREADS_SENSOR (QS_SENSOR_STREAM ? 384 : 256)
 #endif
@@ -116,7 +121,7 @@ struct PairMeta {
 // passed through; the last one re-initialises it = sensor.reset).  srows = the pair's sensor_state rows in shared memory.
 __device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const SimView<float>& v, const Row* srows, int lane, int64_t nA,
                                              const qs::P2 y[13], const qs::P2 vq[4], qs::P2 f_m, const PairMeta& m,
-                                             qs::P2 sn[qs::kSensorStateDim], qs::P2 so[14]) {
+                                             qs::P2 sn[qs::kSensorStateDim], qs::P2 so[14], const qs::P2* zpre = nullptr) {
     using namespace qs;
     P2 rot[9], acc[3];
     accel_read2(p, f_m, y, rot, acc);
@@ -127,7 +132,7 @@ __device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const Si
     rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
     rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
     rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
-    sensor_step2(p, rng, y, acc, rot, f_m, sn, so);
+    sensor_step2(p, rng, y, acc, rot, f_m, sn, so, zpre);
     const bool w0 = m.warm[0], w1 = m.warm[1];
     if (__any_sync(0xffffffffu, w0 | w1)) {
 #pragma unroll
@@ -166,7 +171,8 @@ __device__ __forceinline__ void sensor_store(const SimView<float>& v, int64_t n0
 // observation for envs in a warm-up step).  The last warm-up step of an episode re-initialises the sensor (sensor.reset).
 template <typename Out>
 __device__ __forceinline__ void sensor_phase_stream(const DevParams<float>& p, const SimView<float>& v, Row* srows, int lane, int64_t nA,
-                                                    const qs::P2 y[13], qs::P2 f_m, const PairMeta& m, bool any_warm, Out&& out) {
+                                                    const qs::P2 y[13], qs::P2 f_m, const PairMeta& m, bool any_warm, Out&& out,
+                                                    const qs::P2* zpre = nullptr) {
     using namespace qs;
     SensorMem sm;
     sm.st = reinterpret_cast<float2*>(srows[0]) + lane;
@@ -176,7 +182,7 @@ __device__ __forceinline__ void sensor_phase_stream(const DevParams<float>& p, c
     rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
     rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
     rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
-    sensor_step2_stream(p, rng, y, f_m, sm, out);
+    sensor_step2_stream(p, rng, y, f_m, sm, out, zpre);
     if (any_warm) {
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
@@ -452,7 +458,23 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
 #undef QS_PAIR_PRE
         // ---- phase 2: both envs through the RK4 stages on the packed pipe
         const Ctrl2 c2 = pack_ctrl(ctl[0], ctl[1]);
+#if QS_SENSOR_FUSED_NORMALS
+        P2 zpre[SENSOR ? 24 : 1];
+        if constexpr (SENSOR) {
+            SensorRng2 rng;                                    // counters of the step being taken: (env, episode, i after the increment)
+            rng.seed = v.seed; rng.rk = v.rk;
+            rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
+            rng.ep[0] = e[0].episode; rng.ep[1] = e[1].episode;
+            rng.step[0] = (uint32_t)e[0].i; rng.step[1] = (uint32_t)e[1].i;
+            integrate_rk4_2_fused(p, c2, y, [&](int st) {
+                if (st < 3) sensor_normals_block2(rng, st, &zpre[8 * st]);
+            });
+        } else {
+            integrate_rk4_2(p, c2, y);
+        }
+#else
         integrate_rk4_2(p, c2, y);
+#endif
         // ---- phase 3 per env: observation tail, Euler angles, done, reward
         // -DQS_PAIR_PACKED_POST: phase 3 on the packed pipe (step_post2).  Measured 100.6 vs 102.0 us with the sensor model and
         // 46.9 vs 47.05 us without (1,048,576 envs); NOT the default yet: test_step_loaders_agree[65536-True-1-False-3] fails
@@ -570,7 +592,11 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
                 P2 sn[kSensorStateDim], so[14], vq[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) vq[k] = pk(o[0].vq[k], o[1].vq[k]);
+#if QS_SENSOR_FUSED_NORMALS
+                sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so, zpre);
+#else
                 sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
+#endif
                 __syncwarp();                  // every lane is done with the sensor rows of the stage
                 if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
                 sensor_store(v, n0, lane, sn, so);

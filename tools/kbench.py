@@ -72,17 +72,21 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
     emit({"case": "rollout" + ("+rec" if rec else ""), "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
 
 
-def case_policy(N=1 << 20, K=128, iters=3, sigma=0.1, record=True):
+def case_policy(N=1 << 20, K=128, iters=3, sigma=0.1, record=True, critic=False):
     import numpy as np
     g = dict(np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "actor_128.npz")))
     env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=0, device=DEV)
     env.reset()
-    env.load_actor(g, action_std=sigma)
-    kw = dict(record_obs=record, record_actions=record, record_logprob=record, record_reward=record, record_done=record)
+    crit = None
+    if critic:                                          # critic of the same shape; the actor's hidden layers stand in for trained weights
+        crit = {"critic_0_weight": g["actor_0_weight"], "critic_0_bias": g["actor_0_bias"], "critic_2_weight": g["actor_2_weight"],
+                "critic_2_bias": g["actor_2_bias"], "critic_4_weight": g["actor_4_weight"][:1], "critic_4_bias": g["actor_4_bias"][:1]}
+    env.load_actor(g, action_std=sigma, critic=crit)
+    kw = dict(record_obs=record, record_actions=record, record_logprob=record, record_reward=record, record_done=record, record_values=critic)
     ms = time_ms(lambda: env.policy_rollout(K, **kw), iters, warm=2)
     s = env.stats()
-    print("policy_rollout N=%d K=%d sigma=%.2f record=%d   %8.2f us/step  %.3e env-steps/s   (%.1f ms per %d-step rollout; solved %.3f, mean len %.0f)"
-          % (N, K, sigma, record, ms * 1e3 / K, N * K / ms * 1e3, ms, K, s["solved_frac"], s["mean_length"]), flush=True)
+    print("policy_rollout%s N=%d K=%d sigma=%.2f record=%d   %8.2f us/step  %.3e env-steps/s   (%.1f ms per %d-step rollout; solved %.3f, mean len %.0f)"
+          % ("+critic" if critic else "", N, K, sigma, record, ms * 1e3 / K, N * K / ms * 1e3, ms, K, s["solved_frac"], s["mean_length"]), flush=True)
 
 
 if __name__ == "__main__":
@@ -97,6 +101,11 @@ if __name__ == "__main__":
         case_step(N=1 << 16, iters=5, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "profpolicy" in which:
         case_policy(N=1 << 18, K=32, iters=1)
+    if "policycritic" in which:
+        case_policy(critic=True)
+        case_policy()
+    if "profpolicycritic" in which:
+        case_policy(N=1 << 18, K=32, iters=1, critic=True)
     if "policy" in which:
         case_policy()
         case_policy(record=False)
