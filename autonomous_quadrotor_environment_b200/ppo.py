@@ -4,11 +4,14 @@
     rollout   BatchedQuad.policy_rollout   history -> actor (tcgen05) -> Normal sample -> quad.step, K steps per launch
     values    critic head of the same kernel (second pair of tcgen05 GEMMs on the same history tile; fused_critic=False: torch GEMMs)
     GAE       qs_gae / qs_adv_normalize    hand-written backward scan + masked normalisation on the [K][N] buffers
-    update    K_epochs full-batch clipped-surrogate steps (ppo.py:164-206), gradients accumulated over env chunks and
-              all-reduced across ranks (the path's second collective: ~0.2 MB per step), Adam
+    update    K_epochs full-batch clipped-surrogate steps (ppo.py:164-206): qs_ppo_grad (forward AND backward of each
+              75-128-128-{4,1} network on tcgen05, weight-gradient accumulators resident in tensor memory) for the actor and
+              the critic, one all-reduce of the flat gradient across ranks (the path's second collective: ~0.2 MB per step),
+              qs_adam_step on the flat FP32 master parameters
 
-Nothing of the 1M x 128 rollout leaves the GPU.  PyTorch supplies autograd, Adam and the GEMMs of the update; the rollout,
-the simulator and the scans are the CUDA kernels of libquadsim.
+Nothing of the 1M x 128 rollout leaves the GPU, and on a CUDA device no part of an iteration runs in PyTorch: torch supplies
+the device buffers and the NCCL plumbing.  update_impl="torch" (autograd + torch.optim.Adam over the same flat parameters) is
+what runs on a CPU device — the gloo tests of the host logic — and is the FP32 comparison of the kernel in tests/test_ppo.py.
 """
 from __future__ import annotations
 
@@ -70,13 +73,32 @@ class BatchedPPO:
 
     def __init__(self, env, hidden: int = 128, action_std: float = 0.1, lr: float = 5e-4, betas=(0.9, 0.999), gamma: float = 0.99,
                  lmbda: float = 0.99, K_epochs: int = 10, eps_clip: float = 0.2, chunk_envs: int = 16384, seed: int = 0,
-                 tf32: bool = True, fused_critic: bool = True):
+                 tf32: bool = True, fused_critic: bool = True, update_impl: str | None = None, device=None):
         self.env = env
         self.fused_critic = bool(fused_critic)   # state values from the critic head of the fused rollout kernel (BF16 tensor cores)
-        self.dev = env.device if env is not None else torch.device("cpu")     # env=None: update()-only use (tests on CPU / gloo)
+        self.dev = env.device if env is not None else torch.device(device or "cpu")     # env=None: update()-only use (tests)
         torch.manual_seed(seed)
         self.policy = ActorCritic(hidden, 75, 4, action_std).to(self.dev)
+        # one flat FP32 master vector [actor w1 b1 w2 b2 w3 b3 | critic ...]; the module's parameters are views of it
+        params = list(self.policy.actor.parameters()) + list(self.policy.critic.parameters())
+        self._flat = torch.cat([p.detach().reshape(-1) for p in params]).contiguous()
+        o = 0
+        for p in params:
+            p.data = self._flat[o:o + p.numel()].view_as(p); o += p.numel()
+        self._n_actor = sum(p.numel() for p in self.policy.actor.parameters())
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=lr, betas=betas)
+        self.update_impl = update_impl or ("kernel" if self.dev.type == "cuda" else "torch")
+        if self.update_impl not in ("kernel", "torch"):
+            raise ValueError("update_impl must be 'kernel' or 'torch'")
+        if self.update_impl == "kernel":
+            if self.dev.type != "cuda" or hidden != 128:
+                raise RuntimeError("update_impl='kernel' is the sm_100a path: CUDA device and hidden=128 (model.py:24) required")
+            self.lib = env.lib if env is not None else L.load_library()
+            self._grad = torch.zeros_like(self._flat)
+            self._exp_avg, self._exp_avg_sq = torch.zeros_like(self._flat), torch.zeros_like(self._flat)
+            self._scratch = torch.empty(1024, dtype=torch.float32, device=self.dev)
+            self._adam_step = 0
+            self.lr, self.betas = float(lr), (float(betas[0]), float(betas[1]))
         self.gamma, self.lmbda, self.K_epochs, self.eps_clip = gamma, lmbda, K_epochs, eps_clip
         self.chunk = int(chunk_envs)
         self.tf32 = bool(tf32)            # TF32 tensor-core GEMMs for the update's autograd (FP32 accumulate); False = IEEE FP32
@@ -125,10 +147,14 @@ class BatchedPPO:
         # (BF16 operands, tanh.approx) differ from the update's FP32/TF32 re-evaluation by O(0.1-1) in the tails, which would
         # clip or over-weight those samples: they are kept as a diagnostic (batch["logprob_kernel"]) and the ratio's
         # denominator is re-evaluated here, on the recorded actions, by the network the update differentiates.
+        # update_impl="kernel": qs_ppo_grad's first epoch records them from its own forward pass (QS_PPO_RECORD_LOGP).
         logprob = torch.empty(K, 4, N, dtype=torch.float32, device=self.dev)
+        kernel_update = self.update_impl == "kernel"
+        if kernel_update and not self.fused_critic:
+            raise RuntimeError("update_impl='kernel' takes the state values from the fused critic head (fused_critic=True)")
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.tf32
-        for n0 in range(0, N, self.chunk):
+        for n0 in range(0, N if not kernel_update else 0, self.chunk):
             n1 = min(N, n0 + self.chunk)
             x = self.network_inputs(hist0, entries, n0, n1)
             if not self.fused_critic:
@@ -147,11 +173,75 @@ class BatchedPPO:
             dist.all_reduce(self.moments)                                 # normalise over the GLOBAL batch
         L.check(env.lib.qs_adv_normalize(K * N, rec["done"].data_ptr(), self.moments.data_ptr(), adv.data_ptr(), weight.data_ptr(), st))
         return dict(hist0=hist0, entries=entries, actions=rec["actions"], logprob=logprob, logprob_kernel=rec["logprob"], reward=rec["reward"],
-                    done=rec["done"], value=value, returns=ret, adv=adv, weight=weight, count=float(self.moments[0].item()))
+                    done=rec["done"], value=value, returns=ret, adv=adv, weight=weight, count=float(self.moments[0].item()),
+                    logprob_pending=kernel_update)
+
+    # ---------------------------------------------------------------------------------------------------------
+    def _net_ptrs(self, flat, critic: bool):
+        """qs_ppo_net over one network's slice of a flat vector (PyTorch Linear layout, [out][in])."""
+        out = 1 if critic else 4
+        o = self._n_actor if critic else 0
+        ptrs = []
+        for n in (128 * 75, 128, 128 * 128, 128, out * 128, out):
+            ptrs.append(flat.data_ptr() + 4 * o); o += n
+        return L.qs_ppo_net(*ptrs)
+
+    def _batch_tensors(self, batch):
+        t = {k: batch[k].contiguous().float() for k in ("hist0", "entries", "actions", "adv", "returns", "weight")}
+        logp = batch["logprob"]
+        if not (logp.is_contiguous() and logp.dtype == torch.float32):
+            raise ValueError("batch['logprob'] must be a contiguous float32 (K,4,N) tensor (QS_PPO_RECORD_LOGP writes it in place)")
+        t["logprob"] = logp
+        return t
+
+    def _grad_pass(self, t, K, N, count, record: bool, loss_row):
+        """self._grad <- d(loss)/d(parameters) of the whole local batch: zero + qs_ppo_grad(actor) + qs_ppo_grad(critic)."""
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        self._grad.zero_()
+        bt = L.qs_ppo_batch(N, K, L.QS_PPO_RECORD_LOGP if record else 0, t["hist0"].data_ptr(), t["entries"].data_ptr(),
+                            t["actions"].data_ptr(), t["logprob"].data_ptr(), t["adv"].data_ptr(), t["returns"].data_ptr(), t["weight"].data_ptr())
+        for which in (L.QS_PPO_ACTOR, L.QS_PPO_CRITIC):
+            net, grad = self._net_ptrs(self._flat, which == L.QS_PPO_CRITIC), self._net_ptrs(self._grad, which == L.QS_PPO_CRITIC)
+            L.check(self.lib.qs_ppo_grad(C.byref(bt), C.byref(net), C.byref(grad), which, self.policy.std, self.eps_clip, float(count),
+                                         loss_row[which].data_ptr(), self._scratch.data_ptr(), st))
+
+    def gradients(self, batch, record_logprob: bool = False):
+        """One full-batch gradient of the local shard (no all-reduce, no optimizer step): (flat gradient, [actor, critic] loss)."""
+        K, N = batch["adv"].shape
+        loss = torch.zeros(2, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            self._grad_pass(self._batch_tensors(batch), K, N, batch["count"], record_logprob, loss)
+        return self._grad.clone(), loss
+
+    def _update_kernel(self, batch):
+        """The K_epochs steps on qs_ppo_grad / qs_adam_step.  No host synchronisation inside the loop."""
+        K, N = batch["adv"].shape
+        world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        t = self._batch_tensors(batch)
+        pending = bool(batch.get("logprob_pending", False))
+        st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
+        loss = torch.zeros(self.K_epochs, 2, dtype=torch.float64, device=self.dev)
+        with torch.cuda.device(self.dev):
+            for e in range(self.K_epochs):
+                self._grad_pass(t, K, N, batch["count"], pending and e == 0, loss[e])
+                if world > 1:
+                    dist.all_reduce(self._grad)                           # ~0.2 MB: sum of the per-rank partial gradients
+                self._adam_step += 1
+                L.check(self.lib.qs_adam_step(self._flat.numel(), self._flat.data_ptr(), self._grad.data_ptr(), self._exp_avg.data_ptr(),
+                                              self._exp_avg_sq.data_ptr(), self._adam_step, self.lr, self.betas[0], self.betas[1], 1e-8, st))
+        batch["logprob_pending"] = False
+        if world > 1:
+            dist.all_reduce(loss)
+        # the constant entropy bonus of ppo.py:200 (fixed std: no gradient) enters the reported loss only
+        return [float(x) - 0.006 * 4 * self.policy._entropy for x in loss.sum(dim=1).tolist()]
 
     def update(self, batch):
         """PPO.update (:143-206): K_epochs full-batch steps (the reference's randperm does not change a full-batch mean)."""
-        K, N = batch["reward"].shape
+        if self.update_impl == "kernel":
+            losses = self._update_kernel(batch)
+            self._sync_actor()
+            return losses
+        K, N = batch["adv"].shape
         world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         count = batch["count"]                                            # global number of valid transitions
         losses = []

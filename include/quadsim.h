@@ -296,6 +296,37 @@ int qs_gae(int64_t n_envs, int32_t horizon, float gamma, float lambda, const flo
            const uint8_t* done, float* returns_out, float* adv_out, double* moments, void* stream);
 /* ppo.py:141  adv <- (adv - mean) / (std + 1e-10) in place (population std), 0 for warm-up steps; weight (nullable) <- 1/0. */
 int qs_adv_normalize(int64_t total, const uint8_t* done, const double* moments, float* adv, float* weight, void* stream);
+/* The network update of the reference's PPO trainer (environment/controller/ppo.py:143-209, model.py:19-88) on the time-major rollout
+ * buffers, hand-written for sm_100a: forward AND backward of one 75-128-128-{4,1} network on tcgen05 tensor cores (BF16 operands, FP32
+ * accumulation in tensor memory), one full-batch gradient per call.  All pointers device, FP32. */
+typedef struct qs_ppo_batch {
+    int64_t n_envs;               /* N                                                                                         */
+    int32_t horizon;              /* K recorded steps                                                                          */
+    int32_t flags;                /* QS_PPO_RECORD_LOGP or 0                                                                    */
+    const float* hist0;           /* [75][N]     dl_in_gen buffer at rollout start, oldest entry first (dl_auxiliary.py:15-23)  */
+    const float* entries;         /* [K][15][N]  the entry pushed after step t: action(4), v(3), q(4), dq(4) (dl_auxiliary.py:27-30) */
+    const float* actions;         /* [K][4][N]   memory.actions (actor)                                                        */
+    float* logp_old;              /* [K][4][N]   memory.logprobs (actor); WRITTEN by the call under QS_PPO_RECORD_LOGP               */
+    const float* adv;             /* [K][N]      normalised advantages (actor; qs_gae + qs_adv_normalize)                      */
+    const float* ret;             /* [K][N]      returns (critic)                                                              */
+    const float* weight;          /* [K][N]      1 = transition, 0 = warm-up step of an asynchronous reset                     */
+} qs_ppo_batch;
+typedef struct qs_ppo_net {       /* one network, PyTorch Linear layout [out][in]: (128,75) (128) (128,128) (128) (OUT,128) (OUT) */
+    const float* w1; const float* b1; const float* w2; const float* b2; const float* w3; const float* b3;
+} qs_ppo_net;
+/* flags: the call's own forward pass supplies memory.logprobs — the reference's policy_old is an exact copy of policy when the update
+ * starts (ppo.py:206), so the first epoch's ratio is exactly 1; the per-dimension log-probs are stored to logp_old for the later epochs */
+#define QS_PPO_RECORD_LOGP 1
+#define QS_PPO_ACTOR 0            /* OUT = 4, tanh output; loss = -min(r A, clip(r, 1 -+ eps) A), r = exp(sum logp - sum logp_old)  ppo.py:187-195 */
+#define QS_PPO_CRITIC 1           /* OUT = 1; loss = 0.5 (V - R)^2                                                           ppo.py:194     */
+/* ACCUMULATES d(sum of weight * loss / count)/d(parameters) into *grad (same six shapes as *net; zeroed by the caller — gradients of
+ * several ranks or batches add up) and the summed weighted loss / count into *loss_sum (device double, nullable).  count = the GLOBAL
+ * number of valid transitions (loss.mean() of ppo.py:203); scratch = 516 floats of device memory. */
+int qs_ppo_grad(const qs_ppo_batch* batch, const qs_ppo_net* net, const qs_ppo_net* grad, int which, float sigma, float eps_clip,
+                double count, double* loss_sum, void* scratch, void* stream);
+/* torch.optim.Adam.step (the optimizer of ppo.py:105; eps 1e-8 there) on one flat FP32 parameter vector; step = 1, 2, ... */
+int qs_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
+                 float beta2, float eps, void* stream);
 /* Same contract as qs_step but with HOST buffers (pinned or pageable): H2D of the actions, the step
  * kernel and D2H of obs/reward/done are enqueued on `stream` and the call returns after they finish. */
 int qs_step_host(qs_handle h, const void* action_host, void* obs_host, void* reward_host, uint8_t* done_host, void* stream);

@@ -32,10 +32,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header(tmp_path):
     prog = tmp_path / "sz.c"
-    prog.write_text('#include "quadsim.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d\\n",'
+    prog.write_text('#include "quadsim.h"\n#include <stdio.h>\n#include <stddef.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %d %zu %zu\\n",'
                     'sizeof(qs_params),sizeof(qs_config),sizeof(qs_field_desc),sizeof(qs_stats),sizeof(qs_rollout_args),'
                     'sizeof(qs_controller),sizeof(qs_control_rollout_args),sizeof(qs_policy_rollout_args),sizeof(qs_actor),'
-                    'offsetof(qs_config,params),offsetof(qs_config,workspace),(int)QS_FIELD_COUNT_);return 0;}\n')
+                    'offsetof(qs_config,params),offsetof(qs_config,workspace),(int)QS_FIELD_COUNT_,sizeof(qs_ppo_batch),sizeof(qs_ppo_net));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).decode().split()
@@ -52,6 +52,7 @@ def test_struct_layouts_match_header(tmp_path):
     assert sizes[9] == L.qs_config.params.offset
     assert sizes[10] == L.qs_config.workspace.offset
     assert sizes[11] == L.QS_FIELD_COUNT
+    assert sizes[12] == C.sizeof(L.qs_ppo_batch) and sizes[13] == C.sizeof(L.qs_ppo_net)
 
 
 def test_default_config_is_the_reference_constants():

@@ -137,7 +137,7 @@ def test_ppo_iteration_on_device():
     N, K = 4096, 32
     env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=2, device=dev)
     env.reset()
-    ppo = P.BatchedPPO(env, hidden=128, K_epochs=2, chunk_envs=1024, seed=1, tf32=False)
+    ppo = P.BatchedPPO(env, hidden=128, K_epochs=2, chunk_envs=1024, seed=1, tf32=False, update_impl="torch")
     b = ppo.collect(K)
     assert b["value"].shape == (K + 1, N) and b["adv"].shape == (K, N) and 0 < b["count"] <= K * N
     x = ppo.network_inputs(b["hist0"], b["entries"], 0, 512)[:K]
@@ -162,3 +162,160 @@ def test_ppo_iteration_on_device():
     after = torch.cat([p.detach().reshape(-1) for p in ppo.policy.parameters()])
     assert all(np.isfinite(out["losses"])) and np.isfinite(out["mean_reward"]) and not torch.equal(before, after)
     assert torch.equal(env._actor[1]["w1"], ppo.policy.actor[0].weight.detach())
+
+
+def _bf16_st(x):
+    """Round to BF16 in the forward pass, identity in the backward pass (the kernel's operand rounding, seen by autograd)."""
+    return x + (x.bfloat16().float() - x).detach()
+
+
+def _torch_grads(ppo, b, bf16_forward):
+    """Gradient of the PPO loss (ppo.py:183-203) w.r.t. the flat parameter vector by torch autograd in FP32 (TF32 off);
+    bf16_forward: W1, W2, the inputs and the first hidden activation are rounded to BF16 like the kernel's MMA operands."""
+    K, N = b["adv"].shape
+    x = ppo.network_inputs(b["hist0"], b["entries"], 0, N)[:K]
+    rnd = _bf16_st if bf16_forward else (lambda v: v)
+
+    def mlp(seq, out_tanh):
+        h1 = torch.tanh(torch.nn.functional.linear(rnd(x), rnd(seq[0].weight), seq[0].bias))
+        h2 = torch.tanh(torch.nn.functional.linear(rnd(h1), rnd(seq[2].weight), seq[2].bias))
+        o = torch.nn.functional.linear(h2, seq[4].weight, seq[4].bias)
+        return torch.tanh(o) if out_tanh else o
+
+    pol = ppo.policy
+    mean, value = mlp(pol.actor, True), mlp(pol.critic, False).squeeze(-1)
+    a = b["actions"].permute(0, 2, 1)
+    logp = -((a - mean) ** 2) / (2 * pol._var) - pol._log_std - 0.5 * np.log(2 * np.pi)
+    ratio = torch.exp(logp.sum(-1) - b["logprob"].permute(0, 2, 1).sum(-1))
+    surr = torch.min(ratio * b["adv"], torch.clamp(ratio, 1 - ppo.eps_clip, 1 + ppo.eps_clip) * b["adv"])
+    la = (-(surr) * b["weight"]).sum() / b["count"]
+    lc = (0.5 * (value - b["returns"]) ** 2 * b["weight"]).sum() / b["count"]
+    params = list(pol.actor.parameters()) + list(pol.critic.parameters())
+    g = torch.autograd.grad(la + lc, params)
+    return torch.cat([t.reshape(-1) for t in g]), float(la), float(lc), logp.detach()
+
+
+def _kernel_batch(K, N, seed, dev, ppo, spread):
+    """Synthetic rollout buffers: BF16-representable history, actions = mean + sigma z, old log-probs = the FP32 ones + spread * noise
+    (spread > 0 pushes a good part of the ratios out of [1 - eps, 1 + eps], so the clipped branch is exercised)."""
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=gen).to(dev)
+    b = dict(hist0=(r(75, N) * 0.7).bfloat16().float(), entries=(r(K, 15, N) * 0.7).bfloat16().float(), adv=r(K, N), returns=r(K, N) * 2)
+    b["weight"] = (torch.rand(K, N, generator=gen) > 0.15).float().to(dev)
+    b["count"] = float(b["weight"].sum())
+    with torch.no_grad():
+        x = ppo.network_inputs(b["hist0"], b["entries"], 0, N)[:K]
+        mean = ppo.policy.actor(x)
+        a = mean + ppo.policy.std * r(K, N, 4)
+        lp = ppo.policy.logprob(x, a)
+    b["actions"] = a.permute(0, 2, 1).contiguous()
+    b["logprob"] = (lp + spread * r(K, N, 4)).permute(0, 2, 1).contiguous()
+    return b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,N,sigma", [(6, 300, 0.1), (3, 128, 0.5), (17, 1000, 0.1)])
+def test_ppo_grad_kernel_vs_autograd(K, N, sigma):
+    """qs_ppo_grad (tcgen05 forward + backward, BF16 operands) vs torch autograd on the same buffers: every parameter tensor's gradient
+    within 1 % (relative L2) of the autograd gradient of the BF16-operand forward, and the losses within 1e-3; against the plain FP32
+    network the bound is the one BF16 operands allow (sigma = 0.1 amplifies a 3e-3 error of the mean into 3 % of (a - mean))."""
+    dev = torch.device("cuda", 0)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        ppo = P.BatchedPPO(None, hidden=128, action_std=sigma, seed=11, device=dev)
+        assert ppo.update_impl == "kernel"
+        b = _kernel_batch(K, N, 5, dev, ppo, spread=0.08)
+        g_k, loss_k = ppo.gradients(b)
+        g_e, la_e, lc_e, _ = _torch_grads(ppo, b, True)
+        g_f, la_f, lc_f, _ = _torch_grads(ppo, b, False)
+        assert abs(float(loss_k[0]) - la_e) < 2e-3 * max(1.0, abs(la_e)) and abs(float(loss_k[1]) - lc_e) < 2e-3 * max(1.0, abs(lc_e)), (loss_k, la_e, lc_e)
+        o = 0
+        names = ["actor." + n for n, _ in ppo.policy.actor.named_parameters()] + ["critic." + n for n, _ in ppo.policy.critic.named_parameters()]
+        params = list(ppo.policy.actor.parameters()) + list(ppo.policy.critic.parameters())
+        for name, p in zip(names, params):
+            n = p.numel()
+            k, e, f = g_k[o:o + n], g_e[o:o + n], g_f[o:o + n]
+            rel_e = float((k - e).norm() / e.norm()); rel_f = float((k - f).norm() / f.norm())
+            assert rel_e < 1e-2, (name, rel_e, rel_f)
+            # sanity bound only: a few hundred samples, and ratios next to the clip boundary switch branch under BF16 operands
+            assert rel_f < (0.3 if name.startswith("actor") else 3e-2), (name, rel_e, rel_f)
+            o += n
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+@pytest.mark.gpu
+def test_ppo_grad_records_its_own_logprobs():
+    """QS_PPO_RECORD_LOGP: memory.logprobs come from the update network's own forward pass (policy_old == policy, ppo.py:206), the
+    first epoch's ratio is exactly 1 -> the surrogate's value is -mean(adv) and a second pass without the flag reproduces the gradient."""
+    dev = torch.device("cuda", 0)
+    ppo = P.BatchedPPO(None, hidden=128, seed=4, device=dev)
+    b = _kernel_batch(5, 700, 8, dev, ppo, spread=0.0)
+    lp_f32 = b["logprob"].clone()
+    b["logprob"] = torch.full_like(lp_f32, float("nan"))
+    g1, loss1 = ppo.gradients(b, record_logprob=True)
+    assert torch.isfinite(b["logprob"]).all()
+    expect = -float((b["adv"] * b["weight"]).sum() / b["count"])
+    assert abs(float(loss1[0]) - expect) < 1e-5 * max(1.0, abs(expect))
+    # BF16 operands vs the FP32 network: |mean error| ~ 3e-3 -> log-prob error ~ |z| * 0.03 (sigma = 0.1)
+    err = (b["logprob"] - lp_f32).abs()
+    assert float(err.median()) < 0.05 and float(err.quantile(0.99)) < 1.0
+    g2, loss2 = ppo.gradients(b, record_logprob=False)
+    assert float((g1 - g2).norm() / g1.norm()) < 1e-5 and abs(float(loss1[0] - loss2[0])) < 1e-6
+
+
+@pytest.mark.gpu
+def test_adam_kernel_vs_torch_optimizer():
+    from autonomous_quadrotor_environment_b200 import _lib as L
+    lib = L.load_library()
+    dev = torch.device("cuda", 0)
+    gen = torch.Generator().manual_seed(2)
+    n = 100_003
+    p0 = torch.randn(n, generator=gen).to(dev)
+    ref = torch.nn.Parameter(p0.clone()); opt = torch.optim.Adam([ref], lr=5e-4, betas=(0.9, 0.999))
+    p = p0.clone(); m = torch.zeros_like(p); v = torch.zeros_like(p)
+    for step in range(1, 6):
+        g = torch.randn(n, generator=gen).to(dev) * (10.0 ** (step - 3))
+        ref.grad = g.clone(); opt.step()
+        L.check(lib.qs_adam_step(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), step, 5e-4, 0.9, 0.999, 1e-8,
+                                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
+        assert torch.allclose(p, ref.detach(), rtol=0, atol=2e-7), float((p - ref.detach()).abs().max())
+
+
+@pytest.mark.gpu
+def test_ppo_kernel_update_tracks_the_torch_update():
+    """Two epochs of the hand-written update (qs_ppo_grad + qs_adam_step) vs the autograd + torch.optim.Adam update from the same
+    parameters on the same batch: the parameter DISPLACEMENTS agree (Adam's normalised steps amplify gradient noise where the gradient
+    is near zero, so the comparison is the cosine of the two displacement vectors and the losses)."""
+    dev = torch.device("cuda", 0)
+    a = P.BatchedPPO(None, hidden=128, seed=6, K_epochs=2, device=dev)
+    t = P.BatchedPPO(None, hidden=128, seed=6, K_epochs=2, device=dev, update_impl="torch", tf32=False, chunk_envs=512)
+    assert torch.equal(a._flat, t._flat)
+    start = a._flat.clone()
+    b = _kernel_batch(8, 2048, 12, dev, a, spread=0.05)
+    la = a.update(dict(b)); lt = t.update(dict(b))
+    da, dt_ = a._flat - start, t._flat - start
+    cos = float((da * dt_).sum() / (da.norm() * dt_.norm()))
+    assert cos > 0.97, cos
+    assert abs(la[0] - lt[0]) < 5e-3 * max(1.0, abs(lt[0])) and abs(la[1] - lt[1]) < 2e-2 * max(1.0, abs(lt[1])), (la, lt)
+
+
+@pytest.mark.gpu
+def test_ppo_iteration_kernel_path():
+    """The default on a CUDA device: collect (fused actor + critic rollout, GAE) -> update on qs_ppo_grad/qs_adam_step; the rollout
+    kernel picks up the new weights; the loss of the second epoch is computed with the recorded log-probs."""
+    from autonomous_quadrotor_environment_b200 import BatchedQuad
+    dev = torch.device("cuda", 0)
+    N, K = 4096, 32
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=2, device=dev)
+    env.reset()
+    ppo = P.BatchedPPO(env, hidden=128, K_epochs=3, seed=1)
+    assert ppo.update_impl == "kernel"
+    before = ppo._flat.clone()
+    out = ppo.iterate(K)
+    assert all(np.isfinite(out["losses"])) and np.isfinite(out["mean_reward"]) and not torch.equal(before, ppo._flat)
+    assert out["losses"][-1] < out["losses"][0]
+    assert torch.equal(env._actor[1]["w1"], ppo.policy.actor[0].weight.detach())
+    out2 = ppo.iterate(K)
+    assert all(np.isfinite(out2["losses"]))
