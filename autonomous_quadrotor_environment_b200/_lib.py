@@ -36,7 +36,7 @@ EXPORTED_SYMBOLS = [
     "qs_default_config", "qs_workspace_bytes", "qs_create", "qs_destroy", "qs_seed", "qs_reset", "qs_step",
     "qs_rollout", "qs_policy_rollout", "qs_control_rollout", "qs_default_controller", "qs_gae", "qs_adv_normalize", "qs_step_host", "qs_set_step_loader", "qs_get_step_loader", "qs_field_info", "qs_get", "qs_set", "qs_stats_device", "qs_stats_read",
     "qs_euler_quat", "qs_quat_euler", "qs_deriv_quat", "qs_quat_rot_mat", "qs_drone_eq", "qs_f2w", "qs_philox_raw",
-    "qs_sensor_call", "qs_ppo_grad", "qs_adam_step", "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest", "qs_umma_selftest_ts",
+    "qs_sensor_call", "qs_ppo_grad", "qs_adam_step", "qs_last_error", "qs_version", "qs_fp32_peak_probe", "qs_umma_selftest", "qs_umma_selftest_ts", "qs_umma_selftest_mn",
 ]
 
 
@@ -180,8 +180,9 @@ def load_library():
         "qs_f2w": (C.c_int, [C.c_int, P(qs_params), i64, C.c_int, vp, vp, vp, vp, vp]),
         "qs_philox_raw": (C.c_int, [u64, i64, i64, u32, u32, u32, vp, vp]),
         "qs_sensor_call": (C.c_int, [C.c_int, P(qs_params), C.c_double, i64, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]),
-        "qs_ppo_grad": (C.c_int, [P(qs_ppo_batch), P(qs_ppo_net), P(qs_ppo_net), C.c_int, C.c_float, C.c_float, C.c_double, vp, vp, vp]),
+        "qs_ppo_grad": (C.c_int, [P(qs_ppo_batch), P(qs_ppo_net), P(qs_ppo_net), C.c_int, C.c_float, C.c_float, C.c_double, vp, vp]),
         "qs_adam_step": (C.c_int, [i64, vp, vp, vp, vp, C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, vp]),
+        "qs_umma_selftest_mn": (C.c_int, [C.c_int, C.c_int, vp, vp, vp, vp]),
         "qs_last_error": (C.c_char_p, []),
         "qs_version": (C.c_int, []),
         "qs_fp32_peak_probe": (C.c_int, [C.c_int, C.c_int, C.c_int, P(C.c_float), vp]),

@@ -6,22 +6,25 @@
 //                          operands, FP32 TMEM accumulators), FP32 gradients accumulated over the launch
 //   adam_kernel            torch.optim.Adam's step (ppo.py:105, default eps 1e-8, no weight decay) on FP32 master weights
 //
-// One CTA of 128 threads per SM walks env tiles of 128 envs through all K recorded steps; thread = sample = TMEM lane.
-// Per (tile, step), with X the [128 x 80] history tile of the rollout kernel (15 floats per entry padded to 16, pad = 1: bias column):
-//   Z1 = X W1^T           SS-form MMA, 5 x K16 (one per history slot of the ring)                          -> TMEM [64,192)
-//   H1 = tanh(Z1)         packed BF16 -> TMEM [0,64) (A operand of layer 2, TS form) and, TRANSPOSED, -> smem H1^T [j][s]
-//   Z2 = H1 W2^T + b2     TS-form MMA, 8 x K16 (+ one K16 block [1 1 0..] x [b2_hi b2_lo 0..])                  -> TMEM [64,192)
-//   H2 = tanh(Z2); out = W3 H2 + b3 (FP32 pipe, weights in constant memory); loss gradient dZ3 per sample (registers)
-//   dW3 += H2^T dZ3       H2^T [j][s] written transposed to smem, SS-form MMA M=128 (j) N=16 K=128 (s)          -> TMEM [480,496)
-//   dZ2 = (W3^T dZ3) (1 - H2^2)   packed BF16 -> TMEM [192,256) (A operand, TS form) and transposed -> smem dZ^T [j][s]
-//   dW2 += dZ2^T H1       SS-form MMA M=128 (j2) N=128 (j1) K=128 (s); db2 += dZ2^T 1 (N=16 block against a ones tile)  -> TMEM [256,384), [464,480)
-//   dH1 = dZ2 W2          TS-form MMA against W2^T staged K(=j2)-major                                          -> TMEM [64,192)
-//   dZ1 = dH1 (1 - H1^2)  (H1 re-read from TMEM [0,64)) transposed -> smem dZ^T
-//   dW1 += dZ1^T X        5 x (M=128, N=16, K=128) against X^T [i][s] kept as a second, transposed ring; the pad columns of
-//                         slots 0 / 1 carry b1 (hi / lo pieces in the forward): db1 = column 15 of dW1                  -> TMEM [384,464)
-// The weight-gradient accumulators stay in TENSOR MEMORY for the whole launch (496 of the 512 columns) and are added to the FP32
-// gradient buffers in HBM once per CTA.  Every operand with K = sample index needs the transpose of what a thread (= sample) holds:
-// those tiles are written with 2-byte scattered shared-memory stores in the canonical K-major layout (umma.cuh).
+// One CTA of 512 threads per SM walks work units = (128-env tile, chunk of recorded steps); sample = TMEM lane = tid & 127, and the four
+// threads of a sample (tid >> 7) own 32 of the 128 hidden columns each.  Every activation / gradient tile is written ONCE, row = sample,
+// with 16-byte shared-memory stores in the canonical [row][col] layout of umma.cuh, and serves the tensor core twice: as a K-major
+// operand (K = hidden index) of the forward / input-gradient products and as an MN-major operand (K = sample index) of the
+// weight-gradient products — no transposed copies exist.  Per (tile, step), X = [128 x 16 per slot] history ring of the rollout kernel
+// (15 floats per entry + pad = 1: bias column; six slots so the next entry lands in a slot no pending MMA reads):
+//   Z1 = X W1^T             SS, 5 x K16 (one per history slot, W1 indexed by age)                                      -> TMEM Z
+//   H1 = tanh(Z1)           -> smem H1 [s][j]
+//   Z2 = H1 W2^T + b2       SS, 8 x K16 + one K16 block [1 1 0..] x [b2_hi b2_lo 0..]                                   -> TMEM Z
+//   H2 = tanh(Z2) -> smem H2 [s][j]; out = W3 H2 + b3 on the FP32 pipe (partial sums of the four column owners exchanged through
+//   shared memory); the loss and dZ3 per sample in registers; dZ2 = (W3^T dZ3)(1 - H2^2) -> smem dZ [s][j]
+//   dW3 += H2^T dZ3   (A = H2 MN-major, B = dZ3 [s][16] MN-major)      dW2 += dZ2^T H1   (A = dZ MN-major, B = H1 MN-major)
+//   db2 += dZ2^T 1    (B = the ones block of the bias fold)            dH1 = dZ2 W2      (A = dZ K-major, B = W2 [j2][j1] MN-major) -> TMEM Z
+//   dZ1 = dH1 (1 - H1^2)    -> smem dZ [s][j] (over dZ2)
+//   dW1 += dZ1^T X          five N = 16 products, one per history slot (B = that slot's columns of X, MN-major); the pad column of X
+//                           makes column 15 of every block db1
+//   next step's Z1 is issued in the same batch as dW1.
+// The weight-gradient accumulators stay in TENSOR MEMORY for the whole launch (240 columns next to the 128 of Z) and are added to the
+// FP32 gradient buffers in HBM once per CTA.
 #pragma once
 #include "umma.cuh"
 
@@ -30,6 +33,8 @@ namespace ppo {
 constexpr int kM = 128;          // samples per tile = UMMA M / K
 constexpr int kH = 128;          // hidden width
 constexpr int kSlots = 5, kSlotK = 16, kKin = kSlots * kSlotK;   // 80
+constexpr int kRing = 6, kXext = kRing * kSlotK;                 // 96 columns of X: five live history slots + the one being written
+constexpr int kSplit = 4, kThreads = kM * kSplit, kCW = kH / kSplit;   // 512 threads, 32 hidden columns per thread
 
 struct Batch {
     int64_t N;                   // envs
@@ -51,45 +56,78 @@ struct Grad {                    // FP32, same shapes, ACCUMULATED (atomicAdd); 
     double* loss;
 };
 
-// shared-memory map (bytes)
-constexpr int oX = 0;                                 // [128 s][80]   K-major in the input index (A of layer 1)
-constexpr int oXT = oX + kM * kKin * 2;               // [80 i][128 s] K-major in the sample index (B of dW1)
-constexpr int oH1T = oXT + kKin * kM * 2;             // [128 j][128 s]  H1^T, then H2^T (B of dW2 / A of dW3)
-constexpr int oDZT = oH1T + kH * kM * 2;              // [128 j][128 s]  dZ2^T, then dZ1^T (A of dW2 / dW1)
-constexpr int oW1 = oDZT + kH * kM * 2;               // [128 j][80]
-constexpr int oW2 = oW1 + kH * kKin * 2;              // [128 j2][128 j1]  (B of layer 2)
-constexpr int oW2T = oW2 + kH * kH * 2;               // [128 j1][128 j2]  (B of dH1 = dZ2 W2)
-constexpr int oOnes = oW2T + kH * kH * 2;             // [128 s][16]  columns 0,1 = 1 (A of the b2 block, K-major in the 16)
-constexpr int oW2x = oOnes + kM * 16 * 2;             // [128 j][16]  columns 0,1 = b2 (hi, lo)
-constexpr int oOnesT = oW2x + kH * 16 * 2;            // [16 n][128 s] row 0 = 1 (B of db2), K-major in s
-constexpr int oDZ3T = oOnesT + 16 * kM * 2;           // [16 k][128 s] dZ3^T (B of dW3)
-constexpr int kSmemBytes = oDZ3T + 16 * kM * 2;
+// shared-memory map (bytes); every tile is [row][col] in umma_canon_offset(row, col, cols)
+constexpr int oX = 0;                                 // [128 s][96]    history ring (A of layer 1, B of dW1)
+constexpr int oH1 = oX + kM * kXext * 2;              // [128 s][128 j] H1 (A of layer 2, B of dW2)
+constexpr int oH2 = oH1 + kM * kH * 2;                // [128 s][128 j] H2 (A of dW3)
+constexpr int oDZ = oH2 + kM * kH * 2;                // [128 s][128 j] dZ2, then dZ1 (A of dW2 / db2 / dH1, then of dW1)
+constexpr int oW1 = oDZ + kM * kH * 2;                // [128 j][80]    (B of layer 1; column = 16 age + e)
+constexpr int oW2 = oW1 + kH * kKin * 2;              // [128 j2][128 j1] (B of layer 2 K-major, B of dH1 MN-major)
+constexpr int oOnes = oW2 + kH * kH * 2;              // [128 s][16]    columns 0,1 = 1 (A of the b2 block; B of db2)
+constexpr int oW2x = oOnes + kM * 16 * 2;             // [128 j][16]    columns 0,1 = b2 (hi, lo)
+constexpr int oDZ3 = oW2x + kH * 16 * 2;              // [128 s][16]    dZ3 in columns 0..OUT-1 (B of dW3)
+constexpr int oPart = oDZ3 + kM * 16 * 2;             // float [4 part][4 k][128 s]  partial sums of the output layer
+constexpr int oIn = oPart + kSplit * 4 * kM * 4;      // float [10][128 s]  per-sample inputs of the loss: act(4), logp_old(4), adv | ret, weight
+constexpr int oW3 = oIn + 10 * kM * 4;                 // float4 [128 j] = w3[0..3][j] (critic: .x only), then float [4] b3: the FP32 output layer
+constexpr int kSmemBytes = oW3 + kH * 16 + 16;
 
 // TMEM column map
-constexpr uint32_t cH1 = 0, cZ = 64, cDZ2 = 192, cDW2 = 256, cDW1 = 384, cDB2 = 464, cDW3 = 480, kCols = 512;
-
-__constant__ float c_w3[2][kH * 4];     // [net][j*4 + k] = w3[k][j]  (critic: k = 0 only)
-__constant__ float c_b3[2][4];
+constexpr uint32_t cZ = 0, cDW2 = 128, cDW1 = 256, cDB2 = 336, cDW3 = 352, cT1 = 368, kCols = 512;   // cT1: 64 columns, 1 - H1^2 packed BF16
 
 using namespace qs;
 
+__device__ __forceinline__ void cp_async4(float* dst_smem, const float* src) {        // global -> shared without a register stop-over
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
 __device__ __forceinline__ void st_bf16(unsigned char* base, uint32_t off, float x) {
     *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(x);
 }
+// 32 consecutive columns of a thread's own row: four 16-byte stores / loads (a quarter-warp covers 128 contiguous bytes: no conflicts)
+__device__ __forceinline__ void st_row32(unsigned char* tile, int row, int col0, const float v[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint4 q;
+        q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
+        q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
+        *reinterpret_cast<uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, kH)) = q;
+    }
+}
+__device__ __forceinline__ void ld_row32(const unsigned char* tile, int row, int col0, float v[32]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 q = *reinterpret_cast<const uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, kH));
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
+            v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+        }
+    }
+}
 
 template <int NET>
-__global__ void __launch_bounds__(kM, 1)
+__global__ void __launch_bounds__(kThreads, 1)
 ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, const __grid_constant__ Grad g, float sigma,
-                float eps_clip, float inv_count) {
+                float eps_clip, float inv_count, int chunk_len, int n_chunks) {
     constexpr int OUT = NET == 0 ? 4 : 1;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_loss;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x, s = tid & (kM - 1), part = tid >> 7, warp = tid >> 5;
+    float* s_part = reinterpret_cast<float*>(smem + oPart);
+    float* s_in = reinterpret_cast<float*>(smem + oIn);
+    for (int idx = tid; idx < 10 * kM; idx += kThreads) s_in[idx] = 0.f;
+    float* s_w3 = reinterpret_cast<float*>(smem + oW3);          // [j][4], every lane of a warp reads the same address (broadcast)
+    float* s_b3 = s_w3 + kH * 4;
+    for (int idx = tid; idx < kH * 4; idx += kThreads) s_w3[idx] = (idx & 3) < OUT ? w.w3[(idx & 3) * kH + (idx >> 2)] : 0.f;
+    if (tid < 4) s_b3[tid] = tid < OUT ? w.b3[tid] : 0.f;
 
     // ---- one-time: FP32 master weights -> BF16 operand tiles
-    for (int idx = tid; idx < kH * kKin; idx += kM) {            // W1: input 15*slot + e -> K index 16*slot + e; pad columns carry b1
+    for (int idx = tid; idx < kH * kKin; idx += kThreads) {      // W1: input 15*age + e -> column 16*age + e; pad columns carry b1
         const int n = idx / kKin, kk = idx % kKin, a = kk / kSlotK, e = kk % kSlotK;
         float x = 0.f;
         if (e < 15) x = w.w1[n * 75 + a * 15 + e];
@@ -97,22 +135,16 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
         else if (a == 1) x = w.b1[n] - __bfloat162float(__float2bfloat16(w.b1[n]));
         st_bf16(smem + oW1, umma_canon_offset(n, kk, kKin), x);
     }
-    for (int idx = tid; idx < kH * kH; idx += kM) {
+    for (int idx = tid; idx < kH * kH; idx += kThreads) {
         const int n = idx / kH, kk = idx % kH;
-        const float x = w.w2[n * kH + kk];
-        st_bf16(smem + oW2, umma_canon_offset(n, kk, kH), x);    // [j2][j1]
-        st_bf16(smem + oW2T, umma_canon_offset(kk, n, kH), x);   // [j1][j2]
+        st_bf16(smem + oW2, umma_canon_offset(n, kk, kH), w.w2[n * kH + kk]);    // [j2][j1]
     }
-    for (int idx = tid; idx < kH * 16; idx += kM) {
+    for (int idx = tid; idx < kH * 16; idx += kThreads) {
         const int n = idx / 16, kk = idx % 16;
         const float bb = w.b2[n], hi = __bfloat162float(__float2bfloat16(bb));
         st_bf16(smem + oOnes, umma_canon_offset(n, kk, 16), kk < 2 ? 1.f : 0.f);
         st_bf16(smem + oW2x, umma_canon_offset(n, kk, 16), kk == 0 ? hi : (kk == 1 ? bb - hi : 0.f));
-    }
-    for (int idx = tid; idx < 16 * kM; idx += kM) {
-        const int n = idx / kM, kk = idx % kM;
-        st_bf16(smem + oOnesT, umma_canon_offset(n, kk, kM), n == 0 ? 1.f : 0.f);
-        st_bf16(smem + oDZ3T, umma_canon_offset(n, kk, kM), 0.f);
+        st_bf16(smem + oDZ3, umma_canon_offset(n, kk, 16), 0.f);
     }
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); s_loss = 0.f; }
     if (tid < 32) tmem_alloc(&tmem_slot, kCols);
@@ -121,109 +153,149 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
     __syncthreads();
     tc_fence_after();
     const uint32_t tb = tmem_slot;
-    const uint32_t lane = tb + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane = tb + ((uint32_t)((warp & 3) * 32) << 16);     // a warp reads the 32 TMEM lanes of its quarter
+    const uint32_t uX = smem_u32(smem + oX), uH1 = smem_u32(smem + oH1), uH2 = smem_u32(smem + oH2), uDZ = smem_u32(smem + oDZ),
+                   uW1 = smem_u32(smem + oW1), uW2 = smem_u32(smem + oW2), uOnes = smem_u32(smem + oOnes), uW2x = smem_u32(smem + oW2x),
+                   uDZ3 = smem_u32(smem + oDZ3);
     uint32_t phase = 0;
     bool have_acc = false;                                       // the weight-gradient accumulators hold something
     float loss_local = 0.f;
-    float db3_local[4] = {0.f, 0.f, 0.f, 0.f};                   // db3[k] = sum_s dZ3[s][k]
+    float db3_local[4] = {0.f, 0.f, 0.f, 0.f};                   // db3[k] = sum_s dZ3[s][k]  (part 0 only)
     const float inv_var = 1.f / (sigma * sigma);
     const float log_norm = -__logf(sigma) - 0.918938533f;
+    const int col0 = part * kCW;
 
-    auto commit_wait = [&]() {                                   // all threads: wait for the MMAs thread 0 has issued
-        if (tid == 0) umma_commit(&bar);
-        mbar_wait(&bar, phase); phase ^= 1;
-        tc_fence_after();
-    };
+    auto commit = [&]() { if (tid == 0) umma_commit(&bar); };
+    auto wait = [&]() { mbar_wait(&bar, phase); phase ^= 1; tc_fence_after(); };
     auto sync_before_issue = [&]() {                             // operands written by all threads -> visible to the tensor core
         tc_fence_before();
         fence_proxy_async_smem();
         __syncthreads();
         if (tid == 0) tc_fence_after();
     };
+    auto issue_layer1 = [&](int head) {
+#pragma unroll
+        for (int a = 0; a < kSlots; ++a) {
+            int sl = head + a; sl = sl >= kRing ? sl - kRing : sl;
+            umma_gemm_k(tb + cZ, uX, kXext, sl * kSlotK, uW1, kKin, a * kSlotK, kSlotK, kH, a > 0);
+        }
+    };
+    // the four history values this thread stages per slot: elements 4*part .. 4*part+3 of the 16-wide block (element 15 = 1)
+    auto ring_store = [&](int slot, const float x[4]) {
+        uint2 q;
+        q.x = pack_bf16x2(x[0], x[1]); q.y = pack_bf16x2(x[2], x[3]);
+        *reinterpret_cast<uint2*>(smem + oX + umma_canon_offset(s, slot * kSlotK + 4 * part, kXext)) = q;
+    };
 
     const int64_t n_tiles = (b.N + kM - 1) / kM;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int64_t n = tile * kM + tid;
+    const int64_t n_units = n_tiles * n_chunks;
+    for (int64_t u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int64_t tile = u / n_chunks;
+        const int t0 = (int)(u % n_chunks) * chunk_len;
+        const int t1 = t0 + chunk_len < b.K ? t0 + chunk_len : b.K;
+        if (t0 >= t1) continue;
+        const int64_t n = tile * kM + s;
         const bool active = n < b.N;
-        // history ring: physical slot s_ holds age s_ at t = 0 (hist0, oldest first)
-        __syncthreads();                                         // previous tile's MMAs on sX / sXT are complete (waited), all threads done
+        // history at step t0 = seq[t0 .. t0+4], seq = [the five entries of hist0 (oldest first), entries[0], entries[1], ...]
+        // (every MMA of the previous unit has completed: the unit ends with a wait)
 #pragma unroll
-        for (int s_ = 0; s_ < kSlots; ++s_) {
+        for (int a = 0; a < kSlots; ++a) {
+            const int i = t0 + a;
+            float x[4];
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float x = q < 15 ? (active ? b.hist0[(int64_t)(s_ * 15 + q) * b.N + n] : 0.f) : 1.f;
-                st_bf16(smem + oX, umma_canon_offset(tid, s_ * kSlotK + q, kKin), x);
-                st_bf16(smem + oXT, umma_canon_offset(s_ * kSlotK + q, tid, kM), x);
+            for (int r = 0; r < 4; ++r) {
+                const int q = 4 * part + r;
+                x[r] = q < 15 ? (active ? (i < kSlots ? b.hist0[(int64_t)(i * 15 + q) * b.N + n] : b.entries[((int64_t)(i - kSlots) * 15 + q) * b.N + n]) : 0.f) : 1.f;
             }
+            ring_store(a, x);
         }
         int head = 0;
-        for (int t = 0; t < b.K; ++t) {
+        sync_before_issue();
+        if (tid == 0) issue_layer1(head);
+        commit();
+        for (int t = t0; t < t1; ++t) {
             const int64_t tn = (int64_t)t * b.N + n;
-            const float wgt = active ? b.weight[tn] * inv_count : 0.f;
+            // ---- this step's per-sample inputs (in flight while the MMAs run)
+            float e_new[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int q = 4 * part + r;
+                e_new[r] = q < 15 ? (active ? b.entries[((int64_t)t * 15 + q) * b.N + n] : 0.f) : 1.f;
+            }
+            // the loss's inputs go straight to shared memory (cp.async), one item per column owner; rows of padding samples stay 0
+            const bool record = NET == 0 && (b.flags & QS_PPO_RECORD_LOGP) != 0;   // memory.logprobs of policy_old == policy (ppo.py:206)
+            if (active) {
+                if (NET == 0) {
+                    cp_async4(&s_in[part * kM + s], &b.actions[((int64_t)t * 4 + part) * b.N + n]);
+                    if (!record) cp_async4(&s_in[(4 + part) * kM + s], &b.logp_old[((int64_t)t * 4 + part) * b.N + n]);
+                    if (part == 0) cp_async4(&s_in[8 * kM + s], &b.adv[tn]);
+                } else if (part == 0) cp_async4(&s_in[8 * kM + s], &b.ret[tn]);
+                if (part == 1) cp_async4(&s_in[9 * kM + s], &b.weight[tn]);
+            }
             // ================= forward
+            wait();                                               // Z1 (and the previous step's dW1)
+            float acc[32];
+            tmem_ld_32x32b_x32(lane + cZ + (uint32_t)col0, acc);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) acc[i] = tanh_fast(acc[i]);
+            st_row32(smem + oH1, s, col0, acc);
+            {   // tanh' = 1 - H1^2 from the FP32 activation, parked in tensor memory until dZ1 (BF16 of the FACTOR: a saturated unit's
+                // 1 - h^2 computed from a BF16-rounded h would be off by tens of percent)
+                uint32_t tp[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) tp[i] = pack_bf16x2(1.f - acc[2 * i] * acc[2 * i], 1.f - acc[2 * i + 1] * acc[2 * i + 1]);
+                tmem_st_32x32b_x16(lane + cT1 + (uint32_t)(col0 >> 1), tp);
+                tmem_st_wait();
+            }
             sync_before_issue();
             if (tid == 0) {
-#pragma unroll
-                for (int a = 0; a < kSlots; ++a) {
-                    int s_ = head + a; s_ = s_ >= kSlots ? s_ - kSlots : s_;
-                    umma_gemm_k(tb + cZ, smem_u32(smem + oX), kKin, s_ * kSlotK, smem_u32(smem + oW1), kKin, a * kSlotK, kSlotK, kH, a > 0);
-                }
+                umma_gemm_k(tb + cZ, uH1, kH, 0, uW2, kH, 0, kH, kH, false);
+                umma_bf16(tb + cZ, umma_smem_desc(uOnes, 128u, 256u), umma_smem_desc(uW2x, 128u, 256u), umma_idesc_bf16_f32(128, kH), true);
             }
-            commit_wait();
-            // H1 = tanh(Z1): packed BF16 -> TMEM [0,64) and transposed -> sH1T
-#pragma unroll 1
-            for (int c = 0; c < kH; c += 32) {
-                float acc[32];
-                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)c, acc);
-                uint32_t o[16];
+            commit();
+            wait();
+            // H2 and the output layer on the FP32 pipe: this thread's 32 hidden units
+            tmem_ld_32x32b_x32(lane + cZ + (uint32_t)col0, acc);
+            float po[OUT];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[i] = tanh_fast(acc[i]);
+            for (int k = 0; k < OUT; ++k) po[k] = 0.f;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
-                tmem_st_32x32b_x16(lane + cH1 + (uint32_t)(c >> 1), o);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) st_bf16(smem + oH1T, umma_canon_offset(c + i, tid, kM), acc[i]);
+            for (int i = 0; i < 32; ++i) {
+                acc[i] = tanh_fast(acc[i]);
+                if (OUT == 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w3[(col0 + i) * 4]);
+                    po[0] = fmaf(acc[i], w4.x, po[0]); po[1 % OUT] = fmaf(acc[i], w4.y, po[1 % OUT]);
+                    po[2 % OUT] = fmaf(acc[i], w4.z, po[2 % OUT]); po[3 % OUT] = fmaf(acc[i], w4.w, po[3 % OUT]);
+                } else po[0] = fmaf(acc[i], s_w3[(col0 + i) * 4], po[0]);
             }
-            tmem_st_wait();
-            sync_before_issue();
-            if (tid == 0) {
-                constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kH);
+            st_row32(smem + oH2, s, col0, acc);
 #pragma unroll
-                for (int k = 0; k < kH; k += 16)
-                    umma_bf16_ts(tb + cZ, tb + cH1 + (uint32_t)(k >> 1),
-                                 umma_smem_desc(smem_u32(smem + oW2) + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(kH >> 3) * 128u), idesc, k > 0);
-                umma_bf16(tb + cZ, umma_smem_desc(smem_u32(smem + oOnes), 128u, 256u), umma_smem_desc(smem_u32(smem + oW2x), 128u, 256u), idesc, true);
-            }
-            commit_wait();
-            // output layer on the FP32 pipe
-            float out[4] = {c_b3[NET][0], c_b3[NET][1], c_b3[NET][2], c_b3[NET][3]};
-#pragma unroll 1
-            for (int c = 0; c < kH; c += 32) {
-                float acc[32];
-                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)c, acc);
+            for (int k = 0; k < OUT; ++k) s_part[(part * 4 + k) * kM + s] = po[k];
+            cp_async_wait_all();
+            __syncthreads();
+            const float wgt = s_in[9 * kM + s] * inv_count;
+            float out[OUT];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h2 = tanh_fast(acc[i]);
-#pragma unroll
-                    for (int k = 0; k < OUT; ++k) out[k] = fmaf(h2, c_w3[NET][(c + i) * 4 + k], out[k]);
-                }
-            }
+            for (int k = 0; k < OUT; ++k)
+                out[k] = s_b3[k] + ((s_part[(0 * 4 + k) * kM + s] + s_part[(1 * 4 + k) * kM + s]) + (s_part[(2 * 4 + k) * kM + s] + s_part[(3 * 4 + k) * kM + s]));
             // ================= loss and its gradient w.r.t. the pre-activation of the output layer (per sample, x weight / count)
             float dz3[4] = {0.f, 0.f, 0.f, 0.f};
             if (NET == 0) {
-                float mean[4], a[4], lp_new = 0.f, lp_old = 0.f;
-                const bool record = (b.flags & QS_PPO_RECORD_LOGP) != 0;                      // memory.logprobs of policy_old == policy (ppo.py:206)
+                float mean[4], lp[4], act[4], lp_new = 0.f, lp_old = 0.f;
+                const float adv = s_in[8 * kM + s];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     mean[k] = tanh_fast(out[k]);                                              // model.py:33-34
-                    a[k] = active ? b.actions[((int64_t)t * 4 + k) * b.N + n] : 0.f;
-                    const float d = a[k] - mean[k];
-                    const float lp = -0.5f * d * d * inv_var + log_norm;                      // Normal.log_prob, model.py:82
-                    lp_new += lp;
-                    if (record) { if (active) b.logp_old[((int64_t)t * 4 + k) * b.N + n] = lp; lp_old += lp; }
-                    else lp_old += active ? b.logp_old[((int64_t)t * 4 + k) * b.N + n] : 0.f;
+                    act[k] = s_in[k * kM + s];
+                    const float d = act[k] - mean[k];
+                    lp[k] = -0.5f * d * d * inv_var + log_norm;                               // Normal.log_prob, model.py:82
+                    lp_new += lp[k];
+                    lp_old += record ? lp[k] : s_in[(4 + k) * kM + s];
                 }
-                const float adv = active ? b.adv[tn] : 0.f;
+                if (record && active && part == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) b.logp_old[((int64_t)t * 4 + k) * b.N + n] = lp[k];
+                }
                 const float ratio = __expf(lp_new - lp_old);                                  // ppo.py:187
                 const float surr1 = ratio * adv;                                              // :192
                 const float rc = fminf(fmaxf(ratio, 1.f - eps_clip), 1.f + eps_clip);
@@ -231,140 +303,115 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                 // torch.min(surr1, surr2): the gradient flows through the selected branch; clamp passes it inside [1-eps, 1+eps] only
                 const bool through = (surr1 <= surr2) || (ratio >= 1.f - eps_clip && ratio <= 1.f + eps_clip);
                 const float dl_dlp = through ? -adv * ratio : 0.f;                            // d(-min)/d(sum of log-probs)
-                loss_local += wgt * (-fminf(surr1, surr2));
+                if (part == 0) loss_local += wgt * (-fminf(surr1, surr2));
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    dz3[k] = wgt * dl_dlp * (a[k] - mean[k]) * inv_var * (1.f - mean[k] * mean[k]);
+                    dz3[k] = wgt * dl_dlp * (act[k] - mean[k]) * inv_var * (1.f - mean[k] * mean[k]);
             } else {
-                const float ret = active ? b.ret[tn] : 0.f;
-                const float d = out[0] - ret;                                                 // 0.5 * MSE, ppo.py:194
-                loss_local += wgt * 0.5f * d * d;
+                const float d = out[0] - s_in[8 * kM + s];                                    // 0.5 * MSE, ppo.py:194
+                if (part == 0) loss_local += wgt * 0.5f * d * d;
                 dz3[0] = wgt * d;
             }
+            if (part == 0) {
 #pragma unroll
-            for (int k = 0; k < OUT; ++k) db3_local[k] += dz3[k];
+                for (int k = 0; k < OUT; ++k) db3_local[k] += dz3[k];
+                uint2 q;
+                q.x = pack_bf16x2(dz3[0], dz3[1]); q.y = pack_bf16x2(dz3[2], dz3[3]);
+                *reinterpret_cast<uint2*>(smem + oDZ3 + umma_canon_offset(s, 0, 16)) = q;
+            }
             // ================= backward
-            // H2^T -> smem (over H1^T: the layer-2 MMAs that read TMEM H1 are complete; H1^T itself is needed again only by dW2, which
-            // is issued AFTER H1^T has been rewritten below — so H2^T goes to the dZ^T buffer, not here) and dZ3^T
-#pragma unroll 1
-            for (int c = 0; c < kH; c += 32) {
-                float acc[32];
-                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)c, acc);
+            // dZ2 = (W3^T dZ3)(1 - H2^2)
 #pragma unroll
-                for (int i = 0; i < 32; ++i) st_bf16(smem + oDZT, umma_canon_offset(c + i, tid, kM), tanh_fast(acc[i]));
+            for (int i = 0; i < 32; ++i) {
+                float dh;
+                if (OUT == 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s_w3[(col0 + i) * 4]);
+                    dh = fmaf(dz3[3], w4.w, fmaf(dz3[2], w4.z, fmaf(dz3[1], w4.y, dz3[0] * w4.x)));
+                } else dh = dz3[0] * s_w3[(col0 + i) * 4];
+                acc[i] = dh * (1.f - acc[i] * acc[i]);
             }
-#pragma unroll
-            for (int k = 0; k < OUT; ++k) st_bf16(smem + oDZ3T, umma_canon_offset(k, tid, kM), dz3[k]);
-            sync_before_issue();
-            if (tid == 0) {                                       // dW3[j][k] += sum_s H2^T[j][s] dZ3^T[k][s]
-                umma_gemm_k(tb + cDW3, smem_u32(smem + oDZT), kM, 0, smem_u32(smem + oDZ3T), kM, 0, kM, 16, have_acc);
-            }
-            commit_wait();
-            // dZ2 = (W3^T dZ3) (1 - H2^2): packed -> TMEM [192,256), transposed -> sDZT (the dW3 MMA that read it has completed)
-#pragma unroll 1
-            for (int c = 0; c < kH; c += 32) {
-                float acc[32];
-                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)c, acc);
-                uint32_t o[16];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float h2 = tanh_fast(acc[i]);
-                    float dh = 0.f;
-#pragma unroll
-                    for (int k = 0; k < OUT; ++k) dh = fmaf(dz3[k], c_w3[NET][(c + i) * 4 + k], dh);
-                    acc[i] = dh * (1.f - h2 * h2);
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) o[i] = pack_bf16x2(acc[2 * i], acc[2 * i + 1]);
-                tmem_st_32x32b_x16(lane + cDZ2 + (uint32_t)(c >> 1), o);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) st_bf16(smem + oDZT, umma_canon_offset(c + i, tid, kM), acc[i]);
-            }
-            tmem_st_wait();
+            st_row32(smem + oDZ, s, col0, acc);
             sync_before_issue();
             if (tid == 0) {
-                // dW2[j2][j1] += sum_s dZ2^T[j2][s] H1^T[j1][s];  db2[j2] += sum_s dZ2^T[j2][s] 1
-                umma_gemm_k(tb + cDW2, smem_u32(smem + oDZT), kM, 0, smem_u32(smem + oH1T), kM, 0, kM, kH, have_acc);
-                umma_gemm_k(tb + cDB2, smem_u32(smem + oDZT), kM, 0, smem_u32(smem + oOnesT), kM, 0, kM, 16, have_acc);
-                // dH1[s][j1] = sum_j2 dZ2[s][j2] W2[j2][j1]: A = dZ2 from TMEM, B = W2^T [j1][j2]
-                constexpr uint32_t idesc = umma_idesc_bf16_f32(128, kH);
-#pragma unroll
-                for (int k = 0; k < kH; k += 16)
-                    umma_bf16_ts(tb + cZ, tb + cDZ2 + (uint32_t)(k >> 1),
-                                 umma_smem_desc(smem_u32(smem + oW2T) + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(kH >> 3) * 128u), idesc, k > 0);
+                umma_gemm_mn(tb + cDW3, uH2, kH, 0, uDZ3, 16, 0, 16, have_acc);       // dW3[j][k]   += sum_s H2[s][j] dZ3[s][k]
+                umma_gemm_mn(tb + cDW2, uDZ, kH, 0, uH1, kH, 0, kH, have_acc);         // dW2[j2][j1] += sum_s dZ2[s][j2] H1[s][j1]
+                umma_gemm_mn(tb + cDB2, uDZ, kH, 0, uOnes, 16, 0, 16, have_acc);       // db2[j2]     += sum_s dZ2[s][j2] 1
+                umma_gemm_k_mn(tb + cZ, uDZ, kH, uW2, kH, 0, kH, kH, false);            // dH1[s][j1]   = sum_j2 dZ2[s][j2] W2[j2][j1]
             }
-            commit_wait();
-            // dZ1 = dH1 (1 - H1^2), transposed -> sDZT (the dW2 / db2 MMAs that read it have completed)
-#pragma unroll 1
-            for (int c = 0; c < kH; c += 32) {
-                float acc[32], h1p[16];
-                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)c, acc);
-                tmem_ld_32x32b_x16(lane + cH1 + (uint32_t)(c >> 1), h1p);
+            commit();
+            wait();
+            // dZ1 = dH1 (1 - H1^2), over dZ2 (its readers have completed)
+            {
+                float tp[16];
+                tmem_ld_32x32b_x32(lane + cZ + (uint32_t)col0, acc);
+                tmem_ld_32x32b_x16(lane + cT1 + (uint32_t)(col0 >> 1), tp);
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const uint32_t pk = __float_as_uint(h1p[i]);
-                    const float ha = __uint_as_float(pk << 16), hb = __uint_as_float(pk & 0xFFFF0000u);
-                    st_bf16(smem + oDZT, umma_canon_offset(c + 2 * i, tid, kM), acc[2 * i] * (1.f - ha * ha));
-                    st_bf16(smem + oDZT, umma_canon_offset(c + 2 * i + 1, tid, kM), acc[2 * i + 1] * (1.f - hb * hb));
+                    const uint32_t pk = __float_as_uint(tp[i]);
+                    acc[2 * i] *= __uint_as_float(pk << 16);
+                    acc[2 * i + 1] *= __uint_as_float(pk & 0xFFFF0000u);
                 }
+                st_row32(smem + oDZ, s, col0, acc);
             }
+            // next step's input: the entry recorded after step t takes the free ring slot (dl_auxiliary.py:25-32)
+            int spare = head + kSlots; spare = spare >= kRing ? spare - kRing : spare;
+            ring_store(spare, e_new);
             sync_before_issue();
-            if (tid == 0) {                                       // dW1[j][16 a + e] += sum_s dZ1^T[j][s] X^T[16 slot + e][s]
+            if (tid == 0) {                                       // dW1[j][16 a + e] += sum_s dZ1[s][j] X[s][16 slot(a) + e]
 #pragma unroll
                 for (int a = 0; a < kSlots; ++a) {
-                    int s_ = head + a; s_ = s_ >= kSlots ? s_ - kSlots : s_;
-                    const uint32_t brow = smem_u32(smem + oXT) + umma_canon_offset(s_ * kSlotK, 0, kM);
-                    umma_gemm_k(tb + cDW1 + (uint32_t)(a * kSlotK), smem_u32(smem + oDZT), kM, 0, brow, kM, 0, kM, 16, have_acc);
+                    int sl = head + a; sl = sl >= kRing ? sl - kRing : sl;
+                    umma_gemm_mn(tb + cDW1 + (uint32_t)(a * kSlotK), uDZ, kH, 0, uX, kXext, sl * kSlotK, 16, have_acc);
                 }
             }
-            commit_wait();
             have_acc = true;
-            // ================= next step's input: the entry recorded after step t replaces the oldest slot (dl_auxiliary.py:25-32)
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float x = q < 15 ? (active ? b.entries[((int64_t)t * 15 + q) * b.N + n] : 0.f) : 1.f;
-                st_bf16(smem + oX, umma_canon_offset(tid, head * kSlotK + q, kKin), x);
-                st_bf16(smem + oXT, umma_canon_offset(head * kSlotK + q, tid, kM), x);
-            }
-            head = head + 1 == kSlots ? 0 : head + 1;
+            head = head + 1 == kRing ? 0 : head + 1;
+            if (tid == 0 && t + 1 < t1) issue_layer1(head);
+            commit();
         }
+        wait();                                                   // the unit's last dW1
     }
-    // ---- accumulators -> HBM gradients (thread = row j of every accumulator)
+    // ---- accumulators -> HBM gradients (thread = row j of every accumulator; the four parts split the columns)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     if (have_acc) {
-        const int j = tid;
-#pragma unroll 1
-        for (int c = 0; c < kH; c += 32) {
-            float acc[32];
-            tmem_ld_32x32b_x32(lane + cDW2 + (uint32_t)c, acc);
+        const int j = s;
+        float acc[32];
+        tmem_ld_32x32b_x32(lane + cDW2 + (uint32_t)col0, acc);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) atomicAdd(&g.w2[j * kH + c + i], acc[i]);
-        }
+        for (int i = 0; i < 32; ++i) atomicAdd(&g.w2[j * kH + col0 + i], acc[i]);
         float d1[16];
-#pragma unroll 1
-        for (int a = 0; a < kSlots; ++a) {
+        for (int a = part; a < kSlots; a += kSplit) {
             tmem_ld_32x32b_x16(lane + cDW1 + (uint32_t)(a * kSlotK), d1);
 #pragma unroll
             for (int e = 0; e < 15; ++e) atomicAdd(&g.w1[j * 75 + a * 15 + e], d1[e]);
             if (a == 0) atomicAdd(&g.b1[j], d1[15]);             // the bias rides in the pad column (every slot's pad column sees the same sum)
         }
-        tmem_ld_32x32b_x16(lane + cDB2, d1);
-        atomicAdd(&g.b2[j], d1[0]);
-        tmem_ld_32x32b_x16(lane + cDW3, d1);
+        if (part == 1) {
+            tmem_ld_32x32b_x16(lane + cDB2, d1);
+            atomicAdd(&g.b2[j], d1[0]);
+        }
+        if (part == 2) {
+            tmem_ld_32x32b_x16(lane + cDW3, d1);
 #pragma unroll
-        for (int k = 0; k < OUT; ++k) atomicAdd(&g.w3[k * kH + j], d1[k]);
+            for (int k = 0; k < OUT; ++k) atomicAdd(&g.w3[k * kH + j], d1[k]);
+        }
     }
-    // b3 gradient and the loss: per-thread sums -> warp shuffle -> HBM
+    // b3 gradient and the loss: per-thread sums (part 0) -> warp shuffle -> HBM
+    if (part == 0) {
 #pragma unroll
-    for (int k = 0; k < OUT; ++k) {
-        float x = db3_local[k];
+        for (int k = 0; k < OUT; ++k) {
+            float x = db3_local[k];
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
+            if ((tid & 31) == 0 && x != 0.f) atomicAdd(&g.b3[k], x);
+        }
+        float x = loss_local;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(0xffffffffu, x, d);
-        if ((tid & 31) == 0 && x != 0.f) atomicAdd(&g.b3[k], x);
+        if ((tid & 31) == 0) atomicAdd(&s_loss, x);
     }
-    atomicAdd(&s_loss, loss_local);
     __syncthreads();
     if (tid == 0 && g.loss) atomicAdd(g.loss, (double)s_loss);
     tc_fence_before();
@@ -372,11 +419,42 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
     if (tid < 32) tmem_dealloc(tb, kCols);
 }
 
-// [j][4] packing of an output layer for constant memory (+ the bias), OUT rows of w3
-__global__ void k_pack_out(const float* __restrict__ w3, const float* __restrict__ b3, int out_dim, float* __restrict__ dst) {
-    const int j = threadIdx.x;
-    if (j < kH) { for (int k = 0; k < 4; ++k) dst[j * 4 + k] = k < out_dim ? w3[k * kH + j] : 0.f; }
-    if (j < 4) dst[kH * 4 + j] = j < out_dim ? b3[j] : 0.f;
+// ---------------------------------------------------------------------------------------------------------------
+// self-test of the MN-major operand path: mode 0: D[128][N] = At^T Bt, At [128 k][128 m], Bt [128 k][N] (both MN-major);
+// mode 1: D[128][N] = A Bt, A [128 m][128 k] K-major, Bt [128 k][N] MN-major.  Row-major FP32 in / out.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_umma_selftest_mn(int mode, int N, const float* A, const float* B, float* D) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + 128 * 128 * 2;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int c = 0; c < 128; ++c) st_bf16(sA, umma_canon_offset(tid, c, 128), A[tid * 128 + c]);
+    for (int c = 0; c < N; ++c) st_bf16(sB, umma_canon_offset(tid, c, N), B[tid * N + c]);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    if (warp == 0) tmem_alloc(&tmem_base_slot, 128);
+    tc_fence_before();
+    fence_proxy_async_smem();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    if (tid == 0) {
+        if (mode == 0) umma_gemm_mn(tmem_base, smem_u32(sA), 128, 0, smem_u32(sB), N, 0, N, false);
+        else umma_gemm_k_mn(tmem_base, smem_u32(sA), 128, smem_u32(sB), N, 0, 128, N, false);
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    for (int c = 0; c < N; c += 16) {
+        float v[16];
+        tmem_ld_32x32b_x16(lane_addr + (uint32_t)c, v);
+        for (int i = 0; i < 16; ++i) D[tid * N + c + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
 }
 
 // torch.optim.Adam.step (ppo.py:105; amsgrad off, weight_decay 0, eps 1e-8):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
@@ -399,8 +477,8 @@ __global__ void adam_kernel(int64_t n, float* __restrict__ p, const float* __res
 // C ABI
 // ------------------------------------------------------------------------------------------------------------------------------
 extern "C" int qs_ppo_grad(const qs_ppo_batch* bt, const qs_ppo_net* net, const qs_ppo_net* grad, int which, float sigma, float eps_clip,
-                           double count, double* loss_sum, void* scratch, void* stream) {
-    if (!bt || !net || !grad || !scratch) return fail(QS_EINVAL, "qs_ppo_grad: NULL argument");
+                           double count, double* loss_sum, void* stream) {
+    if (!bt || !net || !grad) return fail(QS_EINVAL, "qs_ppo_grad: NULL argument");
     if (which != QS_PPO_ACTOR && which != QS_PPO_CRITIC) return fail(QS_EINVAL, "qs_ppo_grad: which must be QS_PPO_ACTOR or QS_PPO_CRITIC");
     if (bt->n_envs < 1 || bt->horizon < 1 || !bt->hist0 || !bt->entries || !bt->weight) return fail(QS_EINVAL, "qs_ppo_grad: bad batch");
     if (which == QS_PPO_ACTOR && (!bt->actions || !bt->logp_old || !bt->adv || !(sigma > 0.f)))
@@ -421,19 +499,35 @@ extern "C" int qs_ppo_grad(const qs_ppo_batch* bt, const qs_ppo_net* net, const 
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int out_dim = which == QS_PPO_ACTOR ? 4 : 1;
-    float* tmp = (float*)scratch;                                // >= 516 floats
-    ppo::k_pack_out<<<1, ppo::kH, 0, st>>>(net->w3, net->b3, out_dim, tmp);
-    QS_CUDA(cudaMemcpyToSymbolAsync(ppo::c_w3, tmp, sizeof(float) * ppo::kH * 4, (size_t)which * sizeof(float) * ppo::kH * 4, cudaMemcpyDeviceToDevice, st));
-    QS_CUDA(cudaMemcpyToSymbolAsync(ppo::c_b3, tmp + ppo::kH * 4, sizeof(float) * 4, (size_t)which * sizeof(float) * 4, cudaMemcpyDeviceToDevice, st));
     ppo::Batch b{bt->n_envs, bt->horizon, bt->flags, bt->hist0, bt->entries, bt->actions, (float*)bt->logp_old, bt->adv, bt->ret, bt->weight};
     ppo::Net nw{net->w1, net->b1, net->w2, net->b2, net->w3, net->b3};
     ppo::Grad g{gr[0], gr[1], gr[2], gr[3], gr[4], gr[5], loss_sum};
+    // work units = (128-env tile, chunk of steps): the history at any step is a window of the entries buffer, so a tile's steps split
+    // freely; enough units for ~6 per SM (tail balance), chunks of at least 16 steps (a chunk start costs ~1.5 steps)
     const int64_t tiles = (bt->n_envs + ppo::kM - 1) / ppo::kM;
-    const int grid = (int)(tiles < sms ? tiles : sms);
+    int64_t n_chunks = (6 * (int64_t)sms + tiles - 1) / tiles;
+    const int64_t max_chunks = bt->horizon / 16 > 1 ? bt->horizon / 16 : 1;
+    if (n_chunks > max_chunks) n_chunks = max_chunks;
+    if (n_chunks < 1) n_chunks = 1;
+    const int chunk_len = (int)((bt->horizon + n_chunks - 1) / n_chunks);
+    n_chunks = (bt->horizon + chunk_len - 1) / chunk_len;
+    const int64_t units = tiles * n_chunks;
+    const int grid = (int)(units < sms ? units : sms);
     const float inv_count = (float)(1.0 / count);
-    if (which == QS_PPO_ACTOR) ppo::ppo_grad_kernel<0><<<grid, ppo::kM, ppo::kSmemBytes, st>>>(b, nw, g, sigma, eps_clip, inv_count);
-    else ppo::ppo_grad_kernel<1><<<grid, ppo::kM, ppo::kSmemBytes, st>>>(b, nw, g, sigma, eps_clip, inv_count);
+    if (which == QS_PPO_ACTOR)
+        ppo::ppo_grad_kernel<0><<<grid, ppo::kThreads, ppo::kSmemBytes, st>>>(b, nw, g, sigma, eps_clip, inv_count, chunk_len, (int)n_chunks);
+    else
+        ppo::ppo_grad_kernel<1><<<grid, ppo::kThreads, ppo::kSmemBytes, st>>>(b, nw, g, sigma, eps_clip, inv_count, chunk_len, (int)n_chunks);
+    QS_CUDA(cudaGetLastError());
+    return QS_OK;
+}
+
+extern "C" int qs_umma_selftest_mn(int mode, int N, const float* A, const float* B, float* D, void* stream) {
+    if ((mode != 0 && mode != 1) || N < 16 || N > 128 || (N % 16) || !A || !B || !D)
+        return fail(QS_EINVAL, "qs_umma_selftest_mn: mode 0/1, 16 <= N <= 128 (multiple of 16)");
+    const size_t smem = (size_t)128 * 128 * 2 + (size_t)128 * N * 2;
+    QS_CUDA(cudaFuncSetAttribute(ppo::k_umma_selftest_mn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ppo::k_umma_selftest_mn<<<1, 128, smem, (cudaStream_t)stream>>>(mode, N, A, B, D);
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }

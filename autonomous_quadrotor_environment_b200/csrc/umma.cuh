@@ -35,6 +35,16 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_f32(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// The same with the "major" bits: a_mn / b_mn = 1 declares the operand MN-major, i.e. stored with the M (or N) index contiguous and
+// K as the row index.  The no-swizzle MN-major canonical layout has the same 128-byte core block (8 K-rows x 16 bytes = 8 MN elements);
+// in its descriptor SBO is the stride between 8-element MN groups and LBO the stride between 8-row K groups.  A tile written as
+// [row r][col c] with umma_canon_offset(r, c, C) is therefore BOTH a K-major operand with K = c (LBO 128, SBO C/8*128) and an MN-major
+// operand with K = r (LBO C/8*128, SBO 128): the weight-gradient products X^T dZ take their operands from the forward pass's own
+// tiles without any transpose.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_f32_major(int M, int N, bool a_mn, bool b_mn) {
+    return umma_idesc_bf16_f32(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+
 // ---- TMEM ------------------------------------------------------------------------------------------------------
 // executed by ONE full warp; writes the TMEM base address to *slot (shared memory)
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {
@@ -135,6 +145,31 @@ __device__ __forceinline__ void umma_gemm_k(uint32_t tmem_d, uint32_t a_smem, in
     for (int k = 0; k < k_len; k += 16) {
         const uint64_t da = umma_smem_desc(a_smem + (uint32_t)((a_k0 + k) >> 3) * 128u, 128u, (uint32_t)(KA >> 3) * 128u);
         const uint64_t db = umma_smem_desc(b_smem + (uint32_t)((b_k0 + k) >> 3) * 128u, 128u, (uint32_t)(KB >> 3) * 128u);
+        umma_bf16(tmem_d, da, db, idesc, accumulate_first || k > 0);
+    }
+}
+
+// D[128 x N] (+)= A^T B with BOTH operands MN-major over the same K = 128 rows: A stored [128 k][a_ext] (columns a_c0 .. a_c0+127 are
+// the M index), B stored [128 k][b_ext] (columns b_c0 .. b_c0+N-1 are the N index), canonical [row][col] layout.  8 MMAs of K = 16.
+__device__ __forceinline__ void umma_gemm_mn(uint32_t tmem_d, uint32_t a_smem, int a_ext, int a_c0, uint32_t b_smem, int b_ext, int b_c0,
+                                             int N, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc_bf16_f32_major(128, N, true, true);
+    const uint32_t lbo_a = (uint32_t)(a_ext >> 3) * 128u, lbo_b = (uint32_t)(b_ext >> 3) * 128u;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const uint64_t da = umma_smem_desc(a_smem + (uint32_t)(a_c0 >> 3) * 128u + (uint32_t)(2 * k) * lbo_a, lbo_a, 128u);
+        const uint64_t db = umma_smem_desc(b_smem + (uint32_t)(b_c0 >> 3) * 128u + (uint32_t)(2 * k) * lbo_b, lbo_b, 128u);
+        umma_bf16(tmem_d, da, db, idesc, accumulate_first || k > 0);
+    }
+}
+// D[128 x N] (+)= A B with A K-major [128 m][K = k_len] (extent a_ext) and B MN-major, stored [k_len k][b_ext] (columns b_c0.. = N index)
+__device__ __forceinline__ void umma_gemm_k_mn(uint32_t tmem_d, uint32_t a_smem, int a_ext, uint32_t b_smem, int b_ext, int b_c0, int k_len,
+                                               int N, bool accumulate_first) {
+    const uint32_t idesc = umma_idesc_bf16_f32_major(128, N, false, true);
+    const uint32_t lbo_b = (uint32_t)(b_ext >> 3) * 128u;
+    for (int k = 0; k < k_len; k += 16) {
+        const uint64_t da = umma_smem_desc(a_smem + (uint32_t)(k >> 3) * 128u, 128u, (uint32_t)(a_ext >> 3) * 128u);
+        const uint64_t db = umma_smem_desc(b_smem + (uint32_t)(b_c0 >> 3) * 128u + (uint32_t)(k >> 3) * lbo_b, lbo_b, 128u);
         umma_bf16(tmem_d, da, db, idesc, accumulate_first || k > 0);
     }
 }

@@ -96,7 +96,6 @@ class BatchedPPO:
             self.lib = env.lib if env is not None else L.load_library()
             self._grad = torch.zeros_like(self._flat)
             self._exp_avg, self._exp_avg_sq = torch.zeros_like(self._flat), torch.zeros_like(self._flat)
-            self._scratch = torch.empty(1024, dtype=torch.float32, device=self.dev)
             self._adam_step = 0
             self.lr, self.betas = float(lr), (float(betas[0]), float(betas[1]))
         self.gamma, self.lmbda, self.K_epochs, self.eps_clip = gamma, lmbda, K_epochs, eps_clip
@@ -203,7 +202,7 @@ class BatchedPPO:
         for which in (L.QS_PPO_ACTOR, L.QS_PPO_CRITIC):
             net, grad = self._net_ptrs(self._flat, which == L.QS_PPO_CRITIC), self._net_ptrs(self._grad, which == L.QS_PPO_CRITIC)
             L.check(self.lib.qs_ppo_grad(C.byref(bt), C.byref(net), C.byref(grad), which, self.policy.std, self.eps_clip, float(count),
-                                         loss_row[which].data_ptr(), self._scratch.data_ptr(), st))
+                                         loss_row[which].data_ptr(), st))
 
     def gradients(self, batch, record_logprob: bool = False):
         """One full-batch gradient of the local shard (no all-reduce, no optimizer step): (flat gradient, [actor, critic] loss)."""

@@ -321,9 +321,10 @@ typedef struct qs_ppo_net {       /* one network, PyTorch Linear layout [out][in
 #define QS_PPO_CRITIC 1           /* OUT = 1; loss = 0.5 (V - R)^2                                                           ppo.py:194     */
 /* ACCUMULATES d(sum of weight * loss / count)/d(parameters) into *grad (same six shapes as *net; zeroed by the caller — gradients of
  * several ranks or batches add up) and the summed weighted loss / count into *loss_sum (device double, nullable).  count = the GLOBAL
- * number of valid transitions (loss.mean() of ppo.py:203); scratch = 516 floats of device memory. */
+ * number of valid transitions (loss.mean() of ppo.py:203).  The history at any step is a window of `entries`, so the launch splits
+ * every 128-env tile's steps into chunks for load balance; summation order (FP32 atomics) is not fixed from run to run. */
 int qs_ppo_grad(const qs_ppo_batch* batch, const qs_ppo_net* net, const qs_ppo_net* grad, int which, float sigma, float eps_clip,
-                double count, double* loss_sum, void* scratch, void* stream);
+                double count, double* loss_sum, void* stream);
 /* torch.optim.Adam.step (the optimizer of ppo.py:105; eps 1e-8 there) on one flat FP32 parameter vector; step = 1, 2, ... */
 int qs_adam_step(int64_t n, float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int32_t step, float lr, float beta1,
                  float beta2, float eps, void* stream);
@@ -405,6 +406,10 @@ int qs_umma_selftest(int N, int K, const float* A, const float* B, float* D, voi
 /* The same product with the A operand staged in TENSOR memory (tcgen05.st by the thread that owns the row, TS form of
  * tcgen05.mma): 16 <= N <= 128 (multiple of 16), 32 <= K <= 128 (multiple of 32). */
 int qs_umma_selftest_ts(int N, int K, const float* A, const float* B, float* D, void* stream);
+/* The MN-major operand path of qs_ppo_grad (operands stored with K = the row index, so one tile serves a forward product and a
+ * weight-gradient product without a transpose), K = 128: mode 0: D[128][N] = At^T Bt with At [128 k][128 m], Bt [128 k][N];
+ * mode 1: D[128][N] = A Bt with A [128 m][128 k] K-major, Bt [128 k][N] MN-major. */
+int qs_umma_selftest_mn(int mode, int N, const float* A, const float* B, float* D, void* stream);
 
 /* ---- misc ----------------------------------------------------------------------------------- */
 const char* qs_last_error(void);

@@ -592,6 +592,21 @@ def test_umma_selftest_gemm_a_operand_in_tensor_memory():
         assert (D - ref).abs().max().item() < 1e-3, (N, K, (D - ref).abs().max().item())
 
 
+def test_umma_selftest_gemm_mn_major_operands():
+    """MN-major operands (K = row index of the stored tile): the weight-gradient products of qs_ppo_grad read the forward pass's own
+    activation tiles, no transposed copies (mode 0: both operands MN-major; mode 1: A K-major, B MN-major = dZ W)."""
+    lib = L.load_library()
+    torch.manual_seed(2)
+    for N in (16, 80, 128):
+        A = torch.randn(128, 128, device=DEV); B = torch.randn(128, N, device=DEV); D = torch.zeros(128, N, device=DEV)
+        L.check(lib.qs_umma_selftest_mn(0, N, A.data_ptr(), B.data_ptr(), D.data_ptr(), None))
+        ref = A.bfloat16().float().t() @ B.bfloat16().float()
+        assert (D - ref).abs().max().item() < 1e-3, (0, N, (D - ref).abs().max().item())
+        L.check(lib.qs_umma_selftest_mn(1, N, A.data_ptr(), B.data_ptr(), D.data_ptr(), None))
+        ref = A.bfloat16().float() @ B.bfloat16().float()
+        assert (D - ref).abs().max().item() < 1e-3, (1, N, (D - ref).abs().max().item())
+
+
 def _torch_actor(W, x):
     h = torch.tanh(x @ W["actor_0_weight"].t() + W["actor_0_bias"])
     h = torch.tanh(h @ W["actor_2_weight"].t() + W["actor_2_bias"])

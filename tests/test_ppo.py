@@ -192,12 +192,57 @@ def _torch_grads(ppo, b, bf16_forward):
     lc = (0.5 * (value - b["returns"]) ** 2 * b["weight"]).sum() / b["count"]
     params = list(pol.actor.parameters()) + list(pol.critic.parameters())
     g = torch.autograd.grad(la + lc, params)
-    return torch.cat([t.reshape(-1) for t in g]), float(la), float(lc), logp.detach()
+    return torch.cat([t.reshape(-1) for t in g]), float(la.detach()), float(lc.detach()), logp.detach()
+
+
+def _bf(v):
+    return v.bfloat16().float()
+
+
+def _kernel_arithmetic_grads(ppo, b, rnd=_bf):
+    """The arithmetic of qs_ppo_grad restated in torch, operand roundings included (csrc/ppo_update.cuh): BF16 MMA operands (X, W1, W2,
+    H1, H2, dZ3, dZ2, dZ1 and the parked 1 - H1^2), FP32 accumulation, FP32 output layer and loss, the gradient of torch.min/clamp as
+    a branch select.  rnd = identity turns it into a plain manual backward pass (checked against autograd on the CPU).
+    Returns (flat gradient, actor loss, critic loss, per-dimension log-probs (K, N, 4))."""
+    K, N = b["adv"].shape
+    x = ppo.network_inputs(b["hist0"], b["entries"], 0, N)[:K].reshape(K * N, 75)
+    wgt = (b["weight"] / b["count"]).reshape(-1)
+    pol, eps = ppo.policy, ppo.eps_clip
+    grads, losses, logp = [], [], None
+    for net, seq in ((0, pol.actor), (1, pol.critic)):
+        W1, b1, W2, b2, W3, b3 = [p.detach() for p in seq.parameters()]
+        h1 = torch.tanh(rnd(x) @ rnd(W1).t() + b1)
+        h2 = torch.tanh(rnd(h1) @ rnd(W2).t() + b2)
+        out = h2 @ W3.t() + b3
+        if net == 0:
+            mean = torch.tanh(out)
+            a = b["actions"].permute(0, 2, 1).reshape(K * N, 4)
+            d = a - mean
+            logp = -0.5 * d * d / pol._var - pol._log_std - 0.5 * np.log(2 * np.pi)
+            ratio = torch.exp(logp.sum(-1) - b["logprob"].permute(0, 2, 1).reshape(K * N, 4).sum(-1))
+            adv = b["adv"].reshape(-1)
+            surr1, surr2 = ratio * adv, torch.clamp(ratio, 1 - eps, 1 + eps) * adv
+            through = (surr1 <= surr2) | ((ratio >= 1 - eps) & (ratio <= 1 + eps))
+            losses.append(float((wgt * -torch.minimum(surr1, surr2)).sum()))
+            dl = torch.where(through, -adv * ratio, torch.zeros_like(adv))
+            dz3 = (wgt * dl)[:, None] * d / pol._var * (1 - mean * mean)
+        else:
+            dv = out.squeeze(-1) - b["returns"].reshape(-1)
+            losses.append(float((wgt * 0.5 * dv * dv).sum()))
+            dz3 = (wgt * dv)[:, None]
+        dW3, db3 = rnd(dz3).t() @ rnd(h2), dz3.sum(0)
+        dz2 = rnd((dz3 @ W3) * (1 - h2 * h2))
+        dW2, db2 = dz2.t() @ rnd(h1), dz2.sum(0)
+        dz1 = rnd((dz2 @ rnd(W2)) * rnd(1 - h1 * h1))
+        dW1, db1 = dz1.t() @ rnd(x), dz1.sum(0)
+        grads += [dW1, db1, dW2, db2, dW3, db3]
+    return torch.cat([t.reshape(-1) for t in grads]), losses[0], losses[1], logp.reshape(K, N, 4)
 
 
 def _kernel_batch(K, N, seed, dev, ppo, spread):
-    """Synthetic rollout buffers: BF16-representable history, actions = mean + sigma z, old log-probs = the FP32 ones + spread * noise
-    (spread > 0 pushes a good part of the ratios out of [1 - eps, 1 + eps], so the clipped branch is exercised)."""
+    """Synthetic rollout buffers: BF16-representable history, actions = mean + sigma z.  spread > 0: old log-probs such that the ratio of
+    the BF16-operand forward pass is drawn from [0.9, 1.1], [0.3, 0.7] and [1.35, 2] (both clip branches, and no sample within 5 % of
+    a clip boundary: MUFU.TANH vs tanh moves a ratio by ~1 %, and a sample that changes branch changes the gradient by its whole term)."""
     gen = torch.Generator().manual_seed(seed)
     r = lambda *s: torch.randn(*s, generator=gen).to(dev)
     b = dict(hist0=(r(75, N) * 0.7).bfloat16().float(), entries=(r(K, 15, N) * 0.7).bfloat16().float(), adv=r(K, N), returns=r(K, N) * 2)
@@ -205,31 +250,50 @@ def _kernel_batch(K, N, seed, dev, ppo, spread):
     b["count"] = float(b["weight"].sum())
     with torch.no_grad():
         x = ppo.network_inputs(b["hist0"], b["entries"], 0, N)[:K]
-        mean = ppo.policy.actor(x)
-        a = mean + ppo.policy.std * r(K, N, 4)
-        lp = ppo.policy.logprob(x, a)
+        a = ppo.policy.actor(x) + ppo.policy.std * r(K, N, 4)
     b["actions"] = a.permute(0, 2, 1).contiguous()
-    b["logprob"] = (lp + spread * r(K, N, 4)).permute(0, 2, 1).contiguous()
+    b["logprob"] = torch.zeros(K, 4, N, device=dev)
+    lp = _kernel_arithmetic_grads(ppo, b)[3]
+    if spread > 0:
+        u = torch.rand(K, N, generator=gen).to(dev); sel = torch.randint(0, 3, (K, N), generator=gen).to(dev)
+        ratio = torch.where(sel == 0, 0.9 + 0.2 * u, torch.where(sel == 1, 0.3 + 0.4 * u, 1.35 + 0.65 * u))
+        lp = lp - (torch.log(ratio) / 4).unsqueeze(-1)
+    b["logprob"] = lp.permute(0, 2, 1).contiguous()
     return b
 
 
+def test_manual_backward_equals_autograd_cpu():
+    """The restatement the kernel is compared with, rounding switched off, IS the autograd gradient of the PPO loss (ppo.py:183-203)."""
+    ppo = P.BatchedPPO(None, hidden=128, seed=11)
+    b = _kernel_batch(4, 96, 5, torch.device("cpu"), ppo, spread=1.0)
+    ident = lambda v: v
+    g_m, la_m, lc_m, _ = _kernel_arithmetic_grads(ppo, b, ident)
+    g_a, la_a, lc_a, _ = _torch_grads(ppo, b, False)
+    assert abs(la_m - la_a) < 1e-5 and abs(lc_m - lc_a) < 1e-5
+    assert float((g_m - g_a).norm() / g_a.norm()) < 1e-4
+    frac_low = float((torch.exp(_kernel_arithmetic_grads(ppo, b)[3].sum(-1) - b["logprob"].permute(0, 2, 1).sum(-1)) < 0.8).float().mean())
+    assert 0.2 < frac_low < 0.5                                 # the clipped branches are populated
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("K,N,sigma", [(6, 300, 0.1), (3, 128, 0.5), (17, 1000, 0.1)])
+@pytest.mark.parametrize("K,N,sigma", [(6, 300, 0.1), (3, 128, 0.5), (17, 1000, 0.1), (70, 200, 0.1)])
 def test_ppo_grad_kernel_vs_autograd(K, N, sigma):
-    """qs_ppo_grad (tcgen05 forward + backward, BF16 operands) vs torch autograd on the same buffers: every parameter tensor's gradient
-    within 1 % (relative L2) of the autograd gradient of the BF16-operand forward, and the losses within 1e-3; against the plain FP32
-    network the bound is the one BF16 operands allow (sigma = 0.1 amplifies a 3e-3 error of the mean into 3 % of (a - mean))."""
+    """qs_ppo_grad (tcgen05 forward + backward, BF16 operands) on synthetic rollout buffers, including a horizon that the launch splits
+    into step chunks (70 steps): every parameter tensor's gradient within 5e-3 (relative L2) of the same arithmetic restated in torch
+    (BF16 operand roundings included; what is left is MUFU.TANH vs tanh and the summation order), losses within 1e-3; against plain
+    FP32 autograd only what BF16 operands allow (sigma = 0.1 turns a 3e-3 error of the mean into 3 % of (a - mean), and bias gradients
+    are sums with heavy cancellation)."""
     dev = torch.device("cuda", 0)
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = False
     try:
         ppo = P.BatchedPPO(None, hidden=128, action_std=sigma, seed=11, device=dev)
         assert ppo.update_impl == "kernel"
-        b = _kernel_batch(K, N, 5, dev, ppo, spread=0.08)
+        b = _kernel_batch(K, N, 5, dev, ppo, spread=1.0)
         g_k, loss_k = ppo.gradients(b)
-        g_e, la_e, lc_e, _ = _torch_grads(ppo, b, True)
+        g_e, la_e, lc_e, _ = _kernel_arithmetic_grads(ppo, b)
         g_f, la_f, lc_f, _ = _torch_grads(ppo, b, False)
-        assert abs(float(loss_k[0]) - la_e) < 2e-3 * max(1.0, abs(la_e)) and abs(float(loss_k[1]) - lc_e) < 2e-3 * max(1.0, abs(lc_e)), (loss_k, la_e, lc_e)
+        assert abs(float(loss_k[0]) - la_e) < 1e-3 * max(1.0, abs(la_e)) and abs(float(loss_k[1]) - lc_e) < 1e-3 * max(1.0, abs(lc_e)), (loss_k, la_e, lc_e)
         o = 0
         names = ["actor." + n for n, _ in ppo.policy.actor.named_parameters()] + ["critic." + n for n, _ in ppo.policy.critic.named_parameters()]
         params = list(ppo.policy.actor.parameters()) + list(ppo.policy.critic.parameters())
@@ -237,9 +301,8 @@ def test_ppo_grad_kernel_vs_autograd(K, N, sigma):
             n = p.numel()
             k, e, f = g_k[o:o + n], g_e[o:o + n], g_f[o:o + n]
             rel_e = float((k - e).norm() / e.norm()); rel_f = float((k - f).norm() / f.norm())
-            assert rel_e < 1e-2, (name, rel_e, rel_f)
-            # sanity bound only: a few hundred samples, and ratios next to the clip boundary switch branch under BF16 operands
-            assert rel_f < (0.3 if name.startswith("actor") else 3e-2), (name, rel_e, rel_f)
+            assert rel_e < 5e-3, (name, rel_e, rel_f)
+            assert rel_f < (0.3 if name.startswith("actor") else 5e-2), (name, rel_e, rel_f)
             o += n
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
@@ -280,7 +343,7 @@ def test_adam_kernel_vs_torch_optimizer():
         ref.grad = g.clone(); opt.step()
         L.check(lib.qs_adam_step(n, p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), step, 5e-4, 0.9, 0.999, 1e-8,
                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)))
-        assert torch.allclose(p, ref.detach(), rtol=0, atol=2e-7), float((p - ref.detach()).abs().max())
+        assert torch.allclose(p, ref.detach(), rtol=0, atol=5e-7), float((p - ref.detach()).abs().max())
 
 
 @pytest.mark.gpu
@@ -293,7 +356,7 @@ def test_ppo_kernel_update_tracks_the_torch_update():
     t = P.BatchedPPO(None, hidden=128, seed=6, K_epochs=2, device=dev, update_impl="torch", tf32=False, chunk_envs=512)
     assert torch.equal(a._flat, t._flat)
     start = a._flat.clone()
-    b = _kernel_batch(8, 2048, 12, dev, a, spread=0.05)
+    b = _kernel_batch(8, 2048, 12, dev, a, spread=1.0)
     la = a.update(dict(b)); lt = t.update(dict(b))
     da, dt_ = a._flat - start, t._flat - start
     cos = float((da * dt_).sum() / (da.norm() * dt_.norm()))
