@@ -10,21 +10,22 @@
 // threads of a sample (tid >> 7) own 32 of the 128 hidden columns each.  Every activation / gradient tile is written ONCE, row = sample,
 // with 16-byte shared-memory stores in the canonical [row][col] layout of umma.cuh, and serves the tensor core twice: as a K-major
 // operand (K = hidden index) of the forward / input-gradient products and as an MN-major operand (K = sample index) of the
-// weight-gradient products — no transposed copies exist.  Per (tile, step), X = [128 x 16 per slot] history ring of the rollout kernel
-// (15 floats per entry + pad = 1: bias column; six slots so the next entry lands in a slot no pending MMA reads):
-//   Z1 = X W1^T             SS, 5 x K16 (one per history slot, W1 indexed by age)                                      -> TMEM Z
-//   H1 = tanh(Z1)           -> smem H1 [s][j]
-//   Z2 = H1 W2^T + b2       SS, 8 x K16 + one K16 block [1 1 0..] x [b2_hi b2_lo 0..]                                   -> TMEM Z
+// weight-gradient products — no transposed copies exist.  Per (tile, step), X = [128 x 80] the five history entries oldest first
+// (15 floats per entry + pad = 1: bias column), double-buffered: a sample's row is shifted by one entry into the other buffer while the
+// products of this step still read the current one:
+//   Z1 = X W1^T             5 x K16, N = 128                                                                           -> TMEM Z
+//   H1 = tanh(Z1)           -> smem H1 [s][144]: 128 activations + the constant columns [1 1 0..] of the bias fold
+//   Z2 = [H1 1 1] [W2 b2_hi b2_lo]^T      9 x K16, N = 128                                                              -> TMEM Z
 //   H2 = tanh(Z2) -> smem H2 [s][j]; out = W3 H2 + b3 on the FP32 pipe (partial sums of the four column owners exchanged through
 //   shared memory); the loss and dZ3 per sample in registers; dZ2 = (W3^T dZ3)(1 - H2^2) -> smem dZ [s][j]
-//   dW3 += H2^T dZ3   (A = H2 MN-major, B = dZ3 [s][16] MN-major)      dW2 += dZ2^T H1   (A = dZ MN-major, B = H1 MN-major)
-//   db2 += dZ2^T 1    (B = the ones block of the bias fold)            dH1 = dZ2 W2      (A = dZ K-major, B = W2 [j2][j1] MN-major) -> TMEM Z
-//   dZ1 = dH1 (1 - H1^2)    -> smem dZ [s][j] (over dZ2)
-//   dW1 += dZ1^T X          five N = 16 products, one per history slot (B = that slot's columns of X, MN-major); the pad column of X
-//                           makes column 15 of every block db1
-//   next step's Z1 is issued in the same batch as dW1.
-// The weight-gradient accumulators stay in TENSOR MEMORY for the whole launch (240 columns next to the 128 of Z) and are added to the
-// FP32 gradient buffers in HBM once per CTA.
+//   group 1:  dW3 += H2^T dZ3  (A = H2 MN-major, B = dZ3 [s][16] MN-major, N = 16)
+//             dH1  = dZ2 W2    (A = dZ K-major, B = W2 [j2][j1] MN-major, N = 128)                                       -> TMEM Z
+//   group 2:  [dW2 | db2] += dZ2^T [H1 1 1]   (A = dZ MN-major, B = the H1 tile MN-major, N = 144) — runs while the threads compute
+//   dZ1 = dH1 (1 - H1^2)    -> smem, into the H2 tile (dW3 has completed)
+//   group 3:  next step's Z1 (waited for first), then dW1 += dZ1^T X (A = dZ1 MN-major, B = X MN-major, N = 80; the pad columns of X
+//             make column 15 of every 16-wide block db1) — runs under the next step's first epilogue.
+// The weight-gradient accumulators stay in TENSOR MEMORY for the whole launch (240 columns next to the 128 of Z and 64 of parked
+// tanh' factors) and are added to the FP32 gradient buffers in HBM once per CTA.
 #pragma once
 #include "umma.cuh"
 
@@ -33,7 +34,7 @@ namespace ppo {
 constexpr int kM = 128;          // samples per tile = UMMA M / K
 constexpr int kH = 128;          // hidden width
 constexpr int kSlots = 5, kSlotK = 16, kKin = kSlots * kSlotK;   // 80
-constexpr int kRing = 6, kXext = kRing * kSlotK;                 // 96 columns of X: five live history slots + the one being written
+constexpr int kH1ext = kH + 16;                                  // H1 / W2 tiles carry the 16-wide bias block of layer 2 as columns 128..143
 constexpr int kSplit = 4, kThreads = kM * kSplit, kCW = kH / kSplit;   // 512 threads, 32 hidden columns per thread
 
 struct Batch {
@@ -57,22 +58,20 @@ struct Grad {                    // FP32, same shapes, ACCUMULATED (atomicAdd); 
 };
 
 // shared-memory map (bytes); every tile is [row][col] in umma_canon_offset(row, col, cols)
-constexpr int oX = 0;                                 // [128 s][96]    history ring (A of layer 1, B of dW1)
-constexpr int oH1 = oX + kM * kXext * 2;              // [128 s][128 j] H1 (A of layer 2, B of dW2)
-constexpr int oH2 = oH1 + kM * kH * 2;                // [128 s][128 j] H2 (A of dW3)
-constexpr int oDZ = oH2 + kM * kH * 2;                // [128 s][128 j] dZ2, then dZ1 (A of dW2 / db2 / dH1, then of dW1)
+constexpr int oX = 0;                                 // 2 x [128 s][80]  history, oldest entry first (A of layer 1, B of dW1), ping-pong
+constexpr int oH1 = oX + 2 * kM * kKin * 2;           // [128 s][144]   H1 | 1 1 0.. (A of layer 2, B of dW2 | db2)
+constexpr int oH2 = oH1 + kM * kH1ext * 2;            // [128 s][128 j] H2 (A of dW3), then dZ1 (A of dW1)
+constexpr int oDZ = oH2 + kM * kH * 2;                // [128 s][128 j] dZ2 (A of dW2 | db2 and of dH1)
 constexpr int oW1 = oDZ + kM * kH * 2;                // [128 j][80]    (B of layer 1; column = 16 age + e)
-constexpr int oW2 = oW1 + kH * kKin * 2;              // [128 j2][128 j1] (B of layer 2 K-major, B of dH1 MN-major)
-constexpr int oOnes = oW2 + kH * kH * 2;              // [128 s][16]    columns 0,1 = 1 (A of the b2 block; B of db2)
-constexpr int oW2x = oOnes + kM * 16 * 2;             // [128 j][16]    columns 0,1 = b2 (hi, lo)
-constexpr int oDZ3 = oW2x + kH * 16 * 2;              // [128 s][16]    dZ3 in columns 0..OUT-1 (B of dW3)
+constexpr int oW2 = oW1 + kH * kKin * 2;              // [128 j2][144]  W2 | b2_hi b2_lo 0.. (B of layer 2 K-major, B of dH1 MN-major)
+constexpr int oDZ3 = oW2 + kH * kH1ext * 2;           // [128 s][16]    dZ3 in columns 0..OUT-1 (B of dW3)
 constexpr int oPart = oDZ3 + kM * 16 * 2;             // float [4 part][4 k][128 s]  partial sums of the output layer
 constexpr int oIn = oPart + kSplit * 4 * kM * 4;      // float [10][128 s]  per-sample inputs of the loss: act(4), logp_old(4), adv | ret, weight
 constexpr int oW3 = oIn + 10 * kM * 4;                 // float4 [128 j] = w3[0..3][j] (critic: .x only), then float [4] b3: the FP32 output layer
 constexpr int kSmemBytes = oW3 + kH * 16 + 16;
 
 // TMEM column map
-constexpr uint32_t cZ = 0, cDW2 = 128, cDW1 = 256, cDB2 = 336, cDW3 = 352, cT1 = 368, kCols = 512;   // cT1: 64 columns, 1 - H1^2 packed BF16
+constexpr uint32_t cZ = 0, cDW2 = 128, cDB2 = cDW2 + 128, cDW1 = 272, cDW3 = 352, cT1 = 368, kCols = 512;   // [dW2 | db2] = 144 columns; cT1: 64 columns, 1 - H1^2 packed BF16
 
 using namespace qs;
 
@@ -86,28 +85,15 @@ __device__ __forceinline__ void st_bf16(unsigned char* base, uint32_t off, float
     *reinterpret_cast<__nv_bfloat16*>(base + off) = __float2bfloat16(x);
 }
 // 32 consecutive columns of a thread's own row: four 16-byte stores / loads (a quarter-warp covers 128 contiguous bytes: no conflicts)
-__device__ __forceinline__ void st_row32(unsigned char* tile, int row, int col0, const float v[32]) {
+__device__ __forceinline__ void st_row32(unsigned char* tile, int ext, int row, int col0, const float v[32]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         uint4 q;
         q.x = pack_bf16x2(v[8 * i + 0], v[8 * i + 1]); q.y = pack_bf16x2(v[8 * i + 2], v[8 * i + 3]);
         q.z = pack_bf16x2(v[8 * i + 4], v[8 * i + 5]); q.w = pack_bf16x2(v[8 * i + 6], v[8 * i + 7]);
-        *reinterpret_cast<uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, kH)) = q;
+        *reinterpret_cast<uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, ext)) = q;
     }
 }
-__device__ __forceinline__ void ld_row32(const unsigned char* tile, int row, int col0, float v[32]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint4 q = *reinterpret_cast<const uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, kH));
-        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            v[8 * i + 2 * k] = __uint_as_float(w[k] << 16);
-            v[8 * i + 2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
-        }
-    }
-}
-
 template <int NET>
 __global__ void __launch_bounds__(kThreads, 1)
 ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, const __grid_constant__ Grad g, float sigma,
@@ -137,13 +123,13 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
     }
     for (int idx = tid; idx < kH * kH; idx += kThreads) {
         const int n = idx / kH, kk = idx % kH;
-        st_bf16(smem + oW2, umma_canon_offset(n, kk, kH), w.w2[n * kH + kk]);    // [j2][j1]
+        st_bf16(smem + oW2, umma_canon_offset(n, kk, kH1ext), w.w2[n * kH + kk]);    // [j2][j1]
     }
     for (int idx = tid; idx < kH * 16; idx += kThreads) {
         const int n = idx / 16, kk = idx % 16;
         const float bb = w.b2[n], hi = __bfloat162float(__float2bfloat16(bb));
-        st_bf16(smem + oOnes, umma_canon_offset(n, kk, 16), kk < 2 ? 1.f : 0.f);
-        st_bf16(smem + oW2x, umma_canon_offset(n, kk, 16), kk == 0 ? hi : (kk == 1 ? bb - hi : 0.f));
+        st_bf16(smem + oH1, umma_canon_offset(n, kH + kk, kH1ext), kk < 2 ? 1.f : 0.f);
+        st_bf16(smem + oW2, umma_canon_offset(n, kH + kk, kH1ext), kk == 0 ? hi : (kk == 1 ? bb - hi : 0.f));
         st_bf16(smem + oDZ3, umma_canon_offset(n, kk, 16), 0.f);
     }
     if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); s_loss = 0.f; }
@@ -155,8 +141,8 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
     const uint32_t tb = tmem_slot;
     const uint32_t lane = tb + ((uint32_t)((warp & 3) * 32) << 16);     // a warp reads the 32 TMEM lanes of its quarter
     const uint32_t uX = smem_u32(smem + oX), uH1 = smem_u32(smem + oH1), uH2 = smem_u32(smem + oH2), uDZ = smem_u32(smem + oDZ),
-                   uW1 = smem_u32(smem + oW1), uW2 = smem_u32(smem + oW2), uOnes = smem_u32(smem + oOnes), uW2x = smem_u32(smem + oW2x),
-                   uDZ3 = smem_u32(smem + oDZ3);
+                   uW1 = smem_u32(smem + oW1), uW2 = smem_u32(smem + oW2), uDZ3 = smem_u32(smem + oDZ3);
+    constexpr uint32_t kXbytes = kM * kKin * 2;
     uint32_t phase = 0;
     bool have_acc = false;                                       // the weight-gradient accumulators hold something
     float loss_local = 0.f;
@@ -173,18 +159,12 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
         __syncthreads();
         if (tid == 0) tc_fence_after();
     };
-    auto issue_layer1 = [&](int head) {
-#pragma unroll
-        for (int a = 0; a < kSlots; ++a) {
-            int sl = head + a; sl = sl >= kRing ? sl - kRing : sl;
-            umma_gemm_k(tb + cZ, uX, kXext, sl * kSlotK, uW1, kKin, a * kSlotK, kSlotK, kH, a > 0);
-        }
-    };
-    // the four history values this thread stages per slot: elements 4*part .. 4*part+3 of the 16-wide block (element 15 = 1)
-    auto ring_store = [&](int slot, const float x[4]) {
+    auto issue_layer1 = [&](int cur) { umma_gemm_k(tb + cZ, uX + (uint32_t)cur * kXbytes, kKin, 0, uW1, kKin, 0, kKin, kH, false); };
+    // the four history values this thread stages per entry: elements 4*part .. 4*part+3 of the 16-wide block (element 15 = 1)
+    auto entry_store = [&](int buf, int age, const float x[4]) {
         uint2 q;
         q.x = pack_bf16x2(x[0], x[1]); q.y = pack_bf16x2(x[2], x[3]);
-        *reinterpret_cast<uint2*>(smem + oX + umma_canon_offset(s, slot * kSlotK + 4 * part, kXext)) = q;
+        *reinterpret_cast<uint2*>(smem + oX + buf * kXbytes + umma_canon_offset(s, age * kSlotK + 4 * part, kKin)) = q;
     };
 
     const int64_t n_tiles = (b.N + kM - 1) / kM;
@@ -207,11 +187,11 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                 const int q = 4 * part + r;
                 x[r] = q < 15 ? (active ? (i < kSlots ? b.hist0[(int64_t)(i * 15 + q) * b.N + n] : b.entries[((int64_t)(i - kSlots) * 15 + q) * b.N + n]) : 0.f) : 1.f;
             }
-            ring_store(a, x);
+            entry_store(0, a, x);
         }
-        int head = 0;
+        int cur = 0;
         sync_before_issue();
-        if (tid == 0) issue_layer1(head);
+        if (tid == 0) issue_layer1(cur);
         commit();
         for (int t = t0; t < t1; ++t) {
             const int64_t tn = (int64_t)t * b.N + n;
@@ -238,7 +218,7 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
             tmem_ld_32x32b_x32(lane + cZ + (uint32_t)col0, acc);
 #pragma unroll
             for (int i = 0; i < 32; ++i) acc[i] = tanh_fast(acc[i]);
-            st_row32(smem + oH1, s, col0, acc);
+            st_row32(smem + oH1, kH1ext, s, col0, acc);
             {   // tanh' = 1 - H1^2 from the FP32 activation, parked in tensor memory until dZ1 (BF16 of the FACTOR: a saturated unit's
                 // 1 - h^2 computed from a BF16-rounded h would be off by tens of percent)
                 uint32_t tp[16];
@@ -248,10 +228,7 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                 tmem_st_wait();
             }
             sync_before_issue();
-            if (tid == 0) {
-                umma_gemm_k(tb + cZ, uH1, kH, 0, uW2, kH, 0, kH, kH, false);
-                umma_bf16(tb + cZ, umma_smem_desc(uOnes, 128u, 256u), umma_smem_desc(uW2x, 128u, 256u), umma_idesc_bf16_f32(128, kH), true);
-            }
+            if (tid == 0) umma_gemm_k(tb + cZ, uH1, kH1ext, 0, uW2, kH1ext, 0, kH1ext, kH, false);
             commit();
             wait();
             // H2 and the output layer on the FP32 pipe: this thread's 32 hidden units
@@ -268,7 +245,7 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                     po[2 % OUT] = fmaf(acc[i], w4.z, po[2 % OUT]); po[3 % OUT] = fmaf(acc[i], w4.w, po[3 % OUT]);
                 } else po[0] = fmaf(acc[i], s_w3[(col0 + i) * 4], po[0]);
             }
-            st_row32(smem + oH2, s, col0, acc);
+            st_row32(smem + oH2, kH, s, col0, acc);
 #pragma unroll
             for (int k = 0; k < OUT; ++k) s_part[(part * 4 + k) * kM + s] = po[k];
             cp_async_wait_all();
@@ -330,17 +307,18 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                 } else dh = dz3[0] * s_w3[(col0 + i) * 4];
                 acc[i] = dh * (1.f - acc[i] * acc[i]);
             }
-            st_row32(smem + oDZ, s, col0, acc);
+            st_row32(smem + oDZ, kH, s, col0, acc);
             sync_before_issue();
             if (tid == 0) {
                 umma_gemm_mn(tb + cDW3, uH2, kH, 0, uDZ3, 16, 0, 16, have_acc);       // dW3[j][k]   += sum_s H2[s][j] dZ3[s][k]
-                umma_gemm_mn(tb + cDW2, uDZ, kH, 0, uH1, kH, 0, kH, have_acc);         // dW2[j2][j1] += sum_s dZ2[s][j2] H1[s][j1]
-                umma_gemm_mn(tb + cDB2, uDZ, kH, 0, uOnes, 16, 0, 16, have_acc);       // db2[j2]     += sum_s dZ2[s][j2] 1
-                umma_gemm_k_mn(tb + cZ, uDZ, kH, uW2, kH, 0, kH, kH, false);            // dH1[s][j1]   = sum_j2 dZ2[s][j2] W2[j2][j1]
+                umma_gemm_k_mn(tb + cZ, uDZ, kH, uW2, kH1ext, 0, kH, kH, false);        // dH1[s][j1]   = sum_j2 dZ2[s][j2] W2[j2][j1]
             }
             commit();
+            // [dW2 | db2][j2][j1 | 128] += sum_s dZ2[s][j2] [H1 | 1][s][..]: no commit of its own — it runs under the dZ1 epilogue below and
+            // is covered by the next commit
+            if (tid == 0) umma_gemm_mn(tb + cDW2, uDZ, kH, 0, uH1, kH1ext, 0, kH1ext, have_acc);
             wait();
-            // dZ1 = dH1 (1 - H1^2), over dZ2 (its readers have completed)
+            // dZ1 = dH1 (1 - H1^2) into the H2 tile (dW3, its reader, has completed)
             {
                 float tp[16];
                 tmem_ld_32x32b_x32(lane + cZ + (uint32_t)col0, acc);
@@ -351,25 +329,30 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
                     acc[2 * i] *= __uint_as_float(pk << 16);
                     acc[2 * i + 1] *= __uint_as_float(pk & 0xFFFF0000u);
                 }
-                st_row32(smem + oDZ, s, col0, acc);
+                st_row32(smem + oH2, kH, s, col0, acc);
             }
-            // next step's input: the entry recorded after step t takes the free ring slot (dl_auxiliary.py:25-32)
-            int spare = head + kSlots; spare = spare >= kRing ? spare - kRing : spare;
-            ring_store(spare, e_new);
-            sync_before_issue();
-            if (tid == 0) {                                       // dW1[j][16 a + e] += sum_s dZ1[s][j] X[s][16 slot(a) + e]
+            // next step's input (dl_auxiliary.py:25-32): this sample's row moves up by one entry into the other buffer (this thread: the
+            // 16 columns of entry part+1 -> entry part), the entry recorded after step t becomes the newest
+            {
+                const unsigned char* src = smem + oX + cur * kXbytes;
+                unsigned char* dst = smem + oX + (cur ^ 1) * kXbytes;
 #pragma unroll
-                for (int a = 0; a < kSlots; ++a) {
-                    int sl = head + a; sl = sl >= kRing ? sl - kRing : sl;
-                    umma_gemm_mn(tb + cDW1 + (uint32_t)(a * kSlotK), uDZ, kH, 0, uX, kXext, sl * kSlotK, 16, have_acc);
-                }
+                for (int i = 0; i < 2; ++i)
+                    *reinterpret_cast<uint4*>(dst + umma_canon_offset(s, part * kSlotK + 8 * i, kKin)) =
+                        *reinterpret_cast<const uint4*>(src + umma_canon_offset(s, (part + 1) * kSlotK + 8 * i, kKin));
+                entry_store(cur ^ 1, kSlots - 1, e_new);
             }
-            have_acc = true;
-            head = head + 1 == kRing ? 0 : head + 1;
-            if (tid == 0 && t + 1 < t1) issue_layer1(head);
+            sync_before_issue();
+            if (tid == 0 && t + 1 < t1) issue_layer1(cur ^ 1);   // first in the queue after dW2: the next epilogue waits for it alone
             commit();
+            // dW1[j][16 a + e] += sum_s dZ1[s][j] X[s][16 a + e]; covered by the next commit (layer 2 of the next step / the unit's end)
+            if (tid == 0) umma_gemm_mn(tb + cDW1, uH2, kH, 0, uX + (uint32_t)cur * kXbytes, kKin, 0, kKin, have_acc);
+            have_acc = true;
+            cur ^= 1;
         }
-        wait();                                                   // the unit's last dW1
+        wait();                                                   // the last step's commit ...
+        commit();
+        wait();                                                   // ... and the unit's last dW1
     }
     // ---- accumulators -> HBM gradients (thread = row j of every accumulator; the four parts split the columns)
     tc_fence_before();

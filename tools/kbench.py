@@ -37,6 +37,32 @@ def time_ms(fn, iters, warm=20):
     return e0.elapsed_time(e1) / iters
 
 
+def case_ppo_grad(N=1 << 16, K=128, iters=5, warm=2):
+    """qs_ppo_grad on synthetic rollout buffers: ms per full-batch gradient of one network, tensor-core rate in the FLOPs of
+    the forward + backward products (2 x (80+128+16) x 128 forward incl. the bias block, 2 x (128+16+16+128+80) x 128 backward)."""
+    from autonomous_quadrotor_environment_b200.ppo import BatchedPPO
+    ppo = BatchedPPO(None, hidden=128, seed=0, device=DEV)
+    g = torch.Generator(device=DEV); g.manual_seed(1)
+    r = lambda *s: torch.randn(*s, device=DEV, generator=g)
+    b = dict(hist0=r(75, N).bfloat16().float(), entries=r(K, 15, N).bfloat16().float(), actions=r(K, 4, N) * 0.3,
+             logprob=r(K, 4, N) * 0.1 + 1.38, adv=r(K, N), returns=r(K, N), weight=torch.ones(K, N, device=DEV), count=float(K * N))
+    t = ppo._batch_tensors(b)
+    loss = torch.zeros(2, dtype=torch.float64, device=DEV)
+    st = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
+    flops = 2.0 * 128 * ((80 + 128 + 16) + (128 + 16 + 16 + 128 + 80)) * K * N
+    for which, name in ((L.QS_PPO_ACTOR, "actor"), (L.QS_PPO_CRITIC, "critic")):
+        bt = L.qs_ppo_batch(N, K, 0, t["hist0"].data_ptr(), t["entries"].data_ptr(), t["actions"].data_ptr(), t["logprob"].data_ptr(),
+                            t["adv"].data_ptr(), t["returns"].data_ptr(), t["weight"].data_ptr())
+        net, grad = ppo._net_ptrs(ppo._flat, which == L.QS_PPO_CRITIC), ppo._net_ptrs(ppo._grad, which == L.QS_PPO_CRITIC)
+
+        def fn():
+            L.check(ppo.lib.qs_ppo_grad(C.byref(bt), C.byref(net), C.byref(grad), which, 0.1, 0.2, float(K * N), loss[which].data_ptr(), st))
+
+        ms = time_ms(fn, iters, warm=warm)
+        print("ppo_grad %-6s N=%d K=%d   %9.3f ms  %.3e samples/s  %.1f TFLOP/s (BF16 tensor, algorithmic)  %.2f us per 128-sample tile-step per SM"
+              % (name, N, K, ms, N * K / ms * 1e3, flops / ms * 1e-9, ms * 1e3 / (N / 128 * K / 148)), flush=True)
+
+
 def case_step(N=1 << 20, iters=300, **kw):
     cfg = dict(T=5, auto_reset=False, async_reset=False, precision="f32", integrator="rk4", substeps=1, n=1000, act_scale=1.0)
     cfg.update(kw)
@@ -97,6 +123,11 @@ if __name__ == "__main__":
         case_step(async_reset=True, T=5, iters=20, sensor_noise=True)
     if "profrollout" in which:
         case_rollout(n=10 ** 9, K=32, iters=2)
+    if "ppograd" in which:
+        case_ppo_grad()
+        case_ppo_grad(N=1 << 20, K=128, iters=2)
+    if "profppograd" in which:
+        case_ppo_grad(N=1 << 15, K=64, iters=1, warm=1)
     if "proff64" in which:
         case_step(N=1 << 16, iters=5, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "profpolicy" in which:
