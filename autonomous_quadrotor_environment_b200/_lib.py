@@ -111,7 +111,7 @@ class qs_control_rollout_args(C.Structure):
 
 
 class qs_ppo_batch(C.Structure):
-    _fields_ = [("n_envs", C.c_int64), ("horizon", C.c_int32), ("flags", C.c_int32), ("hist0", C.c_void_p), ("entries", C.c_void_p),
+    _fields_ = [("n_envs", C.c_int64), ("horizon", C.c_int32), ("flags", C.c_int32), ("hist0", C.c_void_p), ("entries", C.c_void_p), ("obs", C.c_void_p),
                 ("actions", C.c_void_p), ("logp_old", C.c_void_p), ("adv", C.c_void_p), ("ret", C.c_void_p), ("weight", C.c_void_p)]
 
 

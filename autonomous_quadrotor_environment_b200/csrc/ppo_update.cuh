@@ -42,7 +42,8 @@ struct Batch {
     int32_t K;                   // recorded steps
     int32_t flags;               // QS_PPO_RECORD_LOGP: write logp_old from this forward pass (ratio = 1) instead of reading it
     const float* hist0;          // [75][N]   dl_in_gen buffer at rollout start, oldest entry first
-    const float* entries;        // [K][15][N] history entry pushed after step t: [action(4), v(3), q(4), dq(4)] (BF16-rounded)
+    const float* entries;        // [K][15][N] history entry pushed after step t: [action(4), v(3), q(4), dq(4)]; nullptr: built from
+    const float* obs;            // [K][14][N] the recorded observations (rows 1,3,5 and 6..13) and `actions`
     const float* actions;        // [K][4][N]
     float* logp_old;             // [K][4][N]  (actor; written when flags & QS_PPO_RECORD_LOGP)
     const float* adv;            // [K][N]     normalised advantages (actor)
@@ -94,6 +95,14 @@ __device__ __forceinline__ void st_row32(unsigned char* tile, int ext, int row, 
         *reinterpret_cast<uint4*>(tile + umma_canon_offset(row, col0 + 8 * i, ext)) = q;
     }
 }
+// element q (0..14) of the history entry pushed after step t (dl_auxiliary.py:27-30: action(4), obs[1,3,5], obs[6:14])
+__device__ __forceinline__ float entry_value(const Batch& b, int t, int q, int64_t n) {
+    if (b.entries) return b.entries[((int64_t)t * 15 + q) * b.N + n];
+    if (q < 4) return b.actions[((int64_t)t * 4 + q) * b.N + n];
+    const int row = q < 7 ? 2 * (q - 4) + 1 : q - 1;
+    return b.obs[((int64_t)t * 14 + row) * b.N + n];
+}
+
 template <int NET>
 __global__ void __launch_bounds__(kThreads, 1)
 ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, const __grid_constant__ Grad g, float sigma,
@@ -185,7 +194,7 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int q = 4 * part + r;
-                x[r] = q < 15 ? (active ? (i < kSlots ? b.hist0[(int64_t)(i * 15 + q) * b.N + n] : b.entries[((int64_t)(i - kSlots) * 15 + q) * b.N + n]) : 0.f) : 1.f;
+                x[r] = q < 15 ? (active ? (i < kSlots ? b.hist0[(int64_t)(i * 15 + q) * b.N + n] : entry_value(b, i - kSlots, q, n)) : 0.f) : 1.f;
             }
             entry_store(0, a, x);
         }
@@ -200,7 +209,7 @@ ppo_grad_kernel(const __grid_constant__ Batch b, const __grid_constant__ Net w, 
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int q = 4 * part + r;
-                e_new[r] = q < 15 ? (active ? b.entries[((int64_t)t * 15 + q) * b.N + n] : 0.f) : 1.f;
+                e_new[r] = q < 15 ? (active ? entry_value(b, t, q, n) : 0.f) : 1.f;
             }
             // the loss's inputs go straight to shared memory (cp.async), one item per column owner; rows of padding samples stay 0
             const bool record = NET == 0 && (b.flags & QS_PPO_RECORD_LOGP) != 0;   // memory.logprobs of policy_old == policy (ppo.py:206)
@@ -463,7 +472,8 @@ extern "C" int qs_ppo_grad(const qs_ppo_batch* bt, const qs_ppo_net* net, const 
                            double count, double* loss_sum, void* stream) {
     if (!bt || !net || !grad) return fail(QS_EINVAL, "qs_ppo_grad: NULL argument");
     if (which != QS_PPO_ACTOR && which != QS_PPO_CRITIC) return fail(QS_EINVAL, "qs_ppo_grad: which must be QS_PPO_ACTOR or QS_PPO_CRITIC");
-    if (bt->n_envs < 1 || bt->horizon < 1 || !bt->hist0 || !bt->entries || !bt->weight) return fail(QS_EINVAL, "qs_ppo_grad: bad batch");
+    if (bt->n_envs < 1 || bt->horizon < 1 || !bt->hist0 || !bt->weight) return fail(QS_EINVAL, "qs_ppo_grad: bad batch");
+    if (!bt->entries && !(bt->obs && bt->actions)) return fail(QS_EINVAL, "qs_ppo_grad: needs entries, or obs and actions to build them from");
     if (which == QS_PPO_ACTOR && (!bt->actions || !bt->logp_old || !bt->adv || !(sigma > 0.f)))
         return fail(QS_EINVAL, "qs_ppo_grad: the actor needs actions, logp_old, adv and sigma > 0");
     if (which == QS_PPO_CRITIC && !bt->ret) return fail(QS_EINVAL, "qs_ppo_grad: the critic needs returns");
@@ -482,7 +492,7 @@ extern "C" int qs_ppo_grad(const qs_ppo_batch* bt, const qs_ppo_net* net, const 
     }
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    ppo::Batch b{bt->n_envs, bt->horizon, bt->flags, bt->hist0, bt->entries, bt->actions, (float*)bt->logp_old, bt->adv, bt->ret, bt->weight};
+    ppo::Batch b{bt->n_envs, bt->horizon, bt->flags, bt->hist0, bt->entries, bt->obs, bt->actions, (float*)bt->logp_old, bt->adv, bt->ret, bt->weight};
     ppo::Net nw{net->w1, net->b1, net->w2, net->b2, net->w3, net->b3};
     ppo::Grad g{gr[0], gr[1], gr[2], gr[3], gr[4], gr[5], loss_sum};
     // work units = (128-env tile, chunk of steps): the history at any step is a window of the entries buffer, so a tile's steps split

@@ -138,7 +138,9 @@ class BatchedPPO:
         hist0 = env.history.t().contiguous().clone()                      # (75, N)
         rec = env.policy_rollout(horizon, record_obs=True, record_actions=True, record_logprob=True, record_reward=True,
                                  record_done=True, record_values=self.fused_critic)
-        entries = self.history_entries(rec)
+        kernel_update = self.update_impl == "kernel"
+        # update_impl="kernel": qs_ppo_grad builds the history entries from the recorded observations and actions on the fly
+        entries = None if kernel_update else self.history_entries(rec)
         K, N = horizon, env.N
         value = rec["value"] if self.fused_critic else torch.empty(K + 1, N, dtype=torch.float32, device=self.dev)
         # old_logprobs of the update's ratio (ppo.py:187) must come from the SAME evaluation path as the new ones: the reference's
@@ -148,7 +150,6 @@ class BatchedPPO:
         # denominator is re-evaluated here, on the recorded actions, by the network the update differentiates.
         # update_impl="kernel": qs_ppo_grad's first epoch records them from its own forward pass (QS_PPO_RECORD_LOGP).
         logprob = torch.empty(K, 4, N, dtype=torch.float32, device=self.dev)
-        kernel_update = self.update_impl == "kernel"
         if kernel_update and not self.fused_critic:
             raise RuntimeError("update_impl='kernel' takes the state values from the fused critic head (fused_critic=True)")
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
@@ -171,7 +172,7 @@ class BatchedPPO:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
             dist.all_reduce(self.moments)                                 # normalise over the GLOBAL batch
         L.check(env.lib.qs_adv_normalize(K * N, rec["done"].data_ptr(), self.moments.data_ptr(), adv.data_ptr(), weight.data_ptr(), st))
-        return dict(hist0=hist0, entries=entries, actions=rec["actions"], logprob=logprob, logprob_kernel=rec["logprob"], reward=rec["reward"],
+        return dict(hist0=hist0, entries=entries, obs=rec["obs"], actions=rec["actions"], logprob=logprob, logprob_kernel=rec["logprob"], reward=rec["reward"],
                     done=rec["done"], value=value, returns=ret, adv=adv, weight=weight, count=float(self.moments[0].item()),
                     logprob_pending=kernel_update)
 
@@ -186,7 +187,11 @@ class BatchedPPO:
         return L.qs_ppo_net(*ptrs)
 
     def _batch_tensors(self, batch):
-        t = {k: batch[k].contiguous().float() for k in ("hist0", "entries", "actions", "adv", "returns", "weight")}
+        t = {k: batch[k].contiguous().float() for k in ("hist0", "actions", "adv", "returns", "weight")}
+        for k in ("entries", "obs"):                               # entries, or the recorded observations to build them from
+            t[k] = batch[k].contiguous().float() if batch.get(k) is not None else None
+        if t["entries"] is None and t["obs"] is None:
+            raise ValueError("the batch needs 'entries' (K,15,N) or 'obs' (K,14,N)")
         logp = batch["logprob"]
         if not (logp.is_contiguous() and logp.dtype == torch.float32):
             raise ValueError("batch['logprob'] must be a contiguous float32 (K,4,N) tensor (QS_PPO_RECORD_LOGP writes it in place)")
@@ -197,8 +202,9 @@ class BatchedPPO:
         """self._grad <- d(loss)/d(parameters) of the whole local batch: zero + qs_ppo_grad(actor) + qs_ppo_grad(critic)."""
         st = C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream)
         self._grad.zero_()
-        bt = L.qs_ppo_batch(N, K, L.QS_PPO_RECORD_LOGP if record else 0, t["hist0"].data_ptr(), t["entries"].data_ptr(),
-                            t["actions"].data_ptr(), t["logprob"].data_ptr(), t["adv"].data_ptr(), t["returns"].data_ptr(), t["weight"].data_ptr())
+        ptr = lambda x: x.data_ptr() if x is not None else None
+        bt = L.qs_ppo_batch(N, K, L.QS_PPO_RECORD_LOGP if record else 0, t["hist0"].data_ptr(), ptr(t["entries"]),
+                            None if t["entries"] is not None else ptr(t["obs"]), t["actions"].data_ptr(), t["logprob"].data_ptr(), t["adv"].data_ptr(), t["returns"].data_ptr(), t["weight"].data_ptr())
         for which in (L.QS_PPO_ACTOR, L.QS_PPO_CRITIC):
             net, grad = self._net_ptrs(self._flat, which == L.QS_PPO_CRITIC), self._net_ptrs(self._grad, which == L.QS_PPO_CRITIC)
             L.check(self.lib.qs_ppo_grad(C.byref(bt), C.byref(net), C.byref(grad), which, self.policy.std, self.eps_clip, float(count),

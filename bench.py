@@ -269,6 +269,43 @@ def policy_measure(args, dev, rank, world, steps, warm):
             "stats": env.stats(all_reduce=False), "mean_reward_last_rollout": mean_r}
 
 
+def ppo_iteration_measure(args, dev, iters=2):
+    """One PPO iteration (ppo.py:125-209) on 1M envs x 128 steps, entirely on the device: device time of collect and update, and the
+    tensor-core rate of the update's gradient kernel in the FLOPs of its products as issued."""
+    import torch
+    from autonomous_quadrotor_environment_b200 import BatchedQuad
+    from autonomous_quadrotor_environment_b200.ppo import BatchedPPO
+    N, K = args.envs_per_gpu or (1 << 20), args.horizon
+    env = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", async_reset=True, seed=0, device=dev)
+    env.reset()
+    ppo = BatchedPPO(env, hidden=128, K_epochs=10, seed=0)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    t_collect, t_update, losses = [], [], None
+    for it in range(iters + 1):                                 # the first iteration is the warm-up
+        ev[0].record()
+        batch = ppo.collect(K)
+        ev[1].record()
+        losses = ppo.update(batch)
+        ev[2].record()
+        torch.cuda.synchronize(dev)
+        if it > 0:
+            t_collect.append(ev[0].elapsed_time(ev[1])); t_update.append(ev[1].elapsed_time(ev[2]))
+        del batch
+    mc, mu = sum(t_collect) / len(t_collect), sum(t_update) / len(t_update)
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    tf_peak = float(peaks.get("bf16_tflops_sustained", 1367.3))
+    # per sample and network as issued: forward K = 80 + 144 against N = 128; backward dW3 (N 16) + dH1 (N 128) + [dW2|db2] (N 144) + dW1 (N 80), K = 128
+    flops = 2.0 * 128 * ((80 + 144) + (16 + 128 + 144 + 80)) * 2 * ppo.K_epochs * float(N) * K
+    ach = flops / (mu * 1e-3) / 1e12
+    return {"envs_per_gpu": N, "horizon": K, "K_epochs": ppo.K_epochs, "collect_ms": mc, "update_ms": mu,
+            "value": N * K / ((mc + mu) * 1e-3), "unit": "env-steps/s collected AND trained on (one PPO iteration)",
+            "losses_last_iteration": [losses[0], losses[-1]],
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained", "kernel": "ppo_grad_kernel<actor|critic>",
+                         "note": "update_ms covers 2 x K_epochs gradient launches + Adam; the kernel is bound by its four MMA -> epilogue "
+                                 "round trips per (128-sample tile, step), profiles/r02_prof_ppo_grad.txt"}}
+
+
 def run_policy_workload(args):
     """--workload policy: configs[4] as the headline line.  Same metric (env-steps/s)."""
     import torch
@@ -593,6 +630,13 @@ def main():
             variants["policy_rollout_1Mx128"] = policy_measure(args, dev, 0, 1, steps=4, warm=2)
         except Exception as ex:                                  # a variant must not take the headline line down with it
             variants["policy_rollout_1Mx128"] = {"error": repr(ex)}
+
+        # (c) SURVEY.md 8(f)1: one PPO iteration on the same 1M x 128 rollout — collect (fused actor + critic rollout, GAE) and the
+        #     K_epochs = 10 network update on qs_ppo_grad / qs_adam_step (forward + backward on tcgen05)
+        try:
+            variants["ppo_iteration_1Mx128"] = ppo_iteration_measure(args, dev)
+        except Exception as ex:
+            variants["ppo_iteration_1Mx128"] = {"error": repr(ex)}
 
     if rank == 0:
         line = {

@@ -304,7 +304,9 @@ typedef struct qs_ppo_batch {
     int32_t horizon;              /* K recorded steps                                                                          */
     int32_t flags;                /* QS_PPO_RECORD_LOGP or 0                                                                    */
     const float* hist0;           /* [75][N]     dl_in_gen buffer at rollout start, oldest entry first (dl_auxiliary.py:15-23)  */
-    const float* entries;         /* [K][15][N]  the entry pushed after step t: action(4), v(3), q(4), dq(4) (dl_auxiliary.py:27-30) */
+    const float* entries;         /* [K][15][N]  the entry pushed after step t: action(4), v(3), q(4), dq(4) (dl_auxiliary.py:27-30);
+                                                    NULL: taken from `actions` and rows 1,3,5,6..13 of `obs` (no materialised copy)     */
+    const float* obs;             /* [K][14][N]  observations recorded by qs_policy_rollout (read when entries == NULL)                */
     const float* actions;         /* [K][4][N]   memory.actions (actor)                                                        */
     float* logp_old;              /* [K][4][N]   memory.logprobs (actor); WRITTEN by the call under QS_PPO_RECORD_LOGP               */
     const float* adv;             /* [K][N]      normalised advantages (actor; qs_gae + qs_adv_normalize)                      */

@@ -375,6 +375,13 @@ def test_ppo_iteration_kernel_path():
     env.reset()
     ppo = P.BatchedPPO(env, hidden=128, K_epochs=3, seed=1)
     assert ppo.update_impl == "kernel"
+    # the history entries built on the fly from the recorded observations / actions == the materialised (K,15,N) buffer
+    b = ppo.collect(K)
+    assert b["entries"] is None and b["logprob_pending"]
+    g1, l1 = ppo.gradients(b, record_logprob=True)
+    b2 = dict(b); b2["entries"] = P.BatchedPPO.history_entries({"obs": b["obs"], "actions": b["actions"]}); b2["obs"] = None
+    g2, l2 = ppo.gradients(b2)
+    assert float((g1 - g2).norm() / g1.norm()) < 1e-5 and torch.allclose(l1, l2, rtol=1e-6, atol=1e-9)
     before = ppo._flat.clone()
     out = ppo.iterate(K)
     assert all(np.isfinite(out["losses"])) and np.isfinite(out["mean_reward"]) and not torch.equal(before, ppo._flat)

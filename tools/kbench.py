@@ -51,7 +51,7 @@ def case_ppo_grad(N=1 << 16, K=128, iters=5, warm=2):
     st = C.c_void_p(torch.cuda.current_stream(DEV).cuda_stream)
     flops = 2.0 * 128 * ((80 + 128 + 16) + (128 + 16 + 16 + 128 + 80)) * K * N
     for which, name in ((L.QS_PPO_ACTOR, "actor"), (L.QS_PPO_CRITIC, "critic")):
-        bt = L.qs_ppo_batch(N, K, 0, t["hist0"].data_ptr(), t["entries"].data_ptr(), t["actions"].data_ptr(), t["logprob"].data_ptr(),
+        bt = L.qs_ppo_batch(N, K, 0, t["hist0"].data_ptr(), t["entries"].data_ptr(), None, t["actions"].data_ptr(), t["logprob"].data_ptr(),
                             t["adv"].data_ptr(), t["returns"].data_ptr(), t["weight"].data_ptr())
         net, grad = ppo._net_ptrs(ppo._flat, which == L.QS_PPO_CRITIC), ppo._net_ptrs(ppo._grad, which == L.QS_PPO_CRITIC)
 
