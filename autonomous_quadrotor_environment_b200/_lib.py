@@ -95,7 +95,7 @@ class qs_actor(C.Structure):
 class qs_policy_rollout_args(C.Structure):
     _fields_ = [("horizon", C.c_int32), ("reserved", C.c_int32), ("obs_out", C.c_void_p), ("action_out", C.c_void_p),
                 ("logprob_out", C.c_void_p), ("reward_out", C.c_void_p), ("done_out", C.c_void_p), ("hist", C.c_void_p),
-                ("value_out", C.c_void_p)]
+                ("value_out", C.c_void_p), ("sensed_obs_out", C.c_void_p)]
 
 
 class qs_controller(C.Structure):

@@ -274,9 +274,10 @@ class BatchedQuad:
         return self._hist.t()
 
     def policy_rollout(self, horizon: int, record_obs=False, record_actions=True, record_logprob=True,
-                       record_reward=True, record_done=True, record_values=False):
+                       record_reward=True, record_done=True, record_values=False, record_sensed=False):
         """K fused steps of  history -> actor MLP (tcgen05) -> Normal sample -> quad.step -> history push  in ONE launch
-        (the loop of environment/controller/ppo.py:238-257).  Returns the recorded (K,C,N) buffers."""
+        (the loop of environment/controller/ppo.py:238-257).  On a sensor_noise handle the sensor model runs after every step and the
+        history takes the SENSED observation (record_sensed -> out["sensed_obs"], (K,14,N)).  Returns the recorded (K,C,N) buffers."""
         if getattr(self, "_actor", None) is None:
             raise RuntimeError("call load_actor() first")
         _ = self.history
@@ -297,6 +298,8 @@ class BatchedQuad:
             out["done"] = torch.empty(horizon, self.N, dtype=torch.uint8, device=self.device); a.done_out = out["done"].data_ptr()
         if record_values:                      # (K+1,N): V of the network input of every step + the bootstrap row (load_actor(critic=...))
             out["value"] = torch.empty(horizon + 1, self.N, dtype=f32, device=self.device); a.value_out = out["value"].data_ptr()
+        if record_sensed:
+            out["sensed_obs"] = torch.empty(horizon, 14, self.N, dtype=f32, device=self.device); a.sensed_obs_out = out["sensed_obs"].data_ptr()
         L.check(self.lib.qs_policy_rollout(self._h, C.byref(self._actor[0]), C.byref(a), self._stream()))
         return out
 

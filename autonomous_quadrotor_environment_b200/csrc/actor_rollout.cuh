@@ -159,6 +159,7 @@ struct PolicyIO {
     uint8_t* done_out;    // [K][N]     or NULL  (bit0 done, bit1 warm-up step)
     float* hist;          // [75][N] in/out: dl_in_gen.deep_learning_input per env (oldest entry first), or NULL
     float* value_out;     // [K+1][N] or NULL (critic handles): V of the network input of step t; row K = V of the input after the last step
+    float* sensed_out;    // [K][14][N] or NULL (QS_FLAG_SENSOR_NOISE handles): the sensed observation the history takes
 };
 
 #ifndef QS_POLICY_GROUPS
@@ -291,7 +292,7 @@ __device__ __forceinline__ void actor_hidden_epilogue_tmem(uint32_t lane_addr) {
     tmem_st_wait();
 }
 
-template <bool TS, bool CRITIC>
+template <bool TS, bool CRITIC, bool SENSOR>
 __global__ void __launch_bounds__(kPM * PolicyCfg<TS, CRITIC>::kG, 1)
 policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_constant__ SimView<float> v,
                       const __grid_constant__ ActorView act, const __grid_constant__ PolicyIO io) {
@@ -527,12 +528,42 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             bool warm = false;
             if (p.flags & F_ASYNC_RESET) warm = async_warmup_prologue(p, e, a);
             const bool was_done = (e.flags & EF_DONE) != 0;
-            step_core<float, 0, true>(p, e, a, o, nullptr);
+            Ctrl<float> c;
+            step_core<float, 0, true>(p, e, a, o, SENSOR ? &c : nullptr);
             if (warm) o.reward = 0.f; else e.ep_return += o.reward;
             reward = o.reward; done = o.done; solved = o.solved; warm_last = warm;
             if (active && done && !was_done) { count_episode(ls, p, e, o); any_end = true; }
-            if ((p.flags & F_ASYNC_RESET) && done) async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+            // QS_FLAG_SENSOR_NOISE (quadrotor_env.py:579-724): the sensor model after the step, exactly as in rollout_kernel — the sensor
+            // rows stay in HBM, one out-of-line copy of the model per kernel; warm-up steps bypass it, the last one re-initialises it
+            if (SENSOR && active)
+                sensor_update(p, v, n, e, c, o.vq[0], o.vq[1], o.vq[2], o.vq[3], warm ? ((e.flags >> EF_WARM_SHIFT) ? 2 : 1) : 0);
+            if ((p.flags & F_ASYNC_RESET) && done) {
+                async_resample(p, v.seed, v.env_id_offset + (uint32_t)n, e, o.vq);
+                if (SENSOR && active) {
+#pragma unroll
+                    for (int k = 0; k < 10; ++k) v.sensed_obs[k * v.ld + n] = e.y[k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v.sensed_obs[(10 + k) * v.ld + n] = o.vq[k];
+                }
+            }
+            // what the policy observes: the sensed observation on sensor handles (the loop of visual_landing/rl_worker.py:164-175 feeds
+            // sensor_sp's states_sens to the network), the true one otherwise
+            float so[14];
+            if (SENSOR) {
+#pragma unroll
+                for (int k = 0; k < 14; ++k) so[k] = active ? v.sensed_obs[k * v.ld + n] : 0.f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 10; ++k) so[k] = e.y[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) so[10 + k] = o.vq[k];
+            }
             if (active) {
+                if (SENSOR && io.sensed_out) {
+                    float* st_ = io.sensed_out + (int64_t)t * 14 * v.N;
+#pragma unroll
+                    for (int k = 0; k < 14; ++k) st_[k * v.N + n] = so[k];
+                }
                 if (io.obs_out) {
                     float* ot = io.obs_out + (int64_t)t * 14 * v.N;
 #pragma unroll
@@ -557,9 +588,9 @@ policy_rollout_kernel(const __grid_constant__ DevParams<float> p, const __grid_c
             {
                 uint4 lo, hi;
                 lo.x = pack_bf16x2(a[0], a[1]); lo.y = pack_bf16x2(a[2], a[3]);
-                lo.z = pack_bf16x2(e.y[1], e.y[3]); lo.w = pack_bf16x2(e.y[5], e.y[6]);
-                hi.x = pack_bf16x2(e.y[7], e.y[8]); hi.y = pack_bf16x2(e.y[9], o.vq[0]);
-                hi.z = pack_bf16x2(o.vq[1], o.vq[2]); hi.w = pack_bf16x2(o.vq[3], 1.f);
+                lo.z = pack_bf16x2(so[1], so[3]); lo.w = pack_bf16x2(so[5], so[6]);
+                hi.x = pack_bf16x2(so[7], so[8]); hi.y = pack_bf16x2(so[9], so[10]);
+                hi.z = pack_bf16x2(so[11], so[12]); hi.w = pack_bf16x2(so[13], 1.f);
                 *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK, kPKin)) = lo;
                 *reinterpret_cast<uint4*>(sX + umma_canon_offset(tid, head * kPSlotK + 8, kPKin)) = hi;
                 head = head + 1 == kPSlots ? 0 : head + 1;
@@ -608,8 +639,10 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     const uint32_t f = h->cfg.flags;
     if (h->cfg.precision != QS_F32 || h->cfg.integrator != QS_RK4 || !(f & QS_FLAG_DIRECT_CONTROL))
         return fail(QS_ESTATE, "qs_policy_rollout: needs an FP32 / RK4 / direct-control handle");
-    if (f & (QS_FLAG_AUX | QS_FLAG_SENSOR_NOISE | QS_FLAG_AUTO_RESET | QS_FLAG_ROBUST))
-        return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / SENSOR_NOISE / ROBUST / strict AUTO_RESET (use ASYNC_RESET)");
+    if (f & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET | QS_FLAG_ROBUST))
+        return fail(QS_ESTATE, "qs_policy_rollout: not available with AUX / ROBUST / strict AUTO_RESET (use ASYNC_RESET)");
+    const bool sensor = (f & QS_FLAG_SENSOR_NOISE) != 0;
+    if (args->sensed_obs_out && !sensor) return fail(QS_ESTATE, "qs_policy_rollout: sensed_obs_out needs a QS_FLAG_SENSOR_NOISE handle");
     QS_USE_DEVICE(h);
     const bool critic = actor->cw1 != nullptr;
     if (critic && (!actor->cb1 || !actor->cw2 || !actor->cb2 || !actor->cw3 || !actor->cb3))
@@ -618,7 +651,7 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     ActorView av{actor->w1, actor->b1, actor->w2, actor->b2, actor->w3, actor->b3, actor->action_std,
                  actor->cw1, actor->cb1, actor->cw2, actor->cb2};
     PolicyIO io{args->horizon, (float*)args->obs_out, (float*)args->action_out, (float*)args->logprob_out,
-                (float*)args->reward_out, args->done_out, (float*)args->hist, (float*)args->value_out};
+                (float*)args->reward_out, args->done_out, (float*)args->hist, (float*)args->value_out, (float*)args->sensed_obs_out};
     constexpr bool kTS = QS_POLICY_TS != 0;
     if (critic && !kTS) return fail(QS_ESTATE, "qs_policy_rollout: the critic head needs the TS build (QS_POLICY_TS=1)");
     {   // output layers -> constant memory, stream-ordered (the action stage of the handle is free during a policy rollout)
@@ -636,18 +669,21 @@ extern "C" int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_po
     constexpr int kG = PolicyCfg<kTS>::kG;
     const int64_t need = (tiles + kG - 1) / kG;
     if (grid > need) grid = need;
+#define QS_LAUNCH_POLICY(CR, SE)                                                                                                  \
+    do {                                                                                                                          \
+        using Cfg = PolicyCfg<kTS, CR>;                                                                                           \
+        QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS, CR, SE>), Cfg::kBytes);                                                    \
+        policy_rollout_kernel<kTS, CR, SE><<<(int)grid, kPM * kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io); \
+    } while (0)
     if constexpr (kTS) {
         if (critic) {
-            using Cfg = PolicyCfg<kTS, true>;
-            QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS, true>), Cfg::kBytes);
-            policy_rollout_kernel<kTS, true><<<(int)grid, kPM * kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+            if (sensor) QS_LAUNCH_POLICY(true, true); else QS_LAUNCH_POLICY(true, false);
             QS_CUDA(cudaGetLastError());
             return QS_OK;
         }
     }
-    using Cfg = PolicyCfg<kTS, false>;
-    QS_SET_SMEM_ONCE(h, (policy_rollout_kernel<kTS, false>), Cfg::kBytes);
-    policy_rollout_kernel<kTS, false><<<(int)grid, kPM * kG, Cfg::kBytes, (cudaStream_t)stream>>>(h->pf, make_view<float>(h), av, io);
+    if (sensor) QS_LAUNCH_POLICY(false, true); else QS_LAUNCH_POLICY(false, false);
+#undef QS_LAUNCH_POLICY
     QS_CUDA(cudaGetLastError());
     return QS_OK;
 }

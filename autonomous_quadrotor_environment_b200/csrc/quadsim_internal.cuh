@@ -245,6 +245,48 @@ __device__ __forceinline__ void count_episode(LocalStats& ls, const DevParams<R>
     ls.v[6] += (float)e.abs_sum;
 }
 
+// Sensor sub-pass for one env (QS_FLAG_SENSOR_NOISE).  mode 0: one step of the sensor model; mode 1: sensor.reset
+// from the true state (end of an episode's warm-up) and pass the true observation through; mode 2: pass-through only.
+template <typename R>
+__device__ __forceinline__ void sensor_update_inl(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R>& e,
+                                                  const Ctrl<R>& c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
+    R obs[14];
+    if (mode == 0) {
+        R s[kSensorStateDim], z[32], dy[13], qn[4], rot[9];
+#pragma unroll
+        for (int k = 0; k < 17; ++k) s[k] = v.sensor_state[k * v.ld + n];
+        drone_rhs(p, c, e.y, dy);                                  // trailing drone_eq call: accel at the new state
+        quat_normalize(&e.y[6], qn);
+        quat_rot_mat(qn, rot);
+        const R g[3] = {dy[1], dy[3], dy[5] - p.g};               // :371
+        const R acc_read[3] = {rot[0] * g[0] + rot[3] * g[1] + rot[6] * g[2], rot[1] * g[0] + rot[4] * g[1] + rot[7] * g[2],
+                               rot[2] * g[0] + rot[5] * g[1] + rot[8] * g[2]};
+        sensor_normals(v.seed, v.env_id_offset + (uint32_t)n, e.episode, (uint32_t)e.i, p.s_gps_blend > R(0), z);
+        sensor_step(p, z, e.y, acc_read, rot, c.f_m, s, obs);
+#pragma unroll
+        for (int k = 0; k < kSensorStateDim; ++k) v.sensor_state[k * v.ld + n] = s[k];
+    } else {
+        if (mode == 1) {
+            R s[kSensorStateDim];
+            sensor_reset(p, v.seed, v.env_id_offset + (uint32_t)n, e.episode, e.y, s);
+#pragma unroll
+            for (int k = 0; k < kSensorStateDim; ++k) v.sensor_state[k * v.ld + n] = s[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 10; ++k) obs[k] = e.y[k];
+        obs[10] = vq0; obs[11] = vq1; obs[12] = vq2; obs[13] = vq3;
+    }
+#pragma unroll
+    for (int k = 0; k < 14; ++k) v.sensed_obs[k * v.ld + n] = obs[k];
+}
+
+// out-of-line variant for cold paths (explicit / strict resets): arguments by value, callers' structs stay in registers
+template <typename R>
+__device__ __noinline__ void sensor_update(const DevParams<R>& p, const SimView<R>& v, int64_t n, const Env<R> e,
+                                           const Ctrl<R> c, const R vq0, const R vq1, const R vq2, const R vq3, int mode) {
+    sensor_update_inl(p, v, n, e, c, vq0, vq1, vq2, vq3, mode);
+}
+
 template <typename R> struct StepIO {
     const R* action;     // [4][N]
     R* obs;              // [14][N] or NULL

@@ -136,8 +136,11 @@ class BatchedPPO:
         """One rollout + values + GAE.  Returns the batch dict (all tensors on the device, time-major)."""
         env = self.env
         hist0 = env.history.t().contiguous().clone()                      # (75, N)
-        rec = env.policy_rollout(horizon, record_obs=True, record_actions=True, record_logprob=True, record_reward=True,
-                                 record_done=True, record_values=self.fused_critic)
+        sensed = bool(env._cfg.flags & L.QS_FLAG_SENSOR_NOISE)             # the policy's observation is the sensed one there
+        rec = env.policy_rollout(horizon, record_obs=not sensed, record_actions=True, record_logprob=True, record_reward=True,
+                                 record_done=True, record_values=self.fused_critic, record_sensed=sensed)
+        if sensed:
+            rec["obs"] = rec["sensed_obs"]
         kernel_update = self.update_impl == "kernel"
         # update_impl="kernel": qs_ppo_grad builds the history entries from the recorded observations and actions on the fly
         entries = None if kernel_update else self.history_entries(rec)

@@ -220,6 +220,8 @@ typedef struct qs_policy_rollout_args {
     void* hist;           /* [75][N] float in/out: dl_in_gen.deep_learning_input per env, oldest first; NULL = zeros */
     void* value_out;      /* [K+1][N]   float or NULL : critic value of the network input of step t (needs qs_actor.cw1..cb3); row K = */
                           /*                            value of the input after the last step (the GAE bootstrap, ppo.py:125-141)      */
+    void* sensed_obs_out; /* [K][14][N] float or NULL : QS_FLAG_SENSOR_NOISE handles — there the HISTORY takes the sensed observation  */
+                          /*                            (the policy flies on sensor_sp's states_sens, visual_landing/rl_worker.py:164) */
 } qs_policy_rollout_args;
 
 /* Classical comparison controllers of the reference as in-kernel control laws: LQR
@@ -278,7 +280,8 @@ int qs_reset(qs_handle h, const void* det_state, const uint8_t* mask, void* obs_
 int qs_step(qs_handle h, const void* action, void* obs, void* reward, uint8_t* done, uint8_t* solved, void* stream);
 /* K fused env steps (see qs_rollout_args). */
 int qs_rollout(qs_handle h, const qs_rollout_args* args, void* stream);
-/* K fused policy steps (see qs_policy_rollout_args); FP32 / RK4 / direct-control handles only. */
+/* K fused policy steps (see qs_policy_rollout_args); FP32 / RK4 / direct-control handles only; with QS_FLAG_SENSOR_NOISE the sensor
+ * model runs after every step and the actor's observation history is built from the SENSED observation. */
 int qs_policy_rollout(qs_handle h, const qs_actor* actor, const qs_policy_rollout_args* args, void* stream);
 /* PID gains of pid_vel_control.py:17-27 (clipped / not clipped); the LQR gains are left zero (host computes the AREs). */
 int qs_default_controller(qs_controller* c, int kind, int clipped);

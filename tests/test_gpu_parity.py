@@ -651,6 +651,50 @@ def test_fused_actor_rollout_deterministic():
     assert torch.equal(ref.state, env.state)
 
 
+def test_fused_actor_rollout_on_sensed_observations():
+    """QS_FLAG_SENSOR_NOISE handle (the loop of visual_landing/rl_worker.py:164-175): the policy flies on the SENSED
+    observation.  sigma = 0: (1) every action equals the FP32 torch actor on the history rebuilt from the recorded (action, sensed obs)
+    stream; (2) replaying the recorded actions through the plain sensor rollout reproduces the true AND the sensed observations
+    bit-for-bit (same dynamics, same sensor model, same Philox counters); (3) sensed != true on ordinary steps."""
+    g = load_golden("actor_128.npz")
+    W = {k: torch.as_tensor(v, device=DEV) for k, v in g.items() if k.startswith("actor_")}
+    N, K, seed = 700, 40, 21
+    mk = lambda: BatchedQuad(N, 0.01, 300, training=False, direct_control=1, T=5, precision="f32", async_reset=True, sensor_noise=True,
+                             seed=seed, device=DEV)
+    env, ref = mk(), mk()
+    oh, ah = env.reset(); ref.reset()
+    hist = torch.zeros(N, 75, device=DEV)
+    for k in range(5):
+        hist = torch.cat([hist[:, 15:], torch.cat([ah[k], oh[k][:, 1:6:2], oh[k][:, 6:14]], dim=1)], dim=1)
+    env.history.copy_(hist)
+    env.load_actor(g, action_std=0.0)
+    rec = env.policy_rollout(K, record_obs=True, record_sensed=True)
+    worst = 0.0
+    for t in range(K):
+        mean = _torch_actor(W, hist.bfloat16().float())
+        a_t, s_t = rec["actions"][t].t(), rec["sensed_obs"][t].t()
+        warm = ((rec["done"][t] >> 1) & 1).bool()
+        worst = max(worst, (a_t - mean)[~warm].abs().max().item())
+        hist = torch.cat([hist[:, 15:], torch.cat([a_t, s_t[:, 1:6:2], s_t[:, 6:14]], dim=1)], dim=1)
+    assert worst < 0.03, worst
+    assert torch.allclose(env.history, hist.bfloat16().float(), atol=0, rtol=0)
+    live = ((rec["done"] & 3) == 0).unsqueeze(1).expand_as(rec["obs"])
+    diff = (rec["sensed_obs"] - rec["obs"]).abs()
+    assert float(diff[live].max()) > 1e-4                       # the sensor model is in the loop ...
+    assert float(diff[:, :6][live[:, :6]].max()) < 1.0          # ... and dead-reckons position / velocity close to the truth
+    ref.set_step_loader(2)                                      # the scalar step_core + sensor sub-pass the policy kernel runs
+    replay = ref.rollout(K, actions=rec["actions"].contiguous(), record_obs=True, record_done=True, record_sensed=True)
+    assert torch.equal(replay["done"], rec["done"])
+    assert torch.equal(replay["obs"], rec["obs"])
+    assert torch.equal(replay["sensed_obs"], rec["sensed_obs"])
+    assert torch.equal(ref.state, env.state)
+    # a plain handle refuses the sensed record; the critic head composes with the sensor variant
+    plain = BatchedQuad(256, 0.01, 300, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=1, device=DEV)
+    plain.reset(); plain.load_actor(g, action_std=0.1)
+    with pytest.raises(RuntimeError):
+        plain.policy_rollout(4, record_sensed=True)
+
+
 def test_fused_actor_rollout_closed_loop_solves_and_samples():
     g = load_golden("actor_128.npz")
     N = 8192

@@ -389,3 +389,11 @@ def test_ppo_iteration_kernel_path():
     assert torch.equal(env._actor[1]["w1"], ppo.policy.actor[0].weight.detach())
     out2 = ppo.iterate(K)
     assert all(np.isfinite(out2["losses"]))
+    # the same iteration on a sensor handle: rollout, values and update all see the SENSED observation
+    envs = BatchedQuad(1024, 0.01, 1000, training=True, direct_control=1, T=5, precision="f32", async_reset=True, sensor_noise=True, seed=2, device=dev)
+    envs.reset()
+    ppos = P.BatchedPPO(envs, hidden=128, K_epochs=2, seed=1)
+    bs = ppos.collect(16)
+    assert bs["obs"].shape == (16, 14, 1024) and bool(torch.isfinite(bs["obs"]).all()) and bool(torch.isfinite(bs["value"]).all())
+    outs = ppos.update(bs)
+    assert all(np.isfinite(outs))
