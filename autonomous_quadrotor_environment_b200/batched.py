@@ -131,11 +131,23 @@ class BatchedQuad:
             self._views[f] = v
         return v
 
-    def _as_soa(self, x, channels: int) -> torch.Tensor:
-        """Return a contiguous (C,N) tensor holding x (given as (N,C) or (C,N))."""
+    def _as_soa(self, x, channels: int, layout=None) -> torch.Tensor:
+        """Return a contiguous (C,N) tensor holding x, given as (N,C) — the reference's layout with a leading env axis — or (C,N).
+        layout: "nc" / "cn" / None = by shape; with N == C the shape does not tell and the layout must be named."""
         x = torch.as_tensor(x, dtype=self.dtype, device=self.device)
         if x.dim() == 1 and self.N == 1:
             x = x.view(1, channels)
+        if layout not in (None, "nc", "cn"):
+            raise ValueError("layout must be 'nc', 'cn' or None")
+        if layout is None and self.N == channels and self.N > 1 and x.shape == (self.N, channels):
+            raise ValueError("a (%d,%d) tensor is ambiguous for %d envs x %d channels: pass layout='nc' (env-major, the reference's "
+                             "layout) or layout='cn' (channel-major)" % (self.N, channels, self.N, channels))
+        if layout == "cn" and x.shape == (channels, self.N):
+            return x.contiguous()
+        if layout == "cn":
+            raise ValueError("expected shape (%d,%d), got %s" % (channels, self.N, tuple(x.shape)))
+        if layout == "nc" and x.shape != (self.N, channels):
+            raise ValueError("expected shape (%d,%d), got %s" % (self.N, channels, tuple(x.shape)))
         if x.shape == (self.N, channels):
             xt = x.t()
             return xt if xt.is_contiguous() else xt.contiguous()
@@ -163,7 +175,7 @@ class BatchedQuad:
         L.check(self.lib.qs_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF))
         self._cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF       # get_checkpoint() saves the key in force
 
-    def reset(self, det_state=None, mask=None):
+    def reset(self, det_state=None, mask=None, layout=None):
         """quad.reset (quadrotor_env.py:408-454) for the masked envs (all if mask is None).
 
         det_state: (N,13) initial states, or None for the random branch (sampled on the device).
@@ -172,7 +184,7 @@ class BatchedQuad:
         if self._obs_hist is None:
             self._obs_hist = torch.zeros(self.T, 14, self.N, dtype=self.dtype, device=self.device)
             self._act_hist = torch.zeros(self.T, 4, self.N, dtype=self.dtype, device=self.device)
-        det = None if det_state is None else self._as_soa(det_state, 13)
+        det = None if det_state is None else self._as_soa(det_state, 13, layout)
         m = None
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
@@ -192,9 +204,9 @@ class BatchedQuad:
         L.check(self.lib.qs_step(self._h, C.c_void_p(action_soa.data_ptr()), None, None, None, None, self._stream()))
         return self.obs, self.reward, self.done
 
-    def step(self, action):
+    def step(self, action, layout=None):
         """quad.step (quadrotor_env.py:458-498): action (N,4) -> (obs (N,14), reward (N,), done (N,) uint8)."""
-        return self.step_soa(self._as_soa(action, 4))
+        return self.step_soa(self._as_soa(action, 4, layout))
 
     def rollout(self, horizon: int, actions=None, record_obs=False, record_actions=False, record_reward=False,
                 record_done=False, record_sensed=False):
@@ -382,8 +394,8 @@ class BatchedQuad:
         L.check(self.lib.qs_get(self._h, L.QS_FIELD_STATE, C.c_void_p(out.data_ptr()), self._stream()))
         return out.t()
 
-    def set_state(self, state):
-        s = self._as_soa(state, 13)
+    def set_state(self, state, layout=None):
+        s = self._as_soa(state, 13, layout)
         L.check(self.lib.qs_set(self._h, L.QS_FIELD_STATE, C.c_void_p(s.data_ptr()), self._stream()))
 
     @property

@@ -231,6 +231,24 @@ def test_reset_queue_overflow_falls_back_in_lane():
     assert int(done2.sum()) == 0 and bool(env.warmup.all())
 
 
+def test_square_action_tensor_needs_a_named_layout():
+    """4 envs x 4 action channels: the shape cannot tell (N,C) from (C,N) — step() refuses to guess; both named layouts agree."""
+    mk = lambda: BatchedQuad(4, 0.01, 100, training=True, direct_control=1, T=1, precision="f64", seed=3, device=DEV)
+    a, b = mk(), mk()
+    st0, _ = qo.sample_reset_state(5, np.arange(4), 0)
+    a.reset(torch.as_tensor(st0, device=DEV)); b.reset(torch.as_tensor(st0, device=DEV))
+    act = torch.rand(4, 4, dtype=torch.float64, device=DEV) * 2 - 1            # (N,4)
+    with pytest.raises(ValueError):
+        a.step(act)
+    oa, _, _ = a.step(act, layout="nc")
+    ob, _, _ = b.step(act.t().contiguous(), layout="cn")
+    assert torch.equal(oa, ob)
+    ora = qo.BatchQuadOracle(4, 0.01, 100, training=True, direct_control=1, T=1, integrator="rk45")
+    ora.reset(st0)
+    o_ref, _, _ = ora.step(act.cpu().numpy())
+    assert np.abs(oa.cpu().numpy() - o_ref).max() < 1e-9
+
+
 def test_random_reset_on_device_matches_oracle_sampler():
     N, seed = 2048, 77
     for prec, tol in (("f64", 1e-12), ("f32", 2e-5)):
