@@ -466,7 +466,26 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
         h_abs = M_<R>::fmin(M_<R>::fmin(R(100) * h0, h1), t_bound);
     }
     // ---- solver.step() until t >= t_bound
-    R K2[13], K3[13], K4[13], K5[13], K6[13], K7[13], yn[13];
+    // rk_step (rk.py:14-70) as ONE rolled stage loop: stage s = 1..5 evaluates K[s] at y + h * (A[s][0..s-1] . K[0..s-1]), "stage 6" is
+    // y_new = y + h * (B . K[0..5]) with K[6] = f(y_new) (Dormand-Prince: the last row of A is B), so the RHS has a single call site and
+    // the code of the loop body exists once (the unrolled form, six inlined copies of drone_eq, stalled on instruction fetch and kept
+    // 3.2 KB of stage vectors and spills per thread in local memory).  Like SciPy's np.dot over K[:s], the zero coefficients take part.
+    static constexpr double kA[6][6] = {
+        {QS_DP_A21, 0, 0, 0, 0, 0},
+        {QS_DP_A31, QS_DP_A32, 0, 0, 0, 0},
+        {QS_DP_A41, QS_DP_A42, QS_DP_A43, 0, 0, 0},
+        {QS_DP_A51, QS_DP_A52, QS_DP_A53, QS_DP_A54, 0, 0},
+        {QS_DP_A61, QS_DP_A62, QS_DP_A63, QS_DP_A64, QS_DP_A65, 0},
+        {QS_DP_B1, 0, QS_DP_B3, QS_DP_B4, QS_DP_B5, QS_DP_B6}};
+    static constexpr double kE[7] = {QS_DP_E1, 0, QS_DP_E3, QS_DP_E4, QS_DP_E5, QS_DP_E6, QS_DP_E7};
+    R K[7][13];                                  // K[0] = f(y) (first same as last), K[1..5] stages 2..6, K[6] = f(y_new)
+    R yn[13];
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+        K[0][j] = f[j];
+#pragma unroll
+        for (int q = 1; q < 7; ++q) K[q][j] = R(0);            // rows a stage does not use yet are loaded (and not added)
+    }
     for (int guard = 0; guard < 100000; ++guard) {
         R min_step = R(10) * M_<R>::abs(M_<R>::next_up(t) - t);
         if (h_abs < min_step) h_abs = min_step;
@@ -477,38 +496,36 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
             if (t_new - t_bound > R(0)) t_new = t_bound;
             R h = t_new - t;
             h_abs = M_<R>::abs(h);
-            // rk_step: K1 = f
+#pragma unroll 1
+            for (int s = 1; s <= 6; ++s) {
 #pragma unroll
-            for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A21)) * h;
-            drone_rhs<R, ROBUST>(p, c, tmp, K2);
+                for (int j = 0; j < 13; ++j) tmp[j] = K[0][j] * R(kA[s - 1][0]);
+                // q unrolled with a uniform predicate: the stage vectors live in local memory and their loads must be in flight
+                // together, not one row per trip of a rolled loop
 #pragma unroll
-            for (int j = 0; j < 13; ++j) tmp[j] = y[j] + (f[j] * R(QS_DP_A31) + K2[j] * R(QS_DP_A32)) * h;
-            drone_rhs<R, ROBUST>(p, c, tmp, K3);
+                for (int q = 1; q < 6; ++q) {
+                    const R a = R(kA[s - 1][q]);
+                    const bool use = q < s;
 #pragma unroll
-            for (int j = 0; j < 13; ++j)
-                tmp[j] = y[j] + (f[j] * R(QS_DP_A41) + K2[j] * R(QS_DP_A42) + K3[j] * R(QS_DP_A43)) * h;
-            drone_rhs<R, ROBUST>(p, c, tmp, K4);
+                    for (int j = 0; j < 13; ++j) tmp[j] = use ? tmp[j] + K[q][j] * a : tmp[j];
+                }
 #pragma unroll
-            for (int j = 0; j < 13; ++j)
-                tmp[j] = y[j] + (f[j] * R(QS_DP_A51) + K2[j] * R(QS_DP_A52) + K3[j] * R(QS_DP_A53) + K4[j] * R(QS_DP_A54)) * h;
-            drone_rhs<R, ROBUST>(p, c, tmp, K5);
-#pragma unroll
-            for (int j = 0; j < 13; ++j)
-                tmp[j] = y[j] + (f[j] * R(QS_DP_A61) + K2[j] * R(QS_DP_A62) + K3[j] * R(QS_DP_A63) + K4[j] * R(QS_DP_A64) +
-                                 K5[j] * R(QS_DP_A65)) * h;
-            drone_rhs<R, ROBUST>(p, c, tmp, K6);
-#pragma unroll
-            for (int j = 0; j < 13; ++j)
-                yn[j] = y[j] + h * (f[j] * R(QS_DP_B1) + K3[j] * R(QS_DP_B3) + K4[j] * R(QS_DP_B4) + K5[j] * R(QS_DP_B5) +
-                                    K6[j] * R(QS_DP_B6));
-            drone_rhs<R, ROBUST>(p, c, yn, K7);
+                for (int j = 0; j < 13; ++j) yn[j] = y[j] + tmp[j] * h;
+                drone_rhs<R, ROBUST>(p, c, yn, K[s]);
+            }
             nfev += 6;
+#pragma unroll
+            for (int j = 0; j < 13; ++j) tmp[j] = K[0][j] * R(kE[0]);
+#pragma unroll
+            for (int q = 1; q < 7; ++q) {
+                const R eq = R(kE[q]);
+#pragma unroll
+                for (int j = 0; j < 13; ++j) tmp[j] += K[q][j] * eq;
+            }
 #pragma unroll
             for (int j = 0; j < 13; ++j) {
                 R sc = atol + M_<R>::fmax(M_<R>::abs(y[j]), M_<R>::abs(yn[j])) * rtol;
-                R e = (f[j] * R(QS_DP_E1) + K3[j] * R(QS_DP_E3) + K4[j] * R(QS_DP_E4) + K5[j] * R(QS_DP_E5) +
-                       K6[j] * R(QS_DP_E6) + K7[j] * R(QS_DP_E7)) * h;
-                tmp[j] = e / sc;
+                tmp[j] = tmp[j] * h / sc;
             }
             R err = rms13(tmp);
             if (err < R(1)) {
@@ -527,7 +544,7 @@ __device__ __noinline__ int integrate_rk45(const DevParams<R>& p, const Ctrl<R>&
         }
         if (failed && !accepted) break;          // TOO_SMALL_STEP: solve_ivp stops, last accepted y is kept
 #pragma unroll
-        for (int j = 0; j < 13; ++j) { y[j] = yn[j]; f[j] = K7[j]; }
+        for (int j = 0; j < 13; ++j) { y[j] = yn[j]; K[0][j] = K[6][j]; }
         if (failed || t - t_bound >= R(0)) break;
     }
     return nfev;

@@ -373,7 +373,7 @@ __device__ __forceinline__ void step_epilogue(const DevParams<R>& p, const SimVi
 
 // Loader A — direct: every thread issues its 27 coalesced LDGs up front (one 128-byte line per warp request).
 template <typename R, int INTEG, bool DIRECT, bool SENSOR, bool ROBUST = false>
-__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
+__global__ void __launch_bounds__(kBlock, (qs_min_ctas<R, INTEG>()))
 step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                    const __grid_constant__ StepIO<R> io) {
     __shared__ int s_queue[kResetQueueCap];
@@ -403,7 +403,7 @@ step_kernel_direct(const __grid_constant__ DevParams<R> p, const __grid_constant
 constexpr int kStages = QS_STAGES;
 
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
-__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
+__global__ void __launch_bounds__(kBlock, (qs_min_ctas<R, INTEG>()))
 step_kernel_tma(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                 const __grid_constant__ StepIO<R> io) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -500,7 +500,7 @@ reset_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ Sim
 }
 
 template <typename R, int INTEG, bool DIRECT, bool SENSOR>
-__global__ void __launch_bounds__(kBlock, QS_MIN_CTAS)
+__global__ void __launch_bounds__(kBlock, (qs_min_ctas<R, INTEG>()))
 rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ SimView<R> v,
                const __grid_constant__ RolloutIO<R> io) {
     LocalStats ls;
@@ -597,7 +597,8 @@ static int grid_step(const qs_sim* s) {
         return v < 1 ? QS_MIN_CTAS : v;
     }();
     const int64_t tiles = (s->slice_count + kTile - 1) / kTile;
-    int64_t g = (int64_t)s->sm_count * ctas_per_sm;
+    const bool f64_rk45 = s->cfg.precision == QS_F64 && s->cfg.integrator == QS_RK45;      // compiled for one 255-register CTA per SM
+    int64_t g = (int64_t)s->sm_count * (f64_rk45 ? 1 : ctas_per_sm);
     if (g > tiles) g = tiles;
     return (int)(g < 1 ? 1 : g);
 }

@@ -142,6 +142,9 @@ template <typename R> static inline SimView<R> make_view(const qs_sim* s) {
 #define QS_STAGES 3           // depth of the TMA staging ring
 #endif
 constexpr int kBlock = QS_BLOCK;
+// The FP64 replica of SciPy's RK45 keeps seven stage vectors of 13 doubles: its kernels are compiled for ONE resident CTA per SM (255
+// registers per thread) instead of QS_MIN_CTAS.
+template <typename R, int INTEG> constexpr int qs_min_ctas() { return (sizeof(R) == 8 && INTEG == 1) ? 1 : QS_MIN_CTAS; }
 
 template <typename R>
 __device__ __forceinline__ void load_env(const SimView<R>& v, int64_t n, Env<R>& e) {

@@ -128,6 +128,11 @@ if __name__ == "__main__":
         case_ppo_grad(N=1 << 20, K=128, iters=2)
     if "profppograd" in which:
         case_ppo_grad(N=1 << 15, K=64, iters=1, warm=1)
+    if "f64" in which:
+        case_step(N=1 << 16, iters=100, precision="f64", integrator="rk45", async_reset=True, T=5)
+        case_step(N=1 << 18, iters=50, precision="f64", integrator="rk45", async_reset=True, T=5)
+        case_step(N=4096, iters=200, precision="f64", integrator="rk45", async_reset=True, T=5)
+        case_rollout(N=1 << 16, K=32, iters=4, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "proff64" in which:
         case_step(N=1 << 16, iters=5, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "profpolicy" in which:
