@@ -1003,6 +1003,44 @@ def test_full_size_properties_1M_envs():
     assert int(a.episode.sum().item()) == N + int(s["n_episodes"])
 
 
+def test_full_size_headline_config_properties():
+    """BASELINE.json configs[2] as bench.py times it — 1,048,576 envs, FP32 RK4, sensor noise, asynchronous auto-reset, T=5, the
+    two-envs-per-lane step kernel with the packed sensor model — through properties that do not need the oracle: (1) sharding is
+    invisible (two half-size handles with env-id offsets == the whole, bit for bit: state, sensed observation, episode counters);
+    (2) K fused steps in one launch (sensor state on chip) == K single-step launches on the same action stream; (3) accounting."""
+    N, K = 1 << 20, 24
+    mk = lambda n, off: BatchedQuad(n, 0.01, 1000, T=5, precision="f32", async_reset=True, sensor_noise=True, seed=0,
+                                    env_id_offset=off, device=DEV)
+    whole, lo, hi, fused = mk(N, 0), mk(N // 2, 0), mk(N // 2, N // 2), mk(N, 0)
+    for e in (whole, lo, hi, fused):
+        e.reset()
+    assert whole.step_loader == 3
+    g = torch.Generator(device=DEV); g.manual_seed(7)
+    acts = (torch.rand(K, 4, N, device=DEV, generator=g) * 2 - 1).contiguous()
+    for t in range(K):
+        whole.step_soa(acts[t])
+        lo.step_soa(acts[t, :, :N // 2].contiguous()); hi.step_soa(acts[t, :, N // 2:].contiguous())
+    fused.rollout(K, actions=acts)
+    for name in ("state", "sensed_obs", "episode", "reward", "done_flags"):
+        w = getattr(whole, name)
+        parts = torch.cat([getattr(lo, name), getattr(hi, name)], dim=0)
+        assert torch.equal(w, parts), name
+        assert torch.equal(w, getattr(fused, name)), "fused rollout: " + name
+    st, so = whole.state, whole.sensed_obs
+    assert torch.isfinite(st).all() and torch.isfinite(so).all()
+    assert (st[:, 6:10].norm(dim=1) - 1).abs().max() < 1e-3
+    s = whole.stats()
+    assert s["n_steps"] == N * K and s["n_episodes"] > N // 100
+    assert s["n_solved"] + s["n_broken"] + s["n_timeout"] == s["n_episodes"]
+    assert int(whole.episode.sum().item()) == N + int(s["n_episodes"])
+    sl, sh = lo.stats(), hi.stats()
+    assert sl["n_episodes"] + sh["n_episodes"] == s["n_episodes"] and abs(sl["sum_return"] + sh["sum_return"] - s["sum_return"]) < 1e-6 * abs(s["sum_return"])
+    # the sensor is in the loop: on ordinary steps the sensed velocity differs from the true one, by centimetres per second
+    live = (whole.done_flags & 3) == 0
+    dv = (so[:, 1:6:2] - st[:, 1:6:2]).abs()[live]
+    assert 1e-5 < float(dv.mean()) < 0.5
+
+
 @pytest.mark.gpu
 def test_handle_on_second_device_while_first_is_current():
     """One process driving two GPUs: a handle created on cuda:1 keeps launching there (kernels, shared-memory attributes,
