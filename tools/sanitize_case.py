@@ -10,7 +10,7 @@ from autonomous_quadrotor_environment_b200 import BatchedQuad
 from autonomous_quadrotor_environment_b200 import controllers
 
 DEV = "cuda:0"
-which = sys.argv[1:] or ["step", "rollout", "control", "policy", "f64"]
+which = sys.argv[1:] or ["step", "rollout", "control", "policy", "f64", "ppo"]
 g = torch.Generator(device=DEV); g.manual_seed(3)
 
 if "step" in which:                                   # qs_step: the four loaders, sensor rows, async / strict auto-reset
@@ -61,3 +61,13 @@ if "f64" in which:                                    # parity mode: FP64 RK45 r
     for t in range(6):
         env.step_soa((torch.rand(4, 515, device=DEV, generator=g, dtype=torch.float64) * 2 - 1).contiguous())
     torch.cuda.synchronize(); print("f64 rk45 ok", flush=True)
+
+
+if "ppo" in which:                                    # round 2: critic head, sensed-observation policy rollout, qs_ppo_grad / qs_adam_step
+    from autonomous_quadrotor_environment_b200.ppo import BatchedPPO
+    for sensor in (False, True):
+        env = BatchedQuad(128 * 3 + 21, 0.01, 1000, T=5, precision="f32", async_reset=True, sensor_noise=sensor, seed=5, device=DEV)
+        env.reset()
+        ppo = BatchedPPO(env, hidden=128, K_epochs=2, seed=1)
+        out = ppo.iterate(40)                         # 40 steps: the gradient launch splits them into chunks
+        torch.cuda.synchronize(); print("ppo iteration sensor=%d ok  losses %s" % (sensor, out["losses"]), flush=True)
