@@ -110,14 +110,18 @@ __device__ __forceinline__ void accel_read2(const DevParams<float>& p, P2 f_m, c
 
 // One env step of the sensor model for a pair.  y = TRUE state after the step, acc_read / rot from accel_read2, f_m = F/M.
 // Updates s, writes obs14 (rl_worker.py:171-173).
-// zpre: NULL, or the 24 normals of blocks 0..2 drawn ahead of time (integrate_rk4_2_fused: zpre[8 b + k] = normal k of block b)
+// zpre: NULL, or the 24 normals of blocks 0..2 drawn ahead of time (integrate_rk4_2_fused: zpre[8 b + k] = normal k of block b).
+// ZS > 0: zpre is NOT null and normal j of the pair sits at zpre[j * ZS] (the producer warps of step_kernel_pair leave the normals
+// of a chunk as rows of 64 floats in shared memory: ZS = 32); the Philox / Box-Muller code of blocks 0..2 is then not instantiated.
+template <int ZS = 0>
 __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const SensorRng2& rng, const P2 y[13], const P2 acc_read[3],
                                              const P2 rot[9], P2 f_m, P2 s[kSensorStateDim], P2 obs[14], const P2* zpre = nullptr) {
     const P2 dt = bc(p.dt), sa = bc(p.s_accel_std), sg = bc(p.s_gyro_std), sm = bc(p.s_mag_std), ng = bc(-p.g);
+    constexpr int kZs = ZS > 0 ? ZS : 1;
     P2 z0[8], z1[8];
-    if (zpre) {
+    if (ZS > 0 || zpre) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { z0[k] = zpre[k]; z1[k] = zpre[8 + k]; }
+        for (int k = 0; k < 8; ++k) { z0[k] = zpre[k * kZs]; z1[k] = zpre[(8 + k) * kZs]; }
     } else
     sensor_normals_block2(rng, 0, z0);                                                     // z[0..7]
     // ---- accel_int :700-715
@@ -125,7 +129,7 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
     P2 acc1[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) acc1[k] = pfma(sa, z0[k], padd(acc_read[k], s[0]));
-    if (!zpre) sensor_normals_block2(rng, 1, z1);                                          // z[8..15]
+    if (ZS == 0 && !zpre) sensor_normals_block2(rng, 1, z1);                               // z[8..15]
     P2 Rm[9];
     {   // triad()
         s[0] = pfma(s[2], dt, s[0]);
@@ -182,9 +186,9 @@ __device__ __forceinline__ void sensor_step2(const DevParams<float>& p, const Se
         }
     }
     // ---- triad :649-697 (updates self.R for the next step)
-    if (zpre) {
+    if (ZS > 0 || zpre) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) z0[k] = zpre[16 + k];
+        for (int k = 0; k < 8; ++k) z0[k] = zpre[(16 + k) * kZs];
     } else
     sensor_normals_block2(rng, 2, z0);                                                     // P[16..23]: z[22..26] = P[16..20]
     {

@@ -9,8 +9,8 @@ static bool launch_fast(qs_sim* s, const StepIO<float>& io, cudaStream_t st) {
     if (s->cfg.flags & (QS_FLAG_AUX | QS_FLAG_AUTO_RESET)) return false;   // strict lock-step resets / AUX rows keep the CTA-wide kernel
     if (s->step_loader == 3) {
         constexpr int threads = SENSOR ? pr::kThreadsSensor : pr::kThreadsPlain;
-        constexpr int warps = threads / 32;
-        constexpr size_t smem = (size_t)(SENSOR ? pr::kRowsSensor : pr::kRowsPlain) * 256 * warps;
+        constexpr int warps = (SENSOR ? pr::kConsumerThreadsSensor : pr::kThreadsPlain) / 32;     // the warps that own chunks
+        constexpr size_t smem = SENSOR ? pr::kSmemSensor : pr::kSmemPlain;
         QS_SET_SMEM_ONCE(s, (step_kernel_pair<DIRECT, SENSOR>), smem);
         const int64_t chunks = (s->slice_count + 63) / 64;
         int64_t g = (int64_t)s->sm_count;

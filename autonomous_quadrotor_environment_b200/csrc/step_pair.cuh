@@ -52,10 +52,27 @@ constexpr int kRowsSensor = 46;
 #ifndef QS_PAIR_THREADS_SENSOR
 #define QS_PAIR_THREADS_SENSOR (QS_SENSOR_STREAM ? 384 : 256)
 #endif
+#ifndef QS_PAIR_PRODUCER
+#define QS_PAIR_PRODUCER 0          // 1 = sensor kernel: an extra warpgroup (4 warps, setmaxnreg 56) draws the sensor model's normals (Philox +
+#endif                              // Box-Muller, blocks 0..2 of every env-step) one chunk ahead into shared memory for the chunk warps, whose
+                                    // code then needs 161 registers instead of 210.  Measured (1,048,576 envs, us per step, with / without
+                                    // resets): inline normals 100.8 / 86.8; 8 chunk warps + 4 producers 105.3 / 84.3; 12 chunk warps at 152
+                                    // registers (74 B of spills, single normals buffer) + 4 producers 119.7 / 91.9 — tuning builds only
 constexpr int kThreadsPlain = QS_PAIR_THREADS;
-constexpr int kThreadsSensor = QS_PAIR_THREADS_SENSOR;
+constexpr int kConsumerThreadsSensor = QS_PAIR_THREADS_SENSOR;                 // the warps that own chunks
+constexpr bool kProducer = QS_PAIR_PRODUCER != 0 && !QS_SENSOR_STREAM && !QS_SENSOR_FUSED_NORMALS &&
+                           (QS_PAIR_THREADS_SENSOR == 256 || QS_PAIR_THREADS_SENSOR == 384);
+constexpr int kProducerWarps = kProducer ? 4 : 0;                              // one warpgroup (setmaxnreg works per warpgroup)
+constexpr int kServed = (kConsumerThreadsSensor / 32) / 4;                     // chunk warps per producer warp: j serves kServed*j ...
+constexpr int kThreadsSensor = kConsumerThreadsSensor + 32 * kProducerWarps;
+constexpr int kZRows = 24;                                                     // normals per env-step handed over (blocks 0..2)
+constexpr int kZBufs = QS_PAIR_THREADS_SENSOR == 256 ? 2 : 1;                  // normals buffers per chunk warp (shared memory: 227 KB)
+constexpr int kConsumerRegs = QS_PAIR_THREADS_SENSOR == 256 ? 216 : 152;       // 8 x 32 x 216 (12 x 32 x 152) + 4 x 32 x 56 <= 65,536
 constexpr int kQueueCapPlain = 2048;
 constexpr int kQueueCapSensor = 1024;
+constexpr size_t kSmemPlain = (size_t)26 * 256 * (kThreadsPlain / 32);
+// sensor kernel: per chunk warp 46 stage rows (+ 2 x 24 rows of pre-drawn normals, double-buffered, in producer mode)
+constexpr size_t kSmemSensor = (size_t)(46 + (kProducer ? kZBufs * kZRows : 0)) * 256 * (kConsumerThreadsSensor / 32);
 
 typedef float Row[64];
 
@@ -119,6 +136,7 @@ struct PairMeta {
 // Sensor phase of a pair, arithmetic only: trailing drone_eq evaluation at the new state (rotation matrix, accelerometer
 // reading), the packed sensor model, then the warm-up rules (warm-up steps bypass the model: state kept, true observation
 // passed through; the last one re-initialises it = sensor.reset).  srows = the pair's sensor_state rows in shared memory.
+template <int ZS = 0>
 __device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const SimView<float>& v, const Row* srows, int lane, int64_t nA,
                                              const qs::P2 y[13], const qs::P2 vq[4], qs::P2 f_m, const PairMeta& m,
                                              qs::P2 sn[qs::kSensorStateDim], qs::P2 so[14], const qs::P2* zpre = nullptr) {
@@ -132,7 +150,7 @@ __device__ __forceinline__ void sensor_phase(const DevParams<float>& p, const Si
     rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
     rng.ep[0] = m.episode[0]; rng.ep[1] = m.episode[1];
     rng.step[0] = m.step_i[0]; rng.step[1] = m.step_i[1];
-    sensor_step2(p, rng, y, acc, rot, f_m, sn, so, zpre);
+    sensor_step2<ZS>(p, rng, y, acc, rot, f_m, sn, so, zpre);
     const bool w0 = m.warm[0], w1 = m.warm[1];
     if (__any_sync(0xffffffffu, w0 | w1)) {
 #pragma unroll
@@ -363,6 +381,47 @@ __device__ __forceinline__ void reset_queue_step(const DevParams<float>& p, cons
     }
 }
 
+// Producer warp of the sensor kernel: for the chunks of its two chunk warps, in their order, draw blocks 0..2 of the sensor stream of
+// every env-step (sensor_normals_block2: Philox4x32-10 + Box-Muller, the same arithmetic the chunk warp would run inline) into the
+// chunk warp's normals buffer.  Counters of the step being taken: (global env id, episode, step_i + 1) read from the handle's rows —
+// the chunk warp stores the incremented step counter only after it has waited for this buffer (the episode counter changes only
+// when a finished env is re-sampled, after its chunk's sensor phase).  full / empty: one
+// mbarrier per (chunk warp, buffer), count 32 (every lane arrives for itself).
+__device__ __forceinline__ void normals_producer(const SimView<float>& v, Row* zbase, uint64_t* s_full, uint64_t* s_empty, int pw, int lane,
+                                                 int64_t n_chunks, int64_t stride) {
+    using namespace qs;
+    for (int it = 0;; ++it) {
+        bool any = false;
+#pragma unroll 1
+        for (int j = 0; j < kServed; ++j) {
+            const int cw = kServed * pw + j;
+            const int64_t c = (int64_t)cw * gridDim.x + blockIdx.x + (int64_t)it * stride;
+            if (c >= n_chunks) continue;
+            any = true;
+            const int slot = cw * kZBufs + (it % kZBufs);
+            mbar_wait(&s_empty[slot], ((uint32_t)(it / kZBufs) & 1u) ^ 1u);      // free from the start: the first wait per buffer falls through
+            const int64_t n0 = c << 6;
+            const float2 si = reinterpret_cast<const float2*>(v.obs17 + (int64_t)wp::kMStepI * v.ld + n0)[lane];
+            const float2 ep = reinterpret_cast<const float2*>(v.obs17 + (int64_t)wp::kMEpisode * v.ld + n0)[lane];
+            SensorRng2 rng;
+            rng.seed = v.seed; rng.rk = v.rk;
+            rng.id[0] = v.env_id_offset + (uint32_t)(n0 + 2 * lane); rng.id[1] = rng.id[0] + 1u;
+            rng.ep[0] = __float_as_uint(ep.x); rng.ep[1] = __float_as_uint(ep.y);
+            rng.step[0] = (uint32_t)(__float_as_int(si.x) + 1); rng.step[1] = (uint32_t)(__float_as_int(si.y) + 1);
+            Row* zr = zbase + (size_t)slot * kZRows;
+#pragma unroll 1
+            for (int b = 0; b < 3; ++b) {
+                P2 z[8];
+                sensor_normals_block2(rng, b, z);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) reinterpret_cast<float2*>(zr[8 * b + k])[lane] = z[k].v;
+            }
+            mbar_arrive(&s_full[slot]);                          // every lane releases its own stores (count 32)
+        }
+        if (!any) break;
+    }
+}
+
 }  // namespace pr
 
 template <bool DIRECT, bool SENSOR>
@@ -372,17 +431,39 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
     using namespace pr;
     constexpr int kRows = SENSOR ? kRowsSensor : kRowsPlain;
     constexpr int kQueueCap = SENSOR ? kQueueCapSensor : kQueueCapPlain;
-    constexpr int kThreads = SENSOR ? kThreadsSensor : kThreadsPlain;
-    constexpr int kWarps = kThreads / 32;
+    constexpr int kThreads = SENSOR ? kThreadsSensor : kThreadsPlain;                 // all threads of the CTA
+    constexpr bool kProd = SENSOR && kProducer;
+    constexpr int kWarps = (SENSOR ? kConsumerThreadsSensor : kThreadsPlain) / 32;    // chunk warps
+    constexpr int kChunkThreads = kWarps * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_queue[kQueueCap];
     __shared__ int s_qn, s_qhead;
+    __shared__ uint64_t s_full[kProd ? kZBufs * kWarps : 1], s_empty[kProd ? kZBufs * kWarps : 1];
     const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    Row* st = reinterpret_cast<Row*>(smem_raw) + (size_t)w * kRows;
+    Row* st = reinterpret_cast<Row*>(smem_raw) + (size_t)(w < kWarps ? w : 0) * kRows;
     Row* srows = st + kRowSensor;                            // SENSOR: the pair's sensor_state rows
+    Row* zbase = reinterpret_cast<Row*>(smem_raw) + (size_t)kWarps * kRows;          // [chunk warp][kZBufs][24] rows of normals
     for (int i = tid; i < kQueueCap; i += kThreads) s_queue[i] = 0xFFFFFFFFu;
-    if (tid == 0) { s_qn = 0; s_qhead = 0; }
+    if (tid == 0) {
+        s_qn = 0; s_qhead = 0;
+        if (kProd) {
+            for (int i = 0; i < kZBufs * kWarps; ++i) { mbar_init(&s_full[i], 32); mbar_init(&s_empty[i], 32); }
+            mbar_fence_init();
+        }
+    }
     __syncthreads();
+    if (kProd) {
+        if (w >= kWarps) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+            normals_producer(v, zbase, s_full, s_empty, w - kWarps, lane, (v.N + 63) >> 6, (int64_t)gridDim.x * kWarps);
+            __syncthreads();                   // the chunk warps' "every push has been made"
+            LocalStats none;
+            none.clear();
+            flush_stats(none, false, v.stats);
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kConsumerRegs));
+    }
 
     Ext x;
     const bool n2 = (v.N & 1) == 0, n4 = (v.N & 3) == 0;
@@ -408,7 +489,8 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         prefetch(v, io.action, x, c << 6, st, lane);
         if (SENSOR) prefetch_sensor(v, c << 6, srows, lane);
     }
-    for (; c < n_chunks; c += stride) {
+    uint32_t it = 0;                                         // chunks done by this warp (normals buffer = it & 1)
+    for (; c < n_chunks; c += stride, ++it) {
         // cp.async groups complete in order.  SENSOR: pending here = {state(c), sensor(c)}; the state rows are needed now
         if (SENSOR) cp_wait<1>(); else cp_wait<0>();
         __syncwarp();
@@ -515,7 +597,9 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
             stg2(g2, ld2, wp::kMShaping, e[0].prev_shaping, e[1].prev_shaping);
             stg2(g2, ld2, wp::kMAbsSum, e[0].abs_sum, e[1].abs_sum);
             stg2(g2, ld2, wp::kMEpRet, e[0].ep_return, e[1].ep_return);
-            stg2(g2, ld2, wp::kMStepI, __int_as_float(e[0].i), __int_as_float(e[1].i));
+            // producer mode: the producer warp reads the step counters of this chunk from these rows — they are stored only after
+            // its normals have been waited for (sensor phase below)
+            if (!kProd) stg2(g2, ld2, wp::kMStepI, __int_as_float(e[0].i), __int_as_float(e[1].i));
             stg2(g2, ld2, wp::kMEpisode, __uint_as_float(e[0].episode), __uint_as_float(e[1].episode));
             stg2(g2, ld2, wp::kMReward, o[0].reward, o[1].reward);
             const uint16_t bf = (uint16_t)((e[0].flags & 0xffu) | ((e[1].flags & 0xffu) << 8));
@@ -595,7 +679,16 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
 #if QS_SENSOR_FUSED_NORMALS
                 sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so, zpre);
 #else
-                sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
+                if constexpr (kProd) {
+                    const int slot = w * kZBufs + (int)(it % kZBufs);
+                    mbar_wait(&s_full[slot], (it / kZBufs) & 1u);      // the producer warp has drawn this chunk's normals
+                    stg2(reinterpret_cast<float2*>(v.obs17 + n0) + lane, ld2, wp::kMStepI, __int_as_float(e[0].i), __int_as_float(e[1].i));
+                    const P2* zp = reinterpret_cast<const P2*>(zbase[(size_t)slot * kZRows]) + lane;
+                    sensor_phase<32>(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so, zp);
+                    mbar_arrive(&s_empty[slot]);                   // every lane has read its normals (count 32)
+                } else {
+                    sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
+                }
 #endif
                 __syncwarp();                  // every lane is done with the sensor rows of the stage
                 if (has_next) prefetch_sensor(v, (c + stride) << 6, srows, lane); else cp_commit();
@@ -611,7 +704,7 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         const int head = s_qhead;
         const int qn = s_qn < kQueueCap ? s_qn : kQueueCap;
         __threadfence_block();
-        for (int q = head + tid; q < qn; q += kThreads) wp::resample_env<SENSOR>(p, v, io, (int64_t)s_queue[q]);
+        for (int q = head + tid; q < qn; q += kChunkThreads) wp::resample_env<SENSOR>(p, v, io, (int64_t)s_queue[q]);
     }
     flush_stats(ls, any_end, v.stats);
     if (blockIdx.x == 0 && tid == 0) atomicAdd(&v.stats[7], (double)v.N);
