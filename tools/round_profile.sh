@@ -11,5 +11,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --
 timeout 300 tools/prof2.sh ${R}_prof_step_pair_sensor "step_kernel_pair" 30 16384 profsensor > /dev/null 2>&1
 timeout 300 tools/prof2.sh ${R}_prof_policy_critic "policy_rollout_kernel" 1 2048 profpolicycritic > /dev/null 2>&1
 timeout 200 python tools/kbench.py policycritic > gpurun_out/${R}_kbench_policy.txt 2>&1
+timeout 300 tools/prof2.sh ${R}_prof_ppo_grad "ppo_grad_kernel" 1 16384 profppograd > /dev/null 2>&1
+timeout 200 python tools/kbench.py ppograd > gpurun_out/${R}_kbench_ppo_grad.txt 2>&1
+timeout 200 python tools/kbench.py f64 > gpurun_out/${R}_kbench_f64.txt 2>&1
 timeout 300 python tools/train_ppo.py --envs 65536 --iters 4 > gpurun_out/${R}_train_ppo.txt 2>&1
 ls -la gpurun_out | tail -n 20
