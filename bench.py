@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--T", type=int, default=5)
     ap.add_argument("--e2e-steps", type=int, default=100)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline leg (N=1, rank 0)")
+    ap.add_argument("--ref-seconds", type=float, default=90.0, help="--impl reference: CPU time the bounded sample is sized for")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sensor-noise", type=int, default=1)
     ap.add_argument("--variant-steps", type=int, default=2000, help="timed steps of the sensor_noise=0 variant (0 = skip)")
@@ -139,7 +140,7 @@ def run_reference_arm(args):
     from oracle import cpu_reference as cr
     n_gpu_envs = args.envs_per_gpu or (1 << 20 if args.gpus == 1 else 1 << 21)
     if cr.available():
-        r = python_reference_run(90.0, args.T, steps=args.steps, warmup=args.warmup)
+        r = python_reference_run(args.ref_seconds, args.T, steps=args.steps, warmup=args.warmup)
         rate, dt, cores, n = r["rate"], r["seconds"], r["cores"], r["n_envs"]
         kind, dtype = "reference", "f64"
         how = ("the reference's own quad.step (unmodified Python/NumPy/SciPy, bytecode build oracle/_ref), %d worker processes x %d "
@@ -147,7 +148,7 @@ def run_reference_arm(args):
     else:
         probe_n = 4096
         rate, _, cores = cpu_reference_run(probe_n, 4, 1, args.T)
-        n = int(max(256, min(65536, rate * 90.0 / max(1, args.steps + args.warmup))))
+        n = int(max(256, min(65536, rate * args.ref_seconds / max(1, args.steps + args.warmup))))
         rate, dt, cores = cpu_reference_run(n, args.steps, args.warmup, args.T)
         kind, dtype = "port", "f64"
         how = "reference algorithm (FP64 RK45 rtol 1e-3), C port oracle/quad_oracle.c with OpenMP (oracle/_ref not shipped with this tree)"

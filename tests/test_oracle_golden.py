@@ -257,3 +257,27 @@ def test_mission_generator_is_bit_identical_to_the_reference():
         assert np.array_equal(err, g[name + "_errors"]), name
     with pytest.raises(ValueError):
         mission(0.01).gen_trajectory(300, 100, np.zeros(3), velocity=np.ones(3))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the arm the driver runs beside ours): one JSON line on stdout with the contract's keys, produced by
+    the reference's own quad.step on the host cores (bytecode build oracle/_ref, built here from /root/reference) or — where that
+    build is absent — by the C port, and saying which."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "1",
+                          "--ref-seconds", "4"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"].startswith("env-steps/sec") and d["unit"] == "env-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and "workload" in d["config"]
+    if os.path.isdir("/root/reference"):
+        assert d["cpu_baseline"]["kind"] == "reference"
