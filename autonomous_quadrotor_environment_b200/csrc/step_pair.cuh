@@ -58,8 +58,16 @@ constexpr int kRowsSensor = 46;
                                     // code then needs 161 registers instead of 210.  Measured (1,048,576 envs, us per step, with / without
                                     // resets): inline normals 100.8 / 86.8; 8 chunk warps + 4 producers 105.3 / 84.3; 12 chunk warps at 152
                                     // registers (74 B of spills, single normals buffer) + 4 producers 119.7 / 91.9 — tuning builds only
+#ifndef QS_PAIR_SELF_NORMALS
+#define QS_PAIR_SELF_NORMALS 0      // 1 = sensor kernel: every chunk warp draws the 24 normals of its chunk right after loading it, while few
+#endif                              // registers are live, and parks them in its own rows of shared memory (each lane reads back what it wrote:
+                                    // no synchronisation); the sensor phase then runs without the Philox state next to the sensor state:
+                                    // 168 registers, 12 warps per SM (-DQS_PAIR_THREADS_SENSOR=384) WITHOUT spills.  Measured (us per step of
+                                    // 1,048,576 envs, with / without resets): 8 warps 103.6 / 84.4, 10 warps 108.5 / 91.6, 12 warps 102.5 / 90.8
+                                    // against 100.7 / 86.7 of the default — tuning builds only
 constexpr int kThreadsPlain = QS_PAIR_THREADS;
 constexpr int kConsumerThreadsSensor = QS_PAIR_THREADS_SENSOR;                 // the warps that own chunks
+constexpr bool kSelfNormals = QS_PAIR_SELF_NORMALS != 0 && !QS_PAIR_PRODUCER && !QS_SENSOR_STREAM && !QS_SENSOR_FUSED_NORMALS;
 constexpr bool kProducer = QS_PAIR_PRODUCER != 0 && !QS_SENSOR_STREAM && !QS_SENSOR_FUSED_NORMALS &&
                            (QS_PAIR_THREADS_SENSOR == 256 || QS_PAIR_THREADS_SENSOR == 384);
 constexpr int kProducerWarps = kProducer ? 4 : 0;                              // one warpgroup (setmaxnreg works per warpgroup)
@@ -72,7 +80,7 @@ constexpr int kQueueCapPlain = 2048;
 constexpr int kQueueCapSensor = 1024;
 constexpr size_t kSmemPlain = (size_t)26 * 256 * (kThreadsPlain / 32);
 // sensor kernel: per chunk warp 46 stage rows (+ 2 x 24 rows of pre-drawn normals, double-buffered, in producer mode)
-constexpr size_t kSmemSensor = (size_t)(46 + (kProducer ? kZBufs * kZRows : 0)) * 256 * (kConsumerThreadsSensor / 32);
+constexpr size_t kSmemSensor = (size_t)(46 + (kProducer ? kZBufs * kZRows : (kSelfNormals ? kZRows : 0))) * 256 * (kConsumerThreadsSensor / 32);
 
 typedef float Row[64];
 
@@ -517,6 +525,22 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         if (has_next) prefetch(v, io.action, x, (c + stride) << 6, st, lane);
         else if (SENSOR) cp_commit();           // keep the group count uniform: {sensor(c), state(next) or empty}
 
+        if constexpr (SENSOR && kSelfNormals) {
+            // counters of the step being taken: (global env id, episode, step_i + 1); 24 normals -> this warp's rows, lane's own columns
+            SensorRng2 rng;
+            rng.seed = v.seed; rng.rk = v.rk;
+            rng.id[0] = v.env_id_offset + (uint32_t)nA; rng.id[1] = rng.id[0] + 1u;
+            rng.ep[0] = __float_as_uint(ep.x); rng.ep[1] = __float_as_uint(ep.y);
+            rng.step[0] = (uint32_t)(__float_as_int(si.x) + 1); rng.step[1] = (uint32_t)(__float_as_int(si.y) + 1);
+            Row* zr = zbase + (size_t)w * kZRows;
+#pragma unroll 1
+            for (int b = 0; b < 3; ++b) {
+                P2 z[8];
+                sensor_normals_block2(rng, b, z);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) reinterpret_cast<float2*>(zr[8 * b + k])[lane] = z[k].v;
+            }
+        }
         Env<float> e[2];
         StepOut<float> o[2];
         Ctrl<float> ctl[2];
@@ -686,6 +710,9 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
                     const P2* zp = reinterpret_cast<const P2*>(zbase[(size_t)slot * kZRows]) + lane;
                     sensor_phase<32>(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so, zp);
                     mbar_arrive(&s_empty[slot]);                   // every lane has read its normals (count 32)
+                } else if constexpr (kSelfNormals) {
+                    const P2* zp = reinterpret_cast<const P2*>(zbase[(size_t)w * kZRows]) + lane;   // written by this lane above
+                    sensor_phase<32>(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so, zp);
                 } else {
                     sensor_phase(p, v, srows, lane, nA, y, vq, c2.f_m, m, sn, so);
                 }
