@@ -713,6 +713,36 @@ def test_fused_actor_rollout_on_sensed_observations():
         plain.policy_rollout(4, record_sensed=True)
 
 
+def test_policy_rollout_sharding_and_launch_splitting_are_invisible():
+    """configs[4] across ranks: the action noise of the fused policy (Philox stream RNG_POLICY) and the resets are keyed by GLOBAL env id,
+    episode and step, so two half-size handles with env-id offsets reproduce the whole bit for bit (actions, log-probs, values,
+    rewards, state, history); and one 48-step launch == three 16-step launches (the history carries over)."""
+    g = load_golden("actor_128.npz")
+    crit = {"critic_0_weight": g["actor_0_weight"], "critic_0_bias": g["actor_0_bias"], "critic_2_weight": g["actor_2_weight"],
+            "critic_2_bias": g["actor_2_bias"], "critic_4_weight": g["actor_4_weight"][:1], "critic_4_bias": g["actor_4_bias"][:1]}
+    N, K, seed = 2048, 48, 9
+    mk = lambda n, off: BatchedQuad(n, 0.01, 200, training=True, direct_control=1, T=5, precision="f32", async_reset=True, seed=seed,
+                                    env_id_offset=off, device=DEV)
+    whole, lo, hi, split = mk(N, 0), mk(N // 2, 0), mk(N // 2, N // 2), mk(N, 0)
+    recs = []
+    for e in (whole, lo, hi, split):
+        e.reset()
+        e.load_actor(g, action_std=0.1, critic=crit)
+    kw = dict(record_obs=True, record_values=True)
+    rw, rl, rh = whole.policy_rollout(K, **kw), lo.policy_rollout(K, **kw), hi.policy_rollout(K, **kw)
+    for key in ("actions", "logprob", "reward", "done", "obs"):
+        assert torch.equal(rw[key], torch.cat([rl[key], rh[key]], dim=-1)), key
+    assert torch.equal(rw["value"], torch.cat([rl["value"], rh["value"]], dim=-1))
+    assert torch.equal(whole.state, torch.cat([lo.state, hi.state], dim=0))
+    assert torch.equal(whole.history, torch.cat([lo.history, hi.history], dim=0))
+    parts = [split.policy_rollout(16, **kw) for _ in range(3)]
+    for key in ("actions", "logprob", "reward", "done", "obs"):
+        assert torch.equal(rw[key], torch.cat([p[key] for p in parts], dim=0)), key
+    assert torch.equal(rw["value"][:K], torch.cat([p["value"][:16] for p in parts], dim=0))
+    assert torch.equal(whole.state, split.state) and torch.equal(whole.history, split.history)
+    assert int(whole.episode.max()) >= 1                        # some envs were re-sampled on the way
+
+
 def test_fused_actor_rollout_closed_loop_solves_and_samples():
     g = load_golden("actor_128.npz")
     N = 8192
