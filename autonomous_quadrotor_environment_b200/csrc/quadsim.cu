@@ -582,10 +582,14 @@ rollout_kernel(const __grid_constant__ DevParams<R> p, const __grid_constant__ S
 // QS_STEP_LOADER: 0 direct LDG loads, 1 CTA-wide TMA-staged ring, 2 per-warp cp.async pipeline (one env per lane),
 // 3 per-warp pipeline with two envs per lane on the packed FP32 pipe.  Unset = 3 for every FP32 / RK4 handle: 47.6 vs 57 us
 // per step of 1,048,576 envs without the sensor model, 102 vs 108 us with it (packed sensor model, sensor_pair.cuh).
-static int default_step_loader(uint32_t flags) {
+// Handles whose envs take a data-dependent time per step — the adaptive RK45 replica (8 or 14 drone_eq evaluations), strict
+// lock-step auto-reset (T hover steps inside the step of a finishing env) — default to the plain kernel (0): behind the CTA-wide
+// full / empty barriers of the ring every warp waits for the slowest env of the tile (FP64 RK45: 127.7 -> 78.7 us per step of
+// 65,536 envs, 70.4 -> 45.1 us at 4,096; FP32 strict reset: 91.3 -> 85.9 us per step of 1,048,576 envs).
+static int default_step_loader(const qs_config* cfg) {
     static const int v = [] { const char* e = getenv("QS_STEP_LOADER"); return e ? atoi(e) : -1; }();   // thread-safe (C++11)
     if (v >= 0) return v;
-    (void)flags;
+    if (cfg->integrator == QS_RK45 || (cfg->flags & QS_FLAG_AUTO_RESET)) return 0;
     return 3;
 }
 
@@ -697,7 +701,7 @@ extern "C" int qs_create(qs_handle* out, const qs_config* cfg) {
     cudaDeviceProp prop;
     cudaError_t e1 = cudaGetDeviceProperties(&prop, cfg->device);
     s->sm_count = (e1 == cudaSuccess) ? prop.multiProcessorCount : 148;
-    s->step_loader = default_step_loader(cfg->flags);
+    s->step_loader = default_step_loader(cfg);
     if (s->rs == 4) {       // the per-warp pipeline addresses the 4-byte rows as one matrix: make sure the row table still says so
         const char* b = (const char*)s->obs17;
         const size_t rb = (size_t)s->ld * 4;

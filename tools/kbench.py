@@ -133,6 +133,9 @@ if __name__ == "__main__":
         case_step(N=1 << 18, iters=50, precision="f64", integrator="rk45", async_reset=True, T=5)
         case_step(N=4096, iters=200, precision="f64", integrator="rk45", async_reset=True, T=5)
         case_rollout(N=1 << 16, K=32, iters=4, precision="f64", integrator="rk45", async_reset=True, T=5)
+    if "strict" in which:                                            # handles that cannot use the per-warp kernels: strict resets, AUX rows
+        case_step(auto_reset=True, T=5)
+        case_step(N=1 << 18, auto_reset=True, T=5)
     if "proff64" in which:
         case_step(N=1 << 16, iters=5, precision="f64", integrator="rk45", async_reset=True, T=5)
     if "profpolicy" in which:
