@@ -20,6 +20,23 @@
 #endif
 template <bool SENSOR> struct RolloutPairCfg { static constexpr int kThreads = SENSOR ? QS_ROLLOUT_PAIR_THREADS_SENSOR : QS_ROLLOUT_PAIR_THREADS; };
 
+// Actions read from the caller's [K][4][N] tensor (QS_ACT_BUFFER) are fetched ONE STEP AHEAD: every lane copies the four float2 of
+// its pair for step t+1 into its own slots of a two-stage shared-memory buffer with cp.async (8 bytes: the alignment the launcher
+// already requires) before it starts on step t, so that the HBM latency of the load sits under a whole step of arithmetic
+// instead of in front of it (8 warps per SM cannot hide it: 111.7 -> 94.7 us per step of 1,048,576 envs with the sensor model and
+// the recorded stream; gpurun_out/r2u_rollout_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
+#ifndef QS_ROLLOUT_COOP_RESET
+#define QS_ROLLOUT_COOP_RESET 1                 // 0 = every finishing env is re-sampled in the lane that owns it (async_resample)
+#endif
+namespace rp {
+struct ResetSlots { float4 out[8][4]; uint2 desc[8]; };        // per warp: the finishing envs of one pass and their sampled states
+__device__ __forceinline__ void cp_async8(void* dst_smem, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int PENDING> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(PENDING) : "memory"); }
+}  // namespace rp
+
 // SENSOR (QS_FLAG_SENSOR_NOISE): the packed sensor model of the step kernel (sensor_pair.cuh via pr::sensor_phase) runs after
 // every step; the pair's 20 sensor-state rows live in shared memory for the whole horizon (one 256-byte row segment per warp
 // and row: lane l holds its pair as one float2, conflict-free LDS.64 / STS.64), so a K-step launch moves the sensor state
@@ -30,6 +47,11 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                     const __grid_constant__ RolloutIO<float> io) {
     using pr::half_of;
     extern __shared__ __align__(16) float s_sensor[];           // SENSOR: [warps][20] rows of 64 floats (dynamic shared memory)
+    __shared__ __align__(8) float2 s_act[2][4][RolloutPairCfg<SENSOR>::kThreads];      // QS_ACT_BUFFER: [stage][row][thread]
+    const bool act_buf = io.action_source != QS_ACT_PHILOX_UNIFORM;
+#if QS_ROLLOUT_COOP_RESET
+    __shared__ __align__(16) rp::ResetSlots s_rs[RolloutPairCfg<SENSOR>::kThreads / 32];
+#endif
     pr::Row* srows = reinterpret_cast<pr::Row*>(s_sensor) + (threadIdx.x >> 5) * qs::kSensorStateDim;
     const int lane = threadIdx.x & 31;
     LocalStats ls;
@@ -71,11 +93,17 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
         }
         StepOut<float> o[2];
         bool warm[2] = {false, false};
+        if (act_buf && live) {
+            const float2* at = reinterpret_cast<const float2*>(io.actions) + m;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) rp::cp_async8(&s_act[0][k][threadIdx.x], at + (int64_t)k * N2);
+        }
+        rp::cp_async_commit();
         for (int t = 0; t < io.horizon; ++t) {
             float a[2][4], act[2][4];
             Ctrl<float> ctl[2];
             bool was_done[2];
-            if (io.action_source == QS_ACT_PHILOX_UNIFORM) {
+            if (!act_buf) {
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const uint4 u = philox_block(v.seed, v.env_id_offset + (uint32_t)(nA + h), e[h].episode, (uint32_t)e[h].i, RNG_ACTION);
@@ -83,9 +111,15 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                     a[h][2] = 2.f * u32_to_unit<float>(u.z) - 1.f; a[h][3] = 2.f * u32_to_unit<float>(u.w) - 1.f;
                 }
             } else {
-                const float2* at = reinterpret_cast<const float2*>(io.actions + (int64_t)t * 4 * v.N) + m;
+                if (live && t + 1 < io.horizon) {                  // step t+1's actions start their way in now
+                    const float2* at = reinterpret_cast<const float2*>(io.actions + (int64_t)(t + 1) * 4 * v.N) + m;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { const float2 q = live ? at[(int64_t)k * N2] : make_float2(0.f, 0.f); a[0][k] = q.x; a[1][k] = q.y; }
+                    for (int k = 0; k < 4; ++k) rp::cp_async8(&s_act[(t + 1) & 1][k][threadIdx.x], at + (int64_t)k * N2);
+                }
+                rp::cp_async_commit();
+                rp::cp_async_wait<1>();                            // everything but the group just committed has landed: step t's actions
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 q = live ? s_act[t & 1][k][threadIdx.x] : make_float2(0.f, 0.f); a[0][k] = q.x; a[1][k] = q.y; }
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -163,6 +197,92 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                 }
 #endif
             }
+#if QS_ROLLOUT_COOP_RESET
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+                if (live && o[h].done && !was_done[h]) { count_episode(ls, p, e[h], o[h]); any_end = true; }
+            {
+                // Re-sampling by the whole warp.  With ~50-step episodes about one env of a warp's 64 finishes per step: run in the
+                // lane that owns it, the re-sampler (four Philox4x32-10 blocks, six Box-Muller pairs, euler_quat) costs ~480
+                // instructions for one or two active lanes in 72 % of all warp-steps — a quarter of the kernel's instructions.
+                // Here the finishing envs of the warp (both halves) are listed in shared memory, FOUR LANES TAKE ONE ENV — lane b of
+                // a group draws Philox block b of quad.reset's stream and finishes its share of the state (block 0: Euler angles ->
+                // quaternion; blocks 1-3: the clipped normals) — and the owners read their 13 values back: eight envs per pass,
+                // one pass in all but mass time-outs.  Same draws, same arithmetic as sample_reset_state / async_resample (the
+                // bit-for-bit rollout == repeated-steps tests cover it).  Measured at 1,048,576 envs, K = 32: 82.3 -> 75.6 us per step
+                // with the sensor model (94.7 -> 78.1 with actions from a tensor and the recorded stream), 37.5 -> 36.5 without; most
+                // of it is the instruction cache (stall_no_instructions 16 % -> 9 %: two inlined copies of the re-sampler left the loop).
+                const bool need0 = async_reset && o[0].done, need1 = async_reset && o[1].done;
+                const uint32_t m0 = __ballot_sync(0xffffffffu, need0), m1 = __ballot_sync(0xffffffffu, need1);
+                if (m0 | m1) {
+                    rp::ResetSlots& rs = s_rs[threadIdx.x >> 5];
+                    const uint32_t lt = (1u << lane) - 1u;
+                    const int rank[2] = {__popc(m0 & lt), __popc(m0) + __popc(m1 & lt)};
+                    const bool need[2] = {need0, need1};
+                    const int total = __popc(m0) + __popc(m1);
+                    for (int base = 0; base < total; base += 8) {
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            if (need[h] && (unsigned)(rank[h] - base) < 8u)
+                                rs.desc[rank[h] - base] = make_uint2(v.env_id_offset + (uint32_t)(nA + h), e[h].episode + 1u);
+                        __syncwarp();
+                        const int grp = lane >> 2, blk = lane & 3;
+                        if (base + grp < total) {
+                            const uint2 d = rs.desc[grp];
+                            const uint4 u = philox_block(v.seed, d.x, d.y, (uint32_t)blk, RNG_RESET);
+                            float4 r;
+                            if (blk == 0) {
+                                const float ang[3] = {u32_to_unit<float>(u.x) - 0.5f, u32_to_unit<float>(u.y) - 0.5f, u32_to_unit<float>(u.z) - 0.5f};
+                                float q[4];
+                                euler_quat(ang, q);
+                                r = make_float4(q[0], q[1], q[2], q[3]);
+                            } else {
+                                float n[4];
+                                box_muller(u32_to_unit<float>(u.x), u32_to_unit<float>(u.y), &n[0], &n[1]);
+                                box_muller(u32_to_unit<float>(u.z), u32_to_unit<float>(u.w), &n[2], &n[3]);
+                                // block 1: x y z vx | block 2: vy vz wx wy | block 3: wz
+                                const bool b1 = blk == 1, b2 = blk == 2;
+                                const float lo0 = b1 ? -p.pos_clip : b2 ? -p.vel_clip : p.w_clip_lo, hi0 = b1 ? p.pos_clip : b2 ? p.vel_clip : p.w_clip_hi;
+                                const float lo2 = b1 ? -p.pos_clip : p.w_clip_lo, hi2 = b1 ? p.pos_clip : p.w_clip_hi;
+                                const float lo3 = b1 ? -p.vel_clip : p.w_clip_lo, hi3 = b1 ? p.vel_clip : p.w_clip_hi;
+                                r = make_float4(clampr(n[0] * 2.f, lo0, hi0), clampr(n[1] * 2.f, lo0, hi0), clampr(n[2] * 2.f, lo2, hi2),
+                                                clampr(n[3] * 2.f, lo3, hi3));
+                            }
+                            rs.out[grp][blk] = r;
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            if (need[h] && (unsigned)(rank[h] - base) < 8u) {
+                                const float4* ro = rs.out[rank[h] - base];
+                                const float4 q = ro[0], r1 = ro[1], r2 = ro[2], r3 = ro[3];
+                                Env<float>& en = e[h];
+                                en.y[0] = r1.x; en.y[2] = r1.y; en.y[4] = r1.z; en.y[1] = r1.w;
+                                en.y[3] = r2.x; en.y[5] = r2.y; en.y[10] = r2.z; en.y[11] = r2.w; en.y[12] = r3.x;
+                                en.y[6] = q.x; en.y[7] = q.y; en.y[8] = q.z; en.y[9] = q.w;
+                                en.episode += 1u;
+                                en.flags = (uint32_t)p.T << EF_WARM_SHIFT;          // as async_resample
+                                en.i = 0; en.abs_sum = 0.f; en.ep_return = 0.f;
+                                deriv_quat(&en.y[10], &en.y[6], o[h].vq);
+#pragma unroll
+                                for (int k = 0; k < 13; ++k) { if (h == 0) y[k].v.x = e[0].y[k]; else y[k].v.y = e[1].y[k]; }
+                                if (SENSOR) {        // the sensed observation returned with done is the new episode's initial observation
+                                    float* rec = (io.sensed_out && live) ? io.sensed_out + (int64_t)t * 14 * v.N + nA + h : nullptr;
+                                    float* go = v.sensed_obs + nA + h;
+#pragma unroll
+                                    for (int k = 0; k < 14; ++k) {
+                                        const float x = k < 10 ? e[h].y[k] : o[h].vq[k - 10];
+                                        if (rec) rec[(int64_t)k * v.N] = x;
+                                        if (t == io.horizon - 1) go[(int64_t)k * v.ld] = x;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+#else
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 if (live && o[h].done && !was_done[h]) { count_episode(ls, p, e[h], o[h]); any_end = true; }
@@ -182,6 +302,7 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                     }
                 }
             }
+#endif
             if (io.obs_out && live) {
                 float2* ot = reinterpret_cast<float2*>(io.obs_out + (int64_t)t * 14 * v.N) + m;
 #pragma unroll

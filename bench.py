@@ -601,6 +601,39 @@ def main():
                          "flops_per_env_step": FLOPS_PER_ENV_STEP(S_)},
                 "note": "K=%d steps per launch, %d RK4 sub-intervals per env step (h = %.3g ms), no resets" % (KR, S_, 10.0 / S_)}
             del env3
+        # BASELINE.json configs[2] as ONE fused launch per K steps: the headline workload (sensor model, async auto-reset, actions read
+        # from a device tensor, the sensed observation / reward / done of every step recorded) with the env AND sensor state held
+        # on chip for the horizon (rollout_pair_kernel<direct,sensor>): 77 B per env-step instead of 373
+        try:
+            env4 = BatchedQuad(N, 0.01, 1000, training=True, direct_control=1, T=args.T, precision="f32", integrator="rk4",
+                               substeps=args.substeps, async_reset=True, sensor_noise=True, seed=0, env_id_offset=rank * N, device=dev)
+            env4.reset()
+            KS = 32
+            act4 = (torch.rand(KS, 4, N, device=dev, generator=g) * 2 - 1).contiguous()
+            for w in range(8):                                         # 256 untimed steps: past the first episode turnover
+                env4.rollout(KS, actions=act4)
+            rec = None
+            torch.cuda.synchronize(dev)
+            reps = max(2, args.variant_steps // (KS * 8))
+            v0.record()
+            for k in range(reps):
+                rec = env4.rollout(KS, actions=act4, record_sensed=True, record_reward=True, record_done=True)
+            v1.record()
+            torch.cuda.synchronize(dev)
+            sms = v0.elapsed_time(v1) / (reps * KS)
+            sb = 16 + 56 + 4 + 1
+            variants["rollout_sensor_recorded"] = {
+                "value": N / (sms * 1e-3), "unit": UNIT, "steps": reps * KS, "ms_per_env_step_of_all_envs": sms,
+                "kernel": "rollout_pair_kernel<direct,sensor>",
+                "roofline": {"bound": "hbm", "achieved": sb * N / (sms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": sb * N / (sms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_env_step": sb},
+                "fp32_frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (sms * 1e-3) / 1e12 / fp32_peak,
+                "done_frac_last_launch": float(((rec["done"] & 1) != 0).float().mean().item()),
+                "note": "K=%d steps per launch of the headline workload (sensor model + async auto-reset), actions from a (K,4,N) device "
+                        "tensor, sensed observation + reward + done recorded per step; env and sensor state stay on chip" % KS}
+            del env4, act4, rec
+        except Exception as ex:                                      # a variant must not take the headline line down with it
+            variants["rollout_sensor_recorded"] = {"error": repr(ex)}
 
     if world == 1 and args.variant_steps > 0:
         # (a) the per-GPU shard of BASELINE.json configs[3] (2,097,152 envs) on ONE GPU: the like-for-like base point of the

@@ -93,9 +93,16 @@ def case_rollout(N=1 << 20, K=32, iters=10, **kw):
     env.reset()
     rec = cfg.get("record", False)                 # record = the stream a trainer reads: sensed (or true) observation, reward, done
     sens = bool(cfg.get("sensor_noise", False))
-    fn = (lambda: env.rollout(K, record_sensed=sens, record_obs=not sens, record_reward=True, record_done=True)) if rec else (lambda: env.rollout(K))
+    acts = None
+    if cfg.get("actions", False):                  # the API path: actions read from a (K,4,N) device tensor instead of drawn in-kernel
+        import torch
+        acts = (torch.rand(K, 4, N, device=DEV) * 2 - 1).contiguous()
+    fn = ((lambda: env.rollout(K, actions=acts, record_sensed=sens, record_obs=not sens, record_reward=True, record_done=True)) if rec
+          else (lambda: env.rollout(K, actions=acts)))
+    for _ in range(int(cfg.get("preroll", 0))):    # untimed launches: past the first episode turnover
+        env.rollout(K, actions=acts)
     ms = time_ms(fn, iters, warm=3)
-    emit({"case": "rollout" + ("+rec" if rec else ""), "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
+    emit({"case": "rollout" + ("+rec" if rec else "") + ("+actbuf" if acts is not None else ""), "N": N, "K": K, **cfg, "ms": ms, "steps_per_s": N * K / ms * 1e3})
 
 
 def case_policy(N=1 << 20, K=128, iters=3, sigma=0.1, record=True, critic=False):
@@ -133,6 +140,12 @@ if __name__ == "__main__":
         case_step(N=1 << 18, iters=50, precision="f64", integrator="rk45", async_reset=True, T=5)
         case_step(N=4096, iters=200, precision="f64", integrator="rk45", async_reset=True, T=5)
         case_rollout(N=1 << 16, K=32, iters=4, precision="f64", integrator="rk45", async_reset=True, T=5)
+    if "rolloutab" in which:                                         # fused rollouts with resets: re-sampler and action-fetch A/B
+        case_rollout(K=32, iters=8, async_reset=True, T=5, preroll=6)
+        case_rollout(K=32, iters=8, async_reset=True, T=5, preroll=6, actions=True, record=True)
+        case_rollout(K=32, iters=8, async_reset=True, T=5, preroll=6, sensor_noise=True)
+        case_rollout(K=32, iters=8, async_reset=True, T=5, preroll=6, sensor_noise=True, record=True)
+        case_rollout(K=32, iters=8, async_reset=True, T=5, preroll=6, sensor_noise=True, actions=True, record=True)
     if "strict" in which:                                            # handles that cannot use the per-warp kernels: strict resets, AUX rows
         case_step(auto_reset=True, T=5)
         case_step(N=1 << 18, auto_reset=True, T=5)
@@ -169,7 +182,7 @@ if __name__ == "__main__":
         case_rollout(async_reset=True, T=5)
         case_rollout(async_reset=True, T=5, record=True)
     if "profsensorrollout" in which:
-        case_rollout(async_reset=True, T=5, sensor_noise=True, K=32, iters=2)
+        case_rollout(async_reset=True, T=5, sensor_noise=True, K=32, iters=2, preroll=6)
     if "rollout" in which or "all" in which:
         case_rollout(n=10 ** 9)
         case_rollout(async_reset=True, T=5)
