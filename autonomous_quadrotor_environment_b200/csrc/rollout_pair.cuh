@@ -25,6 +25,9 @@ template <bool SENSOR> struct RolloutPairCfg { static constexpr int kThreads = S
 // already requires) before it starts on step t, so that the HBM latency of the load sits under a whole step of arithmetic
 // instead of in front of it (8 warps per SM cannot hide it: 111.7 -> 94.7 us per step of 1,048,576 envs with the sensor model and
 // the recorded stream; gpurun_out/r2u_rollout_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
+#ifndef QS_ROLLOUT_LOCKSTEP
+#define QS_ROLLOUT_LOCKSTEP 0
+#endif
 #ifndef QS_ROLLOUT_COOP_RESET
 #define QS_ROLLOUT_COOP_RESET 1                 // 0 = every finishing env is re-sampled in the lane that owns it (async_resample)
 #endif
@@ -64,7 +67,18 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
     // the last pair (m >= N2) compute on the padding columns of the handle's rows (ld is a multiple of 256 envs) and never touch the
     // caller's unpadded [K][C][N] buffers or the statistics.
     const int64_t N2r = (N2 + 31) & ~(int64_t)31;
+#if QS_ROLLOUT_LOCKSTEP
+    // tuning build: the warps of a CTA take every step together (see QS_PAIR_LOCKSTEP in step_pair.cuh); measured and rejected:
+    // 75.9 -> 79.3 us per step with the sensor model, 36.6 -> 42.0 without.  Warps past the end of the shard only keep the barrier count
+    for (int64_t mb = (int64_t)blockIdx.x * blockDim.x; mb < N2r; mb += stride) {
+        const int64_t m = mb + threadIdx.x;
+        if (m >= N2r) {
+            for (int t = 0; t < io.horizon; ++t) __syncthreads();
+            continue;
+        }
+#else
     for (int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; m < N2r; m += stride) {
+#endif
         const bool live = m < N2;          // (`act` is the clipped-action array below)
         const int64_t nA = 2 * m;
         const float2* g2 = reinterpret_cast<const float2*>(v.obs17) + m;
@@ -100,6 +114,9 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
         }
         rp::cp_async_commit();
         for (int t = 0; t < io.horizon; ++t) {
+#if QS_ROLLOUT_LOCKSTEP
+            __syncthreads();
+#endif
             float a[2][4], act[2][4];
             Ctrl<float> ctl[2];
             bool was_done[2];

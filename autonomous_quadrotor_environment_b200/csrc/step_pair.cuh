@@ -22,6 +22,9 @@
 // spread over ~96 KB of straight-line code thrash the instruction cache; Philox rounds rolled 115; IMAD.WIDE Philox 114.
 // Resets: same per-CTA queue and opportunistic full-warp drains as step_warp.cuh.
 #pragma once
+#ifndef QS_PAIR_LOCKSTEP
+#define QS_PAIR_LOCKSTEP 0
+#endif
 #include "packed_device.cuh"
 #include "sensor_pair.cuh"
 
@@ -498,7 +501,20 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         if (SENSOR) prefetch_sensor(v, c << 6, srows, lane);
     }
     uint32_t it = 0;                                         // chunks done by this warp (normals buffer = it & 1)
+#if QS_PAIR_LOCKSTEP
+    // -DQS_PAIR_LOCKSTEP=1 (tuning build): the chunk warps of a CTA start every chunk together.  Motive: the hot path of the loop
+    // body (2,041 instructions = 32.6 KB with the sensor model) sits right at the SM's 32 KB instruction cache — ncu counts 13.5 %
+    // misses there (sm__icc_request_hit_rate 86.5 %) and the GPC-level cache behind it at 80 % of its request rate
+    // (gcc__cache_requests_type_instruction) — and in step one warp's miss would fetch the line for all.  Measured and rejected
+    // (gpurun_out/r2w_lockstep_ab.txt): 101.6 -> 111.4 us per step of 1,048,576 envs with the sensor model, 47.1 -> 59.6 without:
+    // warps in step also wait for memory and for the MUFU / FMA pipes in step.
+    const uint32_t iters_max = blockIdx.x < n_chunks ? (uint32_t)((n_chunks - 1 - blockIdx.x) / stride + 1) : 0u;   // warp 0's count
+    for (; it < iters_max; c += stride, ++it) {
+        asm volatile("bar.sync 1, %0;" ::"n"(kChunkThreads) : "memory");
+        if (c >= n_chunks) continue;
+#else
     for (; c < n_chunks; c += stride, ++it) {
+#endif
         // cp.async groups complete in order.  SENSOR: pending here = {state(c), sensor(c)}; the state rows are needed now
         if (SENSOR) cp_wait<1>(); else cp_wait<0>();
         __syncwarp();
