@@ -23,8 +23,11 @@ template <bool SENSOR> struct RolloutPairCfg { static constexpr int kThreads = S
 // Actions read from the caller's [K][4][N] tensor (QS_ACT_BUFFER) are fetched ONE STEP AHEAD: every lane copies the four float2 of
 // its pair for step t+1 into its own slots of a two-stage shared-memory buffer with cp.async (8 bytes: the alignment the launcher
 // already requires) before it starts on step t, so that the HBM latency of the load sits under a whole step of arithmetic
-// instead of in front of it (8 warps per SM cannot hide it: 111.7 -> 94.7 us per step of 1,048,576 envs with the sensor model and
-// the recorded stream; gpurun_out/r2u_rollout_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
+// instead of in front of it (8 warps per SM cannot hide it): 84.1 -> 78.2 us per step of 1,048,576 envs with the sensor model and
+// the recorded stream, 43.0 -> 36.9 without the sensor model (-DQS_ROLLOUT_ACT_PREFETCH=0 is the A/B build; profiles/r02_rollout_prefetch_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
+#ifndef QS_ROLLOUT_ACT_PREFETCH
+#define QS_ROLLOUT_ACT_PREFETCH 1               // 0 = tensor actions loaded where they are consumed (A/B)
+#endif
 #ifndef QS_ROLLOUT_LOCKSTEP
 #define QS_ROLLOUT_LOCKSTEP 0
 #endif
@@ -107,12 +110,14 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
         }
         StepOut<float> o[2];
         bool warm[2] = {false, false};
+#if QS_ROLLOUT_ACT_PREFETCH
         if (act_buf && live) {
             const float2* at = reinterpret_cast<const float2*>(io.actions) + m;
 #pragma unroll
             for (int k = 0; k < 4; ++k) rp::cp_async8(&s_act[0][k][threadIdx.x], at + (int64_t)k * N2);
         }
         rp::cp_async_commit();
+#endif
         for (int t = 0; t < io.horizon; ++t) {
 #if QS_ROLLOUT_LOCKSTEP
             __syncthreads();
@@ -128,6 +133,11 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                     a[h][2] = 2.f * u32_to_unit<float>(u.z) - 1.f; a[h][3] = 2.f * u32_to_unit<float>(u.w) - 1.f;
                 }
             } else {
+#if !QS_ROLLOUT_ACT_PREFETCH
+                const float2* at0 = reinterpret_cast<const float2*>(io.actions + (int64_t)t * 4 * v.N) + m;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { const float2 q = live ? at0[(int64_t)k * N2] : make_float2(0.f, 0.f); a[0][k] = q.x; a[1][k] = q.y; }
+#else
                 if (live && t + 1 < io.horizon) {                  // step t+1's actions start their way in now
                     const float2* at = reinterpret_cast<const float2*>(io.actions + (int64_t)(t + 1) * 4 * v.N) + m;
 #pragma unroll
@@ -137,6 +147,7 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
                 rp::cp_async_wait<1>();                            // everything but the group just committed has landed: step t's actions
 #pragma unroll
                 for (int k = 0; k < 4; ++k) { const float2 q = live ? s_act[t & 1][k][threadIdx.x] : make_float2(0.f, 0.f); a[0][k] = q.x; a[1][k] = q.y; }
+#endif
             }
 #pragma unroll
             for (int h = 0; h < 2; ++h) {

@@ -613,6 +613,8 @@ def main():
             for w in range(8):                                         # 256 untimed steps: past the first episode turnover
                 env4.rollout(KS, actions=act4)
             rec = None
+            for w in range(3):                                         # the recorded buffers come out of torch's caching allocator:
+                rec = env4.rollout(KS, actions=act4, record_sensed=True, record_reward=True, record_done=True)   # no cudaMalloc inside the timed region
             torch.cuda.synchronize(dev)
             reps = max(2, args.variant_steps // (KS * 8))
             v0.record()
