@@ -38,6 +38,12 @@ if "rollout" in which:                                # qs_rollout: pair kernel 
         acts = (torch.rand(20, 4, N, device=DEV, generator=g) * 2 - 1).contiguous()
         env.rollout(20, actions=acts, record_obs=True, record_reward=True, record_done=True)
         torch.cuda.synchronize(); print("rollout N=%d ok" % N, flush=True)
+        # sensor model inside the fused rollout: sensor rows in shared memory, warp-wide re-sampler hand-off, action prefetch stages
+        env = BatchedQuad(N, 0.01, 12, T=3, precision="f32", async_reset=True, sensor_noise=True, seed=5, device=DEV)
+        env.reset()
+        env.rollout(20, record_sensed=True, record_reward=True, record_done=True)
+        env.rollout(20, actions=acts, record_sensed=True, record_obs=True, record_reward=True, record_done=True)
+        torch.cuda.synchronize(); print("sensor rollout N=%d ok  episodes=%d" % (N, env.stats()["n_episodes"]), flush=True)
 
 if "control" in which:                                # qs_control_rollout: LQR and PID laws
     for ctl in (controllers.lqr_controller(), controllers.pid_controller(target_vel=(1.0, 0.0, 0.0))):
