@@ -214,6 +214,40 @@ def test_async_rollout_equals_async_steps():
     assert torch.equal(a.episode, b.episode) and int(a.episode.max()) > 1
 
 
+@pytest.mark.parametrize("sensor", [False, True])
+def test_rollout_mass_timeout_is_resampled_by_the_whole_warp(sensor):
+    """Fused rollout with a 6-step time limit: every env that is still flying times out in the same step, so a warp of the pair
+    kernel has up to 64 finishing envs at once — the warp-wide re-sampler (four lanes per env, eight envs per pass) needs several
+    passes — while in between only stragglers finish.  Episode counters, done bytes and the re-sampled states must be those of
+    repeated qs_step launches (queue + compacted re-sampling), through both action sources' shared path."""
+    N, K, seed = 4160 + 62, 40, 23                      # ragged: the last warp is partly padding
+    mk = lambda: BatchedQuad(N, 0.01, 6, T=2, precision="f32", async_reset=True, sensor_noise=sensor, seed=seed, device=DEV)
+    a, b = mk(), mk()
+    a.reset(); b.reset()
+    ep0 = int(a.episode.max())
+    assert int(a.episode.min()) == ep0
+    g = torch.Generator(device=DEV); g.manual_seed(2)
+    acts = (torch.rand(K, 4, N, device=DEV, generator=g) * 0.2 - 0.1).contiguous()     # gentle: nearly every env reaches the limit
+    rec = a.rollout(K, actions=acts, record_obs=True, record_reward=True, record_done=True)
+    most = 0
+    for t in range(K):
+        obs, rew, done = b.step_soa(acts[t].contiguous())
+        assert torch.equal(b.done_flags, rec["done"][t]), t
+        assert torch.allclose(obs.t(), rec["obs"][t], rtol=1e-6, atol=1e-6), t
+        assert torch.allclose(rew, rec["reward"][t], rtol=1e-5, atol=1e-5), t
+        most = max(most, int((rec["done"][t] & 1).sum()))
+    assert most > 0.9 * N                                                             # the mass time-out happened
+    assert torch.equal(a.episode, b.episode) and int(a.episode.min()) >= ep0 + 4
+    assert torch.allclose(a.state, b.state, rtol=1e-6, atol=1e-6)
+    st, _ = qo.sample_reset_state(seed, np.arange(N), ep0 + 1)                              # the first mass re-sampling against the oracle's sampler:
+    first = min(t for t in range(K) if int((rec["done"][t] & 1).sum()) > 0.9 * N)
+    fin = ((rec["done"][first] & 1) != 0).cpu().numpy()
+    earlier = (rec["done"][:first] & 1).sum(dim=0).cpu().numpy()
+    once = fin & (earlier == 0)                              # envs whose first episode ends here: the observation returned with done
+    got = npy(rec["obs"][first].t())[once][:, :10]           # is the new episode's initial observation
+    assert once.sum() > 0.8 * N and np.max(np.abs(got - st[once][:, :10]) / (1 + np.abs(st[once][:, :10]))) < 2e-5
+
+
 def test_reset_queue_overflow_falls_back_in_lane():
     """Every env of a never-reset handle is done (quad.__init__ :154), so the first step finishes 2M episodes at
     once: far more than the per-block reset queue holds.  All of them must still be re-sampled correctly."""
