@@ -816,6 +816,94 @@ __device__ __forceinline__ void step_post(const DevParams<R>& p, Env<R>& e, cons
     o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
 }
 
+// ---- FP32 twin of phase 3 with the rounding of every operation written out.
+// The pair kernels evaluate this phase on the packed FP32 pipe (step_post2, step_pair.cuh): fma.rn.f32x2 / mul.rn.f32x2 / add.rn.f32x2
+// round each half exactly like the scalar fma.rn / mul.rn / add.rn.  The FP32 scalar phase below is the same sequence of operations
+// as explicit intrinsics (the compiler neither contracts nor re-associates them), so the one-env-per-thread kernels and the pair
+// kernels return bit-identical rewards, angles and flags; the per-env tail (thresholds, cascade, flag logic) is one function for both.
+struct PostSums { float v2, e2, ne, nr2, cur, shaping0, pen_c, ef2; };
+
+__device__ __forceinline__ void post_tail(const DevParams<float>& p, Env<float>& e, StepOut<float>& o, const float ang[3],
+                                          const float vq[4], const PostSums& q) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) o.vq[k] = vq[k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o.ang[k] = ang[k];
+        o.ang_vel[k] = div_dt(ang[k] - e.prev_ang[k], p);        // :492
+        e.prev_ang[k] = ang[k];                                  // :493
+    }
+    bool done = (e.flags & EF_DONE) != 0;                        // done_condition :500-509 (>=, sticky; NaN compares false)
+    const float cx9[9] = {e.y[1], e.y[3], e.y[5], ang[0], ang[1], ang[2], e.y[10], e.y[11], e.y[12]};
+#pragma unroll
+    for (int k = 0; k < 9; ++k) done = done | (fabsf(cx9[k]) >= p.bb[k]);
+    const float nrh = fast_sqrtf(q.nr2), neh = q.ne;
+    float shaping = q.shaping0;
+    bool taken = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {                                // cascade :535-542
+        const bool c1 = (!taken) & (nrh < p.tr_r[k]);
+        const bool c2 = c1 & (neh < p.tr_e[k]);
+        shaping += c1 ? p.tr_p[k] : 0.f;
+        shaping += c2 ? p.tr_p[k] : 0.f;
+        taken = taken | c1;
+    }
+    float reward = (e.flags & EF_HAS_SHAPING) ? (shaping - e.prev_shaping) : 0.f;     // :545-547
+    e.prev_shaping = shaping;
+    reward += q.pen_c;                                           // :553-554
+    const bool is_solved = q.cur < p.target_state;               // :562-573  precedence solved > time limit > broken
+    const bool timeout = (!is_solved) & (e.i >= p.n_limit);
+    const bool broken = (!is_solved) & (!timeout) & done;
+    reward = is_solved ? reward + p.solved_reward : (broken ? reward + p.broken_reward : reward);
+    const bool solved = is_solved | (((e.flags & EF_SOLVED) != 0) & (!timeout) & (!broken));
+    done = done | (is_solved & ((p.flags & F_TRAINING) != 0)) | timeout;
+    e.flags = (e.flags & ~EF_LOW) | (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u);
+    e.abs_sum += fast_sqrtf(q.ef2);                              // :575-577
+    o.reward = reward; o.done = done; o.solved = solved; o.broken = broken; o.timeout = timeout;
+}
+
+__device__ __forceinline__ void step_post(const DevParams<float>& p, Env<float>& e, const float act[4], StepOut<float>& o) {
+    const float* y = e.y;
+    auto fma_ = [](float a, float b, float c) { return __fmaf_rn(a, b, c); };
+    auto mul_ = [](float a, float b) { return __fmul_rn(a, b); };
+    auto add_ = [](float a, float b) { return __fadd_rn(a, b); };
+    const float inv = fast_rsqrtf(fma_(y[6], y[6], fma_(y[7], y[7], fma_(y[8], y[8], mul_(y[9], y[9])))));          // :488-489
+    const float q[4] = {mul_(y[6], inv), mul_(y[7], inv), mul_(y[8], inv), mul_(y[9], inv)};
+    float vq[4];
+    {   // deriv_quat :58-69 in the operation order of deriv_quat2 (sensor_pair.cuh)                                :392
+        const float hx = mul_(y[10], 0.5f), hy = mul_(y[11], 0.5f), hz = mul_(y[12], 0.5f);
+        const float nx = mul_(y[10], -0.5f), ny = mul_(y[11], -0.5f), nz = mul_(y[12], -0.5f);
+        vq[0] = fma_(nx, q[1], fma_(ny, q[2], mul_(nz, q[3])));
+        vq[1] = fma_(hx, q[0], fma_(hz, q[2], mul_(ny, q[3])));
+        vq[2] = fma_(hy, q[0], fma_(nz, q[1], mul_(hx, q[3])));
+        vq[3] = fma_(hz, q[0], fma_(hy, q[1], mul_(nx, q[2])));
+    }
+    // quat_euler utility:39-48
+    const float sx = mul_(2.f, fma_(q[0], q[1], mul_(q[2], q[3])));
+    const float cx = fma_(-2.f, fma_(q[1], q[1], mul_(q[2], q[2])), 1.f);
+    const float sy = mul_(2.f, fma_(q[0], q[2], mul_(mul_(q[3], -1.f), q[1])));
+    const float sz = mul_(2.f, fma_(q[0], q[3], mul_(q[1], q[2])));
+    const float cz = fma_(-2.f, fma_(q[2], q[2], mul_(q[3], q[3])), 1.f);
+    const float ang[3] = {fast_atan2f(sx, cx), fast_asinf(asin_arg<float>(sy)), fast_atan2f(sz, cz)};
+    // reward_function :511-573, the sums
+    PostSums r;
+    r.v2 = fma_(y[1], y[1], fma_(y[3], y[3], mul_(y[5], y[5])));
+    r.e2 = fma_(ang[0], ang[0], mul_(ang[1], ang[1]));
+    const float psi2 = mul_(ang[2], ang[2]);
+    const float w2 = fma_(y[10], y[10], fma_(y[11], y[11], mul_(y[12], y[12])));
+    r.cur = add_(r.v2, add_(add_(r.e2, psi2), w2));                                                               // :558
+    r.nr2 = add_(r.v2, psi2);
+    float pen = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { const float d = add_(act[k], -p.zero_control[k]); pen = fma_(d, d, pen); }
+    r.ef2 = fma_(o.effort[0], o.effort[0], fma_(o.effort[1], o.effort[1], fma_(o.effort[2], o.effort[2], mul_(o.effort[3], o.effort[3]))));
+    const float nv = fast_sqrtf(r.v2);
+    r.ne = fast_sqrtf(r.e2);
+    r.shaping0 = mul_(-1.f, fma_(p.sh_v, nv, fma_(p.sh_psi, fabsf(ang[2]), mul_(p.sh_ang, r.ne))));                // :529-531
+    r.pen_c = mul_(pen, -p.p_c);
+    post_tail(p, e, o, ang, vq, r);
+}
+
 // robust_control context of an env (ROBUST kernels only): where its Philox streams and its gust counter live
 struct RobustCtx { uint64_t seed; uint32_t env_id; int32_t* gust_count; };
 

@@ -173,10 +173,15 @@ rollout_pair_kernel(const __grid_constant__ DevParams<float> p, const __grid_con
 #else
             integrate_rk4_2(p, c2, y);
 #endif
+#if QS_PAIR_PACKED_POST
+            pr::step_post2(p, y, e, act, o);        // phase 3 on the packed pipe; sets e[.].y; bit-identical to the scalar phase
+#endif
 #define QS_RP_POST(H)                                                                                         \
             {                                                                                                 \
-                _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);                  \
-                step_post(p, e[H], act[H], o[H]);                                                             \
+                if (!QS_PAIR_PACKED_POST) {                                                                   \
+                    _Pragma("unroll") for (int k = 0; k < 13; ++k) e[H].y[k] = half_of<H>(y[k]);              \
+                    step_post(p, e[H], act[H], o[H]);                                                         \
+                }                                                                                             \
                 o[H].reward = warm[H] ? 0.f : o[H].reward;                                                    \
                 e[H].ep_return += o[H].reward;                                                                \
             }

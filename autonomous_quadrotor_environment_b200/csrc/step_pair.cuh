@@ -22,6 +22,9 @@
 // spread over ~96 KB of straight-line code thrash the instruction cache; Philox rounds rolled 115; IMAD.WIDE Philox 114.
 // Resets: same per-CTA queue and opportunistic full-warp drains as step_warp.cuh.
 #pragma once
+#ifndef QS_PAIR_PACKED_POST
+#define QS_PAIR_PACKED_POST 1
+#endif
 #ifndef QS_PAIR_LOCKSTEP
 #define QS_PAIR_LOCKSTEP 0
 #endif
@@ -318,45 +321,19 @@ __device__ __forceinline__ void step_post2(const DevParams<float>& p, const qs::
     const P2 nv = pk(fast_sqrtf(v2.v.x), fast_sqrtf(v2.v.y)), ne = pk(fast_sqrtf(e2.v.x), fast_sqrtf(e2.v.y));
     const P2 shaping0 = pmul(bc(-1.f), pfma(bc(p.sh_v), nv, pfma(bc(p.sh_psi), pk(fabsf(psi.v.x), fabsf(psi.v.y)), pmul(bc(p.sh_ang), ne))));   // :529-531
     const P2 pen_c = pmul(pen, bc(-p.p_c));
-#define QS_POST2_HALF(H)                                                                                      \
-    {                                                                                                         \
-        const float ang[3] = {half_of<H>(phi), half_of<H>(theta), half_of<H>(psi)};                           \
-        _Pragma("unroll") for (int k = 0; k < 4; ++k) o[H].vq[k] = half_of<H>(vq[k]);                         \
-        _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                                       \
-            o[H].ang[k] = ang[k];                                                                             \
-            o[H].ang_vel[k] = div_dt(ang[k] - e[H].prev_ang[k], p);                                           \
-            e[H].prev_ang[k] = ang[k];                                                                        \
-        }                                                                                                     \
-        bool done = (e[H].flags & EF_DONE) != 0;                                                              \
-        const float cx9[9] = {half_of<H>(y[1]), half_of<H>(y[3]), half_of<H>(y[5]), ang[0], ang[1], ang[2],   \
-                              half_of<H>(y[10]), half_of<H>(y[11]), half_of<H>(y[12])};                       \
-        _Pragma("unroll") for (int k = 0; k < 9; ++k) done = done | (fabsf(cx9[k]) >= p.bb[k]);               \
-        const float nrh = fast_sqrtf(half_of<H>(nr2)), neh = half_of<H>(ne);                                  \
-        float shaping = half_of<H>(shaping0);                                                                 \
-        bool taken = false;                                                                                   \
-        _Pragma("unroll") for (int k = 0; k < 3; ++k) {                                                       \
-            const bool c1 = (!taken) & (nrh < p.tr_r[k]);                                                     \
-            const bool c2 = c1 & (neh < p.tr_e[k]);                                                           \
-            shaping += c1 ? p.tr_p[k] : 0.f;                                                                  \
-            shaping += c2 ? p.tr_p[k] : 0.f;                                                                  \
-            taken = taken | c1;                                                                               \
-        }                                                                                                     \
-        float reward = (e[H].flags & EF_HAS_SHAPING) ? (shaping - e[H].prev_shaping) : 0.f;                   \
-        e[H].prev_shaping = shaping;                                                                          \
-        reward += half_of<H>(pen_c);                                                                          \
-        const bool is_solved = half_of<H>(cur) < p.target_state;                                              \
-        const bool timeout = (!is_solved) & (e[H].i >= p.n_limit);                                            \
-        const bool broken = (!is_solved) & (!timeout) & done;                                                 \
-        reward = is_solved ? reward + p.solved_reward : (broken ? reward + p.broken_reward : reward);         \
-        const bool solved = is_solved | (((e[H].flags & EF_SOLVED) != 0) & (!timeout) & (!broken));           \
-        done = done | (is_solved & ((p.flags & F_TRAINING) != 0)) | timeout;                                  \
-        e[H].flags = (e[H].flags & ~EF_LOW) | (done ? EF_DONE : 0u) | EF_HAS_SHAPING | (solved ? EF_SOLVED : 0u); \
-        e[H].abs_sum += fast_sqrtf(half_of<H>(ef2));                                                          \
-        o[H].reward = reward; o[H].done = done; o[H].solved = solved; o[H].broken = broken; o[H].timeout = timeout; \
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {                 // the per-env tail is the scalar kernels' own (post_tail, quad_device.cuh)
+        const bool hi = h != 0;
+#pragma unroll
+        for (int k = 0; k < 13; ++k) e[h].y[k] = hi ? y[k].v.y : y[k].v.x;
+        const float ang[3] = {hi ? phi.v.y : phi.v.x, hi ? theta.v.y : theta.v.x, hi ? psi.v.y : psi.v.x};
+        const float vqh[4] = {hi ? vq[0].v.y : vq[0].v.x, hi ? vq[1].v.y : vq[1].v.x, hi ? vq[2].v.y : vq[2].v.x, hi ? vq[3].v.y : vq[3].v.x};
+        PostSums r;
+        r.v2 = hi ? v2.v.y : v2.v.x; r.e2 = hi ? e2.v.y : e2.v.x; r.ne = hi ? ne.v.y : ne.v.x; r.nr2 = hi ? nr2.v.y : nr2.v.x;
+        r.cur = hi ? cur.v.y : cur.v.x; r.shaping0 = hi ? shaping0.v.y : shaping0.v.x; r.pen_c = hi ? pen_c.v.y : pen_c.v.x;
+        r.ef2 = hi ? ef2.v.y : ef2.v.x;
+        post_tail(p, e[h], o[h], ang, vqh, r);
     }
-    QS_POST2_HALF(0)
-    QS_POST2_HALF(1)
-#undef QS_POST2_HALF
 }
 
 // QS_FLAG_ASYNC_RESET, once per chunk: push the finished envs of this lane's pair on the CTA's queue (AFTER all of their
@@ -598,12 +575,10 @@ step_kernel_pair(const __grid_constant__ DevParams<float> p, const __grid_consta
         integrate_rk4_2(p, c2, y);
 #endif
         // ---- phase 3 per env: observation tail, Euler angles, done, reward
-        // -DQS_PAIR_PACKED_POST: phase 3 on the packed pipe (step_post2).  Measured 100.6 vs 102.0 us with the sensor model and
-        // 46.9 vs 47.05 us without (1,048,576 envs); NOT the default yet: test_step_loaders_agree[65536-True-1-False-3] fails
-        // against the scalar phase of loader 1 with it — the pitch angle of one env next to gimbal lock differs by 1.5e-4
-        // (asin amplifies the one-ulp difference of its argument 2(q0 q2 - q3 q1), which the packed form rounds in another
-        // order); the comparison needs a bound that follows the conditioning of asin before the switch.
-#ifdef QS_PAIR_PACKED_POST
+        // phase 3 on the packed pipe (step_post2): bit-identical to the scalar FP32 phase of the one-env-per-thread kernels (both are
+        // the same sequence of explicitly rounded operations, quad_device.cuh); -DQS_PAIR_PACKED_POST=0 instantiates the scalar phase
+        // per half instead (A/B: 102.0 vs 100.6 us per step of 1,048,576 envs with the sensor model)
+#if QS_PAIR_PACKED_POST
 #define QS_PAIR_POST_CALL(H)
         step_post2(p, y, e, act, o);
 #else
