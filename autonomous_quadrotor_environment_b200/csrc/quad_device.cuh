@@ -819,8 +819,9 @@ __device__ __forceinline__ void step_post(const DevParams<R>& p, Env<R>& e, cons
 // ---- FP32 twin of phase 3 with the rounding of every operation written out.
 // The pair kernels evaluate this phase on the packed FP32 pipe (step_post2, step_pair.cuh): fma.rn.f32x2 / mul.rn.f32x2 / add.rn.f32x2
 // round each half exactly like the scalar fma.rn / mul.rn / add.rn.  The FP32 scalar phase below is the same sequence of operations
-// as explicit intrinsics (the compiler neither contracts nor re-associates them), so the one-env-per-thread kernels and the pair
-// kernels return bit-identical rewards, angles and flags; the per-env tail (thresholds, cascade, flag logic) is one function for both.
+// as explicit intrinsics (the compiler neither contracts nor re-associates them), so from the same state the one-env-per-thread
+// kernels and the pair kernels return bit-identical rewards, angles and flags; the per-env tail (thresholds, cascade, flag logic) is
+// one function for both.  (The RK4 stages before it are not twinned: scalar drone_eq is contracted by the compiler.)
 struct PostSums { float v2, e2, ne, nr2, cur, shaping0, pen_c, ef2; };
 
 __device__ __forceinline__ void post_tail(const DevParams<float>& p, Env<float>& e, StepOut<float>& o, const float ang[3],
