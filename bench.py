@@ -694,9 +694,9 @@ def main():
                          "kernel": kernel_name, "algorithmic_bytes_per_env_step": algo_bytes,
                          "kernel_ms": kernel_ms,
                          "note": "HBM is the roof of a one-step launch (SURVEY 8(d)); the kernel itself is bound by instruction issue and "
-                                 "the latency of its dependency chains: 2,797 warp-instructions per 64 env-steps with the sensor model "
-                                 "(two envs per lane on FFMA2/FMUL2), 8 warps per SM at 215 registers "
-                                 "(profiles/r01_prof_step_pair_sensor.txt; DESIGN.md lists the variants measured against it)"},
+                                 "the latency of its dependency chains: 2,660 warp-instructions per 64 env-steps with the sensor model "
+                                 "(two envs per lane on FFMA2/FMUL2), 8 warps per SM at 210 registers "
+                                 "(profiles/r02_prof_step_pair_sensor.txt; DESIGN.md lists the variants measured against it)"},
             "fp32": {"achieved_tflops": flops, "peak_tflops_probe": fp32_peak, "frac": flops / fp32_peak,
                      "flops_per_env_step": FLOPS_PER_ENV_STEP(args.substeps),
                      "note": "algorithmic FLOPs (SURVEY.md 8(d)) vs an in-run dependent-FFMA probe"},
