@@ -821,6 +821,39 @@ def test_dropin_quad_reproduces_shipped_lqr_log():
         assert worst < 1e-8, (ep, worst)
 
 
+def test_dropin_quad_survives_pickling_mid_episode():
+    """environment/controller/ppo.py ships its environments to a multiprocessing pool (the compatibility class must
+    be picklable).  A drop-in `quad` pickled in the middle of an episode and loaded again continues exactly like the original:
+    same observations, rewards, done flags and attribute surface, bit for bit (FP64 + RK45 replica), through the episode's end and
+    the next reset (the NumPy global stream both draw from is re-seeded alike)."""
+    import pickle
+    from autonomous_quadrotor_environment_b200.quadrotor_env import quad
+    a = quad(0.01, 60, training=True, euler=0, direct_control=1, T=3, clipped=True, verbose=False)
+    a.seed(7)
+    s0, a0 = a.reset()
+    assert s0.shape == (3, 14) and a0.shape == (3, 4)
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-0.3, 0.3, (80, 4))
+    for k in range(25):
+        a.step(acts[k])
+    blob = pickle.dumps(a)
+    b = pickle.loads(blob)
+    assert b is not a and b._sim is not a._sim
+    for name in ("state", "ang", "ang_vel", "step_effort", "i", "abs_sum", "done", "solved"):
+        assert np.array_equal(np.asarray(getattr(a, name)), np.asarray(getattr(b, name))), name
+    fresh_blob = pickle.dumps(quad(0.01, 60, training=True, direct_control=1, T=3, verbose=False))     # never stepped: no device state yet
+    assert pickle.loads(fresh_blob)._sim is None
+    for k in range(25, 80):
+        oa, ra, da = a.step(acts[k])
+        ob, rb, db = b.step(acts[k])
+        assert np.array_equal(oa, ob) and ra == rb and da == db, k
+        if da:
+            break
+    np.random.seed(11); sa, _ = a.reset()
+    np.random.seed(11); sb, _ = b.reset()
+    assert np.array_equal(sa, sb) and np.array_equal(a.state, b.state)
+
+
 # ----------------------------------------------------------------------------------------------------
 # SURVEY.md §8(f)3: the reference's classical comparison controllers as in-kernel control laws
 # ----------------------------------------------------------------------------------------------------
