@@ -667,6 +667,28 @@ def main():
         except Exception as ex:                                  # a variant must not take the headline line down with it
             variants["policy_rollout_1Mx128"] = {"error": repr(ex)}
 
+        # (b') BASELINE.json configs[0]: ONE env through the reference's own class API — the drop-in quad (N = 1 handle, FP64 + SciPy-RK45
+        #      replica; host action in, host observation / attributes out on every call): wall time per quad.step
+        try:
+            import numpy as np
+            from autonomous_quadrotor_environment_b200.quadrotor_env import quad as dropin_quad
+            q1 = dropin_quad(0.01, 10 ** 6, training=False, euler=0, direct_control=1, T=1, clipped=True, verbose=False)
+            q1.seed(1); q1.reset()
+            for k in range(50):
+                q1.step(np.zeros(4))
+            ts = time.perf_counter()
+            K1 = 500
+            for k in range(K1):
+                q1.step(0.02 * np.sin(0.1 * k + np.arange(4)))
+            us = (time.perf_counter() - ts) / K1 * 1e6
+            variants["single_env_dropin"] = {
+                "value": 1e6 / us, "unit": UNIT, "us_per_step": us, "steps": K1,
+                "note": "compat quad.step of one env (FP64, RK45 replica; kernel launch + host round trip of the whole attribute surface "
+                        "per call); the reference's own quad.step takes 1.48 ms on one core (BASELINE.md)"}
+            del q1
+        except Exception as ex:
+            variants["single_env_dropin"] = {"error": repr(ex)}
+
         # (c) SURVEY.md 8(f)1: one PPO iteration on the same 1M x 128 rollout — collect (fused actor + critic rollout, GAE) and the
         #     K_epochs = 10 network update on qs_ppo_grad / qs_adam_step (forward + backward on tcgen05)
         try:
