@@ -126,6 +126,8 @@ class quad():
             d["_ws_host"] = self._sim._ws.cpu()
         d["_sim"] = None
         d["_fields"] = None
+        for k in ("_ws_pin", "_a_host", "_a_dev"):              # staging buffers are rebuilt on demand
+            d.pop(k, None)
         return d
 
     def __setstate__(self, d):
@@ -167,7 +169,13 @@ class quad():
 
     def _pull(self):
         """One D2H copy of the (few-KB) workspace, then slice the reference's attributes out of it."""
-        ws = self._sim._ws.cpu().numpy()
+        sim = self._sim
+        import torch
+        if getattr(self, "_ws_pin", None) is None:               # pinned mirror: one asynchronous copy + one stream synchronisation
+            self._ws_pin = torch.empty(sim._ws.shape, dtype=sim._ws.dtype, pin_memory=True)
+        self._ws_pin.copy_(sim._ws, non_blocking=True)
+        torch.cuda.current_stream(sim.device).synchronize()
+        ws = self._ws_pin.numpy()                               # every attribute below is a copy (astype), never a view of the mirror
 
         def get(name):
             off, c, ld, dt = self._fields[name]
@@ -246,9 +254,15 @@ class quad():
     def step(self, action):
         """quad.step (:458-498)."""
         sim = self._ensure_sim()
-        a = np.asarray(action, dtype=np.float64).reshape(-1)[:4]
+        a = np.array(action, dtype=np.float64).reshape(-1)[:4]
         self.action = np.clip(a, -1, 1) if self.direct_control_flag else a
-        sim.step(a.reshape(1, 4))
+        import torch
+        if getattr(self, "_a_host", None) is None:               # pinned staging of the 4-float action and its device twin
+            self._a_host = torch.empty(4, 1, dtype=sim.dtype, pin_memory=True)
+            self._a_dev = torch.empty(4, 1, dtype=sim.dtype, device=sim.device)
+        self._a_host[:, 0] = torch.from_numpy(a)
+        self._a_dev.copy_(self._a_host, non_blocking=True)
+        sim.step_soa(self._a_dev)
         self._pull()
         self.action_hist.append(self.clipped_action)
         return self.quat_state, self.reward, self.done
