@@ -628,7 +628,10 @@ def main():
                 "value": N / (sms * 1e-3), "unit": UNIT, "steps": reps * KS, "ms_per_env_step_of_all_envs": sms,
                 "kernel": "rollout_pair_kernel<direct,sensor>",
                 "roofline": {"bound": "hbm", "achieved": sb * N / (sms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": sb * N / (sms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_env_step": sb},
+                             "frac": sb * N / (sms * 1e-3) / 1e9 / hbm_peak, "traffic": None, "algorithmic_bytes_per_env_step": sb,
+                             "note": "with the state on chip the stream is 77 B per env-step and HBM is no longer the limiter: the kernel is bound "
+                                     "by instruction issue and dependency latency (2,600 warp-instructions per 64 env-steps at 8 warps per SM, "
+                                     "FMA pipe 45 % busy; profiles/r02_prof_rollout_pair_sensor.txt)"},
                 "fp32_frac": FLOPS_PER_ENV_STEP(args.substeps) * N / (sms * 1e-3) / 1e12 / fp32_peak,
                 "done_frac_last_launch": float(((rec["done"] & 1) != 0).float().mean().item()),
                 "note": "K=%d steps per launch of the headline workload (sensor model + async auto-reset), actions from a (K,4,N) device "
