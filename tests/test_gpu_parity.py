@@ -248,6 +248,42 @@ def test_rollout_mass_timeout_is_resampled_by_the_whole_warp(sensor):
     assert once.sum() > 0.8 * N and np.max(np.abs(got - st[once][:, :10]) / (1 + np.abs(st[once][:, :10]))) < 2e-5
 
 
+def test_c_abi_error_codes_of_the_rollout_entry_point():
+    """include/quadsim.h: every entry point returns 0 or a negative QS_E* code and leaves a message for qs_last_error(); nothing is
+    launched on a refused call (the handle's state is untouched)."""
+    N = 256
+    env = BatchedQuad(N, 0.01, 100, T=2, precision="f32", async_reset=True, seed=1, device=DEV)
+    env.reset()
+    before = env._ws.clone()
+    lib, st = env.lib, C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def rc_of(**kw):
+        a = L.qs_rollout_args()
+        a.horizon = 4
+        a.action_source = L.QS_ACT_PHILOX_UNIFORM
+        for k, v in kw.items():
+            setattr(a, k, v)
+        rc = lib.qs_rollout(env._h, C.byref(a), st)
+        return rc, lib.qs_last_error().decode()
+
+    for kw, code in (({"horizon": 0}, L.QS_EINVAL), ({"action_source": L.QS_ACT_BUFFER}, L.QS_EINVAL), ({"action_source": 77}, L.QS_EINVAL),
+                     ({"sensed_obs_out": before.data_ptr()}, L.QS_ESTATE)):
+        rc, msg = rc_of(**kw)
+        assert rc == code and "qs_rollout" in msg, (kw, rc, msg)
+    assert lib.qs_rollout(None, None, st) == L.QS_EINVAL
+    torch.cuda.synchronize()
+    assert torch.equal(env._ws, before)                              # refused calls launched nothing
+    aux = BatchedQuad(N, 0.01, 100, T=1, precision="f64", integrator="rk45", aux=True, seed=1, device=DEV)
+    aux.reset()
+    with pytest.raises(L.QuadSimError) as ei:
+        aux.rollout(4)                                               # AUX rows are a single-step feature
+    assert ei.value.code == L.QS_ESTATE
+    rc, _ = rc_of()                                                  # and a well-formed call goes through
+    assert rc == L.QS_OK
+    torch.cuda.synchronize()
+    assert not torch.equal(env._ws, before)
+
+
 def test_reset_queue_overflow_falls_back_in_lane():
     """Every env of a never-reset handle is done (quad.__init__ :154), so the first step finishes 2M episodes at
     once: far more than the per-block reset queue holds.  All of them must still be re-sampled correctly."""
