@@ -181,6 +181,8 @@ if __name__ == "__main__":
         case_rollout(async_reset=True, T=5, sensor_noise=True, K=128, iters=4)
         case_rollout(async_reset=True, T=5)
         case_rollout(async_reset=True, T=5, record=True)
+    if "profrollouts8" in which:                                     # the fused rollout at 8 RK4 sub-intervals, no resets: the FMA-roofline point
+        case_rollout(n=10 ** 9, K=8, iters=2, substeps=8)
     if "profsensorrollout" in which:
         case_rollout(async_reset=True, T=5, sensor_noise=True, K=32, iters=2, preroll=6)
     if "rollout" in which or "all" in which:
