@@ -15,6 +15,8 @@ __global__ void k(unsigned* out, int iters) {
             if (MODE == 2) asm volatile("tanh.approx.f16x2 %0, %0;" : "+r"(x[j]));
             if (MODE == 3) asm volatile("tanh.approx.bf16x2 %0, %0;" : "+r"(x[j]));
             if (MODE == 4) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+r"(x[j]));
+            if (MODE == 5) asm volatile("cvt.rn.bf16x2.f32 %0, %0, %1;" : "+r"(x[j]) : "r"(x[(j + 1) & 7]));        // F2FP.BF16.F32.PACK_AB
+            if (MODE == 6) asm volatile("{.reg .b32 t; add.u32 t, %0, 0x8000; prmt.b32 %0, t, %1, 0x7632;}" : "+r"(x[j]) : "r"(x[(j + 1) & 7]));   // integer pack
         }
     }
     unsigned s = 0;
@@ -35,5 +37,6 @@ template <int MODE> void run(const char* name, int per_instr) {
 }
 int main() {
     run<0>("tanh.approx.f32", 1); run<1>("tanh.approx.f16", 1); run<2>("tanh.approx.f16x2", 2); run<3>("tanh.approx.bf16x2", 2); run<4>("ex2.approx.ftz.f32", 1);
+    run<5>("cvt.rn.bf16x2.f32", 1); run<6>("add + prmt pack", 1);
     return 0;
 }
