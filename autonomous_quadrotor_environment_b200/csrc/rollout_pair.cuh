@@ -24,7 +24,8 @@ template <bool SENSOR> struct RolloutPairCfg { static constexpr int kThreads = S
 // its pair for step t+1 into its own slots of a two-stage shared-memory buffer with cp.async (8 bytes: the alignment the launcher
 // already requires) before it starts on step t, so that the HBM latency of the load sits under a whole step of arithmetic
 // instead of in front of it (8 warps per SM cannot hide it): 84.1 -> 78.2 us per step of 1,048,576 envs with the sensor model and
-// the recorded stream, 43.0 -> 36.9 without the sensor model (-DQS_ROLLOUT_ACT_PREFETCH=0 is the A/B build; profiles/r02_rollout_prefetch_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
+// the recorded stream, 43.0 -> 36.9 without the sensor model (-DQS_ROLLOUT_ACT_PREFETCH=0 is the A/B build;
+// profiles/r02_rollout_prefetch_ab.txt).  A lane only ever reads what it copied itself: no warp synchronisation.
 #ifndef QS_ROLLOUT_ACT_PREFETCH
 #define QS_ROLLOUT_ACT_PREFETCH 1               // 0 = tensor actions loaded where they are consumed (A/B)
 #endif
